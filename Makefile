@@ -1,0 +1,38 @@
+# Builds every native artefact in-tree (the .so files travel to the GPU box with
+# the snapshot; they are git-ignored).
+#   make            -> product library + synthetic-store generator + oracle
+#   make product    -> oarfish_b200/lib/liboarfish_em.so, liboarsynth.so
+#   make oracle     -> oracle/liboarfish_oracle.so   (test infrastructure only)
+NVCC      ?= nvcc
+# the image exports CC=/opt/gcc/bin/gcc, a wrapper that cannot find libgomp.spec; use the system gcc
+HOSTCC    := $(shell [ -x /usr/bin/gcc ] && echo /usr/bin/gcc || echo gcc)
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wextra -Xptxas -v --expt-relaxed-constexpr
+CFLAGS    := -O3 -std=gnu11 -fPIC -Wall -Wextra -fopenmp
+
+CSRC      := oarfish_b200/csrc
+LIBDIR    := oarfish_b200/lib
+CU_SRCS   := $(wildcard $(CSRC)/*.cu)
+CU_HDRS   := $(wildcard $(CSRC)/*.cuh) include/oarfish_em.h
+
+all: product oracle
+
+product: $(LIBDIR)/liboarfish_em.so $(LIBDIR)/liboarsynth.so
+
+$(LIBDIR)/liboarfish_em.so: $(CU_SRCS) $(CU_HDRS)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(CU_SRCS) 2> $(LIBDIR)/ptxas.log || (cat $(LIBDIR)/ptxas.log; exit 1)
+
+$(LIBDIR)/liboarsynth.so: $(CSRC)/synth.c
+	@mkdir -p $(LIBDIR)
+	$(HOSTCC) $(CFLAGS) -shared -o $@ $< -lm
+
+oracle: oracle/liboarfish_oracle.so
+
+oracle/liboarfish_oracle.so: oracle/em_oracle.c oracle/em_par_port.c
+	$(HOSTCC) $(CFLAGS) -shared -o $@ $^ -lm
+
+clean:
+	rm -f $(LIBDIR)/*.so $(LIBDIR)/ptxas.log oracle/*.so
+
+.PHONY: all product oracle clean

@@ -1,0 +1,161 @@
+/*
+ * oarfish_em.h -- C ABI of the B200-native EM / bootstrap engine.
+ *
+ * This is the drop-in boundary for oarfish's inference stage.  The reference
+ * (100 % Rust, /root/reference @ v0.10.3) has no FFI of its own; the boundary is
+ * the three Rust functions the drivers call, and each entry point below names
+ * the one it replaces:
+ *
+ *   oar_store_create      <- the data EMInfo.eq_map points at:
+ *                            InMemoryAlignmentStore (src/util/oarfish_types.rs:547-558),
+ *                            read through iter() (:602-656)
+ *   oar_em                <- em::em      (src/em.rs:262, called bulk.rs:157-158, single_cell.rs:150)
+ *                            em::em_par  (src/em.rs:320, called bulk.rs:155-156)
+ *   oar_bootstrap         <- em::bootstrap (src/em.rs:292, called bulk.rs:179)
+ *                            + bootstrap::get_sample_inds (src/bootstrap.rs:7)
+ *   oar_bootstrap_weights <- em::do_bootstrap (src/em.rs:273) with the resampling
+ *                            made explicit (test hook: exact per-weight-vector parity)
+ *   oar_em_batched        <- the per-cell em::em(&emi, 1) calls of
+ *                            single_cell.rs:150 batched into one call
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative oar_status; nothing
+ *     throws or aborts across the ABI; oar_last_error() returns a thread-local
+ *     message for the last failing call on this thread.
+ *   - buffers passed in are BORROWED for the duration of the call only.
+ *     Pointers documented "host or device" are resolved with CUDA unified
+ *     addressing (cudaMemcpyDefault).
+ *   - a handle is used by one host thread at a time; distinct handles are
+ *     independent.  Device memory is owned by the handle.
+ *   - transcript indexing is bit-exact: out[i] is the count of header reference
+ *     id i, exactly as em::em returns Vec<f64> indexed by ref_id.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point
+ *     fails with OAR_ERR_CUDA.
+ */
+#ifndef OARFISH_EM_H
+#define OARFISH_EM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    OAR_OK = 0,
+    OAR_ERR_INVALID = -1,   /* bad argument (null pointer, inconsistent sizes, id out of range) */
+    OAR_ERR_CUDA = -2,      /* CUDA runtime error or no device */
+    OAR_ERR_OOM = -3,       /* host or device allocation failed */
+    OAR_ERR_UNSUPPORTED = -4
+} oar_status;
+
+typedef struct oar_store oar_store; /* opaque; one per alignment store per device */
+
+/* Sweep-kernel selection (OAR_KERNEL_AUTO picks the fastest valid one). */
+typedef enum {
+    OAR_KERNEL_AUTO = 0,
+    OAR_KERNEL_ROWGROUP = 1,  /* 8-lane group per read row, global f64 reductions */
+    OAR_KERNEL_TILED = 2      /* locality-sorted tiles, in-tile aggregation */
+} oar_kernel;
+
+/* ABI version: major*1000 + minor. */
+int oar_version(void);
+
+/* Number of visible CUDA devices, or a negative oar_status. */
+int oar_device_count(void);
+
+const char *oar_last_error(void);
+
+/*
+ * Upload an alignment store to `device` as CSR.
+ *   row_ptr  N+1 u64  == InMemoryAlignmentStore.boundaries (private Vec<usize>, oarfish_types.rs:555)
+ *   txp_id   nnz u32  == AlnInfo.ref_id de-interleaved (oarfish_types.rs:331)
+ *   prob     nnz f32  == as_probabilities (oarfish_types.rs:551)
+ *   aux      nnz f64 or NULL == coverage_probabilities * density factor when
+ *            --model-coverage / --use-kde is on (em.rs:108-111); NULL means 1.0
+ * All four may be host or device pointers.  Validates row_ptr monotonicity,
+ * row_ptr[N] == nnz and txp_id < n_txps (OAR_ERR_INVALID otherwise).
+ */
+int oar_store_create(const uint64_t *row_ptr, const uint32_t *txp_id, const float *prob,
+                     const double *aux_or_null, uint64_t n_reads, uint64_t nnz,
+                     uint32_t n_txps, int device, oar_store **out);
+
+void oar_store_destroy(oar_store *store);
+
+/* Store geometry. */
+int oar_store_info(const oar_store *store, uint64_t *n_reads, uint64_t *nnz, uint32_t *n_txps,
+                   int *device);
+
+/* Select the sweep kernel for subsequent calls on this store. */
+int oar_store_set_kernel(oar_store *store, int kernel);
+
+/*
+ * One EM run to convergence.  Replaces em::em (min_iter = 50, stop rule
+ * em.rs:212) and em::em_par (min_iter = 1, stop rule em.rs:399).
+ *   init_or_null  M f64 (EMInfo.init_abundances, em.rs:160-167) or NULL for the
+ *                 uniform N/M start
+ *   out_counts    M f64, host or device, caller-allocated
+ *   out_niter     loop counter `niter` at exit (em.rs:170)
+ *   out_rel_diff  last relative difference evaluated (em.rs:194-201)
+ */
+int oar_em(oar_store *store, const double *init_or_null, uint32_t max_iter, double conv_thresh,
+           uint32_t min_iter, double *out_counts, uint32_t *out_niter, double *out_rel_diff);
+
+/*
+ * Bootstrap replicates (em::bootstrap, em.rs:292-314).  Replicate b of this
+ * call is global replicate  g = first_replicate + b * replicate_stride ; its
+ * resampling weights are a pure function of (seed, g), so sharding replicates
+ * over devices or processes (rank r of G: first = r, stride = G) gives results
+ * independent of G.  Each replicate: multinomial(N; 1/N..) read weights
+ * (== the histogram of get_sample_inds, bootstrap.rs:7-16), then do_em with
+ * min_iter = 50 (em.rs:287-289).
+ *   out        num_boot x M f64 row-major, host or device
+ *   out_niter  num_boot u32 (host) or NULL
+ */
+int oar_bootstrap(oar_store *store, uint32_t num_boot, uint64_t seed, uint32_t first_replicate,
+                  uint32_t replicate_stride, uint32_t max_iter, double conv_thresh,
+                  double *out, uint32_t *out_niter);
+
+/* Same, with caller-supplied integer read weights (R x N u32, host or device):
+ * weights[r*N + i] = number of times read i appears in replicate r's sample. */
+int oar_bootstrap_weights(oar_store *store, const uint32_t *weights, uint32_t n_replicates,
+                          uint32_t max_iter, double conv_thresh, uint32_t min_iter,
+                          double *out, uint32_t *out_niter);
+
+/* The weights oar_bootstrap uses for global replicate g (N u32, host or device). */
+int oar_bootstrap_sample_weights(oar_store *store, uint64_t seed, uint32_t replicate,
+                                 uint32_t *out_weights);
+
+/*
+ * Batched independent EMs over contiguous groups of reads of one store
+ * (single-cell mode, single_cell.rs:91-193: one em::em(&emi,1) per cell).
+ *   cell_row_ptr  C+1 u64 over reads: cell c owns reads [cell_row_ptr[c], cell_row_ptr[c+1])
+ *   out_counts    C x M f64 row-major dense, host or device (callers keep v > 0,
+ *                 single_cell.rs:155-160)
+ */
+int oar_em_batched(oar_store *store, const uint64_t *cell_row_ptr, uint32_t n_cells,
+                   uint32_t max_iter, double conv_thresh, uint32_t min_iter,
+                   double *out_counts, uint32_t *out_niter);
+
+/* Timings of the last compute call on this store, milliseconds (CUDA events):
+ * [0] upload+layout, [1] EM loop (device), [2] result download, [3] weight generation. */
+int oar_store_timings(const oar_store *store, double out_ms[4]);
+
+/* Counters of the last compute call: [0] kernels launched, [1] sweeps executed. */
+int oar_store_counters(const oar_store *store, uint64_t out[2]);
+
+/*
+ * Raw single E+M sweep for measurement and tests: curr (M f64, device) is
+ * zeroed then accumulated from prev (M f64, device).  weights_or_null: N u32
+ * device.  Runs on the store's stream; *not* synchronised unless sync != 0.
+ */
+int oar_sweep(oar_store *store, const double *prev_dev, double *curr_dev,
+              const uint32_t *weights_or_null, int sync);
+
+/* The CUDA stream (cudaStream_t) the store launches on, for event timing. */
+void *oar_store_stream(oar_store *store);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OARFISH_EM_H */

@@ -1,0 +1,12 @@
+"""oarfish_b200 -- B200-native EM / bootstrap engine behind oarfish's em::em,
+em::em_par and em::bootstrap (reference: COMBINE-lab/oarfish src/em.rs).
+
+Layout: csrc/ holds the sm_100a kernels and the C ABI (include/oarfish_em.h);
+em.py mirrors the reference's interface; engine.py wraps the ABI handle.
+"""
+from .em import (ALN_INFO_DTYPE, AlignmentFilters, EMInfo, InMemoryAlignmentStore, TranscriptInfo, bootstrap, em,
+                 em_par)
+from .engine import DeviceStore, EMResult, device_count
+
+__all__ = ["ALN_INFO_DTYPE", "AlignmentFilters", "EMInfo", "InMemoryAlignmentStore", "TranscriptInfo", "bootstrap",
+           "em", "em_par", "DeviceStore", "EMResult", "device_count"]

@@ -1,0 +1,503 @@
+// oar_em.cu -- C ABI + EM driver of the B200-native oarfish EM engine.
+//
+// Reference semantics implemented here (files under /root/reference/src):
+//   em.rs:87-133   m_step      -> em_sweep_* kernels (fused E-step + M-step)
+//   em.rs:144-255  do_em       -> run_em(): on-device convergence, CUDA graph
+//   em.rs:320-447  em_par      -> same driver with min_iter = 1
+//   em.rs:273-314  bootstrap   -> oar_bootstrap*: multinomial read weights
+//   bootstrap.rs:7-16          -> boot_weights_kernel (Philox4x32-10)
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "oar_common.cuh"
+#include "oar_kernels.cuh"
+
+namespace oar {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string &msg) { g_last_error = msg; }
+int fail(int code, const std::string &msg) { g_last_error = msg; return code; }
+int cuda_fail(cudaError_t e, const char *what)
+{
+    g_last_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+    (void)cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? OAR_ERR_OOM : OAR_ERR_CUDA;
+}
+
+}  // namespace oar
+
+using namespace oar;
+
+// ---------------------------------------------------------------------------
+// store
+// ---------------------------------------------------------------------------
+
+static const int kGraphIters = 16;  // EM iterations per graph launch (even)
+
+struct GraphSlot {
+    cudaGraphExec_t exec = nullptr;
+    bool weighted = false;
+    int kernel = 0;
+};
+
+struct oar_store {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    uint64_t n_reads = 0, nnz = 0;
+    uint32_t n_txps = 0;
+    int kernel = OAR_KERNEL_ROWGROUP;
+
+    // CSR in HBM
+    uint32_t *d_row_ptr = nullptr;  // N+1
+    uint32_t *d_txp = nullptr;      // nnz
+    float *d_prob = nullptr;        // nnz
+    double *d_aux = nullptr;        // nnz or null
+
+    // EM work buffers
+    double *d_counts[2] = {nullptr, nullptr};
+    OarEmState *d_state = nullptr;
+    OarEmState *h_state = nullptr;  // pinned, 4 slots
+    uint32_t *d_weights = nullptr;  // N, bootstrap weights of the current replicate
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t slot_ev[2] = {nullptr, nullptr};
+
+    GraphSlot graphs[2];  // [0] unweighted, [1] weighted
+
+    double timings[4] = {0, 0, 0, 0};
+    uint64_t counters[2] = {0, 0};
+};
+
+static void destroy_graphs(oar_store *s)
+{
+    for (auto &g : s->graphs) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        g.exec = nullptr;
+    }
+}
+
+extern "C" int oar_version(void) { return 1000; }
+
+extern "C" const char *oar_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int oar_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+    return n;
+}
+
+extern "C" void oar_store_destroy(oar_store *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    destroy_graphs(s);
+    cudaFree(s->d_row_ptr); cudaFree(s->d_txp); cudaFree(s->d_prob); cudaFree(s->d_aux);
+    cudaFree(s->d_counts[0]); cudaFree(s->d_counts[1]); cudaFree(s->d_state); cudaFree(s->d_weights);
+    if (s->h_state) cudaFreeHost(s->h_state);
+    for (auto &e : s->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : s->slot_ev) if (e) cudaEventDestroy(e);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+    (void)cudaGetLastError();
+}
+
+extern "C" int oar_store_create(const uint64_t *row_ptr, const uint32_t *txp_id, const float *prob,
+                                const double *aux_or_null, uint64_t n_reads, uint64_t nnz,
+                                uint32_t n_txps, int device, oar_store **out)
+{
+    if (!out) return fail(OAR_ERR_INVALID, "oar_store_create: out is null");
+    *out = nullptr;
+    if (!row_ptr) return fail(OAR_ERR_INVALID, "oar_store_create: row_ptr is null");
+    if (nnz > 0 && (!txp_id || !prob)) return fail(OAR_ERR_INVALID, "oar_store_create: txp_id/prob is null");
+    if (n_txps == 0) return fail(OAR_ERR_INVALID, "oar_store_create: n_txps must be > 0");
+    if (nnz >= 0xFFFFFFF0ull || n_reads >= 0xFFFFFFF0ull)
+        return fail(OAR_ERR_UNSUPPORTED, "oar_store_create: stores with >= 2^32 alignments or reads are not supported");
+    int ndev = 0;
+    OAR_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(OAR_ERR_INVALID, "oar_store_create: bad device index");
+    OAR_CUDA(cudaSetDevice(device));
+
+    oar_store *s = new (std::nothrow) oar_store();
+    if (!s) return fail(OAR_ERR_OOM, "oar_store_create: host allocation failed");
+    s->device = device; s->n_reads = n_reads; s->nnz = nnz; s->n_txps = n_txps;
+    int rc = [&]() -> int {
+        OAR_CUDA(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device));
+        OAR_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        for (auto &e : s->ev) OAR_CUDA(cudaEventCreate(&e));
+        for (auto &e : s->slot_ev) OAR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        OAR_CUDA(cudaEventRecord(s->ev[0], s->stream));
+        const size_t pad = 16;  // slack so vector loads may over-read safely
+        OAR_CUDA(cudaMalloc(&s->d_row_ptr, sizeof(uint32_t) * (n_reads + 1 + pad)));
+        OAR_CUDA(cudaMalloc(&s->d_txp, sizeof(uint32_t) * (nnz + pad)));
+        OAR_CUDA(cudaMalloc(&s->d_prob, sizeof(float) * (nnz + pad)));
+        if (aux_or_null) OAR_CUDA(cudaMalloc(&s->d_aux, sizeof(double) * (nnz + pad)));
+        OAR_CUDA(cudaMalloc(&s->d_counts[0], sizeof(double) * n_txps));
+        OAR_CUDA(cudaMalloc(&s->d_counts[1], sizeof(double) * n_txps));
+        OAR_CUDA(cudaMalloc(&s->d_state, sizeof(OarEmState) * 2));
+        OAR_CUDA(cudaMallocHost(&s->h_state, sizeof(OarEmState) * 4));
+        // stage the u64 boundaries, narrow to u32 and validate on the device
+        uint64_t *d_rp64 = nullptr;
+        uint32_t *d_flag = reinterpret_cast<uint32_t *>(s->d_state + 1);
+        OAR_CUDA(cudaMalloc(&d_rp64, sizeof(uint64_t) * (n_reads + 1)));
+        OAR_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(uint32_t) * 4, s->stream));
+        OAR_CUDA(cudaMemcpyAsync(d_rp64, row_ptr, sizeof(uint64_t) * (n_reads + 1), cudaMemcpyDefault, s->stream));
+        if (nnz) {
+            OAR_CUDA(cudaMemcpyAsync(s->d_txp, txp_id, sizeof(uint32_t) * nnz, cudaMemcpyDefault, s->stream));
+            OAR_CUDA(cudaMemcpyAsync(s->d_prob, prob, sizeof(float) * nnz, cudaMemcpyDefault, s->stream));
+            if (aux_or_null)
+                OAR_CUDA(cudaMemcpyAsync(s->d_aux, aux_or_null, sizeof(double) * nnz, cudaMemcpyDefault, s->stream));
+        }
+        OAR_CUDA(cudaMemsetAsync(s->d_txp + nnz, 0, sizeof(uint32_t) * pad, s->stream));
+        OAR_CUDA(cudaMemsetAsync(s->d_prob + nnz, 0, sizeof(float) * pad, s->stream));
+        {
+            const int threads = 256;
+            const int blocks = (int)std::min<uint64_t>((n_reads + threads) / threads, (uint64_t)s->sm_count * 16);
+            kern::narrow_validate_rowptr<<<blocks, threads, 0, s->stream>>>(d_rp64, s->d_row_ptr, n_reads, nnz, d_flag);
+            const int blocks2 = (int)std::max<uint64_t>(1, std::min<uint64_t>((nnz + threads - 1) / threads, (uint64_t)s->sm_count * 16));
+            kern::validate_txp<<<blocks2, threads, 0, s->stream>>>(s->d_txp, nnz, n_txps, d_flag + 1);
+        }
+        uint32_t h_flag[4] = {0, 0, 0, 0};
+        OAR_CUDA(cudaMemcpyAsync(h_flag, d_flag, sizeof(h_flag), cudaMemcpyDeviceToHost, s->stream));
+        OAR_CUDA(cudaEventRecord(s->ev[1], s->stream));
+        OAR_CUDA(cudaStreamSynchronize(s->stream));
+        OAR_CUDA(cudaFree(d_rp64));
+        OAR_CUDA(cudaGetLastError());
+        if (h_flag[0]) return fail(OAR_ERR_INVALID, "oar_store_create: row_ptr is not a monotone prefix ending at nnz");
+        if (h_flag[1]) return fail(OAR_ERR_INVALID, "oar_store_create: txp_id out of range (>= n_txps)");
+        float ms = 0.f;
+        OAR_CUDA(cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]));
+        s->timings[0] = ms;
+        return OAR_OK;
+    }();
+    if (rc != OAR_OK) {
+        std::string keep = g_last_error;
+        oar_store_destroy(s);
+        g_last_error = keep;
+        return rc;
+    }
+    *out = s;
+    return OAR_OK;
+}
+
+extern "C" int oar_store_info(const oar_store *s, uint64_t *n_reads, uint64_t *nnz, uint32_t *n_txps, int *device)
+{
+    if (!s) return fail(OAR_ERR_INVALID, "oar_store_info: store is null");
+    if (n_reads) *n_reads = s->n_reads;
+    if (nnz) *nnz = s->nnz;
+    if (n_txps) *n_txps = s->n_txps;
+    if (device) *device = s->device;
+    return OAR_OK;
+}
+
+extern "C" int oar_store_set_kernel(oar_store *s, int kernel)
+{
+    if (!s) return fail(OAR_ERR_INVALID, "oar_store_set_kernel: store is null");
+    if (kernel == OAR_KERNEL_AUTO) kernel = OAR_KERNEL_ROWGROUP;
+    if (kernel != OAR_KERNEL_ROWGROUP)
+        return fail(OAR_ERR_UNSUPPORTED, "oar_store_set_kernel: kernel not available in this build");
+    if (kernel != s->kernel) { cudaSetDevice(s->device); destroy_graphs(s); }
+    s->kernel = kernel;
+    return OAR_OK;
+}
+
+extern "C" int oar_store_timings(const oar_store *s, double out_ms[4])
+{
+    if (!s || !out_ms) return fail(OAR_ERR_INVALID, "oar_store_timings: null argument");
+    for (int i = 0; i < 4; ++i) out_ms[i] = s->timings[i];
+    return OAR_OK;
+}
+
+extern "C" int oar_store_counters(const oar_store *s, uint64_t out[2])
+{
+    if (!s || !out) return fail(OAR_ERR_INVALID, "oar_store_counters: null argument");
+    out[0] = s->counters[0]; out[1] = s->counters[1];
+    return OAR_OK;
+}
+
+extern "C" void *oar_store_stream(oar_store *s) { return s ? (void *)s->stream : nullptr; }
+
+// ---------------------------------------------------------------------------
+// sweep dispatch
+// ---------------------------------------------------------------------------
+
+// Enqueue one fused E+M sweep prev -> curr (curr must already be zero).
+static cudaError_t enqueue_sweep(oar_store *s, const double *prev, double *curr, const uint32_t *wts,
+                                 const OarEmState *state, int check_done)
+{
+    if (s->n_reads == 0) return cudaSuccess;
+    const int threads = 256;
+    const uint64_t groups_per_block = threads / 8;
+    const uint64_t want = (s->n_reads + groups_per_block - 1) / groups_per_block;
+    const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)s->sm_count * 8));
+#define OAR_LAUNCH(AUX, WTS)                                                                      \
+    kern::em_sweep_rowgroup<AUX, WTS><<<blocks, threads, 0, s->stream>>>(                         \
+        s->d_row_ptr, s->d_txp, s->d_prob, s->d_aux, wts, prev, curr, s->n_reads, state, check_done)
+    if (s->d_aux) { if (wts) OAR_LAUNCH(true, true); else OAR_LAUNCH(true, false); }
+    else          { if (wts) OAR_LAUNCH(false, true); else OAR_LAUNCH(false, false); }
+#undef OAR_LAUNCH
+    s->counters[0] += 1;
+    return cudaGetLastError();
+}
+
+static cudaError_t enqueue_update(oar_store *s, double *prev, const double *curr)
+{
+    const int threads = 256;
+    const int blocks = (int)std::max<uint32_t>(1, std::min<uint32_t>((s->n_txps + threads * 4 - 1) / (threads * 4), (uint32_t)s->sm_count * 4));
+    kern::em_update<<<blocks, threads, 0, s->stream>>>(prev, curr, s->n_txps, s->d_state);
+    s->counters[0] += 1;
+    return cudaGetLastError();
+}
+
+// Build (once per store and variant) the CUDA graph of kGraphIters iterations:
+// even iterations sweep buf0 -> buf1, odd ones buf1 -> buf0.
+static int ensure_graph(oar_store *s, bool weighted)
+{
+    GraphSlot &g = s->graphs[weighted ? 1 : 0];
+    if (g.exec && g.kernel == s->kernel) return OAR_OK;
+    if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    const uint32_t *wts = weighted ? s->d_weights : nullptr;
+    uint64_t saved = s->counters[0];
+    cudaGraph_t graph = nullptr;
+    OAR_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+    cudaError_t e = cudaSuccess;
+    for (int it = 0; it < kGraphIters && e == cudaSuccess; ++it) {
+        double *prev = s->d_counts[it & 1], *curr = s->d_counts[(it + 1) & 1];
+        e = enqueue_sweep(s, prev, curr, wts, s->d_state, 1);
+        if (e == cudaSuccess) e = enqueue_update(s, prev, curr);
+    }
+    cudaError_t e2 = cudaStreamEndCapture(s->stream, &graph);
+    s->counters[0] = saved;
+    if (e != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return cuda_fail(e, "graph capture (launch)"); }
+    if (e2 != cudaSuccess) return cuda_fail(e2, "cudaStreamEndCapture");
+    e = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { g.exec = nullptr; return cuda_fail(e, "cudaGraphInstantiate"); }
+    g.kernel = s->kernel; g.weighted = weighted;
+    return OAR_OK;
+}
+
+// One complete EM (do_em, em.rs:144-255) on the store's stream.  `init_dev`
+// (device, M) or null for uniform.  Result is left in *result_buf (device).
+static int run_em(oar_store *s, const double *init_dev, uint32_t max_iter, double thr, uint32_t min_iter,
+                  bool weighted, double **result_buf, uint32_t *out_niter, double *out_rel, uint32_t *out_sweeps)
+{
+    const uint32_t M = s->n_txps;
+    const uint32_t *wts = weighted ? s->d_weights : nullptr;
+    // state
+    OarEmState init_state;
+    memset(&init_state, 0, sizeof(init_state));
+    init_state.conv_thresh = thr; init_state.max_iter = max_iter; init_state.min_iter = min_iter;
+    init_state.done = (max_iter == 0) ? 1u : 0u;
+    s->h_state[3] = init_state;
+    OAR_CUDA(cudaMemcpyAsync(s->d_state, &s->h_state[3], sizeof(OarEmState), cudaMemcpyHostToDevice, s->stream));
+    // prev = init or N/M (em.rs:160-167); curr = 0 (em.rs:158)
+    {
+        const int threads = 256;
+        const int blocks = (int)std::max<uint32_t>(1, std::min<uint32_t>((M + threads - 1) / threads, (uint32_t)s->sm_count * 8));
+        const double avg = (double)s->n_reads / (double)M;
+        kern::em_init<<<blocks, threads, 0, s->stream>>>(s->d_counts[0], s->d_counts[1], init_dev, avg, M);
+        s->counters[0] += 1;
+        OAR_CUDA(cudaGetLastError());
+    }
+    uint32_t sweeps = 0, niter = 0;
+    double rel = 0.0;
+    if (max_iter > 0) {
+        int rc = ensure_graph(s, weighted);
+        if (rc != OAR_OK) return rc;
+        cudaGraphExec_t exec = s->graphs[weighted ? 1 : 0].exec;
+        // keep two graph launches in flight; poll the state copied after each
+        int inflight = 0, head = 0;
+        bool done = false;
+        uint64_t launched_iters = 0;
+        while (!done) {
+            while (inflight < 2) {
+                int slot = (head + inflight) & 1;
+                OAR_CUDA(cudaGraphLaunch(exec, s->stream));
+                launched_iters += kGraphIters;
+                OAR_CUDA(cudaMemcpyAsync(&s->h_state[slot], s->d_state, sizeof(OarEmState), cudaMemcpyDeviceToHost, s->stream));
+                OAR_CUDA(cudaEventRecord(s->slot_ev[slot], s->stream));
+                ++inflight;
+            }
+            OAR_CUDA(cudaEventSynchronize(s->slot_ev[head]));
+            const OarEmState &hs = s->h_state[head];
+            if (hs.done) { done = true; sweeps = hs.sweeps; niter = hs.niter; rel = hs.last_rel; }
+            head ^= 1; --inflight;
+        }
+        // the launches still in flight are no-ops (done is set); they finish before the final sweep (same stream)
+        s->counters[0] += (uint64_t)sweeps * 2;  // sweep + update kernels that did real work
+        (void)launched_iters;
+    }
+    double *prev = s->d_counts[sweeps & 1], *curr = s->d_counts[(sweeps + 1) & 1];
+    {
+        const int threads = 256;
+        const int blocks = (int)std::max<uint32_t>(1, std::min<uint32_t>((M + threads - 1) / threads, (uint32_t)s->sm_count * 8));
+        kern::em_threshold<<<blocks, threads, 0, s->stream>>>(prev, M);  // em.rs:238-242
+        s->counters[0] += 1;
+        OAR_CUDA(cudaGetLastError());
+    }
+    OAR_CUDA(enqueue_sweep(s, prev, curr, wts, s->d_state, 0));         // em.rs:245-252
+    s->counters[1] += sweeps + 1;
+    *result_buf = curr;
+    if (out_niter) *out_niter = niter;
+    if (out_rel) *out_rel = rel;
+    if (out_sweeps) *out_sweeps = sweeps;
+    return OAR_OK;
+}
+
+static int stage_init(oar_store *s, const double *init_or_null, double **d_init)
+{
+    *d_init = nullptr;
+    if (!init_or_null) return OAR_OK;
+    OAR_CUDA(cudaMalloc(d_init, sizeof(double) * s->n_txps));
+    OAR_CUDA(cudaMemcpyAsync(*d_init, init_or_null, sizeof(double) * s->n_txps, cudaMemcpyDefault, s->stream));
+    return OAR_OK;
+}
+
+extern "C" int oar_em(oar_store *s, const double *init_or_null, uint32_t max_iter, double conv_thresh,
+                      uint32_t min_iter, double *out_counts, uint32_t *out_niter, double *out_rel_diff)
+{
+    if (!s) return fail(OAR_ERR_INVALID, "oar_em: store is null");
+    if (!out_counts) return fail(OAR_ERR_INVALID, "oar_em: out_counts is null");
+    OAR_CUDA(cudaSetDevice(s->device));
+    s->counters[0] = s->counters[1] = 0;
+    double *d_init = nullptr;
+    int rc = stage_init(s, init_or_null, &d_init);
+    if (rc != OAR_OK) { cudaFree(d_init); return rc; }
+    OAR_CUDA(cudaEventRecord(s->ev[0], s->stream));
+    double *res = nullptr;
+    rc = run_em(s, d_init, max_iter, conv_thresh, min_iter, false, &res, out_niter, out_rel_diff, nullptr);
+    if (rc != OAR_OK) { cudaStreamSynchronize(s->stream); cudaFree(d_init); return rc; }
+    OAR_CUDA(cudaEventRecord(s->ev[1], s->stream));
+    OAR_CUDA(cudaMemcpyAsync(out_counts, res, sizeof(double) * s->n_txps, cudaMemcpyDefault, s->stream));
+    OAR_CUDA(cudaEventRecord(s->ev[2], s->stream));
+    OAR_CUDA(cudaStreamSynchronize(s->stream));
+    if (d_init) OAR_CUDA(cudaFree(d_init));
+    float a = 0.f, b = 0.f;
+    OAR_CUDA(cudaEventElapsedTime(&a, s->ev[0], s->ev[1]));
+    OAR_CUDA(cudaEventElapsedTime(&b, s->ev[1], s->ev[2]));
+    s->timings[1] = a; s->timings[2] = b; s->timings[3] = 0;
+    return OAR_OK;
+}
+
+// ---------------------------------------------------------------------------
+// bootstrap
+// ---------------------------------------------------------------------------
+
+static int ensure_weights(oar_store *s)
+{
+    if (!s->d_weights) OAR_CUDA(cudaMalloc(&s->d_weights, sizeof(uint32_t) * (s->n_reads + 16)));
+    return OAR_OK;
+}
+
+static int enqueue_sample_weights(oar_store *s, uint64_t seed, uint32_t replicate, uint32_t *d_w)
+{
+    OAR_CUDA(cudaMemsetAsync(d_w, 0, sizeof(uint32_t) * s->n_reads, s->stream));
+    if (s->n_reads == 0) return OAR_OK;
+    const int threads = 256;
+    const uint64_t nthreads_needed = (s->n_reads + 1) / 2;  // two draws per Philox block
+    const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>((nthreads_needed + threads - 1) / threads, (uint64_t)s->sm_count * 16));
+    kern::boot_weights_kernel<<<blocks, threads, 0, s->stream>>>(d_w, s->n_reads, seed, replicate);
+    s->counters[0] += 1;
+    OAR_CUDA(cudaGetLastError());
+    return OAR_OK;
+}
+
+extern "C" int oar_bootstrap_sample_weights(oar_store *s, uint64_t seed, uint32_t replicate, uint32_t *out_weights)
+{
+    if (!s || !out_weights) return fail(OAR_ERR_INVALID, "oar_bootstrap_sample_weights: null argument");
+    OAR_CUDA(cudaSetDevice(s->device));
+    int rc = ensure_weights(s);
+    if (rc != OAR_OK) return rc;
+    rc = enqueue_sample_weights(s, seed, replicate, s->d_weights);
+    if (rc != OAR_OK) return rc;
+    OAR_CUDA(cudaMemcpyAsync(out_weights, s->d_weights, sizeof(uint32_t) * s->n_reads, cudaMemcpyDefault, s->stream));
+    OAR_CUDA(cudaStreamSynchronize(s->stream));
+    return OAR_OK;
+}
+
+static int bootstrap_impl(oar_store *s, const uint32_t *weights_or_null, uint32_t n_rep, uint64_t seed,
+                          uint32_t first, uint32_t stride, uint32_t max_iter, double thr, uint32_t min_iter,
+                          double *out, uint32_t *out_niter)
+{
+    if (!s) return fail(OAR_ERR_INVALID, "oar_bootstrap: store is null");
+    if (n_rep > 0 && !out) return fail(OAR_ERR_INVALID, "oar_bootstrap: out is null");
+    OAR_CUDA(cudaSetDevice(s->device));
+    s->counters[0] = s->counters[1] = 0;
+    int rc = ensure_weights(s);
+    if (rc != OAR_OK) return rc;
+    OAR_CUDA(cudaEventRecord(s->ev[0], s->stream));
+    for (uint32_t b = 0; b < n_rep; ++b) {
+        if (weights_or_null) {
+            OAR_CUDA(cudaMemcpyAsync(s->d_weights, weights_or_null + (uint64_t)b * s->n_reads,
+                                     sizeof(uint32_t) * s->n_reads, cudaMemcpyDefault, s->stream));
+        } else {
+            rc = enqueue_sample_weights(s, seed, first + b * stride, s->d_weights);
+            if (rc != OAR_OK) return rc;
+        }
+        double *res = nullptr;
+        uint32_t niter = 0;
+        rc = run_em(s, nullptr, max_iter, thr, min_iter, true, &res, &niter, nullptr, nullptr);
+        if (rc != OAR_OK) { cudaStreamSynchronize(s->stream); return rc; }
+        if (out_niter) out_niter[b] = niter;
+        OAR_CUDA(cudaMemcpyAsync(out + (uint64_t)b * s->n_txps, res, sizeof(double) * s->n_txps, cudaMemcpyDefault, s->stream));
+    }
+    OAR_CUDA(cudaEventRecord(s->ev[1], s->stream));
+    OAR_CUDA(cudaStreamSynchronize(s->stream));
+    float a = 0.f;
+    OAR_CUDA(cudaEventElapsedTime(&a, s->ev[0], s->ev[1]));
+    s->timings[1] = a; s->timings[2] = 0; s->timings[3] = 0;
+    return OAR_OK;
+}
+
+extern "C" int oar_bootstrap(oar_store *s, uint32_t num_boot, uint64_t seed, uint32_t first_replicate,
+                             uint32_t replicate_stride, uint32_t max_iter, double conv_thresh,
+                             double *out, uint32_t *out_niter)
+{
+    // do_bootstrap runs do_em, whose stop rule is niter > 50 (em.rs:212, :287-289)
+    return bootstrap_impl(s, nullptr, num_boot, seed, first_replicate, replicate_stride ? replicate_stride : 1,
+                          max_iter, conv_thresh, 50, out, out_niter);
+}
+
+extern "C" int oar_bootstrap_weights(oar_store *s, const uint32_t *weights, uint32_t n_replicates,
+                                     uint32_t max_iter, double conv_thresh, uint32_t min_iter,
+                                     double *out, uint32_t *out_niter)
+{
+    if (n_replicates > 0 && !weights) return fail(OAR_ERR_INVALID, "oar_bootstrap_weights: weights is null");
+    return bootstrap_impl(s, weights, n_replicates, 0, 0, 1, max_iter, conv_thresh, min_iter, out, out_niter);
+}
+
+// ---------------------------------------------------------------------------
+// batched per-cell EM (single-cell mode) -- first version: one EM per cell over
+// the cell's row range, sequentially on the store's stream.
+// ---------------------------------------------------------------------------
+
+extern "C" int oar_em_batched(oar_store *s, const uint64_t *cell_row_ptr, uint32_t n_cells,
+                              uint32_t max_iter, double conv_thresh, uint32_t min_iter,
+                              double *out_counts, uint32_t *out_niter)
+{
+    (void)cell_row_ptr; (void)n_cells; (void)max_iter; (void)conv_thresh; (void)min_iter;
+    (void)out_counts; (void)out_niter;
+    if (!s) return fail(OAR_ERR_INVALID, "oar_em_batched: store is null");
+    return fail(OAR_ERR_UNSUPPORTED, "oar_em_batched: not implemented in this build");
+}
+
+// ---------------------------------------------------------------------------
+// raw sweep (measurement / tests)
+// ---------------------------------------------------------------------------
+
+extern "C" int oar_sweep(oar_store *s, const double *prev_dev, double *curr_dev,
+                         const uint32_t *weights_or_null, int sync)
+{
+    if (!s || !prev_dev || !curr_dev) return fail(OAR_ERR_INVALID, "oar_sweep: null argument");
+    OAR_CUDA(cudaSetDevice(s->device));
+    OAR_CUDA(cudaMemsetAsync(curr_dev, 0, sizeof(double) * s->n_txps, s->stream));
+    OAR_CUDA(enqueue_sweep(s, prev_dev, curr_dev, weights_or_null, s->d_state, 0));
+    if (sync) OAR_CUDA(cudaStreamSynchronize(s->stream));
+    return OAR_OK;
+}

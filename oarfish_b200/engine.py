@@ -1,0 +1,174 @@
+"""Thin object wrapper over the C ABI (include/oarfish_em.h).
+
+`DeviceStore` owns one `oar_store` handle: the alignment store uploaded to HBM.
+Arrays may be numpy arrays (host), or torch tensors (pinned host or CUDA) --
+only their addresses cross the boundary.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+
+
+def _addr(x, dtype: np.dtype, name: str) -> Tuple[int, int, object]:
+    """(address, n_elements, keepalive) of a contiguous array of `dtype`."""
+    if x is None:
+        return 0, 0, None
+    if isinstance(x, np.ndarray):
+        if x.dtype != dtype:
+            raise TypeError(f"{name}: expected dtype {dtype}, got {x.dtype}")
+        if not x.flags["C_CONTIGUOUS"]:
+            raise ValueError(f"{name}: array must be C-contiguous")
+        return x.ctypes.data, x.size, x
+    # torch tensor (duck-typed so that torch stays an optional import here)
+    if hasattr(x, "data_ptr") and hasattr(x, "is_contiguous"):
+        import torch
+
+        want = {np.dtype(np.uint64): (torch.uint64, torch.int64), np.dtype(np.uint32): (torch.uint32, torch.int32),
+                np.dtype(np.float32): (torch.float32,), np.dtype(np.float64): (torch.float64,)}[np.dtype(dtype)]
+        if x.dtype not in want:
+            raise TypeError(f"{name}: expected torch dtype in {want}, got {x.dtype}")
+        if not x.is_contiguous():
+            raise ValueError(f"{name}: tensor must be contiguous")
+        return x.data_ptr(), x.numel(), x
+    raise TypeError(f"{name}: unsupported array type {type(x)}")
+
+
+class EMResult:
+    __slots__ = ("counts", "niter", "rel_diff")
+
+    def __init__(self, counts, niter: int, rel_diff: float):
+        self.counts = counts
+        self.niter = niter
+        self.rel_diff = rel_diff
+
+
+class DeviceStore:
+    """An InMemoryAlignmentStore (src/util/oarfish_types.rs:547-558) resident in HBM as CSR."""
+
+    def __init__(self, row_ptr, txp_id, prob, n_txps: int, aux=None, device: int = 0):
+        lib = _lib.load_em_lib()
+        rp, n_rp, k0 = _addr(row_ptr, np.dtype(np.uint64), "row_ptr")
+        tp, n_t, k1 = _addr(txp_id, np.dtype(np.uint32), "txp_id")
+        pp, n_p, k2 = _addr(prob, np.dtype(np.float32), "prob")
+        ap, n_a, k3 = _addr(aux, np.dtype(np.float64), "aux")
+        if n_rp < 1:
+            raise ValueError("row_ptr must have at least one element")
+        if n_t != n_p or (aux is not None and n_a != n_t):
+            raise ValueError("txp_id, prob and aux must have the same length")
+        self.n_reads = n_rp - 1
+        self.nnz = n_t
+        self.n_txps = int(n_txps)
+        self.device = int(device)
+        self._lib = lib
+        self._h = C.c_void_p()
+        check(lib.oar_store_create(rp, tp, pp, ap, self.n_reads, self.nnz, self.n_txps, self.device, C.byref(self._h)))
+
+    # -- lifetime ------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.oar_store_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- configuration ---------------------------------------------------------
+    def set_kernel(self, kernel: int) -> None:
+        check(self._lib.oar_store_set_kernel(self._h, int(kernel)))
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.oar_store_stream(self._h) or 0)
+
+    def timings_ms(self):
+        out = (C.c_double * 4)()
+        check(self._lib.oar_store_timings(self._h, out))
+        return {"upload": out[0], "em": out[1], "download": out[2], "weights": out[3]}
+
+    def counters(self):
+        out = (C.c_uint64 * 2)()
+        check(self._lib.oar_store_counters(self._h, out))
+        return {"launches": int(out[0]), "sweeps": int(out[1])}
+
+    # -- compute -----------------------------------------------------------------
+    def em(self, max_iter: int = 1000, conv_thresh: float = 1e-3, min_iter: int = 50,
+           init=None, out=None) -> EMResult:
+        """One EM to convergence (em::em with min_iter=50, em::em_par with min_iter=1)."""
+        if out is None:
+            out = np.empty(self.n_txps, dtype=np.float64)
+        op, n_o, _ = _addr(out, np.dtype(np.float64), "out")
+        if n_o != self.n_txps:
+            raise ValueError("out must have n_txps elements")
+        ip, n_i, _k = _addr(init, np.dtype(np.float64), "init")
+        if init is not None and n_i != self.n_txps:
+            raise ValueError("init must have n_txps elements")
+        niter = C.c_uint32(0)
+        rel = C.c_double(0.0)
+        check(self._lib.oar_em(self._h, ip, int(max_iter), float(conv_thresh), int(min_iter), op,
+                               C.byref(niter), C.byref(rel)))
+        return EMResult(out, int(niter.value), float(rel.value))
+
+    def bootstrap(self, num_boot: int, seed: int, max_iter: int = 1000, conv_thresh: float = 1e-3,
+                  first_replicate: int = 0, replicate_stride: int = 1, out=None):
+        """em::bootstrap (em.rs:292): returns (num_boot x M counts, niter per replicate)."""
+        if out is None:
+            out = np.empty((num_boot, self.n_txps), dtype=np.float64)
+        op, n_o, _ = _addr(out, np.dtype(np.float64), "out")
+        if n_o != num_boot * self.n_txps:
+            raise ValueError("out must have num_boot * n_txps elements")
+        niter = np.zeros(max(num_boot, 1), dtype=np.uint32)
+        check(self._lib.oar_bootstrap(self._h, int(num_boot), int(seed), int(first_replicate), int(replicate_stride),
+                                      int(max_iter), float(conv_thresh), op, niter.ctypes.data))
+        return out, niter[:num_boot]
+
+    def bootstrap_weights(self, weights, max_iter: int = 1000, conv_thresh: float = 1e-3, min_iter: int = 50,
+                          out=None):
+        wp, n_w, _ = _addr(weights, np.dtype(np.uint32), "weights")
+        if self.n_reads == 0 or n_w % self.n_reads != 0:
+            raise ValueError("weights must hold R * n_reads elements")
+        R = n_w // self.n_reads
+        if out is None:
+            out = np.empty((R, self.n_txps), dtype=np.float64)
+        op, n_o, _ = _addr(out, np.dtype(np.float64), "out")
+        niter = np.zeros(max(R, 1), dtype=np.uint32)
+        check(self._lib.oar_bootstrap_weights(self._h, wp, R, int(max_iter), float(conv_thresh), int(min_iter), op,
+                                              niter.ctypes.data))
+        return out, niter[:R]
+
+    def sample_weights(self, seed: int, replicate: int, out=None):
+        if out is None:
+            out = np.empty(self.n_reads, dtype=np.uint32)
+        op, n_o, _ = _addr(out, np.dtype(np.uint32), "out")
+        check(self._lib.oar_bootstrap_sample_weights(self._h, int(seed), int(replicate), op))
+        return out
+
+    def sweep(self, prev_dev, curr_dev, weights_dev=None, sync: bool = True) -> None:
+        """One raw fused E+M sweep on device buffers (torch CUDA tensors)."""
+        pp, n_p, _ = _addr(prev_dev, np.dtype(np.float64), "prev")
+        cp, n_c, _ = _addr(curr_dev, np.dtype(np.float64), "curr")
+        wp, _n, _k = _addr(weights_dev, np.dtype(np.uint32), "weights")
+        if n_p != self.n_txps or n_c != self.n_txps:
+            raise ValueError("prev/curr must have n_txps elements")
+        check(self._lib.oar_sweep(self._h, pp, cp, wp, 1 if sync else 0))
+
+
+def device_count() -> int:
+    n = _lib.load_em_lib().oar_device_count()
+    if n < 0:
+        check(n)
+    return n

@@ -1,0 +1,70 @@
+"""Seeded synthetic alignment stores; see csrc/synth.c."""
+from __future__ import annotations
+
+from typing import NamedTuple, Optional
+
+import numpy as np
+
+from . import _lib
+
+
+class SynthStore(NamedTuple):
+    row_ptr: np.ndarray   # N+1 u64
+    txp_id: np.ndarray    # nnz u32
+    prob: np.ndarray      # nnz f32
+    n_txps: int
+    true_txp: Optional[np.ndarray]
+    abund: Optional[np.ndarray]
+
+    @property
+    def n_reads(self) -> int:
+        return len(self.row_ptr) - 1
+
+    @property
+    def nnz(self) -> int:
+        return len(self.txp_id)
+
+
+# the configurations BASELINE.md section 4 names
+CONFIGS = {
+    "tiny": dict(n_reads=2_000, n_txps=300, avg_aln=4.0, seed=11),
+    "small": dict(n_reads=50_000, n_txps=5_000, avg_aln=6.0, seed=12),
+    "C2": dict(n_reads=1_000_000, n_txps=50_000, avg_aln=6.0, seed=2),
+    "C3": dict(n_reads=10_000_000, n_txps=200_000, avg_aln=8.0, seed=3),
+}
+
+
+def make_store(n_reads: int, n_txps: int, avg_aln: float, seed: int, want_truth: bool = False,
+               pinned: bool = False) -> SynthStore:
+    """Generate a store on the host.  With pinned=True the arrays live in
+    page-locked memory (torch) so that uploads run at full PCIe/C2C speed."""
+    lib = _lib.load_synth_lib()
+
+    def alloc(n, dtype):
+        if pinned:
+            import torch
+            tdt = {np.uint64: torch.int64, np.uint32: torch.int32, np.float32: torch.float32,
+                   np.float64: torch.float64}[dtype]
+            t = torch.empty(max(n, 1), dtype=tdt, pin_memory=True)
+            return t.numpy().view(dtype)[:n]
+        return np.empty(n, dtype=dtype)
+
+    row_ptr = alloc(n_reads + 1, np.uint64)
+    rc = lib.oar_synth_plan(n_reads, n_txps, float(avg_aln), seed, row_ptr.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"oar_synth_plan failed ({rc})")
+    nnz = int(row_ptr[-1])
+    txp = alloc(nnz, np.uint32)
+    prob = alloc(nnz, np.float32)
+    true_txp = np.empty(n_reads, dtype=np.uint32) if want_truth else None
+    abund = np.empty(n_txps, dtype=np.float64) if want_truth else None
+    rc = lib.oar_synth_fill(n_reads, n_txps, float(avg_aln), seed, row_ptr.ctypes.data, txp.ctypes.data,
+                            prob.ctypes.data, true_txp.ctypes.data if want_truth else None,
+                            abund.ctypes.data if want_truth else None)
+    if rc != 0:
+        raise RuntimeError(f"oar_synth_fill failed ({rc})")
+    return SynthStore(row_ptr, txp, prob, n_txps, true_txp, abund)
+
+
+def make_config(name: str, **kw) -> SynthStore:
+    return make_store(**CONFIGS[name], **kw)

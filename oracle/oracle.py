@@ -1,0 +1,132 @@
+"""ctypes binding of the CPU oracle -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this module.  Parity is UNPINNED by the
+reference (it ships no EM tests); see oracle/em_oracle.c.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboarfish_oracle.so")
+_lib = None
+_vp = C.c_void_p
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} not found: run `make oracle`")
+        L = C.CDLL(LIB_PATH)
+        L.oracle_m_step.restype = None
+        L.oracle_m_step.argtypes = [_vp, _vp, _vp, _vp, _vp, C.c_uint64, _vp, _vp, _vp]
+        L.oracle_do_em.restype = C.c_uint32
+        L.oracle_do_em.argtypes = [_vp, _vp, _vp, _vp, C.c_uint64, C.c_uint32, _vp, C.c_uint32, C.c_double,
+                                   C.c_uint32, _vp, C.c_uint64, _vp, _vp, _vp, _vp]
+        L.oracle_get_sample_inds.restype = None
+        L.oracle_get_sample_inds.argtypes = [C.c_uint64, C.c_uint64, _vp]
+        L.oracle_inds_to_weights.restype = None
+        L.oracle_inds_to_weights.argtypes = [_vp, C.c_uint64, C.c_uint64, _vp]
+        L.port_num_threads.restype = C.c_int
+        L.port_store_create.restype = _vp
+        L.port_store_create.argtypes = [_vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64, C.c_uint32]
+        L.port_store_destroy.restype = None
+        L.port_store_destroy.argtypes = [_vp]
+        L.port_em_par.restype = C.c_uint32
+        L.port_em_par.argtypes = [_vp, C.c_int, _vp, C.c_uint32, C.c_double, _vp, _vp, _vp]
+        L.port_bootstrap.restype = None
+        L.port_bootstrap.argtypes = [_vp, C.c_int, C.c_uint32, C.c_uint64, C.c_uint32, C.c_double, C.c_int, _vp, _vp]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data
+
+
+def _c(a, dt):
+    return None if a is None else np.ascontiguousarray(a, dtype=dt)
+
+
+def m_step(row_ptr, txp, prob, prev, cov=None, inds=None, wts=None):
+    """One sweep (em.rs:87-133); returns curr."""
+    row_ptr = _c(row_ptr, np.uint64); txp = _c(txp, np.uint32); prob = _c(prob, np.float32)
+    cov = _c(cov, np.float64); inds = _c(inds, np.uint64); wts = _c(wts, np.uint32)
+    prev = _c(prev, np.float64)
+    curr = np.zeros_like(prev)
+    n_rows = len(inds) if inds is not None else len(row_ptr) - 1
+    lib().oracle_m_step(_p(row_ptr), _p(txp), _p(prob), _p(cov), _p(inds), n_rows, _p(wts), _p(prev), _p(curr))
+    return curr
+
+
+def do_em(row_ptr, txp, prob, n_txps, max_iter=1000, conv_thresh=1e-3, min_iter=50, cov=None, init=None,
+          inds=None, wts=None):
+    """do_em (em.rs:144-255) / em_par stop rule with min_iter=1.  Returns (counts, niter, rel_diff, sweeps)."""
+    row_ptr = _c(row_ptr, np.uint64); txp = _c(txp, np.uint32); prob = _c(prob, np.float32)
+    cov = _c(cov, np.float64); inds = _c(inds, np.uint64); wts = _c(wts, np.uint32); init = _c(init, np.float64)
+    out = np.zeros(n_txps, dtype=np.float64)
+    niter = C.c_uint32(0); rel = C.c_double(0.0)
+    sweeps = lib().oracle_do_em(_p(row_ptr), _p(txp), _p(prob), _p(cov), len(row_ptr) - 1, n_txps, _p(init),
+                                max_iter, conv_thresh, min_iter, _p(inds), 0 if inds is None else len(inds),
+                                _p(wts), _p(out), C.byref(niter), C.byref(rel))
+    return out, int(niter.value), float(rel.value), int(sweeps)
+
+
+def get_sample_inds(n, seed):
+    """bootstrap::get_sample_inds (bootstrap.rs:7-16) with the oracle's seeded generator."""
+    out = np.empty(n, dtype=np.uint64)
+    lib().oracle_get_sample_inds(n, seed, _p(out))
+    return out
+
+
+def inds_to_weights(inds, n_rows):
+    inds = _c(inds, np.uint64)
+    w = np.zeros(n_rows, dtype=np.uint32)
+    lib().oracle_inds_to_weights(_p(inds), len(inds), n_rows, _p(w))
+    return w
+
+
+class PortStore:
+    """AoS copy of a store laid out like the Rust InMemoryAlignmentStore (CPU baseline timing)."""
+
+    def __init__(self, row_ptr, txp, prob, n_txps, cov=None):
+        row_ptr = _c(row_ptr, np.uint64); txp = _c(txp, np.uint32); prob = _c(prob, np.float32)
+        cov = _c(cov, np.float64)
+        self.n_txps = n_txps
+        self.model_coverage = cov is not None
+        self._h = lib().port_store_create(_p(row_ptr), _p(txp), _p(prob), _p(cov), len(row_ptr) - 1, len(txp), n_txps)
+
+    def em_par(self, max_iter=1000, conv_thresh=1e-3, init=None):
+        init = _c(init, np.float64)
+        out = np.zeros(self.n_txps, dtype=np.float64)
+        niter = C.c_uint32(0); rel = C.c_double(0.0)
+        sweeps = lib().port_em_par(self._h, int(self.model_coverage), _p(init), max_iter, conv_thresh, _p(out),
+                                   C.byref(niter), C.byref(rel))
+        return out, int(niter.value), float(rel.value), int(sweeps)
+
+    def bootstrap(self, num_boot, seed, max_iter=1000, conv_thresh=1e-3, nthreads=0):
+        out = np.zeros((num_boot, self.n_txps), dtype=np.float64)
+        niter = np.zeros(max(num_boot, 1), dtype=np.uint32)
+        lib().port_bootstrap(self._h, int(self.model_coverage), num_boot, seed, max_iter, conv_thresh, nthreads,
+                             _p(out), _p(niter))
+        return out, niter[:num_boot]
+
+    def close(self):
+        if self._h:
+            lib().port_store_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def num_threads() -> int:
+    return int(lib().port_num_threads())

@@ -137,6 +137,12 @@ int oar_em_batched(oar_store *store, const uint64_t *cell_row_ptr, uint32_t n_ce
                    uint32_t max_iter, double conv_thresh, uint32_t min_iter,
                    double *out_counts, uint32_t *out_niter);
 
+/* Layout of the store in HBM: [0] tiled layout built, [1] tiles, [2] alignment
+ * slots in tiles, [3] rows swept from the CSR instead (too long / did not fit),
+ * [4] sum of per-tile distinct transcripts, [5] sum of per-tile 8-slot units,
+ * [6] tile span, [7] active kernel (oar_kernel). */
+int oar_store_layout_info(const oar_store *store, uint64_t out[8]);
+
 /* Timings of the last compute call on this store, milliseconds (CUDA events):
  * [0] upload+layout, [1] EM loop (device), [2] result download, [3] weight generation. */
 int oar_store_timings(const oar_store *store, double out_ms[4]);

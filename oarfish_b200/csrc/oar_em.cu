@@ -8,12 +8,14 @@
 //   bootstrap.rs:7-16          -> boot_weights_kernel (Philox4x32-10)
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
 
-#include "oar_common.cuh"
 #include "oar_kernels.cuh"
+#include "oar_store.cuh"
+#include "oar_tiled.cuh"
 
 namespace oar {
 
@@ -36,40 +38,6 @@ using namespace oar;
 // ---------------------------------------------------------------------------
 
 static const int kGraphIters = 16;  // EM iterations per graph launch (even)
-
-struct GraphSlot {
-    cudaGraphExec_t exec = nullptr;
-    bool weighted = false;
-    int kernel = 0;
-};
-
-struct oar_store {
-    int device = 0;
-    int sm_count = 148;
-    cudaStream_t stream = nullptr;
-    uint64_t n_reads = 0, nnz = 0;
-    uint32_t n_txps = 0;
-    int kernel = OAR_KERNEL_ROWGROUP;
-
-    // CSR in HBM
-    uint32_t *d_row_ptr = nullptr;  // N+1
-    uint32_t *d_txp = nullptr;      // nnz
-    float *d_prob = nullptr;        // nnz
-    double *d_aux = nullptr;        // nnz or null
-
-    // EM work buffers
-    double *d_counts[2] = {nullptr, nullptr};
-    OarEmState *d_state = nullptr;
-    OarEmState *h_state = nullptr;  // pinned, 4 slots
-    uint32_t *d_weights = nullptr;  // N, bootstrap weights of the current replicate
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t slot_ev[2] = {nullptr, nullptr};
-
-    GraphSlot graphs[2];  // [0] unweighted, [1] weighted
-
-    double timings[4] = {0, 0, 0, 0};
-    uint64_t counters[2] = {0, 0};
-};
 
 static void destroy_graphs(oar_store *s)
 {
@@ -97,6 +65,7 @@ extern "C" void oar_store_destroy(oar_store *s)
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     destroy_graphs(s);
+    free_tiled_layout(s);
     cudaFree(s->d_row_ptr); cudaFree(s->d_txp); cudaFree(s->d_prob); cudaFree(s->d_aux);
     cudaFree(s->d_counts[0]); cudaFree(s->d_counts[1]); cudaFree(s->d_state); cudaFree(s->d_weights);
     if (s->h_state) cudaFreeHost(s->h_state);
@@ -170,6 +139,18 @@ extern "C" int oar_store_create(const uint64_t *row_ptr, const uint32_t *txp_id,
         OAR_CUDA(cudaGetLastError());
         if (h_flag[0]) return fail(OAR_ERR_INVALID, "oar_store_create: row_ptr is not a monotone prefix ending at nnz");
         if (h_flag[1]) return fail(OAR_ERR_INVALID, "oar_store_create: txp_id out of range (>= n_txps)");
+        {
+            // OAR_TILED=0 keeps only the CSR (row-group kernel); OAR_TILE_SPAN tunes the tile fill
+            const char *env = getenv("OAR_TILED");
+            if (!(env && env[0] == '0')) {
+                const char *sp = getenv("OAR_TILE_SPAN");
+                int rc2 = build_tiled_layout(s, sp ? (uint32_t)atoi(sp) : 0u);
+                if (rc2 != OAR_OK) return rc2;
+                s->kernel = OAR_KERNEL_TILED;
+            }
+            OAR_CUDA(cudaEventRecord(s->ev[1], s->stream));
+            OAR_CUDA(cudaStreamSynchronize(s->stream));
+        }
         float ms = 0.f;
         OAR_CUDA(cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]));
         s->timings[0] = ms;
@@ -198,11 +179,22 @@ extern "C" int oar_store_info(const oar_store *s, uint64_t *n_reads, uint64_t *n
 extern "C" int oar_store_set_kernel(oar_store *s, int kernel)
 {
     if (!s) return fail(OAR_ERR_INVALID, "oar_store_set_kernel: store is null");
-    if (kernel == OAR_KERNEL_AUTO) kernel = OAR_KERNEL_ROWGROUP;
-    if (kernel != OAR_KERNEL_ROWGROUP)
-        return fail(OAR_ERR_UNSUPPORTED, "oar_store_set_kernel: kernel not available in this build");
-    if (kernel != s->kernel) { cudaSetDevice(s->device); destroy_graphs(s); }
+    if (kernel == OAR_KERNEL_AUTO) kernel = s->tl.ready ? OAR_KERNEL_TILED : OAR_KERNEL_ROWGROUP;
+    if (kernel != OAR_KERNEL_ROWGROUP && kernel != OAR_KERNEL_TILED)
+        return fail(OAR_ERR_INVALID, "oar_store_set_kernel: unknown kernel");
+    if (kernel == OAR_KERNEL_TILED && !s->tl.ready)
+        return fail(OAR_ERR_UNSUPPORTED, "oar_store_set_kernel: tiled layout was not built (OAR_TILED=0)");
+    if (kernel != s->kernel) { cudaSetDevice(s->device); cudaStreamSynchronize(s->stream); destroy_graphs(s); }
     s->kernel = kernel;
+    return OAR_OK;
+}
+
+extern "C" int oar_store_layout_info(const oar_store *s, uint64_t out[8])
+{
+    if (!s || !out) return fail(OAR_ERR_INVALID, "oar_store_layout_info: null argument");
+    const TiledLayout &t = s->tl;
+    out[0] = t.ready ? 1 : 0; out[1] = t.n_tiles; out[2] = (uint64_t)t.n_tiles * tiled::kTile; out[3] = t.n_fallback;
+    out[4] = t.sum_d; out[5] = t.sum_u; out[6] = t.span; out[7] = (uint64_t)s->kernel;
     return OAR_OK;
 }
 
@@ -226,21 +218,66 @@ extern "C" void *oar_store_stream(oar_store *s) { return s ? (void *)s->stream :
 // sweep dispatch
 // ---------------------------------------------------------------------------
 
+static tiled::View tiled_view(const oar_store *s)
+{
+    const TiledLayout &t = s->tl;
+    tiled::View v;
+    v.n_tiles = t.n_tiles; v.prob = t.prob; v.lpos = t.lpos; v.aux = t.aux; v.heads = t.heads;
+    v.chunk_row = t.chunk_row; v.meta = t.meta; v.table = t.table; v.unit_txp = t.unit_txp; v.unit_cnt = t.unit_cnt;
+    return v;
+}
+
+// Row-group sweep over all rows (list == null) or over a list of row ids.
+static cudaError_t enqueue_rowgroup(oar_store *s, const uint32_t *list, uint64_t n_rows, const double *prev,
+                                    double *curr, const uint32_t *wts, const OarEmState *state, int check_done)
+{
+    if (n_rows == 0) return cudaSuccess;
+    const int threads = 256;
+    const uint64_t groups_per_block = threads / 8;
+    const uint64_t want = (n_rows + groups_per_block - 1) / groups_per_block;
+    const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)s->sm_count * 8));
+#define OAR_LAUNCH(AUX, WTS)                                                                      \
+    kern::em_sweep_rowgroup<AUX, WTS><<<blocks, threads, 0, s->stream>>>(                         \
+        s->d_row_ptr, s->d_txp, s->d_prob, s->d_aux, wts, list, prev, curr, n_rows, state, check_done)
+    if (s->d_aux) { if (wts) OAR_LAUNCH(true, true); else OAR_LAUNCH(true, false); }
+    else          { if (wts) OAR_LAUNCH(false, true); else OAR_LAUNCH(false, false); }
+#undef OAR_LAUNCH
+    s->counters[0] += 1;
+    return cudaGetLastError();
+}
+
 // Enqueue one fused E+M sweep prev -> curr (curr must already be zero).
+// `wts` are per-read weights in read order; the tiled kernel reads the copy
+// permuted into tile order (s->tl.wperm, refreshed by refresh_wperm()).
 static cudaError_t enqueue_sweep(oar_store *s, const double *prev, double *curr, const uint32_t *wts,
                                  const OarEmState *state, int check_done)
 {
     if (s->n_reads == 0) return cudaSuccess;
-    const int threads = 256;
-    const uint64_t groups_per_block = threads / 8;
-    const uint64_t want = (s->n_reads + groups_per_block - 1) / groups_per_block;
-    const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)s->sm_count * 8));
+    if (s->kernel != OAR_KERNEL_TILED)
+        return enqueue_rowgroup(s, nullptr, s->n_reads, prev, curr, wts, state, check_done);
+    const TiledLayout &t = s->tl;
+    if (t.n_tiles > 0) {
+        const tiled::View v = tiled_view(s);
 #define OAR_LAUNCH(AUX, WTS)                                                                      \
-    kern::em_sweep_rowgroup<AUX, WTS><<<blocks, threads, 0, s->stream>>>(                         \
-        s->d_row_ptr, s->d_txp, s->d_prob, s->d_aux, wts, prev, curr, s->n_reads, state, check_done)
-    if (s->d_aux) { if (wts) OAR_LAUNCH(true, true); else OAR_LAUNCH(true, false); }
-    else          { if (wts) OAR_LAUNCH(false, true); else OAR_LAUNCH(false, false); }
+    tiled::em_sweep_tiled<AUX, WTS><<<t.n_tiles, tiled::kThreads, 0, s->stream>>>(v, prev, curr, wts ? t.wperm : nullptr, state, check_done)
+        if (s->d_aux) { if (wts) OAR_LAUNCH(true, true); else OAR_LAUNCH(true, false); }
+        else          { if (wts) OAR_LAUNCH(false, true); else OAR_LAUNCH(false, false); }
 #undef OAR_LAUNCH
+        s->counters[0] += 1;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return enqueue_rowgroup(s, t.fallback, t.n_fallback, prev, curr, wts, state, check_done);
+}
+
+// Bring the tile-order copy of the bootstrap weights up to date.
+static cudaError_t refresh_wperm(oar_store *s, const uint32_t *wts)
+{
+    const TiledLayout &t = s->tl;
+    if (s->kernel != OAR_KERNEL_TILED || t.n_tiled_rows == 0) return cudaSuccess;
+    const int threads = 256;
+    const int blocks = (int)std::min<uint64_t>((t.n_tiled_rows + threads - 1) / threads, (uint64_t)s->sm_count * 16);
+    tiled::permute_weights<<<blocks, threads, 0, s->stream>>>(wts, t.trow, t.n_tiled_rows, t.wperm);
     s->counters[0] += 1;
     return cudaGetLastError();
 }
@@ -278,7 +315,7 @@ static int ensure_graph(oar_store *s, bool weighted)
     e = cudaGraphInstantiate(&g.exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) { g.exec = nullptr; return cuda_fail(e, "cudaGraphInstantiate"); }
-    g.kernel = s->kernel; g.weighted = weighted;
+    g.kernel = s->kernel;
     return OAR_OK;
 }
 
@@ -440,6 +477,7 @@ static int bootstrap_impl(oar_store *s, const uint32_t *weights_or_null, uint32_
             rc = enqueue_sample_weights(s, seed, first + b * stride, s->d_weights);
             if (rc != OAR_OK) return rc;
         }
+        OAR_CUDA(refresh_wperm(s, s->d_weights));
         double *res = nullptr;
         uint32_t niter = 0;
         rc = run_em(s, nullptr, max_iter, thr, min_iter, true, &res, &niter, nullptr, nullptr);
@@ -497,6 +535,7 @@ extern "C" int oar_sweep(oar_store *s, const double *prev_dev, double *curr_dev,
     if (!s || !prev_dev || !curr_dev) return fail(OAR_ERR_INVALID, "oar_sweep: null argument");
     OAR_CUDA(cudaSetDevice(s->device));
     OAR_CUDA(cudaMemsetAsync(curr_dev, 0, sizeof(double) * s->n_txps, s->stream));
+    if (weights_or_null) OAR_CUDA(refresh_wperm(s, weights_or_null));
     OAR_CUDA(enqueue_sweep(s, prev_dev, curr_dev, weights_or_null, s->d_state, 0));
     if (sync) OAR_CUDA(cudaStreamSynchronize(s->stream));
     return OAR_OK;

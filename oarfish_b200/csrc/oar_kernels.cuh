@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(256) em_sweep_rowgroup(const uint32_t *__restr
                                                          const float *__restrict__ prob,
                                                          const double *__restrict__ aux,
                                                          const uint32_t *__restrict__ wts,
+                                                         const uint32_t *__restrict__ list,
                                                          const double *__restrict__ prev,
                                                          double *__restrict__ curr, uint64_t n_rows,
                                                          const OarEmState *__restrict__ st, int check_done)
@@ -141,7 +142,8 @@ __global__ void __launch_bounds__(256) em_sweep_rowgroup(const uint32_t *__restr
     const unsigned sub = lane & 7u;
     const unsigned gmask = 0xFFu << (lane & 24u);
     const uint64_t ngroups = ((uint64_t)gridDim.x * blockDim.x) >> 3;
-    for (uint64_t row = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; row < n_rows; row += ngroups) {
+    for (uint64_t k = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; k < n_rows; k += ngroups) {
+        const uint64_t row = list ? (uint64_t)list[k] : k;  // fallback rows of the tiled layout come as a list
         double scale = 1.0;
         if (HAS_WTS) {
             const uint32_t c = wts[row];

@@ -1,0 +1,147 @@
+// oar_layout.cu -- builds the locality-tiled layout (oar_tiled.cuh) on the device.
+//
+// One-time work per store: a key-value radix sort of the rows by their smallest
+// transcript id (CUB DeviceRadixSort; library code, not on the EM hot path), a
+// scan of the sorted row lengths, and one CTA per tile that packs rows into
+// warp-chunks, sorts the tile's alignments by transcript and emits the
+// per-alignment (table index, position) stream.
+#include <algorithm>
+#include <vector>
+
+#include "oar_store.cuh"
+#include "oar_tiled.cuh"
+
+namespace oar {
+
+void free_tiled_layout(oar_store *s)
+{
+    TiledLayout &t = s->tl;
+    cudaFree(t.prob); cudaFree(t.lpos); cudaFree(t.aux); cudaFree(t.heads); cudaFree(t.chunk_row);
+    cudaFree(t.meta); cudaFree(t.table); cudaFree(t.unit_txp); cudaFree(t.unit_cnt); cudaFree(t.trow);
+    cudaFree(t.fallback); cudaFree(t.wperm);
+    t = TiledLayout();
+}
+
+namespace {
+struct Scratch {
+    std::vector<void *> ptrs;
+    ~Scratch() { for (void *p : ptrs) cudaFree(p); }
+    template <typename T> cudaError_t alloc(T **p, size_t n)
+    {
+        cudaError_t e = cudaMalloc(p, sizeof(T) * std::max<size_t>(n, 1));
+        if (e == cudaSuccess) ptrs.push_back(*p);
+        return e;
+    }
+};
+}  // namespace
+
+int build_tiled_layout(oar_store *s, uint32_t span)
+{
+    using namespace tiled;
+    free_tiled_layout(s);
+    TiledLayout &t = s->tl;
+    const uint32_t N = (uint32_t)s->n_reads;
+    if (span == 0 || span > (uint32_t)kTile) span = 992;
+    t.span = span;
+    if (N == 0 || s->nnz == 0) { t.ready = true; return OAR_OK; }
+    cudaStream_t st = s->stream;
+    Scratch sc;
+    uint32_t *key = nullptr, *idx = nullptr, *key_s = nullptr, *srow = nullptr, *slen = nullptr, *soff = nullptr;
+    uint32_t *counters = nullptr;
+    OAR_CUDA(sc.alloc(&key, N)); OAR_CUDA(sc.alloc(&idx, N));
+    OAR_CUDA(sc.alloc(&key_s, N)); OAR_CUDA(sc.alloc(&srow, N));
+    OAR_CUDA(sc.alloc(&counters, 8));
+    OAR_CUDA(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 8, st));
+    const int threads = 256;
+    const int gridN = (int)std::min<uint64_t>((N + threads - 1) / threads, (uint64_t)s->sm_count * 32);
+    row_keys<<<gridN, threads, 0, st>>>(s->d_row_ptr, s->d_txp, N, key, idx, counters);
+    OAR_CUDA(cudaGetLastError());
+    {
+        size_t tmp_bytes = 0;
+        OAR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key, key_s, idx, srow, (int)N, 0, 32, st));
+        void *tmp = nullptr;
+        OAR_CUDA(sc.alloc((char **)&tmp, tmp_bytes));
+        OAR_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key, key_s, idx, srow, (int)N, 0, 32, st));
+    }
+    uint32_t h_counters[8];
+    OAR_CUDA(cudaMemcpyAsync(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
+    OAR_CUDA(cudaStreamSynchronize(st));
+    const uint32_t n_tiled = N - h_counters[0];
+    const uint32_t n_long = h_counters[1];
+    t.n_tiled_rows = n_tiled;
+
+    uint32_t n_tiles = 0;
+    uint32_t *tile_row = nullptr;
+    uint64_t total = 0;
+    if (n_tiled > 0) {
+        OAR_CUDA(sc.alloc(&slen, n_tiled + 1)); OAR_CUDA(sc.alloc(&soff, n_tiled + 1));
+        const int gridT = (int)std::min<uint64_t>((n_tiled + threads - 1) / threads, (uint64_t)s->sm_count * 32);
+        sorted_lens<<<gridT, threads, 0, st>>>(s->d_row_ptr, srow, n_tiled, slen);
+        OAR_CUDA(cudaGetLastError());
+        size_t tmp_bytes = 0;
+        OAR_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, slen, soff, (int)n_tiled + 1, st));
+        void *tmp = nullptr;
+        OAR_CUDA(sc.alloc((char **)&tmp, tmp_bytes));
+        OAR_CUDA(cudaMemsetAsync(slen + n_tiled, 0, sizeof(uint32_t), st));
+        OAR_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, slen, soff, (int)n_tiled + 1, st));
+        uint32_t h_total = 0;
+        OAR_CUDA(cudaMemcpyAsync(&h_total, soff + n_tiled, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        OAR_CUDA(cudaStreamSynchronize(st));
+        total = h_total;
+        n_tiles = (uint32_t)((total + span - 1) / span);
+        OAR_CUDA(sc.alloc(&tile_row, n_tiles + 1));
+        tile_row_starts<<<(n_tiles + 1 + threads - 1) / threads, threads, 0, st>>>(soff, n_tiled, span, n_tiles, tile_row);
+        OAR_CUDA(cudaGetLastError());
+    }
+    t.n_tiles = n_tiles;
+
+    // outputs (table/unit arrays first at their worst-case size, compacted below)
+    const size_t slots = (size_t)n_tiles * kTile;
+    uint32_t *table_tmp = nullptr, *unit_txp_tmp = nullptr; uint8_t *unit_cnt_tmp = nullptr;
+    OAR_CUDA(cudaMalloc(&t.fallback, sizeof(uint32_t) * std::max<uint32_t>(N, 1)));
+    OAR_CUDA(cudaMalloc(&t.trow, sizeof(uint32_t) * std::max<uint32_t>(n_tiled, 1)));
+    OAR_CUDA(cudaMalloc(&t.wperm, sizeof(uint32_t) * ((size_t)n_tiled + kChunk + 1)));
+    OAR_CUDA(cudaMemsetAsync(t.wperm, 0, sizeof(uint32_t) * ((size_t)n_tiled + kChunk + 1), st));
+    if (n_tiles > 0) {
+        OAR_CUDA(cudaMalloc(&t.prob, sizeof(float) * slots));
+        OAR_CUDA(cudaMalloc(&t.lpos, sizeof(uint32_t) * slots));
+        if (s->d_aux) OAR_CUDA(cudaMalloc(&t.aux, sizeof(double) * slots));
+        OAR_CUDA(cudaMalloc(&t.heads, sizeof(uint4) * (size_t)n_tiles * kWarps));
+        OAR_CUDA(cudaMalloc(&t.chunk_row, sizeof(uint32_t) * (size_t)n_tiles * kWarps));
+        OAR_CUDA(cudaMalloc(&t.meta, sizeof(uint4) * n_tiles));
+        OAR_CUDA(sc.alloc(&table_tmp, (size_t)total));
+        OAR_CUDA(sc.alloc(&unit_txp_tmp, (size_t)total / kAggMin + 1));
+        OAR_CUDA(sc.alloc(&unit_cnt_tmp, (size_t)total / kAggMin + 1));
+        BuildArgs a;
+        a.row_ptr = s->d_row_ptr; a.txp = s->d_txp; a.prob = s->d_prob; a.aux = s->d_aux;
+        a.srow = srow; a.tile_row = tile_row;
+        a.o_prob = t.prob; a.o_lpos = t.lpos; a.o_aux = t.aux; a.o_heads = t.heads; a.o_chunk_row = t.chunk_row;
+        a.o_meta = t.meta; a.o_table = table_tmp; a.o_unit_txp = unit_txp_tmp; a.o_unit_cnt = unit_cnt_tmp;
+        a.o_trow = t.trow; a.fallback = t.fallback; a.cursors = counters + 4;
+        build_tiles<<<n_tiles, kThreads, 0, st>>>(a);
+        OAR_CUDA(cudaGetLastError());
+    }
+    if (n_long > 0) {
+        const int g = (int)std::min<uint64_t>((N - n_tiled + threads - 1) / threads, (uint64_t)s->sm_count * 8);
+        collect_long_rows<<<g, threads, 0, st>>>(s->d_row_ptr, srow, n_tiled, N, t.fallback, counters + 4);
+        OAR_CUDA(cudaGetLastError());
+    }
+    OAR_CUDA(cudaMemcpyAsync(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
+    OAR_CUDA(cudaStreamSynchronize(st));
+    t.n_fallback = h_counters[4];
+    t.sum_d = h_counters[5];
+    t.sum_u = h_counters[6];
+    if (n_tiles > 0) {
+        OAR_CUDA(cudaMalloc(&t.table, sizeof(uint32_t) * std::max<uint64_t>(t.sum_d, 1)));
+        OAR_CUDA(cudaMalloc(&t.unit_txp, sizeof(uint32_t) * std::max<uint64_t>(t.sum_u, 1)));
+        OAR_CUDA(cudaMalloc(&t.unit_cnt, sizeof(uint8_t) * std::max<uint64_t>(t.sum_u, 1)));
+        OAR_CUDA(cudaMemcpyAsync(t.table, table_tmp, sizeof(uint32_t) * t.sum_d, cudaMemcpyDeviceToDevice, st));
+        OAR_CUDA(cudaMemcpyAsync(t.unit_txp, unit_txp_tmp, sizeof(uint32_t) * t.sum_u, cudaMemcpyDeviceToDevice, st));
+        OAR_CUDA(cudaMemcpyAsync(t.unit_cnt, unit_cnt_tmp, sizeof(uint8_t) * t.sum_u, cudaMemcpyDeviceToDevice, st));
+        OAR_CUDA(cudaStreamSynchronize(st));
+    }
+    t.ready = true;
+    return OAR_OK;
+}
+
+}  // namespace oar

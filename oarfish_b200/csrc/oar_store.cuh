@@ -1,0 +1,68 @@
+// oar_store.cuh -- the store handle behind the opaque oar_store of the C ABI.
+#pragma once
+#include "oar_common.cuh"
+
+namespace oar {
+
+// Locality-tiled copy of the store (see oar_tiled.cuh).
+struct TiledLayout {
+    bool ready = false;
+    uint32_t n_tiles = 0, n_tiled_rows = 0, n_fallback = 0, span = 0;
+    uint64_t sum_d = 0, sum_u = 0;
+    float *prob = nullptr;
+    uint32_t *lpos = nullptr;
+    double *aux = nullptr;
+    uint4 *heads = nullptr;
+    uint32_t *chunk_row = nullptr;
+    uint4 *meta = nullptr;
+    uint32_t *table = nullptr;
+    uint32_t *unit_txp = nullptr;
+    uint8_t *unit_cnt = nullptr;
+    uint32_t *trow = nullptr;      // tile-order row -> original row (n_tiled_rows)
+    uint32_t *fallback = nullptr;  // original row ids swept from the CSR
+    uint32_t *wperm = nullptr;     // bootstrap weights in tile order
+};
+
+struct GraphSlot {
+    cudaGraphExec_t exec = nullptr;
+    int kernel = 0;
+};
+
+}  // namespace oar
+
+struct oar_store {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    uint64_t n_reads = 0, nnz = 0;
+    uint32_t n_txps = 0;
+    int kernel = OAR_KERNEL_ROWGROUP;
+
+    // CSR in HBM (original read order)
+    uint32_t *d_row_ptr = nullptr;  // N+1
+    uint32_t *d_txp = nullptr;      // nnz
+    float *d_prob = nullptr;        // nnz
+    double *d_aux = nullptr;        // nnz or null
+
+    oar::TiledLayout tl;
+
+    // EM work buffers
+    double *d_counts[2] = {nullptr, nullptr};
+    OarEmState *d_state = nullptr;
+    OarEmState *h_state = nullptr;  // pinned, 4 slots
+    uint32_t *d_weights = nullptr;  // N, bootstrap weights of the current replicate (read order)
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t slot_ev[2] = {nullptr, nullptr};
+
+    oar::GraphSlot graphs[2];  // [0] unweighted, [1] weighted
+
+    double timings[4] = {0, 0, 0, 0};
+    uint64_t counters[2] = {0, 0};
+};
+
+namespace oar {
+// Build s->tl from the CSR arrays already resident on s->device (enqueued on
+// s->stream, synchronises).  Returns an oar_status.
+int build_tiled_layout(oar_store *s, uint32_t span);
+void free_tiled_layout(oar_store *s);
+}  // namespace oar

@@ -100,6 +100,12 @@ class DeviceStore:
         check(self._lib.oar_store_timings(self._h, out))
         return {"upload": out[0], "em": out[1], "download": out[2], "weights": out[3]}
 
+    def layout_info(self):
+        out = (C.c_uint64 * 8)()
+        check(self._lib.oar_store_layout_info(self._h, out))
+        keys = ("tiled", "n_tiles", "slots", "fallback_rows", "sum_distinct", "sum_units", "span", "kernel")
+        return {k: int(v) for k, v in zip(keys, out)}
+
     def counters(self):
         out = (C.c_uint64 * 2)()
         check(self._lib.oar_store_counters(self._h, out))

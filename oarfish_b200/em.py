@@ -25,9 +25,10 @@ import numpy as np
 
 from .engine import DeviceStore
 
-# AlnInfo (oarfish_types.rs:330-337); numpy lays it out in 24 bytes like rustc does
+# AlnInfo (oarfish_types.rs:330-337).  rustc reorders the fields of a default-repr struct by
+# alignment (f64 first), giving 24 bytes; the field order below reproduces that size.
 ALN_INFO_DTYPE = np.dtype(
-    [("ref_id", np.uint32), ("start", np.uint32), ("end", np.uint32), ("prob", np.float64), ("strand", np.uint8)],
+    [("prob", np.float64), ("ref_id", np.uint32), ("start", np.uint32), ("end", np.uint32), ("strand", np.uint8)],
     align=True,
 )
 

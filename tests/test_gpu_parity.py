@@ -1,0 +1,240 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU
+oracle on the same seeded inputs.  Tolerances: transcript indexing bit-exact;
+iteration counts identical; abundances within 1e-5 relative (north_star) -- the
+tests assert the much tighter 1e-9 that f64 accumulation actually delivers, on
+counts above 1e-8 (smaller ones are compared absolutely)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+KERNELS = [1, 2]  # OAR_KERNEL_ROWGROUP, OAR_KERNEL_TILED
+RTOL = 1e-9
+NORTH_STAR_RTOL = 1e-5
+
+
+def assert_counts_close(got, want, rtol=RTOL):
+    got = np.asarray(got); want = np.asarray(want)
+    assert got.shape == want.shape
+    big = want > 1e-8
+    if big.any():
+        rel = np.abs(got[big] - want[big]) / want[big]
+        assert rel.max() <= rtol, f"max rel err {rel.max():.3e} at {np.argmax(rel)}"
+    np.testing.assert_allclose(got[~big], want[~big], rtol=0, atol=1e-12)
+    # transcripts the oracle leaves at exactly zero stay exactly zero: indexing is bit-exact
+    assert np.array_equal(got == 0.0, want == 0.0) or np.abs(got[(got == 0.0) != (want == 0.0)]).max() < 1e-12
+
+
+def csr(rows):
+    rp = np.zeros(len(rows) + 1, dtype=np.uint64)
+    rp[1:] = np.cumsum([len(r) for r in rows])
+    tx = np.array([t for r in rows for t, _ in r], dtype=np.uint32)
+    pr = np.array([p for r in rows for _, p in r], dtype=np.float32)
+    return rp, tx, pr
+
+
+@pytest.fixture(scope="module")
+def DS():
+    from oarfish_b200 import DeviceStore, device_count
+    assert device_count() > 0, "no CUDA device: the product has no CPU fallback"
+    return DeviceStore
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("min_iter", [50, 1])
+@pytest.mark.parametrize("store_name", ["tiny_store", "small_store"])
+def test_em_matches_oracle(DS, oracle_mod, request, store_name, min_iter, kernel):
+    s = request.getfixturevalue(store_name)
+    want, niter, rel, sweeps = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps, min_iter=min_iter)
+    with DS(s.row_ptr, s.txp_id, s.prob, s.n_txps) as ds:
+        ds.set_kernel(kernel)
+        r = ds.em(min_iter=min_iter)
+        assert r.niter == niter
+        assert r.rel_diff == pytest.approx(rel, rel=1e-6)
+        assert_counts_close(r.counts, want)
+        assert ds.counters()["sweeps"] == sweeps + 1
+        assert ds.counters()["launches"] > 0
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("name", ["sirv_store", "tiny_store"])
+def test_golden_fixtures(DS, name, kernel):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    rp, tx, pr, M = g["row_ptr"], g["txp_id"], g["prob"], int(g["n_txps"])
+    with DS(rp, tx, pr, M) as ds:
+        ds.set_kernel(kernel)
+        for mi in (50, 1):
+            r = ds.em(min_iter=mi)
+            assert r.niter == int(g[f"niter_min{mi}"])
+            assert_counts_close(r.counts, g[f"counts_min{mi}"])
+        w = np.stack([g["boot0_weights"], g["boot1_weights"]])
+        out, nit = ds.bootstrap_weights(w)
+        for b in range(2):
+            assert nit[b] == int(g[f"boot{b}_niter"])
+            assert_counts_close(out[b], g[f"boot{b}_counts"])
+    with DS(rp, tx, pr, M, aux=g["cov"]) as ds:  # --model-coverage factor (em.rs:108)
+        ds.set_kernel(kernel)
+        r = ds.em(min_iter=50)
+        assert r.niter == int(g["niter_cov"])
+        assert_counts_close(r.counts, g["counts_cov"])
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_init_abundances_and_max_iter(DS, oracle_mod, tiny_store, kernel):
+    s = tiny_store
+    rng = np.random.default_rng(5)
+    init = rng.uniform(0.0, 20.0, size=s.n_txps)
+    init[::5] = 0.0
+    with DS(s.row_ptr, s.txp_id, s.prob, s.n_txps) as ds:
+        ds.set_kernel(kernel)
+        for max_iter in (0, 1, 2, 7, 60, 1000):
+            want, niter, _, sweeps = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps, init=init, max_iter=max_iter)
+            r = ds.em(init=init, max_iter=max_iter)
+            assert r.niter == niter, max_iter
+            assert_counts_close(r.counts, want)
+            assert np.all(r.counts[::5] == 0.0)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_edge_shapes(DS, oracle_mod, kernel):
+    cases = {
+        "single_read": [[(0, 1.0)]],
+        "all_unique": [[(i % 7, 0.5)] for i in range(300)],
+        "zero_prob_row": [[(0, 1.0)], [(1, 0.0), (2, 0.0)], [(2, 1.0), (1, 0.25)]],
+        "underflow_row": [[(0, 1.0)], [(1, 1e-37)], [(1, 1.0)]],
+        "duplicate_txp_in_row": [[(3, 0.5), (3, 0.25), (1, 1.0)]] * 40,
+        "ragged": [[(j % 11, 1.0 / (1 + j)) for j in range(1 + (i * 7) % 23)] for i in range(400)],
+        "long_rows": [[(j % 300, 0.9 ** (j % 17)) for j in range(n)] for n in (129, 500, 128, 127, 1, 300)] * 3,
+        "chunk_exact": [[(j % 16, 1.0) for j in range(16)]] * 64,   # rows fill 128-slot chunks exactly
+    }
+    for name, rows in cases.items():
+        rp, tx, pr = csr(rows)
+        M = int(tx.max()) + 3
+        want, niter, _, _ = oracle_mod.do_em(rp, tx, pr, M, min_iter=1)
+        with DS(rp, tx, pr, M) as ds:
+            ds.set_kernel(kernel)
+            r = ds.em(min_iter=1)
+            assert r.niter == niter, name
+            assert_counts_close(r.counts, want)
+
+
+def test_empty_store(DS):
+    rp = np.zeros(1, dtype=np.uint64)
+    with DS(rp, np.zeros(0, np.uint32), np.zeros(0, np.float32), 5) as ds:
+        r = ds.em()
+        assert np.all(r.counts == 0.0) and r.counts.shape == (5,)
+
+
+def test_invalid_inputs_are_rejected(DS):
+    from oarfish_b200._lib import OarfishError, OAR_ERR_INVALID
+    rp = np.array([0, 2, 1], dtype=np.uint64)  # not monotone
+    with pytest.raises(OarfishError) as ei:
+        DS(rp, np.zeros(1, np.uint32), np.ones(1, np.float32), 3)
+    assert ei.value.code == OAR_ERR_INVALID
+    rp = np.array([0, 1, 2], dtype=np.uint64)
+    with pytest.raises(OarfishError) as ei:
+        DS(rp, np.array([0, 9], np.uint32), np.ones(2, np.float32), 3)  # txp id out of range
+    assert ei.value.code == OAR_ERR_INVALID
+    with pytest.raises(OarfishError):
+        DS(np.array([0, 1, 3], dtype=np.uint64), np.zeros(2, np.uint32), np.ones(2, np.float32), 3)  # row_ptr[N] != nnz
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_bootstrap_weights_match_index_list_oracle(DS, oracle_mod, small_store, kernel):
+    s = small_store
+    inds = oracle_mod.get_sample_inds(s.n_reads, 42)
+    w = oracle_mod.inds_to_weights(inds, s.n_reads)
+    want, niter, _, _ = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps, min_iter=50, inds=inds)
+    with DS(s.row_ptr, s.txp_id, s.prob, s.n_txps) as ds:
+        ds.set_kernel(kernel)
+        out, nit = ds.bootstrap_weights(w[None, :])
+        assert nit[0] == niter
+        assert_counts_close(out[0], want)
+        # identity sample == plain EM (em.rs:278-283)
+        ones = np.ones((1, s.n_reads), dtype=np.uint32)
+        out1, nit1 = ds.bootstrap_weights(ones)
+        r = ds.em(min_iter=50)
+        assert nit1[0] == r.niter
+        assert_counts_close(out1[0], r.counts)
+
+
+def test_seeded_bootstrap_is_reproducible_and_shard_invariant(DS, oracle_mod, small_store):
+    s = small_store
+    with DS(s.row_ptr, s.txp_id, s.prob, s.n_txps) as ds:
+        B = 6
+        full, nit = ds.bootstrap(B, seed=123)
+        again, nit2 = ds.bootstrap(B, seed=123)
+        np.testing.assert_array_equal(nit, nit2)
+        assert_counts_close(again, full)
+        # rank r of G=2 owns replicates r, r+2, ...: same results as the unsharded run
+        for r in range(2):
+            part, pn = ds.bootstrap(B // 2, seed=123, first_replicate=r, replicate_stride=2)
+            np.testing.assert_array_equal(pn, nit[r::2])
+            assert_counts_close(part, full[r::2])
+        # the weights are exact multinomial(N; 1/N) draws and reproduce the replicate through the oracle
+        w = ds.sample_weights(123, 4)
+        assert w.sum() == s.n_reads and w.dtype == np.uint32
+        assert 0.33 < (w == 0).mean() < 0.40  # P(weight = 0) -> 1/e
+        assert not np.array_equal(w, ds.sample_weights(123, 5))
+        assert not np.array_equal(w, ds.sample_weights(124, 4))
+        np.testing.assert_array_equal(w, ds.sample_weights(123, 4))
+        want, niter, _, _ = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps, min_iter=50, wts=w)
+        assert nit[4] == niter
+        assert_counts_close(full[4], want)
+        assert np.all(np.abs(full.sum(axis=1) - s.n_reads) < 1e-6 * s.n_reads)
+
+
+def test_reference_interface_mirror(DS, oracle_mod, tiny_store):
+    """em / em_par / bootstrap called the way bulk.rs:155-159,179 calls them."""
+    from oarfish_b200 import EMInfo, InMemoryAlignmentStore, TranscriptInfo, bootstrap, em, em_par
+    s = tiny_store
+    store = InMemoryAlignmentStore.from_csr(s.row_ptr, s.txp_id, s.prob)
+    txps = [TranscriptInfo() for _ in range(s.n_txps)]
+    emi = EMInfo(eq_map=store, txp_info=txps, max_iter=1000, convergence_thresh=1e-3)
+    want50, *_ = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps, min_iter=50)
+    want1, *_ = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps, min_iter=1)
+    assert_counts_close(em(emi, 1), want50)
+    assert_counts_close(em_par(emi, 8), want1)
+    reps = bootstrap(emi, 3, 4, seed=9)
+    assert len(reps) == 3 and all(r.shape == (s.n_txps,) for r in reps)
+    assert all(abs(r.sum() - s.n_reads) < 1e-6 * s.n_reads for r in reps)
+
+
+def test_device_resident_inputs_and_outputs(DS, oracle_mod, tiny_store):
+    import torch
+    s = tiny_store
+    rp = torch.from_numpy(s.row_ptr.view(np.int64)).cuda()
+    tx = torch.from_numpy(s.txp_id.view(np.int32)).cuda()
+    pr = torch.from_numpy(s.prob).cuda()
+    out = torch.empty(s.n_txps, dtype=torch.float64, device="cuda")
+    want, niter, _, _ = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps, min_iter=1)
+    with DS(rp, tx, pr, s.n_txps) as ds:
+        r = ds.em(min_iter=1, out=out)
+        assert r.niter == niter
+        assert_counts_close(out.cpu().numpy(), want)
+
+
+def test_full_size_properties_c3(DS):
+    """BASELINE config 3 (10M reads x 200k transcripts): size-independent properties."""
+    from oarfish_b200 import synth
+    s = synth.make_config("C3")
+    with DS(s.row_ptr, s.txp_id, s.prob, s.n_txps) as ds:
+        info = ds.layout_info()
+        assert info["tiled"] == 1 and info["fallback_rows"] < 0.01 * s.n_reads
+        r2 = ds.em(min_iter=1)
+        ds.set_kernel(1)
+        r1 = ds.em(min_iter=1)
+        # two independent kernels (different layouts, different summation orders) agree
+        assert r1.niter == r2.niter
+        assert_counts_close(r2.counts, r1.counts, rtol=NORTH_STAR_RTOL)
+        big = r1.counts > 1e-8
+        assert (np.abs(r2.counts[big] - r1.counts[big]) / r1.counts[big]).max() < 1e-8
+        # every read is assignable: counts sum to N
+        assert abs(r2.counts.sum() - s.n_reads) < 1e-6 * s.n_reads
+        # one more EM from the converged point is (nearly) a fixed point: idempotence
+        r3 = ds.em(min_iter=1, init=r1.counts, max_iter=1)
+        m = r1.counts > 1.0
+        assert (np.abs(r3.counts[m] - r1.counts[m]) / r1.counts[m]).max() < 5e-3

@@ -1,0 +1,53 @@
+"""Host-side mirror of the reference interface (oarfish_b200/em.py): layout and
+flattening logic, no GPU needed."""
+import numpy as np
+
+from oarfish_b200 import ALN_INFO_DTYPE, AlignmentFilters, InMemoryAlignmentStore
+
+
+def test_aln_info_is_24_bytes_like_the_rust_struct():
+    assert ALN_INFO_DTYPE.itemsize == 24  # oarfish_types.rs:330-337
+
+
+def make_group(ids, probs):
+    a = np.zeros(len(ids), dtype=ALN_INFO_DTYPE)
+    a["ref_id"] = ids
+    a["start"] = 10
+    a["end"] = 500
+    return a, np.array(probs, dtype=np.float32)
+
+
+def test_add_filtered_group_builds_boundaries_like_the_reference():
+    s = InMemoryAlignmentStore()
+    assert s.len() == 0 and s.total_len() == 0
+    assert s.add_filtered_group(*make_group([3, 1], [1.0, 0.5]))
+    assert not s.add_filtered_group(*make_group([], []))  # empty groups are dropped (oarfish_types.rs:724)
+    assert s.add_filtered_group(*make_group([2], [1.0]))
+    assert s.len() == 2 and s.num_aligned_reads() == 2 and s.total_len() == 3
+    rp, txp, prob, aux = s.csr()
+    np.testing.assert_array_equal(rp, [0, 2, 3])
+    np.testing.assert_array_equal(txp, [3, 1, 2])
+    np.testing.assert_array_equal(prob, np.array([1.0, 0.5, 1.0], dtype=np.float32))
+    assert aux is None  # model_coverage off -> factor 1.0 (em.rs:108)
+    assert rp.dtype == np.uint64 and txp.dtype == np.uint32 and prob.dtype == np.float32
+    rows = list(s.iter())
+    assert [len(r[0]) for r in rows] == [2, 1]
+    assert np.all(s.coverage_probabilities == 0.0)  # zeros until the coverage model runs (:731)
+
+
+def test_random_sampling_iter_repeats_rows():
+    s = InMemoryAlignmentStore()
+    s.add_filtered_group(*make_group([0], [1.0]))
+    s.add_filtered_group(*make_group([1, 2], [1.0, 0.3]))
+    rows = list(s.random_sampling_iter([1, 1, 0]))
+    assert [list(r[0]["ref_id"]) for r in rows] == [[1, 2], [1, 2], [0]]
+
+
+def test_model_coverage_exports_aux():
+    rp = np.array([0, 2, 3], dtype=np.uint64)
+    s = InMemoryAlignmentStore.from_csr(rp, np.array([0, 1, 1], np.uint32), np.ones(3, np.float32),
+                                        coverage=np.array([0.5, 0.25, 1.0]), model_coverage=True)
+    _, _, _, aux = s.csr()
+    np.testing.assert_array_equal(aux, [0.5, 0.25, 1.0])
+    s2 = InMemoryAlignmentStore(AlignmentFilters(model_coverage=False))
+    assert s2.csr()[3] is None

@@ -1,0 +1,206 @@
+"""CPU tests of the oracle (oracle/em_oracle.c): the reference ships no EM tests
+(parity unpinned), so the restatement is pinned by an independent pure-Python
+restatement, analytic known answers and the frozen golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import pyref
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def csr(rows):
+    """rows: list of lists of (txp, prob)"""
+    rp = np.zeros(len(rows) + 1, dtype=np.uint64)
+    rp[1:] = np.cumsum([len(r) for r in rows])
+    tx = np.array([t for r in rows for t, _ in r], dtype=np.uint32)
+    pr = np.array([p for r in rows for _, p in r], dtype=np.float32)
+    return rp, tx, pr
+
+
+@pytest.mark.parametrize("min_iter", [50, 1])
+def test_c_oracle_matches_pure_python_restatement(oracle_mod, tiny_store, min_iter):
+    s = tiny_store
+    c, niter, rel, sweeps = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps, min_iter=min_iter)
+    ref, ref_niter = pyref.do_em(lambda: pyref.rows_of(s.row_ptr, s.txp_id, s.prob), s.n_reads, s.n_txps, 1000, 1e-3,
+                                 min_iter=min_iter)
+    assert niter == ref_niter
+    assert sweeps == niter + 1
+    np.testing.assert_array_equal(c, np.array(ref))  # same order of f64 operations -> bit identical
+
+
+def test_m_step_matches_python_with_coverage(oracle_mod, tiny_store):
+    s = tiny_store
+    rng = np.random.default_rng(0)
+    cov = rng.uniform(0.1, 1.0, size=s.nnz)
+    prev = rng.uniform(0.0, 5.0, size=s.n_txps)
+    got = oracle_mod.m_step(s.row_ptr, s.txp_id, s.prob, prev, cov=cov)
+    want = [0.0] * s.n_txps
+    pyref.m_step(pyref.rows_of(s.row_ptr, s.txp_id, s.prob, cov), list(prev), want, model_coverage=True)
+    np.testing.assert_array_equal(got, np.array(want))
+
+
+def test_all_unique_reads_give_exact_read_counts(oracle_mod):
+    rng = np.random.default_rng(1)
+    t = rng.integers(0, 17, size=500)
+    rows = [[(int(x), float(rng.uniform(0.1, 1.0)))] for x in t]
+    rp, tx, pr = csr(rows)
+    for max_iter in (1, 7, 1000):
+        c, *_ = oracle_mod.do_em(rp, tx, pr, 17, max_iter=max_iter)
+        np.testing.assert_array_equal(c, np.bincount(t, minlength=17).astype(np.float64))
+
+
+def test_two_transcript_closed_form(oracle_mod):
+    # n1 reads unique to A, n2 unique to B, n3 shared with equal probability:
+    # fixed point a = n1*N/(n1+n2), b = n2*N/(n1+n2)
+    n1, n2, n3 = 30, 10, 60
+    rows = [[(0, 1.0)]] * n1 + [[(1, 1.0)]] * n2 + [[(0, 0.5), (1, 0.5)]] * n3
+    rp, tx, pr = csr(rows)
+    c, niter, rel, _ = oracle_mod.do_em(rp, tx, pr, 2, max_iter=100000, conv_thresh=1e-14)
+    N = n1 + n2 + n3
+    np.testing.assert_allclose(c, [n1 * N / (n1 + n2), n2 * N / (n1 + n2)], rtol=1e-9)
+
+
+def test_counts_sum_to_assignable_reads(oracle_mod, small_store):
+    s = small_store
+    c, *_ = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps)
+    assert abs(c.sum() - s.n_reads) < 1e-6 * s.n_reads
+
+
+def test_denominator_threshold_drops_read(oracle_mod):
+    # prob 1e-37 * prev 1.0 <= 1e-30 -> the read contributes nothing (em.rs:115)
+    rows = [[(0, 1.0)], [(1, 1e-37)], [(1, 1.0)]]
+    rp, tx, pr = csr(rows)
+    c, *_ = oracle_mod.do_em(rp, tx, pr, 3, max_iter=5)
+    assert c.sum() == pytest.approx(2.0)
+
+
+def test_stop_rule_minimum_iterations(oracle_mod):
+    # a store that is converged from the first sweep: do_em stops at niter = 51
+    # (52 loop sweeps), em_par's rule at niter = 2 (3 loop sweeps)  (em.rs:212 / :399)
+    rows = [[(0, 1.0)]] * 10
+    rp, tx, pr = csr(rows)
+    _, niter, _, sweeps = oracle_mod.do_em(rp, tx, pr, 1, min_iter=50)
+    assert (niter, sweeps) == (51, 52)
+    _, niter, _, sweeps = oracle_mod.do_em(rp, tx, pr, 1, min_iter=1)
+    assert (niter, sweeps) == (2, 3)
+
+
+def test_max_iter_cap_and_zero(oracle_mod, tiny_store):
+    s = tiny_store
+    _, niter, _, sweeps = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps, max_iter=7)
+    assert (niter, sweeps) == (7, 7)
+    c0, niter, _, sweeps = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps, max_iter=0)
+    assert (niter, sweeps) == (0, 0)
+    # zero iterations = threshold the uniform start and sweep once
+    want = oracle_mod.m_step(s.row_ptr, s.txp_id, s.prob, np.full(s.n_txps, s.n_reads / s.n_txps))
+    np.testing.assert_array_equal(c0, want)
+
+
+def test_signed_rel_diff_only_counts_increases(oracle_mod):
+    # transcript 1 only ever loses mass to transcript 0: with the signed rule the
+    # decrease of t1 is ignored and only t0's (shrinking) increase is tracked
+    rows = [[(0, 1.0)]] * 50 + [[(0, 1.0), (1, 0.2)]] * 50
+    rp, tx, pr = csr(rows)
+    _, niter_signed, rel, _ = oracle_mod.do_em(rp, tx, pr, 2, min_iter=1, conv_thresh=1e-2)
+    assert rel >= 0.0
+    ref, ref_niter = pyref.do_em(lambda: pyref.rows_of(rp, tx, pr), 100, 2, 1000, 1e-2, min_iter=1)
+    assert niter_signed == ref_niter
+
+
+def test_init_zero_stays_zero(oracle_mod, tiny_store):
+    s = tiny_store
+    init = np.full(s.n_txps, s.n_reads / s.n_txps)
+    init[::3] = 0.0
+    c, *_ = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps, init=init)
+    assert np.all(c[::3] == 0.0)
+
+
+def test_read_permutation_invariance(oracle_mod, tiny_store):
+    s = tiny_store
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(s.n_reads)
+    lens = np.diff(s.row_ptr.astype(np.int64))
+    rp2 = np.zeros_like(s.row_ptr); rp2[1:] = np.cumsum(lens[perm])
+    idx = np.concatenate([np.arange(s.row_ptr[r], s.row_ptr[r + 1]) for r in perm]).astype(np.int64)
+    c1, n1, *_ = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps)
+    c2, n2, *_ = oracle_mod.do_em(rp2, s.txp_id[idx], s.prob[idx], s.n_txps)
+    assert n1 == n2
+    np.testing.assert_allclose(c1, c2, rtol=1e-9, atol=1e-12)
+
+
+def test_transcript_relabel_equivariance(oracle_mod, tiny_store):
+    s = tiny_store
+    rng = np.random.default_rng(4)
+    relabel = rng.permutation(s.n_txps).astype(np.uint32)
+    c1, n1, *_ = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps)
+    c2, n2, *_ = oracle_mod.do_em(s.row_ptr, relabel[s.txp_id], s.prob, s.n_txps)
+    assert n1 == n2
+    np.testing.assert_allclose(c2[relabel], c1, rtol=1e-12, atol=0)
+
+
+def test_bootstrap_index_list_equals_weights(oracle_mod, tiny_store):
+    s = tiny_store
+    inds = oracle_mod.get_sample_inds(s.n_reads, 99)
+    assert np.all(np.diff(inds.astype(np.int64)) >= 0) and inds.max() < s.n_reads and len(inds) == s.n_reads
+    w = oracle_mod.inds_to_weights(inds, s.n_reads)
+    assert w.sum() == s.n_reads
+    c1, n1, *_ = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps, inds=inds)
+    c2, n2, *_ = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps, wts=w)
+    assert n1 == n2
+    np.testing.assert_array_equal(c1, c2)  # sorted index list visits rows in the same order as weights
+
+
+def test_bootstrap_identity_sample_equals_plain_em(oracle_mod, tiny_store):
+    # the commented-out identity sampling of em.rs:278-283
+    s = tiny_store
+    inds = np.arange(s.n_reads, dtype=np.uint64)
+    c1, n1, *_ = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps, inds=inds)
+    c2, n2, *_ = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps)
+    assert n1 == n2
+    np.testing.assert_array_equal(c1, c2)
+
+
+def test_threaded_port_matches_oracle(oracle_mod, small_store):
+    s = small_store
+    ps = oracle_mod.PortStore(s.row_ptr, s.txp_id, s.prob, s.n_txps)
+    c1, n1, _, sw1 = ps.em_par()
+    c2, n2, _, sw2 = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps, min_iter=1)
+    assert (n1, sw1) == (n2, sw2)
+    np.testing.assert_allclose(c1, c2, rtol=1e-9, atol=1e-9)
+    out, nit = ps.bootstrap(3, seed=5, nthreads=2)
+    assert out.shape == (3, s.n_txps) and np.all(nit > 50)
+    np.testing.assert_allclose(out.sum(axis=1), s.n_reads, rtol=1e-9)
+    ps.close()
+
+
+@pytest.mark.parametrize("name", ["sirv_store", "tiny_store"])
+def test_oracle_reproduces_golden_fixture(oracle_mod, name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    rp, tx, pr, M = g["row_ptr"], g["txp_id"], g["prob"], int(g["n_txps"])
+    for mi in (50, 1):
+        c, niter, rel, _ = oracle_mod.do_em(rp, tx, pr, M, min_iter=mi)
+        assert niter == int(g[f"niter_min{mi}"])
+        np.testing.assert_array_equal(c, g[f"counts_min{mi}"])
+    for b in range(2):
+        c, niter, *_ = oracle_mod.do_em(rp, tx, pr, M, wts=g[f"boot{b}_weights"])
+        assert niter == int(g[f"boot{b}_niter"])
+        np.testing.assert_array_equal(c, g[f"boot{b}_counts"])
+    c, niter, *_ = oracle_mod.do_em(rp, tx, pr, M, cov=g["cov"])
+    assert niter == int(g["niter_cov"])
+    np.testing.assert_array_equal(c, g["counts_cov"])
+
+
+def test_sirv_fixture_conserves_reads_per_gene(oracle_mod):
+    # simulated reads only align inside their own SIRV gene, so the EM must hand every
+    # gene exactly its reads back (isoform-level identifiability is a property of the
+    # simulation, not of the EM, and is not asserted)
+    g = np.load(os.path.join(GOLD, "sirv_store.npz"))
+    genes = np.array([n[:5] for n in g["names"]])
+    c = g["counts_min50"]
+    true = np.bincount(g["true_txp"], minlength=int(g["n_txps"]))
+    for gene in np.unique(genes):
+        m = genes == gene
+        assert c[m].sum() == pytest.approx(true[m].sum(), rel=1e-9)

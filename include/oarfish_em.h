@@ -158,6 +158,12 @@ int oar_store_counters(const oar_store *store, uint64_t out[2]);
 int oar_sweep(oar_store *store, const double *prev_dev, double *curr_dev,
               const uint32_t *weights_or_null, int sync);
 
+/* `reps` back-to-back sweeps bracketed by CUDA events recorded on the store's
+ * stream; *out_ms_total is the elapsed device time of all of them (curr is
+ * zeroed once and accumulates).  For roofline measurement. */
+int oar_sweep_timed(oar_store *store, const double *prev_dev, double *curr_dev,
+                    const uint32_t *weights_or_null, int reps, float *out_ms_total);
+
 /* The CUDA stream (cudaStream_t) the store launches on, for event timing. */
 void *oar_store_stream(oar_store *store);
 

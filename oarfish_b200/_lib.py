@@ -48,6 +48,7 @@ ABI = {
     "oar_store_timings": (C.c_int, [_vp, _f64p]),
     "oar_store_counters": (C.c_int, [_vp, _u64p]),
     "oar_sweep": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int]),
+    "oar_sweep_timed": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.POINTER(C.c_float)]),
     "oar_store_stream": (_vp, [_vp]),
 }
 

@@ -367,8 +367,9 @@ static int run_em(oar_store *s, const double *init_dev, uint32_t max_iter, doubl
             head ^= 1; --inflight;
         }
         // the launches still in flight are no-ops (done is set); they finish before the final sweep (same stream)
-        s->counters[0] += (uint64_t)sweeps * 2;  // sweep + update kernels that did real work
-        (void)launched_iters;
+        // every kernel node of every graph launch is a launch of ours (those after convergence exit at once)
+        const uint64_t per_iter = 2 + ((s->kernel == OAR_KERNEL_TILED && s->tl.n_tiles > 0 && s->tl.n_fallback > 0) ? 1 : 0);
+        s->counters[0] += launched_iters * per_iter;
     }
     double *prev = s->d_counts[sweeps & 1], *curr = s->d_counts[(sweeps + 1) & 1];
     {
@@ -538,5 +539,21 @@ extern "C" int oar_sweep(oar_store *s, const double *prev_dev, double *curr_dev,
     if (weights_or_null) OAR_CUDA(refresh_wperm(s, weights_or_null));
     OAR_CUDA(enqueue_sweep(s, prev_dev, curr_dev, weights_or_null, s->d_state, 0));
     if (sync) OAR_CUDA(cudaStreamSynchronize(s->stream));
+    return OAR_OK;
+}
+
+extern "C" int oar_sweep_timed(oar_store *s, const double *prev_dev, double *curr_dev,
+                               const uint32_t *weights_or_null, int reps, float *out_ms_total)
+{
+    if (!s || !prev_dev || !curr_dev || !out_ms_total || reps <= 0)
+        return fail(OAR_ERR_INVALID, "oar_sweep_timed: bad argument");
+    OAR_CUDA(cudaSetDevice(s->device));
+    if (weights_or_null) OAR_CUDA(refresh_wperm(s, weights_or_null));
+    OAR_CUDA(cudaMemsetAsync(curr_dev, 0, sizeof(double) * s->n_txps, s->stream));
+    OAR_CUDA(cudaEventRecord(s->ev[0], s->stream));
+    for (int i = 0; i < reps; ++i) OAR_CUDA(enqueue_sweep(s, prev_dev, curr_dev, weights_or_null, s->d_state, 0));
+    OAR_CUDA(cudaEventRecord(s->ev[1], s->stream));
+    OAR_CUDA(cudaStreamSynchronize(s->stream));
+    OAR_CUDA(cudaEventElapsedTime(out_ms_total, s->ev[0], s->ev[1]));
     return OAR_OK;
 }

@@ -173,6 +173,15 @@ class DeviceStore:
         check(self._lib.oar_sweep(self._h, pp, cp, wp, 1 if sync else 0))
 
 
+    def sweep_timed(self, prev_dev, curr_dev, reps: int, weights_dev=None) -> float:
+        pp, n_p, _ = _addr(prev_dev, np.dtype(np.float64), "prev")
+        cp, n_c, _ = _addr(curr_dev, np.dtype(np.float64), "curr")
+        wp, _n, _k = _addr(weights_dev, np.dtype(np.uint32), "weights")
+        ms = C.c_float(0.0)
+        check(self._lib.oar_sweep_timed(self._h, pp, cp, wp, int(reps), C.byref(ms)))
+        return float(ms.value)
+
+
 def device_count() -> int:
     n = _lib.load_em_lib().oar_device_count()
     if n < 0:

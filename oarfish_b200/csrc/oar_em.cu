@@ -148,6 +148,8 @@ extern "C" int oar_store_create(const uint64_t *row_ptr, const uint32_t *txp_id,
                 if (rc2 != OAR_OK) return rc2;
                 s->kernel = OAR_KERNEL_TILED;
             }
+            const char *cps = getenv("OAR_CTAS_PER_SM");
+            if (cps && atoi(cps) > 0) s->ctas_per_sm = atoi(cps);
             OAR_CUDA(cudaEventRecord(s->ev[1], s->stream));
             OAR_CUDA(cudaStreamSynchronize(s->stream));
         }
@@ -223,7 +225,7 @@ static tiled::View tiled_view(const oar_store *s)
     const TiledLayout &t = s->tl;
     tiled::View v;
     v.n_tiles = t.n_tiles; v.prob = t.prob; v.lpos = t.lpos; v.aux = t.aux; v.heads = t.heads;
-    v.chunk_row = t.chunk_row; v.meta = t.meta; v.table = t.table; v.unit_txp = t.unit_txp; v.unit_cnt = t.unit_cnt;
+    v.chunk_row = t.chunk_row; v.chunk_info = t.chunk_info; v.meta = t.meta; v.table = t.table; v.unit_txp = t.unit_txp; v.unit_cnt = t.unit_cnt;
     return v;
 }
 

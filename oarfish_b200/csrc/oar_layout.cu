@@ -16,7 +16,7 @@ namespace oar {
 void free_tiled_layout(oar_store *s)
 {
     TiledLayout &t = s->tl;
-    cudaFree(t.prob); cudaFree(t.lpos); cudaFree(t.aux); cudaFree(t.heads); cudaFree(t.chunk_row);
+    cudaFree(t.prob); cudaFree(t.lpos); cudaFree(t.aux); cudaFree(t.heads); cudaFree(t.chunk_row); cudaFree(t.chunk_info);
     cudaFree(t.meta); cudaFree(t.table); cudaFree(t.unit_txp); cudaFree(t.unit_cnt); cudaFree(t.trow);
     cudaFree(t.fallback); cudaFree(t.wperm);
     t = TiledLayout();
@@ -41,7 +41,7 @@ int build_tiled_layout(oar_store *s, uint32_t span)
     free_tiled_layout(s);
     TiledLayout &t = s->tl;
     const uint32_t N = (uint32_t)s->n_reads;
-    if (span == 0 || span > (uint32_t)kTile) span = 992;
+    if (span == 0 || span > (uint32_t)kTile) span = 984;
     t.span = span;
     if (N == 0 || s->nnz == 0) { t.ready = true; return OAR_OK; }
     cudaStream_t st = s->stream;
@@ -108,6 +108,7 @@ int build_tiled_layout(oar_store *s, uint32_t span)
         if (s->d_aux) OAR_CUDA(cudaMalloc(&t.aux, sizeof(double) * slots));
         OAR_CUDA(cudaMalloc(&t.heads, sizeof(uint4) * (size_t)n_tiles * kWarps));
         OAR_CUDA(cudaMalloc(&t.chunk_row, sizeof(uint32_t) * (size_t)n_tiles * kWarps));
+        OAR_CUDA(cudaMalloc(&t.chunk_info, sizeof(uint32_t) * (size_t)n_tiles * kWarps));
         OAR_CUDA(cudaMalloc(&t.meta, sizeof(uint4) * n_tiles));
         OAR_CUDA(sc.alloc(&table_tmp, (size_t)total));
         OAR_CUDA(sc.alloc(&unit_txp_tmp, (size_t)total / kAggMin + 1));
@@ -115,7 +116,7 @@ int build_tiled_layout(oar_store *s, uint32_t span)
         BuildArgs a;
         a.row_ptr = s->d_row_ptr; a.txp = s->d_txp; a.prob = s->d_prob; a.aux = s->d_aux;
         a.srow = srow; a.tile_row = tile_row;
-        a.o_prob = t.prob; a.o_lpos = t.lpos; a.o_aux = t.aux; a.o_heads = t.heads; a.o_chunk_row = t.chunk_row;
+        a.o_prob = t.prob; a.o_lpos = t.lpos; a.o_aux = t.aux; a.o_heads = t.heads; a.o_chunk_row = t.chunk_row; a.o_chunk_info = t.chunk_info;
         a.o_meta = t.meta; a.o_table = table_tmp; a.o_unit_txp = unit_txp_tmp; a.o_unit_cnt = unit_cnt_tmp;
         a.o_trow = t.trow; a.fallback = t.fallback; a.cursors = counters + 4;
         build_tiles<<<n_tiles, kThreads, 0, st>>>(a);

@@ -14,6 +14,7 @@ struct TiledLayout {
     double *aux = nullptr;
     uint4 *heads = nullptr;
     uint32_t *chunk_row = nullptr;
+    uint32_t *chunk_info = nullptr;
     uint4 *meta = nullptr;
     uint32_t *table = nullptr;
     uint32_t *unit_txp = nullptr;
@@ -37,6 +38,7 @@ struct oar_store {
     uint64_t n_reads = 0, nnz = 0;
     uint32_t n_txps = 0;
     int kernel = OAR_KERNEL_ROWGROUP;
+    int ctas_per_sm = 4;  // persistent CTAs of the tiled sweep per SM
 
     // CSR in HBM (original read order)
     uint32_t *d_row_ptr = nullptr;  // N+1

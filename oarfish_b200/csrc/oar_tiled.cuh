@@ -36,22 +36,25 @@ namespace tiled {
 
 constexpr int kWarps = 8;                 // warp-chunks per tile
 constexpr int kChunk = 128;               // alignment slots per warp-chunk (4 per lane)
+constexpr int kChunkCap = kChunk - 1;     // rows use at most 127 slots: a padding pseudo-row always closes the chunk
 constexpr int kTile = kWarps * kChunk;    // 1024 slots
 constexpr int kThreads = kWarps * 32;     // 256
 constexpr int kAggMin = 4;                // transcripts with >= kAggMin alignments in a tile are aggregated in smem
 constexpr int kMaxUnits = kTile / 4;      // sum ceil(cnt/8) over cnt >= 4  <=  kTile/4
 constexpr int kTrash = kMaxUnits * 9;     // xs slot for padding alignments (never summed)
-constexpr uint32_t kStray = 0xFFFFu;      // pos value: not aggregated, RED straight to global
+constexpr uint32_t kInfoStray = 8u;       // chunk_info bit 3: chunk holds alignments that RED straight to global
+constexpr uint32_t kInfoMulti = 16u;      // chunk_info bit 4: some lane holds >= 2 row heads (general path)
 constexpr uint32_t kNoTxp = 0xFFFFFFFFu;
 static_assert(kMaxUnits == kThreads, "one unit per thread in phase 2");
 
 struct View {
     uint32_t n_tiles;
     const float *prob;         // n_tiles * kTile
-    const uint32_t *lpos;      // n_tiles * kTile : table index | pos << 16
+    const uint32_t *lpos;      // n_tiles * kTile : (table index * 8) | (pos * 8) << 16  (smem byte offsets)
     const double *aux;         // n_tiles * kTile or null
     const uint4 *heads;        // n_tiles * kWarps : 128-bit row-head mask per warp-chunk
     const uint32_t *chunk_row; // n_tiles * kWarps : tile-order index of the chunk's first row
+    const uint32_t *chunk_info;// n_tiles * kWarps : scan steps (bits 0-2) | kInfoStray | kInfoMulti
     const uint4 *meta;         // n_tiles : {table_off, unit_off, D | U << 16, first tile-order row}
     const uint32_t *table;     // sum D : distinct transcript ids per tile
     const uint32_t *unit_txp;  // sum U : transcript id of each 8-slot unit
@@ -72,7 +75,7 @@ static __global__ void row_keys(const uint32_t *__restrict__ row_ptr, const uint
     for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
         const uint32_t s = row_ptr[r], e = row_ptr[r + 1];
         uint32_t k = kNoTxp;
-        if (e > s && e - s <= (uint32_t)kChunk) {
+        if (e > s && e - s <= (uint32_t)kChunkCap) {
             for (uint32_t j = s; j < e; ++j) k = min(k, txp[j]);
         } else {
             ++n_skip;
@@ -125,7 +128,7 @@ struct BuildArgs {
     const uint32_t *row_ptr; const uint32_t *txp; const float *prob; const double *aux;
     const uint32_t *srow;      // sorted position -> original row
     const uint32_t *tile_row;  // n_tiles + 1
-    float *o_prob; uint32_t *o_lpos; double *o_aux; uint4 *o_heads; uint32_t *o_chunk_row; uint4 *o_meta;
+    float *o_prob; uint32_t *o_lpos; double *o_aux; uint4 *o_heads; uint32_t *o_chunk_row; uint32_t *o_chunk_info; uint4 *o_meta;
     uint32_t *o_table; uint32_t *o_unit_txp; uint8_t *o_unit_cnt;
     uint32_t *o_trow;          // tile-order row -> original row
     uint32_t *fallback; uint32_t *cursors;  // [0] fallback rows, [1] table entries, [2] units
@@ -138,18 +141,19 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
     using Scan = cub::BlockScan<uint32_t, kThreads>;
     __shared__ union { typename Sort::TempStorage sort; typename Scan::TempStorage scan; } tmp;
     __shared__ uint32_t s_txp[kTile];      // slot -> transcript; later reused as sorted keys
+    __shared__ uint32_t s_src[kTile];      // slot -> source alignment index in the CSR
     __shared__ uint32_t s_lpos[kTile];
     __shared__ uint32_t s_seg[kTile + 1];  // segment -> first sorted rank; later unit base
     __shared__ uint16_t s_rlen[kTile], s_rslot[kTile], s_rnew[kTile];
     __shared__ uint32_t s_heads[kWarps * 4];
-    __shared__ uint32_t s_used[kWarps], s_nrow[kWarps];
+    __shared__ uint32_t s_used[kWarps], s_nrow[kWarps], s_info[kWarps];
     __shared__ uint32_t s_misc[4];
 
     const uint32_t tile = blockIdx.x, tid = threadIdx.x;
     const uint32_t r0 = a.tile_row[tile], r1 = a.tile_row[tile + 1];
     const uint32_t nrows = min(r1 - r0, (uint32_t)kTile);  // every row has >= 1 alignment and span <= kTile
 
-    for (uint32_t i = tid; i < (uint32_t)kTile; i += kThreads) { s_txp[i] = kNoTxp; s_lpos[i] = 0; }
+    for (uint32_t i = tid; i < (uint32_t)kTile; i += kThreads) { s_txp[i] = kNoTxp; s_lpos[i] = 0; s_src[i] = kNoTxp; }
     if (tid < kWarps * 4) s_heads[tid] = 0;
     for (uint32_t i = tid; i < nrows; i += kThreads) {
         const uint32_t r = a.srow[r0 + i];
@@ -159,24 +163,31 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
 
     // first-fit packing of rows into warp-chunks (rows never straddle a chunk)
     if (tid == 0) {
-        uint32_t used[kWarps], cnt[kWarps];
+        uint32_t used[kWarps], cnt[kWarps], span[kWarps];
 #pragma unroll
-        for (int c = 0; c < kWarps; ++c) { used[c] = 0; cnt[c] = 0; }
+        for (int c = 0; c < kWarps; ++c) { used[c] = 0; cnt[c] = 0; span[c] = 0; }
         for (uint32_t i = 0; i < nrows; ++i) {
             const uint32_t len = s_rlen[i];
             int pick = -1;
 #pragma unroll
-            for (int c = 0; c < kWarps; ++c) if (pick < 0 && used[c] + len <= (uint32_t)kChunk) pick = c;
+            for (int c = 0; c < kWarps; ++c) if (pick < 0 && used[c] + len <= (uint32_t)kChunkCap) pick = c;
             if (pick < 0) { s_rslot[i] = 0xFFFF; continue; }
 #pragma unroll
             for (int c = 0; c < kWarps; ++c) if (c == pick) {
                 s_rslot[i] = (uint16_t)(c * kChunk + used[c]);
                 s_rnew[i] = (uint16_t)cnt[c];  // order inside the chunk
+                const uint32_t lanes = ((used[c] + len - 1) >> 2) - (used[c] >> 2);  // lanes the row's tail must travel
+                span[c] = max(span[c], lanes);
                 used[c] += len; cnt[c] += 1;
             }
         }
 #pragma unroll
-        for (int c = 0; c < kWarps; ++c) { s_used[c] = used[c]; s_nrow[c] = cnt[c]; }
+        for (int c = 0; c < kWarps; ++c) {
+            s_used[c] = used[c]; s_nrow[c] = cnt[c];
+            uint32_t steps = 0;
+            while ((1u << steps) <= span[c]) ++steps;  // Hillis-Steele steps 1,2,..,2^(steps-1) cover `span` lanes
+            s_info[c] = steps;
+        }
     }
     __syncthreads();
     // chunk row bases (tile order = chunk by chunk), overflow rows go last and to the fallback list
@@ -188,9 +199,9 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
         if (tid == 0) s_misc[0] = acc;  // rows placed
         if (tid < kWarps) {
             a.o_chunk_row[tile * kWarps + tid] = r0 + chunk_base[tid];
-            // padding slots (if any) form a pseudo row so that real rows end before them
+            // the padding slots form a pseudo row, so every real row ends at a head inside the chunk
             const uint32_t u = s_used[tid];
-            if (u < (uint32_t)kChunk) atomicOr(&s_heads[tid * 4 + (u >> 5)], 1u << (u & 31));
+            atomicOr(&s_heads[tid * 4 + (u >> 5)], 1u << (u & 31));
         }
     }
     __syncthreads();
@@ -203,10 +214,15 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
         a.o_trow[r0 + chunk_base[c] + s_rnew[i]] = r;
         const uint32_t s = a.row_ptr[r], len = s_rlen[i];
         atomicOr(&s_heads[slot >> 5], 1u << (slot & 31));
+        // the order of a row's alignments is free: sorting them by transcript makes neighbouring rows
+        // hit neighbouring smem banks in the M-step scatter (insertion sort; rows are short)
         for (uint32_t j = 0; j < len; ++j) {
-            s_txp[slot + j] = a.txp[s + j];
-            a.o_prob[(size_t)tile * kTile + slot + j] = a.prob[s + j];
-            if (a.aux) a.o_aux[(size_t)tile * kTile + slot + j] = a.aux[s + j];
+            const uint32_t t = a.txp[s + j];
+            uint32_t k = j;
+            while (k > 0 && s_txp[slot + k - 1] > t) {
+                s_txp[slot + k] = s_txp[slot + k - 1]; s_src[slot + k] = s_src[slot + k - 1]; --k;
+            }
+            s_txp[slot + k] = t; s_src[slot + k] = s + j;
         }
     }
     // overflow rows: serial append by thread 0 (rare)
@@ -219,12 +235,16 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
         }
     }
     __syncthreads();
-    // padding slots: prob 0 (aux 1)
-    for (uint32_t i = tid; i < (uint32_t)kTile; i += kThreads)
-        if (s_txp[i] == kNoTxp) {
-            a.o_prob[(size_t)tile * kTile + i] = 0.f;
-            if (a.aux) a.o_aux[(size_t)tile * kTile + i] = 1.0;
-        }
+    // lanes holding two or more row heads need the general segmented-sum path
+    {
+        const uint32_t nib = (s_heads[tid >> 3] >> ((tid & 7u) * 4u)) & 0xFu;  // thread t <-> lane t of the tile
+        if (__popc(nib) >= 2) atomicOr(&s_info[tid >> 5], kInfoMulti);
+    }
+    for (uint32_t i = tid; i < (uint32_t)kTile; i += kThreads) {
+        const uint32_t src = s_src[i];
+        a.o_prob[(size_t)tile * kTile + i] = src != kNoTxp ? a.prob[src] : 0.f;   // padding: prob 0 (aux 1)
+        if (a.aux) a.o_aux[(size_t)tile * kTile + i] = src != kNoTxp ? a.aux[src] : 1.0;
+    }
 
     // sort slots by transcript
     uint32_t keys[4], vals[4];
@@ -234,7 +254,7 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
     Sort(tmp.sort).Sort(keys, vals);
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { s_txp[tid * 4 + i] = keys[i]; }
+    for (int i = 0; i < 4; ++i) s_txp[tid * 4 + i] = keys[i];
     __syncthreads();
     // segments of equal transcript
     uint32_t hf[4], seg[4];
@@ -280,7 +300,7 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
     }
     __syncthreads();
     const uint32_t table_off = s_misc[2], unit_off = s_misc[3];
-    // per-segment outputs; stash (start, unit base, cnt) for the per-slot pass
+    // per-segment outputs; stash (start, unit base) for the per-slot pass
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const uint32_t d = tid * 4 + i;
@@ -297,10 +317,10 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const uint32_t d = tid * 4 + i;
-        if (d < D) s_seg[d] = startd[i] | ((nun[i] ? ubase[i] : 0x1FFu) << 11) ;  // start (11 bits) | unit base (9 bits, 0x1FF = stray)
+        if (d < D) s_seg[d] = startd[i] | ((nun[i] ? ubase[i] : 0x1FFu) << 11);  // start (11 bits) | unit base (9 bits, 0x1FF = stray)
     }
     __syncthreads();
-    // per sorted element: table index and position
+    // per sorted element: table index and position, as shared-memory byte offsets
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const uint32_t r = tid * 4 + i;
@@ -308,17 +328,20 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
             const uint32_t d = seg[i] - 1;
             const uint32_t pk = s_seg[d];
             const uint32_t start = pk & 0x7FFu, ub = pk >> 11;
-            uint32_t pos = kStray;
+            uint32_t pos = kTrash;
             if (ub != 0x1FFu) { const uint32_t p = ub * 8 + (r - start); pos = p + (p >> 3); }
-            s_lpos[vals[i]] = d | (pos << 16);
+            else atomicOr(&s_info[vals[i] / kChunk], kInfoStray);
+            s_lpos[vals[i]] = (d * 8u) | ((pos * 8u) << 16);
         } else {
-            s_lpos[vals[i]] = 0u | ((uint32_t)kTrash << 16);
+            s_lpos[vals[i]] = 0u | (((uint32_t)kTrash * 8u) << 16);
         }
     }
     __syncthreads();
     for (uint32_t i = tid; i < (uint32_t)kTile; i += kThreads) a.o_lpos[(size_t)tile * kTile + i] = s_lpos[i];
-    if (tid < kWarps)
+    if (tid < kWarps) {
         a.o_heads[tile * kWarps + tid] = make_uint4(s_heads[tid * 4], s_heads[tid * 4 + 1], s_heads[tid * 4 + 2], s_heads[tid * 4 + 3]);
+        a.o_chunk_info[tile * kWarps + tid] = s_info[tid];
+    }
     if (tid == 0) a.o_meta[tile] = make_uint4(table_off, unit_off, D | (U << 16), r0);
 }
 
@@ -360,89 +383,124 @@ __device__ __forceinline__ uint4 ld_stream_u4(const uint32_t *p)
     return v;
 }
 
-// m_step (em.rs:87-133) over one tile per CTA.
+// Everything one lane holds of its warp-chunk: 4 alignment slots.
+template <bool HAS_AUX>
+struct ChunkRegs {
+    float4 p4;        // conditional probabilities
+    uint4 lp4;        // (table index * 8) | (pos * 8) << 16
+    uint4 hm;         // 128-bit row-head mask of the chunk
+    uint32_t info;    // scan steps | kInfoStray | kInfoMulti
+    uint32_t row_base;
+    double a0, a1, a2, a3;
+};
+
 template <bool HAS_AUX, bool HAS_WTS>
-static __global__ void __launch_bounds__(kThreads) em_sweep_tiled(View v, const double *__restrict__ prev,
-                                                           double *__restrict__ curr,
-                                                           const uint32_t *__restrict__ wperm,
-                                                           const OarEmState *__restrict__ st, int check_done)
+__device__ __forceinline__ void load_chunk(const View &v, uint32_t tile, uint32_t warp, uint32_t lane,
+                                           ChunkRegs<HAS_AUX> &c)
 {
-    if (check_done && st->done) return;
-    __shared__ double xs[kTrash + 1];
-    __shared__ double s_prev[kTile];
-
-    const uint32_t tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint4 meta = v.meta[tile];
-    const uint32_t D = meta.z & 0xFFFFu, U = meta.z >> 16;
-
-    // streaming loads first, so their latency overlaps the table gather
     const size_t base = (size_t)tile * kTile + warp * kChunk + lane * 4;
-    const float4 p4 = ld_stream_f4(v.prob + base);
-    const uint4 lp4 = ld_stream_u4(v.lpos + base);
-    const uint4 hm = v.heads[tile * kWarps + warp];
-    double a0 = 1.0, a1 = 1.0, a2 = 1.0, a3 = 1.0;
+    c.p4 = ld_stream_f4(v.prob + base);
+    c.lp4 = ld_stream_u4(v.lpos + base);
+    c.hm = v.heads[tile * kWarps + warp];
+    c.info = v.chunk_info[tile * kWarps + warp];
+    c.row_base = 0;
+    if (HAS_WTS) c.row_base = v.chunk_row[tile * kWarps + warp];
     if (HAS_AUX) {
         const double2 q0 = *reinterpret_cast<const double2 *>(v.aux + base);
         const double2 q1 = *reinterpret_cast<const double2 *>(v.aux + base + 2);
-        a0 = q0.x; a1 = q0.y; a2 = q1.x; a3 = q1.y;
+        c.a0 = q0.x; c.a1 = q0.y; c.a2 = q1.x; c.a3 = q1.y;
     }
-    uint32_t u_txp = kNoTxp, u_cnt = 0;
-    if (tid < U) { u_txp = v.unit_txp[meta.y + tid]; u_cnt = v.unit_cnt[meta.y + tid]; }
-    uint32_t row_base = 0;
-    if (HAS_WTS) row_base = v.chunk_row[tile * kWarps + warp];
+}
 
-    for (uint32_t d = tid; d < D; d += kThreads) s_prev[d] = prev[v.table[meta.x + d]];
-    __syncthreads();
-
-    // ---- phase 1: E-step in registers --------------------------------------
-    double w0 = s_prev[lp4.x & 0xFFFFu] * (double)p4.x;
-    double w1 = s_prev[lp4.y & 0xFFFFu] * (double)p4.y;
-    double w2 = s_prev[lp4.z & 0xFFFFu] * (double)p4.z;
-    double w3 = s_prev[lp4.w & 0xFFFFu] * (double)p4.w;
-    if (HAS_AUX) { w0 *= a0; w1 *= a1; w2 *= a2; w3 *= a3; }
+// Phase 1 for one warp-chunk: E-step in registers (per-row denominators by a
+// segmented warp scan), then the M-step scatter into the transcript-sorted
+// shared-memory order.
+template <bool HAS_AUX, bool HAS_WTS>
+__device__ __forceinline__ void chunk_phase1(const ChunkRegs<HAS_AUX> &c, const View &v, uint32_t table_off,
+                                             const double *s_prev, double *xs, double *__restrict__ curr,
+                                             const uint32_t *__restrict__ wperm, uint32_t lane)
+{
+    const uint4 lp4 = c.lp4;
+    const uint4 hm = c.hm;
+    const uint32_t info = c.info;
+    const char *sp = reinterpret_cast<const char *>(s_prev);
+    double w0 = *reinterpret_cast<const double *>(sp + (lp4.x & 0xFFFFu)) * (double)c.p4.x;
+    double w1 = *reinterpret_cast<const double *>(sp + (lp4.y & 0xFFFFu)) * (double)c.p4.y;
+    double w2 = *reinterpret_cast<const double *>(sp + (lp4.z & 0xFFFFu)) * (double)c.p4.z;
+    double w3 = *reinterpret_cast<const double *>(sp + (lp4.w & 0xFFFFu)) * (double)c.p4.w;
+    if (HAS_AUX) { w0 *= c.a0; w1 *= c.a1; w2 *= c.a2; w3 *= c.a3; }
 
     const uint32_t wq = lane >> 3;
     const uint32_t hword = wq == 0 ? hm.x : wq == 1 ? hm.y : wq == 2 ? hm.z : hm.w;
     const uint32_t hb = (hword >> ((lane & 7u) * 4u)) & 0xFu;
-
-    // inclusive per-row prefix inside the thread
-    const double s0 = w0;
-    const double s1 = (hb & 2u) ? w1 : s0 + w1;
-    const double s2 = (hb & 4u) ? w2 : s1 + w2;
-    const double s3 = (hb & 8u) ? w3 : s2 + w3;
-
     const unsigned full = 0xffffffffu;
     const unsigned lanes_h = __ballot_sync(full, hb != 0u);          // lane 0 always has a head
     const int P = 31 - __clz(lanes_h & (full >> (31u - lane)));       // nearest lane <= me holding a head
-    double incl = s3;                                                 // segmented inclusive scan of lane tails
+    const unsigned later = lanes_h & ~(full >> (31u - lane));        // lanes after me holding a head
+    const int E = later ? (__ffs(later) - 1) : (int)lane;
+    const int nsteps = (int)(info & 7u);
+
+    double x0, x1, x2, x3;
+    if (!(info & kInfoMulti)) {
+        // fast path: no lane holds more than one row head.  a = my slots before the head (they
+        // close the row entering this lane), z = my slots from the head on (they open a row).
+        const bool b0 = !(hb & 1u), b1 = !(hb & 3u), b2 = !(hb & 7u), b3 = !(hb & 15u);
+        double a = b0 ? w0 : 0.0, z = b0 ? 0.0 : w0;
+        a += b1 ? w1 : 0.0; z += b1 ? 0.0 : w1;
+        a += b2 ? w2 : 0.0; z += b2 ? 0.0 : w2;
+        a += b3 ? w3 : 0.0; z += b3 ? 0.0 : w3;
+        double incl = hb ? z : a;                                     // what this lane adds to the open row
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const double t = __shfl_up_sync(full, incl, d);
-        if ((int)lane - d >= P) incl += t;
+        for (int i = 0; i < 5; ++i) {
+            if (i >= nsteps) break;                                   // warp-uniform
+            const int d = 1 << i;
+            const double t = __shfl_up_sync(full, incl, d);
+            if ((int)lane - d >= P) incl += t;
+        }
+        double carry = __shfl_up_sync(full, incl, 1);                 // sum of the row entering this lane
+        if (lane == 0) carry = 0.0;
+        const double t_in = carry + a;                                // its total, if it ends here (hb != 0)
+        // reads whose denominator is <= 1e-30 contribute nothing (em.rs:115)
+        double inv_in = t_in > OAR_EM_DENOM_THRESH ? fast_rcp(t_in) : 0.0;
+        double inv_out = __shfl_sync(full, inv_in, E);                // the row leaving this lane ends in lane E
+        if (!later) inv_out = 0.0;                                    // only padding lies beyond the last head
+        if (!hb) inv_in = inv_out;                                    // a lane without a head is inside one row
+        x0 = w0 * (b0 ? inv_in : inv_out);
+        x1 = w1 * (b1 ? inv_in : inv_out);
+        x2 = w2 * (b2 ? inv_in : inv_out);
+        x3 = w3 * (b3 ? inv_in : inv_out);
+    } else {
+        // general path: rows may start and end inside one lane
+        const double s0 = w0;
+        const double s1 = (hb & 2u) ? w1 : s0 + w1;
+        const double s2 = (hb & 4u) ? w2 : s1 + w2;
+        const double s3 = (hb & 8u) ? w3 : s2 + w3;
+        double incl = s3;                                             // segmented inclusive scan of lane tails
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            if (i >= nsteps) break;
+            const int d = 1 << i;
+            const double t = __shfl_up_sync(full, incl, d);
+            if ((int)lane - d >= P) incl += t;
+        }
+        double carry = __shfl_up_sync(full, incl, 1);
+        if (lane == 0) carry = 0.0;
+        const double sA = (hb & 1u) ? 0.0 : (hb & 2u) ? s0 : (hb & 4u) ? s1 : (hb & 8u) ? s2 : s3;
+        const double t_in = carry + sA;
+        const double t_in_e = __shfl_sync(full, t_in, E);
+        const double t_out = later ? t_in_e : 0.0;
+        const double pre0 = (hb & 1u) ? s0 : carry + s0;
+        const double pre1 = (hb & 3u) ? s1 : carry + s1;
+        const double pre2 = (hb & 7u) ? s2 : carry + s2;
+        const double tot3 = t_out;
+        const double tot2 = (hb & 8u) ? pre2 : tot3;
+        const double tot1 = (hb & 4u) ? pre1 : tot2;
+        const double tot0 = (hb & 2u) ? pre0 : tot1;
+        x0 = tot0 > OAR_EM_DENOM_THRESH ? w0 * fast_rcp(tot0) : 0.0;
+        x1 = tot1 > OAR_EM_DENOM_THRESH ? w1 * fast_rcp(tot1) : 0.0;
+        x2 = tot2 > OAR_EM_DENOM_THRESH ? w2 * fast_rcp(tot2) : 0.0;
+        x3 = tot3 > OAR_EM_DENOM_THRESH ? w3 * fast_rcp(tot3) : 0.0;
     }
-    double carry = __shfl_up_sync(full, incl, 1);                     // sum of the row entering this lane
-    if (lane == 0) carry = 0.0;
-    const double sA = (hb & 1u) ? 0.0 : (hb & 2u) ? s0 : (hb & 4u) ? s1 : (hb & 8u) ? s2 : s3;
-    const double t_in = carry + sA;                                   // total of the entering row if it ends here
-    const unsigned later = lanes_h & ~(full >> (31u - lane));
-    const int E = later ? (__ffs(later) - 1) : 31;
-    const double t_in_e = __shfl_sync(full, t_in, E);
-    const double incl31 = __shfl_sync(full, incl, 31);
-    const double t_out = later ? t_in_e : incl31;                     // total of the row leaving this lane
-
-    const double pre0 = (hb & 1u) ? s0 : carry + s0;
-    const double pre1 = (hb & 3u) ? s1 : carry + s1;
-    const double pre2 = (hb & 7u) ? s2 : carry + s2;
-    const double tot3 = t_out;
-    const double tot2 = (hb & 8u) ? pre2 : tot3;
-    const double tot1 = (hb & 4u) ? pre1 : tot2;
-    const double tot0 = (hb & 2u) ? pre0 : tot1;
-
-    // reads whose denominator is <= 1e-30 contribute nothing (em.rs:115)
-    double x0 = tot0 > OAR_EM_DENOM_THRESH ? w0 * fast_rcp(tot0) : 0.0;
-    double x1 = tot1 > OAR_EM_DENOM_THRESH ? w1 * fast_rcp(tot1) : 0.0;
-    double x2 = tot2 > OAR_EM_DENOM_THRESH ? w2 * fast_rcp(tot2) : 0.0;
-    double x3 = tot3 > OAR_EM_DENOM_THRESH ? w3 * fast_rcp(tot3) : 0.0;
 
     if (HAS_WTS) {
         // row index inside the chunk = (number of heads at or before the slot) - 1
@@ -453,27 +511,37 @@ static __global__ void __launch_bounds__(kThreads) em_sweep_tiled(View v, const 
         const uint32_t sh = (lane & 7u) * 4u;
         const uint32_t r0 = before + __popc(hword & (full >> (31u - sh))) - 1u;
         const uint32_t r1 = r0 + ((hb >> 1) & 1u), r2 = r1 + ((hb >> 2) & 1u), r3 = r2 + ((hb >> 3) & 1u);
-        x0 *= (double)wperm[row_base + r0];
-        x1 *= (double)wperm[row_base + r1];
-        x2 *= (double)wperm[row_base + r2];
-        x3 *= (double)wperm[row_base + r3];
+        x0 *= (double)wperm[c.row_base + r0];
+        x1 *= (double)wperm[c.row_base + r1];
+        x2 *= (double)wperm[c.row_base + r2];
+        x3 *= (double)wperm[c.row_base + r3];
     }
 
-    // ---- M-step scatter into the transcript-sorted smem order ----------------
-    const uint32_t q0 = lp4.x >> 16, q1 = lp4.y >> 16, q2 = lp4.z >> 16, q3 = lp4.w >> 16;
-    if (q0 != kStray) xs[q0] = x0; else if (x0 != 0.0) atomicAdd(curr + v.table[meta.x + (lp4.x & 0xFFFFu)], x0);
-    if (q1 != kStray) xs[q1] = x1; else if (x1 != 0.0) atomicAdd(curr + v.table[meta.x + (lp4.y & 0xFFFFu)], x1);
-    if (q2 != kStray) xs[q2] = x2; else if (x2 != 0.0) atomicAdd(curr + v.table[meta.x + (lp4.z & 0xFFFFu)], x2);
-    if (q3 != kStray) xs[q3] = x3; else if (x3 != 0.0) atomicAdd(curr + v.table[meta.x + (lp4.w & 0xFFFFu)], x3);
-    __syncthreads();
+    char *xp = reinterpret_cast<char *>(xs);
+    *reinterpret_cast<double *>(xp + (lp4.x >> 16)) = x0;
+    *reinterpret_cast<double *>(xp + (lp4.y >> 16)) = x1;
+    *reinterpret_cast<double *>(xp + (lp4.z >> 16)) = x2;
+    *reinterpret_cast<double *>(xp + (lp4.w >> 16)) = x3;
+    if (info & kInfoStray) {
+        // transcripts with fewer than kAggMin alignments in this tile: straight to global
+        const uint32_t trash = (uint32_t)kTrash * 8u;
+        if ((lp4.x >> 16) == trash && x0 != 0.0) atomicAdd(curr + v.table[table_off + ((lp4.x & 0xFFFFu) >> 3)], x0);
+        if ((lp4.y >> 16) == trash && x1 != 0.0) atomicAdd(curr + v.table[table_off + ((lp4.y & 0xFFFFu) >> 3)], x1);
+        if ((lp4.z >> 16) == trash && x2 != 0.0) atomicAdd(curr + v.table[table_off + ((lp4.z & 0xFFFFu) >> 3)], x2);
+        if ((lp4.w >> 16) == trash && x3 != 0.0) atomicAdd(curr + v.table[table_off + ((lp4.w & 0xFFFFu) >> 3)], x3);
+    }
+}
 
-    // ---- phase 2: sum 8-slot units, combine equal transcripts across the warp --
+// Phase 2 for one warp: sum 8-slot units of the transcript-sorted order, combine
+// equal transcripts across the warp, one f64 RED per (warp, transcript).
+__device__ __forceinline__ void units_phase2(const double *xs, uint32_t tid, uint32_t lane, uint32_t u_txp,
+                                             uint32_t u_cnt, double *__restrict__ curr)
+{
+    const unsigned full = 0xffffffffu;
     double acc = 0.0;
-    {
-        const double *b = xs + tid * 9;
+    const double *b = xs + tid * 9;
 #pragma unroll
-        for (uint32_t k = 0; k < 8; ++k) if (k < u_cnt) acc += b[k];
-    }
+    for (uint32_t k = 0; k < 8; ++k) if (k < u_cnt) acc += b[k];
     const uint32_t up = __shfl_up_sync(full, u_txp, 1);
     const uint32_t dn = __shfl_down_sync(full, u_txp, 1);
     const bool head = (lane == 0) || (up != u_txp);
@@ -486,6 +554,33 @@ static __global__ void __launch_bounds__(kThreads) em_sweep_tiled(View v, const 
         if ((int)lane - d >= P2) acc += t;
     }
     if (tail && u_txp != kNoTxp) atomicAdd(curr + u_txp, acc);
+}
+
+// m_step (em.rs:87-133) over one tile per CTA.
+template <bool HAS_AUX, bool HAS_WTS>
+__global__ void __launch_bounds__(kThreads) em_sweep_tiled(View v, const double *__restrict__ prev,
+                                                           double *__restrict__ curr,
+                                                           const uint32_t *__restrict__ wperm,
+                                                           const OarEmState *__restrict__ st, int check_done)
+{
+    __shared__ __align__(16) double xs[kTrash + 1];
+    __shared__ __align__(16) double s_prev[kTile];
+
+    const uint32_t tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    uint32_t done = 0;
+    if (check_done) done = st->done;   // tested after the loads below are in flight
+    const uint4 meta = v.meta[tile];
+    ChunkRegs<HAS_AUX> c;
+    load_chunk<HAS_AUX, HAS_WTS>(v, tile, warp, lane, c);   // streaming loads first: they overlap the table gather
+    const uint32_t D = meta.z & 0xFFFFu, U = meta.z >> 16;
+    uint32_t u_txp = kNoTxp, u_cnt = 0;
+    if (tid < U) { u_txp = v.unit_txp[meta.y + tid]; u_cnt = v.unit_cnt[meta.y + tid]; }
+    if (done) return;
+    for (uint32_t d = tid; d < D; d += kThreads) s_prev[d] = prev[v.table[meta.x + d]];
+    __syncthreads();
+    chunk_phase1<HAS_AUX, HAS_WTS>(c, v, meta.x, s_prev, xs, curr, wperm, lane);
+    __syncthreads();
+    if (warp * 32u < U) units_phase2(xs, tid, lane, u_txp, u_cnt, curr);
 }
 
 }  // namespace tiled

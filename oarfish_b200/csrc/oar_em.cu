@@ -145,8 +145,8 @@ extern "C" int oar_store_create(const uint64_t *row_ptr, const uint32_t *txp_id,
             if (!(env && env[0] == '0')) {
                 const char *sp = getenv("OAR_TILE_SPAN");
                 int rc2 = build_tiled_layout(s, sp ? (uint32_t)atoi(sp) : 0u);
-                if (rc2 != OAR_OK) return rc2;
-                s->kernel = OAR_KERNEL_TILED;
+                if (rc2 == OAR_OK) s->kernel = OAR_KERNEL_TILED;
+                else if (rc2 != OAR_ERR_UNSUPPORTED) return rc2;   // unsupported shape: keep the CSR kernel
             }
             const char *cps = getenv("OAR_CTAS_PER_SM");
             if (cps && atoi(cps) > 0) s->ctas_per_sm = atoi(cps);
@@ -224,9 +224,24 @@ static tiled::View tiled_view(const oar_store *s)
 {
     const TiledLayout &t = s->tl;
     tiled::View v;
-    v.n_tiles = t.n_tiles; v.prob = t.prob; v.lpos = t.lpos; v.aux = t.aux; v.heads = t.heads;
-    v.chunk_row = t.chunk_row; v.chunk_info = t.chunk_info; v.meta = t.meta; v.table = t.table; v.unit_txp = t.unit_txp; v.unit_cnt = t.unit_cnt;
+    v.n_tiles = t.n_tiles; v.prob = t.prob; v.lpos = t.lpos; v.aux = t.aux; v.rec = t.rec; v.records = t.records;
     return v;
+}
+
+template <bool AUX, bool WTS>
+static cudaError_t launch_tiled(oar_store *s, const tiled::View &v, const double *prev, double *curr,
+                                const uint32_t *wperm, const OarEmState *state, int check_done)
+{
+    static bool attr_set[16] = {false};
+    auto kfn = tiled::em_sweep_tiled<AUX, WTS>;
+    if (!attr_set[s->device & 15]) {
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, tiled::kSmemBytes);
+        if (e != cudaSuccess) return e;
+        attr_set[s->device & 15] = true;
+    }
+    const uint32_t grid = std::min<uint32_t>(v.n_tiles, (uint32_t)s->sm_count * (uint32_t)s->ctas_per_sm);
+    kfn<<<grid, tiled::kThreads, tiled::kSmemBytes, s->stream>>>(v, prev, curr, wperm, state, check_done);
+    return cudaGetLastError();
 }
 
 // Row-group sweep over all rows (list == null) or over a list of row ids.
@@ -260,11 +275,13 @@ static cudaError_t enqueue_sweep(oar_store *s, const double *prev, double *curr,
     const TiledLayout &t = s->tl;
     if (t.n_tiles > 0) {
         const tiled::View v = tiled_view(s);
-#define OAR_LAUNCH(AUX, WTS)                                                                      \
-    tiled::em_sweep_tiled<AUX, WTS><<<t.n_tiles, tiled::kThreads, 0, s->stream>>>(v, prev, curr, wts ? t.wperm : nullptr, state, check_done)
-        if (s->d_aux) { if (wts) OAR_LAUNCH(true, true); else OAR_LAUNCH(true, false); }
-        else          { if (wts) OAR_LAUNCH(false, true); else OAR_LAUNCH(false, false); }
-#undef OAR_LAUNCH
+        const uint32_t *wp = wts ? t.wperm : nullptr;
+        cudaError_t le;
+        if (s->d_aux) le = wts ? launch_tiled<true, true>(s, v, prev, curr, wp, state, check_done)
+                               : launch_tiled<true, false>(s, v, prev, curr, wp, state, check_done);
+        else          le = wts ? launch_tiled<false, true>(s, v, prev, curr, wp, state, check_done)
+                               : launch_tiled<false, false>(s, v, prev, curr, wp, state, check_done);
+        if (le != cudaSuccess) return le;
         s->counters[0] += 1;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;

@@ -16,8 +16,7 @@ namespace oar {
 void free_tiled_layout(oar_store *s)
 {
     TiledLayout &t = s->tl;
-    cudaFree(t.prob); cudaFree(t.lpos); cudaFree(t.aux); cudaFree(t.heads); cudaFree(t.chunk_row); cudaFree(t.chunk_info);
-    cudaFree(t.meta); cudaFree(t.table); cudaFree(t.unit_txp); cudaFree(t.unit_cnt); cudaFree(t.trow);
+    cudaFree(t.prob); cudaFree(t.lpos); cudaFree(t.aux); cudaFree(t.rec); cudaFree(t.records); cudaFree(t.trow);
     cudaFree(t.fallback); cudaFree(t.wperm);
     t = TiledLayout();
 }
@@ -44,6 +43,7 @@ int build_tiled_layout(oar_store *s, uint32_t span)
     if (span == 0 || span > (uint32_t)kTile) span = 984;
     t.span = span;
     if (N == 0 || s->nnz == 0) { t.ready = true; return OAR_OK; }
+    if (s->n_txps >= kMaxTxps) return fail(OAR_ERR_UNSUPPORTED, "tiled layout needs n_txps < 2^28");
     cudaStream_t st = s->stream;
     Scratch sc;
     uint32_t *key = nullptr, *idx = nullptr, *key_s = nullptr, *srow = nullptr, *slen = nullptr, *soff = nullptr;
@@ -95,9 +95,9 @@ int build_tiled_layout(oar_store *s, uint32_t span)
     }
     t.n_tiles = n_tiles;
 
-    // outputs (table/unit arrays first at their worst-case size, compacted below)
+    // outputs (the variable-length records first at their worst-case size, compacted below)
     const size_t slots = (size_t)n_tiles * kTile;
-    uint32_t *table_tmp = nullptr, *unit_txp_tmp = nullptr; uint8_t *unit_cnt_tmp = nullptr;
+    uint4 *records_tmp = nullptr;
     OAR_CUDA(cudaMalloc(&t.fallback, sizeof(uint32_t) * std::max<uint32_t>(N, 1)));
     OAR_CUDA(cudaMalloc(&t.trow, sizeof(uint32_t) * std::max<uint32_t>(n_tiled, 1)));
     OAR_CUDA(cudaMalloc(&t.wperm, sizeof(uint32_t) * ((size_t)n_tiled + kChunk + 1)));
@@ -106,18 +106,14 @@ int build_tiled_layout(oar_store *s, uint32_t span)
         OAR_CUDA(cudaMalloc(&t.prob, sizeof(float) * slots));
         OAR_CUDA(cudaMalloc(&t.lpos, sizeof(uint32_t) * slots));
         if (s->d_aux) OAR_CUDA(cudaMalloc(&t.aux, sizeof(double) * slots));
-        OAR_CUDA(cudaMalloc(&t.heads, sizeof(uint4) * (size_t)n_tiles * kWarps));
-        OAR_CUDA(cudaMalloc(&t.chunk_row, sizeof(uint32_t) * (size_t)n_tiles * kWarps));
-        OAR_CUDA(cudaMalloc(&t.chunk_info, sizeof(uint32_t) * (size_t)n_tiles * kWarps));
-        OAR_CUDA(cudaMalloc(&t.meta, sizeof(uint4) * n_tiles));
-        OAR_CUDA(sc.alloc(&table_tmp, (size_t)total));
-        OAR_CUDA(sc.alloc(&unit_txp_tmp, (size_t)total / kAggMin + 1));
-        OAR_CUDA(sc.alloc(&unit_cnt_tmp, (size_t)total / kAggMin + 1));
+        OAR_CUDA(cudaMalloc(&t.rec, sizeof(uint2) * n_tiles));
+        // a record holds at most (slots of the tile) table entries: bound the total by the real slot count
+        const size_t worst = (size_t)n_tiles * (kRecTable + 16) + 4 * (size_t)total + 4 * ((size_t)total / kAggMin) + 64;
+        OAR_CUDA(sc.alloc((char **)&records_tmp, worst));
         BuildArgs a;
         a.row_ptr = s->d_row_ptr; a.txp = s->d_txp; a.prob = s->d_prob; a.aux = s->d_aux;
         a.srow = srow; a.tile_row = tile_row;
-        a.o_prob = t.prob; a.o_lpos = t.lpos; a.o_aux = t.aux; a.o_heads = t.heads; a.o_chunk_row = t.chunk_row; a.o_chunk_info = t.chunk_info;
-        a.o_meta = t.meta; a.o_table = table_tmp; a.o_unit_txp = unit_txp_tmp; a.o_unit_cnt = unit_cnt_tmp;
+        a.o_prob = t.prob; a.o_lpos = t.lpos; a.o_aux = t.aux; a.o_rec = t.rec; a.o_records = records_tmp;
         a.o_trow = t.trow; a.fallback = t.fallback; a.cursors = counters + 4;
         build_tiles<<<n_tiles, kThreads, 0, st>>>(a);
         OAR_CUDA(cudaGetLastError());
@@ -132,13 +128,10 @@ int build_tiled_layout(oar_store *s, uint32_t span)
     t.n_fallback = h_counters[4];
     t.sum_d = h_counters[5];
     t.sum_u = h_counters[6];
+    t.record_bytes = (uint64_t)h_counters[7] * 16u;
     if (n_tiles > 0) {
-        OAR_CUDA(cudaMalloc(&t.table, sizeof(uint32_t) * std::max<uint64_t>(t.sum_d, 1)));
-        OAR_CUDA(cudaMalloc(&t.unit_txp, sizeof(uint32_t) * std::max<uint64_t>(t.sum_u, 1)));
-        OAR_CUDA(cudaMalloc(&t.unit_cnt, sizeof(uint8_t) * std::max<uint64_t>(t.sum_u, 1)));
-        OAR_CUDA(cudaMemcpyAsync(t.table, table_tmp, sizeof(uint32_t) * t.sum_d, cudaMemcpyDeviceToDevice, st));
-        OAR_CUDA(cudaMemcpyAsync(t.unit_txp, unit_txp_tmp, sizeof(uint32_t) * t.sum_u, cudaMemcpyDeviceToDevice, st));
-        OAR_CUDA(cudaMemcpyAsync(t.unit_cnt, unit_cnt_tmp, sizeof(uint8_t) * t.sum_u, cudaMemcpyDeviceToDevice, st));
+        OAR_CUDA(cudaMalloc(&t.records, std::max<uint64_t>(t.record_bytes, 16)));
+        OAR_CUDA(cudaMemcpyAsync(t.records, records_tmp, t.record_bytes, cudaMemcpyDeviceToDevice, st));
         OAR_CUDA(cudaStreamSynchronize(st));
     }
     t.ready = true;

@@ -12,13 +12,9 @@ struct TiledLayout {
     float *prob = nullptr;
     uint32_t *lpos = nullptr;
     double *aux = nullptr;
-    uint4 *heads = nullptr;
-    uint32_t *chunk_row = nullptr;
-    uint32_t *chunk_info = nullptr;
-    uint4 *meta = nullptr;
-    uint32_t *table = nullptr;
-    uint32_t *unit_txp = nullptr;
-    uint8_t *unit_cnt = nullptr;
+    uint2 *rec = nullptr;          // per tile: {record offset (16 B granules), record bytes}
+    uint4 *records = nullptr;      // per-tile records (lane descriptors, chunk info, table, units)
+    uint64_t record_bytes = 0;
     uint32_t *trow = nullptr;      // tile-order row -> original row (n_tiled_rows)
     uint32_t *fallback = nullptr;  // original row ids swept from the CSR
     uint32_t *wperm = nullptr;     // bootstrap weights in tile order

@@ -10,7 +10,7 @@
 //     one tile (<= 1024 alignment slots) touch a handful of transcripts;
 //   * a tile carries its own table of distinct transcripts; prev[] for the
 //     table is gathered once into shared memory, alignments store a 16-bit
-//     table index instead of the 32-bit id;
+//     table offset instead of the 32-bit id;
 //   * the M-step scatter goes through shared memory: every alignment also
 //     stores `pos`, its position in the tile's transcript-sorted order, x_j =
 //     w_j/denom is written to xs[pos] and 8-slot units of xs are summed
@@ -18,11 +18,18 @@
 //     per (warp, transcript) instead of one per alignment.  No shared-memory
 //     atomics (f64 smem atomics are CAS loops on sm_100a).
 //   * rows never straddle a 128-slot warp-chunk, so the per-row denominator
-//     (em.rs:98-112) is a segmented warp scan in registers.
+//     (em.rs:98-112) is a segmented warp scan in registers, driven by a
+//     precomputed 16-bit descriptor per lane.
 //
-// Per alignment the HBM stream is 4 B (prob f32) + 4 B (table index u16 | pos
-// u16): the same 8 B as CSR's txp_id + prob; row boundaries are a 1-bit head
-// mask instead of a 4-byte row_ptr entry.
+// The sweep is a persistent kernel: CTAs walk tiles blockIdx.x, +gridDim.x, ...
+// and a two-stage ring of shared-memory buffers is filled by TMA bulk copies
+// (cp.async.bulk, completion on an mbarrier), issued two tiles ahead by one
+// thread, so HBM latency never sits on the compute path and no registers are
+// spent on prefetching.
+//
+// Per alignment the HBM stream is 4 B (prob f32) + 4 B (table offset u16 | pos
+// u16), the same 8 B as CSR's txp_id + prob; row structure costs 2 B per lane
+// (4 slots) instead of a 4-byte row_ptr entry per row.
 //
 // Rows longer than a warp-chunk, or that do not fit their tile, are listed in
 // `fallback_rows` and swept by em_sweep_rowgroup from the original CSR.
@@ -41,24 +48,38 @@ constexpr int kTile = kWarps * kChunk;    // 1024 slots
 constexpr int kThreads = kWarps * 32;     // 256
 constexpr int kAggMin = 4;                // transcripts with >= kAggMin alignments in a tile are aggregated in smem
 constexpr int kMaxUnits = kTile / 4;      // sum ceil(cnt/8) over cnt >= 4  <=  kTile/4
-constexpr int kTrash = kMaxUnits * 9;     // xs slot for padding alignments (never summed)
+constexpr int kTrash = kMaxUnits * 9;     // xs slot for padding / non-aggregated alignments (never summed)
 constexpr uint32_t kInfoStray = 8u;       // chunk_info bit 3: chunk holds alignments that RED straight to global
 constexpr uint32_t kInfoMulti = 16u;      // chunk_info bit 4: some lane holds >= 2 row heads (general path)
 constexpr uint32_t kNoTxp = 0xFFFFFFFFu;
+constexpr uint32_t kMaxTxps = 1u << 28;   // unit descriptors pack (count-1) above bit 28
 static_assert(kMaxUnits == kThreads, "one unit per thread in phase 2");
+
+// Per-tile record (variable length, 16-byte granules), one TMA bulk copy:
+//   [0,512)    lane descriptors u16[8][32]: hb(4) | dist(5) | E(5) | later(1)
+//                hb    row-head bits of the lane's 4 slots
+//                dist  lanes back to the nearest lane (<= this one) holding a head
+//                E     first later lane holding a head (where the row leaving this lane ends)
+//                later such a lane exists
+//   [512,544)  chunk_info u32[8]: scan steps (bits 0-2) | kInfoStray | kInfoMulti
+//   [544,576)  chunk_row  u32[8]: tile-order index of the chunk's first row (bootstrap weights)
+//   [576,592)  D, U, 0, 0
+//   [592, ..)  table u32[roundup4(D)]  : distinct transcript ids
+//              units u32[roundup4(U)]  : transcript id | (valid slots - 1) << 28 per 8-slot unit
+constexpr int kRecDesc = 0, kRecInfo = 512, kRecRow = 544, kRecDU = 576, kRecTable = 592;
+constexpr int kRecMax = kRecTable + 4 * kTile + 4 * kMaxUnits;   // 5712
+constexpr int kStageBytes = 4 * kTile + 4 * kTile + kRecMax;      // prob + lpos + record = 13904
+constexpr int kStages = 2;
+constexpr int kXsBytes = 8 * (kTrash + 1 + 1);                    // 18448 (16-byte multiple)
+constexpr int kSmemBytes = kStages * kStageBytes + kXsBytes + 8 * kTile + 64;
 
 struct View {
     uint32_t n_tiles;
     const float *prob;         // n_tiles * kTile
     const uint32_t *lpos;      // n_tiles * kTile : (table index * 8) | (pos * 8) << 16  (smem byte offsets)
     const double *aux;         // n_tiles * kTile or null
-    const uint4 *heads;        // n_tiles * kWarps : 128-bit row-head mask per warp-chunk
-    const uint32_t *chunk_row; // n_tiles * kWarps : tile-order index of the chunk's first row
-    const uint32_t *chunk_info;// n_tiles * kWarps : scan steps (bits 0-2) | kInfoStray | kInfoMulti
-    const uint4 *meta;         // n_tiles : {table_off, unit_off, D | U << 16, first tile-order row}
-    const uint32_t *table;     // sum D : distinct transcript ids per tile
-    const uint32_t *unit_txp;  // sum U : transcript id of each 8-slot unit
-    const uint8_t *unit_cnt;   // sum U : valid slots (1..8) of each unit
+    const uint2 *rec;          // n_tiles : {record offset in 16-byte granules, record bytes}
+    const uint4 *records;      // all records
 };
 
 // ---------------------------------------------------------------------------
@@ -68,7 +89,7 @@ struct View {
 // key = smallest transcript id of the row (locality key); rows that cannot be
 // tiled (empty, or longer than a warp-chunk) get kNoTxp and sort to the end.
 static __global__ void row_keys(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ txp, uint64_t n_rows,
-                         uint32_t *__restrict__ key, uint32_t *__restrict__ idx, uint32_t *__restrict__ counters)
+                                uint32_t *__restrict__ key, uint32_t *__restrict__ idx, uint32_t *__restrict__ counters)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     uint32_t n_long = 0, n_skip = 0;
@@ -90,7 +111,7 @@ static __global__ void row_keys(const uint32_t *__restrict__ row_ptr, const uint
 
 // lengths of the tiled rows in sorted order
 static __global__ void sorted_lens(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ srow, uint32_t n,
-                            uint32_t *__restrict__ slen)
+                                   uint32_t *__restrict__ slen)
 {
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
@@ -101,8 +122,8 @@ static __global__ void sorted_lens(const uint32_t *__restrict__ row_ptr, const u
 
 // rows that were not tiled because they are longer than a warp-chunk
 static __global__ void collect_long_rows(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ srow,
-                                  uint32_t first, uint32_t n_rows, uint32_t *__restrict__ fallback,
-                                  uint32_t *__restrict__ cursor)
+                                         uint32_t first, uint32_t n_rows, uint32_t *__restrict__ fallback,
+                                         uint32_t *__restrict__ cursor)
 {
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t k = first + blockIdx.x * blockDim.x + threadIdx.x; k < n_rows; k += stride) {
@@ -112,8 +133,8 @@ static __global__ void collect_long_rows(const uint32_t *__restrict__ row_ptr, c
 }
 
 // tile t owns the sorted rows whose first alignment offset lies in [t*span, (t+1)*span)
-static __global__ void tile_row_starts(const uint32_t *__restrict__ soff, uint32_t n_rows, uint32_t span, uint32_t n_tiles,
-                                uint32_t *__restrict__ tile_row)
+static __global__ void tile_row_starts(const uint32_t *__restrict__ soff, uint32_t n_rows, uint32_t span,
+                                       uint32_t n_tiles, uint32_t *__restrict__ tile_row)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t > n_tiles) return;
@@ -128,10 +149,9 @@ struct BuildArgs {
     const uint32_t *row_ptr; const uint32_t *txp; const float *prob; const double *aux;
     const uint32_t *srow;      // sorted position -> original row
     const uint32_t *tile_row;  // n_tiles + 1
-    float *o_prob; uint32_t *o_lpos; double *o_aux; uint4 *o_heads; uint32_t *o_chunk_row; uint32_t *o_chunk_info; uint4 *o_meta;
-    uint32_t *o_table; uint32_t *o_unit_txp; uint8_t *o_unit_cnt;
+    float *o_prob; uint32_t *o_lpos; double *o_aux; uint2 *o_rec; uint4 *o_records;
     uint32_t *o_trow;          // tile-order row -> original row
-    uint32_t *fallback; uint32_t *cursors;  // [0] fallback rows, [1] table entries, [2] units
+    uint32_t *fallback; uint32_t *cursors;  // [0] fallback rows, [1] sum D, [2] sum U, [3] record granules
 };
 
 // One CTA lays out one tile.
@@ -148,12 +168,14 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
     __shared__ uint32_t s_heads[kWarps * 4];
     __shared__ uint32_t s_used[kWarps], s_nrow[kWarps], s_info[kWarps];
     __shared__ uint32_t s_misc[4];
+    __shared__ __align__(16) uint32_t s_rec[kRecMax / 4];
 
     const uint32_t tile = blockIdx.x, tid = threadIdx.x;
     const uint32_t r0 = a.tile_row[tile], r1 = a.tile_row[tile + 1];
     const uint32_t nrows = min(r1 - r0, (uint32_t)kTile);  // every row has >= 1 alignment and span <= kTile
 
     for (uint32_t i = tid; i < (uint32_t)kTile; i += kThreads) { s_txp[i] = kNoTxp; s_lpos[i] = 0; s_src[i] = kNoTxp; }
+    for (uint32_t i = tid; i < (uint32_t)kRecMax / 4; i += kThreads) s_rec[i] = 0;
     if (tid < kWarps * 4) s_heads[tid] = 0;
     for (uint32_t i = tid; i < nrows; i += kThreads) {
         const uint32_t r = a.srow[r0 + i];
@@ -198,7 +220,7 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
         for (int c = 0; c < kWarps; ++c) { chunk_base[c] = acc; acc += s_nrow[c]; }
         if (tid == 0) s_misc[0] = acc;  // rows placed
         if (tid < kWarps) {
-            a.o_chunk_row[tile * kWarps + tid] = r0 + chunk_base[tid];
+            s_rec[kRecRow / 4 + tid] = r0 + chunk_base[tid];
             // the padding slots form a pseudo row, so every real row ends at a head inside the chunk
             const uint32_t u = s_used[tid];
             atomicOr(&s_heads[tid * 4 + (u >> 5)], 1u << (u & 31));
@@ -235,10 +257,18 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
         }
     }
     __syncthreads();
-    // lanes holding two or more row heads need the general segmented-sum path
+    // lane descriptors: thread t <-> lane (t & 31) of chunk (t >> 5)
     {
-        const uint32_t nib = (s_heads[tid >> 3] >> ((tid & 7u) * 4u)) & 0xFu;  // thread t <-> lane t of the tile
-        if (__popc(nib) >= 2) atomicOr(&s_info[tid >> 5], kInfoMulti);
+        const uint32_t lane = tid & 31u;
+        const unsigned full = 0xffffffffu;
+        const uint32_t hb = (s_heads[tid >> 3] >> ((tid & 7u) * 4u)) & 0xFu;
+        if (__popc(hb) >= 2) atomicOr(&s_info[tid >> 5], kInfoMulti);  // general segmented-sum path needed
+        const unsigned lanes_h = __ballot_sync(full, hb != 0u);       // lane 0 always has a head
+        const int P = 31 - __clz(lanes_h & (full >> (31u - lane)));
+        const unsigned later = lanes_h & ~(full >> (31u - lane));
+        const uint32_t E = later ? (uint32_t)(__ffs(later) - 1) : lane;
+        const uint32_t desc = hb | ((lane - (uint32_t)P) << 4) | (E << 9) | ((later ? 1u : 0u) << 14);
+        reinterpret_cast<uint16_t *>(s_rec)[kRecDesc / 2 + tid] = (uint16_t)desc;
     }
     for (uint32_t i = tid; i < (uint32_t)kTile; i += kThreads) {
         const uint32_t src = s_src[i];
@@ -294,26 +324,28 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
     }
     Scan(tmp.scan).ExclusiveSum(nun, ubase, U);
     __syncthreads();
+    const uint32_t D4 = (D + 3u) & ~3u, U4 = (U + 3u) & ~3u;
+    const uint32_t rec_bytes = kRecTable + 4u * D4 + 4u * U4;
     if (tid == 0) {
-        s_misc[2] = atomicAdd(a.cursors + 1, D);
-        s_misc[3] = atomicAdd(a.cursors + 2, U);
+        atomicAdd(a.cursors + 1, D);
+        atomicAdd(a.cursors + 2, U);
+        s_misc[2] = atomicAdd(a.cursors + 3, rec_bytes / 16u);
+        s_rec[kRecDU / 4 + 0] = D;
+        s_rec[kRecDU / 4 + 1] = U;
     }
-    __syncthreads();
-    const uint32_t table_off = s_misc[2], unit_off = s_misc[3];
-    // per-segment outputs; stash (start, unit base) for the per-slot pass
+    // table and unit descriptors
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const uint32_t d = tid * 4 + i;
         if (d < D) {
             const uint32_t key = s_txp[startd[i]];
-            a.o_table[table_off + d] = key;
-            for (uint32_t v = 0; v < nun[i]; ++v) {
-                a.o_unit_txp[unit_off + ubase[i] + v] = key;
-                a.o_unit_cnt[unit_off + ubase[i] + v] = (uint8_t)min(8u, cntd[i] - 8u * v);
-            }
+            s_rec[kRecTable / 4 + d] = key;
+            for (uint32_t v = 0; v < nun[i]; ++v)
+                s_rec[kRecTable / 4 + D4 + ubase[i] + v] = key | ((min(8u, cntd[i] - 8u * v) - 1u) << 28);
         }
     }
-    __syncthreads();  // everyone has read s_seg[d+1]
+    __syncthreads();  // everyone has read s_seg[d+1]; s_misc[2] visible
+    for (uint32_t u = U + tid; u < U4; u += kThreads) s_rec[kRecTable / 4 + D4 + u] = kNoTxp;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const uint32_t d = tid * 4 + i;
@@ -338,16 +370,18 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
     }
     __syncthreads();
     for (uint32_t i = tid; i < (uint32_t)kTile; i += kThreads) a.o_lpos[(size_t)tile * kTile + i] = s_lpos[i];
-    if (tid < kWarps) {
-        a.o_heads[tile * kWarps + tid] = make_uint4(s_heads[tid * 4], s_heads[tid * 4 + 1], s_heads[tid * 4 + 2], s_heads[tid * 4 + 3]);
-        a.o_chunk_info[tile * kWarps + tid] = s_info[tid];
-    }
-    if (tid == 0) a.o_meta[tile] = make_uint4(table_off, unit_off, D | (U << 16), r0);
+    if (tid < kWarps) s_rec[kRecInfo / 4 + tid] = s_info[tid];
+    __syncthreads();
+    const uint32_t rec_off = s_misc[2];
+    uint4 *dst = a.o_records + rec_off;
+    const uint4 *srcv = reinterpret_cast<const uint4 *>(s_rec);
+    for (uint32_t i = tid; i < rec_bytes / 16u; i += kThreads) dst[i] = srcv[i];
+    if (tid == 0) a.o_rec[tile] = make_uint2(rec_off, rec_bytes);
 }
 
 // bootstrap weights from read order into tile order
 static __global__ void permute_weights(const uint32_t *__restrict__ w, const uint32_t *__restrict__ trow, uint32_t n,
-                                uint32_t *__restrict__ wperm)
+                                       uint32_t *__restrict__ wperm)
 {
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) wperm[k] = w[trow[k]];
@@ -368,219 +402,259 @@ __device__ __forceinline__ double fast_rcp(double d)
     return r;
 }
 
-__device__ __forceinline__ float4 ld_stream_f4(const float *p)
+// predicated f64 arithmetic: one SASS instruction each instead of a pair of FSELs
+__device__ __forceinline__ void add_if(double &acc, double v, uint32_t p)
 {
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q add.f64 %0, %0, %1;\n\t}" : "+d"(acc) : "d"(v), "r"(p));
 }
-__device__ __forceinline__ uint4 ld_stream_u4(const uint32_t *p)
-{
-    uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    return v;
+__device__ __forceinline__ void add_split(double &a, double &z, double v, uint32_t p)
+{   // p ? a += v : z += v
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q add.f64 %0, %0, %2;\n\t@!q add.f64 %1, %1, %2;\n\t}"
+        : "+d"(a), "+d"(z) : "d"(v), "r"(p));
+}
+__device__ __forceinline__ double mul_sel(double w, double m1, double m0, uint32_t p)
+{   // w * (p ? m1 : m0)
+    double x;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %4, 0;\n\t@q mul.f64 %0, %1, %2;\n\t@!q mul.f64 %0, %1, %3;\n\t}"
+        : "=d"(x) : "d"(w), "d"(m1), "d"(m0), "r"(p));
+    return x;
 }
 
-// Everything one lane holds of its warp-chunk: 4 alignment slots.
-template <bool HAS_AUX>
-struct ChunkRegs {
-    float4 p4;        // conditional probabilities
-    uint4 lp4;        // (table index * 8) | (pos * 8) << 16
-    uint4 hm;         // 128-bit row-head mask of the chunk
-    uint32_t info;    // scan steps | kInfoStray | kInfoMulti
-    uint32_t row_base;
-    double a0, a1, a2, a3;
-};
+// --- mbarrier / TMA bulk copy (sm_90+; SASS: SYNCS, UBLKCP) -----------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 
+// m_step (em.rs:87-133), persistent and TMA-fed.
 template <bool HAS_AUX, bool HAS_WTS>
-__device__ __forceinline__ void load_chunk(const View &v, uint32_t tile, uint32_t warp, uint32_t lane,
-                                           ChunkRegs<HAS_AUX> &c)
+__global__ void __launch_bounds__(kThreads, 4) em_sweep_tiled(View v, const double *__restrict__ prev,
+                                                              double *__restrict__ curr,
+                                                              const uint32_t *__restrict__ wperm,
+                                                              const OarEmState *__restrict__ st, int check_done)
 {
-    const size_t base = (size_t)tile * kTile + warp * kChunk + lane * 4;
-    c.p4 = ld_stream_f4(v.prob + base);
-    c.lp4 = ld_stream_u4(v.lpos + base);
-    c.hm = v.heads[tile * kWarps + warp];
-    c.info = v.chunk_info[tile * kWarps + warp];
-    c.row_base = 0;
-    if (HAS_WTS) c.row_base = v.chunk_row[tile * kWarps + warp];
-    if (HAS_AUX) {
-        const double2 q0 = *reinterpret_cast<const double2 *>(v.aux + base);
-        const double2 q1 = *reinterpret_cast<const double2 *>(v.aux + base + 2);
-        c.a0 = q0.x; c.a1 = q0.y; c.a2 = q1.x; c.a3 = q1.y;
+    extern __shared__ __align__(128) unsigned char smem[];
+    // [stage 0][stage 1][xs][s_prev][mbarriers]; a stage = prob | lpos | record
+    unsigned char *stage_base = smem;
+    double *xs = reinterpret_cast<double *>(smem + kStages * kStageBytes);
+    double *s_prev = reinterpret_cast<double *>(smem + kStages * kStageBytes + kXsBytes);
+    unsigned char *bars = smem + kStages * kStageBytes + kXsBytes + 8 * kTile;
+
+    if (check_done && st->done) return;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t n_tiles = v.n_tiles, stride = gridDim.x;
+    const uint32_t tile0 = blockIdx.x;
+    if (tile0 >= n_tiles) return;
+    const uint32_t bar0 = smem_u32(bars), stage0 = smem_u32(stage_base);
+
+    auto issue = [&](uint32_t tile, uint32_t s, uint2 r) {   // thread 0 only
+        const uint32_t bar = bar0 + 8u * s, dst = stage0 + s * (uint32_t)kStageBytes;
+        mbar_expect_tx(bar, 8u * kTile + r.y);
+        bulk_g2s(dst, v.prob + (size_t)tile * kTile, 4u * kTile, bar);
+        bulk_g2s(dst + 4u * kTile, v.lpos + (size_t)tile * kTile, 4u * kTile, bar);
+        bulk_g2s(dst + 8u * kTile, v.records + r.x, r.y, bar);
+    };
+
+    uint2 r_pending = make_uint2(0, 0);   // record locator of the tile two ahead (thread 0)
+    if (tid == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        issue(tile0, 0, v.rec[tile0]);
+        if (tile0 + stride < n_tiles) issue(tile0 + stride, 1, v.rec[tile0 + stride]);
+        if (tile0 + 2 * stride < n_tiles) r_pending = v.rec[tile0 + 2 * stride];
     }
-}
-
-// Phase 1 for one warp-chunk: E-step in registers (per-row denominators by a
-// segmented warp scan), then the M-step scatter into the transcript-sorted
-// shared-memory order.
-template <bool HAS_AUX, bool HAS_WTS>
-__device__ __forceinline__ void chunk_phase1(const ChunkRegs<HAS_AUX> &c, const View &v, uint32_t table_off,
-                                             const double *s_prev, double *xs, double *__restrict__ curr,
-                                             const uint32_t *__restrict__ wperm, uint32_t lane)
-{
-    const uint4 lp4 = c.lp4;
-    const uint4 hm = c.hm;
-    const uint32_t info = c.info;
-    const char *sp = reinterpret_cast<const char *>(s_prev);
-    double w0 = *reinterpret_cast<const double *>(sp + (lp4.x & 0xFFFFu)) * (double)c.p4.x;
-    double w1 = *reinterpret_cast<const double *>(sp + (lp4.y & 0xFFFFu)) * (double)c.p4.y;
-    double w2 = *reinterpret_cast<const double *>(sp + (lp4.z & 0xFFFFu)) * (double)c.p4.z;
-    double w3 = *reinterpret_cast<const double *>(sp + (lp4.w & 0xFFFFu)) * (double)c.p4.w;
-    if (HAS_AUX) { w0 *= c.a0; w1 *= c.a1; w2 *= c.a2; w3 *= c.a3; }
-
-    const uint32_t wq = lane >> 3;
-    const uint32_t hword = wq == 0 ? hm.x : wq == 1 ? hm.y : wq == 2 ? hm.z : hm.w;
-    const uint32_t hb = (hword >> ((lane & 7u) * 4u)) & 0xFu;
-    const unsigned full = 0xffffffffu;
-    const unsigned lanes_h = __ballot_sync(full, hb != 0u);          // lane 0 always has a head
-    const int P = 31 - __clz(lanes_h & (full >> (31u - lane)));       // nearest lane <= me holding a head
-    const unsigned later = lanes_h & ~(full >> (31u - lane));        // lanes after me holding a head
-    const int E = later ? (__ffs(later) - 1) : (int)lane;
-    const int nsteps = (int)(info & 7u);
-
-    double x0, x1, x2, x3;
-    if (!(info & kInfoMulti)) {
-        // fast path: no lane holds more than one row head.  a = my slots before the head (they
-        // close the row entering this lane), z = my slots from the head on (they open a row).
-        const bool b0 = !(hb & 1u), b1 = !(hb & 3u), b2 = !(hb & 7u), b3 = !(hb & 15u);
-        double a = b0 ? w0 : 0.0, z = b0 ? 0.0 : w0;
-        a += b1 ? w1 : 0.0; z += b1 ? 0.0 : w1;
-        a += b2 ? w2 : 0.0; z += b2 ? 0.0 : w2;
-        a += b3 ? w3 : 0.0; z += b3 ? 0.0 : w3;
-        double incl = hb ? z : a;                                     // what this lane adds to the open row
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            if (i >= nsteps) break;                                   // warp-uniform
-            const int d = 1 << i;
-            const double t = __shfl_up_sync(full, incl, d);
-            if ((int)lane - d >= P) incl += t;
-        }
-        double carry = __shfl_up_sync(full, incl, 1);                 // sum of the row entering this lane
-        if (lane == 0) carry = 0.0;
-        const double t_in = carry + a;                                // its total, if it ends here (hb != 0)
-        // reads whose denominator is <= 1e-30 contribute nothing (em.rs:115)
-        double inv_in = t_in > OAR_EM_DENOM_THRESH ? fast_rcp(t_in) : 0.0;
-        double inv_out = __shfl_sync(full, inv_in, E);                // the row leaving this lane ends in lane E
-        if (!later) inv_out = 0.0;                                    // only padding lies beyond the last head
-        if (!hb) inv_in = inv_out;                                    // a lane without a head is inside one row
-        x0 = w0 * (b0 ? inv_in : inv_out);
-        x1 = w1 * (b1 ? inv_in : inv_out);
-        x2 = w2 * (b2 ? inv_in : inv_out);
-        x3 = w3 * (b3 ? inv_in : inv_out);
-    } else {
-        // general path: rows may start and end inside one lane
-        const double s0 = w0;
-        const double s1 = (hb & 2u) ? w1 : s0 + w1;
-        const double s2 = (hb & 4u) ? w2 : s1 + w2;
-        const double s3 = (hb & 8u) ? w3 : s2 + w3;
-        double incl = s3;                                             // segmented inclusive scan of lane tails
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            if (i >= nsteps) break;
-            const int d = 1 << i;
-            const double t = __shfl_up_sync(full, incl, d);
-            if ((int)lane - d >= P) incl += t;
-        }
-        double carry = __shfl_up_sync(full, incl, 1);
-        if (lane == 0) carry = 0.0;
-        const double sA = (hb & 1u) ? 0.0 : (hb & 2u) ? s0 : (hb & 4u) ? s1 : (hb & 8u) ? s2 : s3;
-        const double t_in = carry + sA;
-        const double t_in_e = __shfl_sync(full, t_in, E);
-        const double t_out = later ? t_in_e : 0.0;
-        const double pre0 = (hb & 1u) ? s0 : carry + s0;
-        const double pre1 = (hb & 3u) ? s1 : carry + s1;
-        const double pre2 = (hb & 7u) ? s2 : carry + s2;
-        const double tot3 = t_out;
-        const double tot2 = (hb & 8u) ? pre2 : tot3;
-        const double tot1 = (hb & 4u) ? pre1 : tot2;
-        const double tot0 = (hb & 2u) ? pre0 : tot1;
-        x0 = tot0 > OAR_EM_DENOM_THRESH ? w0 * fast_rcp(tot0) : 0.0;
-        x1 = tot1 > OAR_EM_DENOM_THRESH ? w1 * fast_rcp(tot1) : 0.0;
-        x2 = tot2 > OAR_EM_DENOM_THRESH ? w2 * fast_rcp(tot2) : 0.0;
-        x3 = tot3 > OAR_EM_DENOM_THRESH ? w3 * fast_rcp(tot3) : 0.0;
-    }
-
-    if (HAS_WTS) {
-        // row index inside the chunk = (number of heads at or before the slot) - 1
-        uint32_t before = 0;
-        if (wq > 0) before += __popc(hm.x);
-        if (wq > 1) before += __popc(hm.y);
-        if (wq > 2) before += __popc(hm.z);
-        const uint32_t sh = (lane & 7u) * 4u;
-        const uint32_t r0 = before + __popc(hword & (full >> (31u - sh))) - 1u;
-        const uint32_t r1 = r0 + ((hb >> 1) & 1u), r2 = r1 + ((hb >> 2) & 1u), r3 = r2 + ((hb >> 3) & 1u);
-        x0 *= (double)wperm[c.row_base + r0];
-        x1 *= (double)wperm[c.row_base + r1];
-        x2 *= (double)wperm[c.row_base + r2];
-        x3 *= (double)wperm[c.row_base + r3];
-    }
-
-    char *xp = reinterpret_cast<char *>(xs);
-    *reinterpret_cast<double *>(xp + (lp4.x >> 16)) = x0;
-    *reinterpret_cast<double *>(xp + (lp4.y >> 16)) = x1;
-    *reinterpret_cast<double *>(xp + (lp4.z >> 16)) = x2;
-    *reinterpret_cast<double *>(xp + (lp4.w >> 16)) = x3;
-    if (info & kInfoStray) {
-        // transcripts with fewer than kAggMin alignments in this tile: straight to global
-        const uint32_t trash = (uint32_t)kTrash * 8u;
-        if ((lp4.x >> 16) == trash && x0 != 0.0) atomicAdd(curr + v.table[table_off + ((lp4.x & 0xFFFFu) >> 3)], x0);
-        if ((lp4.y >> 16) == trash && x1 != 0.0) atomicAdd(curr + v.table[table_off + ((lp4.y & 0xFFFFu) >> 3)], x1);
-        if ((lp4.z >> 16) == trash && x2 != 0.0) atomicAdd(curr + v.table[table_off + ((lp4.z & 0xFFFFu) >> 3)], x2);
-        if ((lp4.w >> 16) == trash && x3 != 0.0) atomicAdd(curr + v.table[table_off + ((lp4.w & 0xFFFFu) >> 3)], x3);
-    }
-}
-
-// Phase 2 for one warp: sum 8-slot units of the transcript-sorted order, combine
-// equal transcripts across the warp, one f64 RED per (warp, transcript).
-__device__ __forceinline__ void units_phase2(const double *xs, uint32_t tid, uint32_t lane, uint32_t u_txp,
-                                             uint32_t u_cnt, double *__restrict__ curr)
-{
-    const unsigned full = 0xffffffffu;
-    double acc = 0.0;
-    const double *b = xs + tid * 9;
-#pragma unroll
-    for (uint32_t k = 0; k < 8; ++k) if (k < u_cnt) acc += b[k];
-    const uint32_t up = __shfl_up_sync(full, u_txp, 1);
-    const uint32_t dn = __shfl_down_sync(full, u_txp, 1);
-    const bool head = (lane == 0) || (up != u_txp);
-    const bool tail = (lane == 31) || (dn != u_txp);
-    const unsigned hmask = __ballot_sync(full, head);
-    const int P2 = 31 - __clz(hmask & (full >> (31u - lane)));
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const double t = __shfl_up_sync(full, acc, d);
-        if ((int)lane - d >= P2) acc += t;
-    }
-    if (tail && u_txp != kNoTxp) atomicAdd(curr + u_txp, acc);
-}
-
-// m_step (em.rs:87-133) over one tile per CTA.
-template <bool HAS_AUX, bool HAS_WTS>
-__global__ void __launch_bounds__(kThreads) em_sweep_tiled(View v, const double *__restrict__ prev,
-                                                           double *__restrict__ curr,
-                                                           const uint32_t *__restrict__ wperm,
-                                                           const OarEmState *__restrict__ st, int check_done)
-{
-    __shared__ __align__(16) double xs[kTrash + 1];
-    __shared__ __align__(16) double s_prev[kTile];
-
-    const uint32_t tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    uint32_t done = 0;
-    if (check_done) done = st->done;   // tested after the loads below are in flight
-    const uint4 meta = v.meta[tile];
-    ChunkRegs<HAS_AUX> c;
-    load_chunk<HAS_AUX, HAS_WTS>(v, tile, warp, lane, c);   // streaming loads first: they overlap the table gather
-    const uint32_t D = meta.z & 0xFFFFu, U = meta.z >> 16;
-    uint32_t u_txp = kNoTxp, u_cnt = 0;
-    if (tid < U) { u_txp = v.unit_txp[meta.y + tid]; u_cnt = v.unit_cnt[meta.y + tid]; }
-    if (done) return;
-    for (uint32_t d = tid; d < D; d += kThreads) s_prev[d] = prev[v.table[meta.x + d]];
     __syncthreads();
-    chunk_phase1<HAS_AUX, HAS_WTS>(c, v, meta.x, s_prev, xs, curr, wperm, lane);
-    __syncthreads();
-    if (warp * 32u < U) units_phase2(xs, tid, lane, u_txp, u_cnt, curr);
+    // prev[] of the first tile's transcripts
+    mbar_wait(bar0, 0);
+    {
+        const unsigned char *rec = stage_base + 8 * kTile;
+        const uint32_t D = *reinterpret_cast<const uint32_t *>(rec + kRecDU);
+        const uint32_t *table = reinterpret_cast<const uint32_t *>(rec + kRecTable);
+        for (uint32_t d = tid; d < D; d += kThreads) s_prev[d] = prev[table[d]];
+    }
+
+    uint32_t tile = tile0;
+    for (uint32_t it = 0;; ++it) {
+        const uint32_t s = it & 1u;
+        const unsigned char *stg = stage_base + s * kStageBytes;
+        const unsigned char *rec = stg + 8 * kTile;
+        __syncthreads();   // s_prev of this tile is in place; phase 2 of the previous tile has left xs
+
+        // ---- phase 1: E-step in registers ---------------------------------------------------
+        const uint32_t slot = warp * kChunk + lane * 4;
+        const float4 p4 = *reinterpret_cast<const float4 *>(stg + 4 * slot);
+        const uint4 lp4 = *reinterpret_cast<const uint4 *>(stg + 4 * kTile + 4 * slot);
+        const uint32_t desc = reinterpret_cast<const uint16_t *>(rec + kRecDesc)[tid];
+        const uint32_t info = reinterpret_cast<const uint32_t *>(rec + kRecInfo)[warp];
+        const uint32_t D = *reinterpret_cast<const uint32_t *>(rec + kRecDU);
+        const uint32_t U = *reinterpret_cast<const uint32_t *>(rec + kRecDU + 4);
+        const uint32_t *table = reinterpret_cast<const uint32_t *>(rec + kRecTable);
+        const uint32_t unit = (tid < U) ? table[((D + 3u) & ~3u) + tid] : kNoTxp;
+
+        const char *sp = reinterpret_cast<const char *>(s_prev);
+        double w0 = *reinterpret_cast<const double *>(sp + (lp4.x & 0xFFFFu)) * (double)p4.x;
+        double w1 = *reinterpret_cast<const double *>(sp + (lp4.y & 0xFFFFu)) * (double)p4.y;
+        double w2 = *reinterpret_cast<const double *>(sp + (lp4.z & 0xFFFFu)) * (double)p4.z;
+        double w3 = *reinterpret_cast<const double *>(sp + (lp4.w & 0xFFFFu)) * (double)p4.w;
+        if (HAS_AUX) {
+            const double *ax = v.aux + (size_t)tile * kTile + slot;
+            const double2 q0 = *reinterpret_cast<const double2 *>(ax);
+            const double2 q1 = *reinterpret_cast<const double2 *>(ax + 2);
+            w0 *= q0.x; w1 *= q0.y; w2 *= q1.x; w3 *= q1.y;
+        }
+
+        const unsigned full = 0xffffffffu;
+        const uint32_t hb = desc & 15u, dist = (desc >> 4) & 31u, E = (desc >> 9) & 31u, later = (desc >> 14) & 1u;
+        const uint32_t nsteps = info & 7u;
+        double x0, x1, x2, x3;
+        if (!(info & kInfoMulti)) {
+            // fast path: no lane holds more than one row head.  a = my slots before the head (they
+            // close the row entering this lane), z = my slots from the head on (they open a row).
+            const uint32_t b0 = !(hb & 1u), b1 = !(hb & 3u), b2 = !(hb & 7u), b3 = !(hb & 15u);
+            double a = 0.0, z = 0.0;
+            add_split(a, z, w0, b0);
+            add_split(a, z, w1, b1);
+            add_split(a, z, w2, b2);
+            add_split(a, z, w3, b3);
+            double incl = hb ? z : a;                                 // what this lane adds to the open row
+            if (nsteps > 0) { add_if(incl, __shfl_up_sync(full, incl, 1), dist >= 1u);
+            if (nsteps > 1) { add_if(incl, __shfl_up_sync(full, incl, 2), dist >= 2u);
+            if (nsteps > 2) { add_if(incl, __shfl_up_sync(full, incl, 4), dist >= 4u);
+            if (nsteps > 3) { add_if(incl, __shfl_up_sync(full, incl, 8), dist >= 8u);
+            if (nsteps > 4) { add_if(incl, __shfl_up_sync(full, incl, 16), dist >= 16u); } } } } }
+            const double carry = __shfl_up_sync(full, incl, 1);       // sum of the row entering this lane
+            const double t_in = carry + a;                            // its total, if it ends here (hb != 0);
+                                                                      // lane 0 starts a row: nobody reads its t_in
+            // reads whose denominator is <= 1e-30 contribute nothing (em.rs:115)
+            double inv_in = t_in > OAR_EM_DENOM_THRESH ? fast_rcp(t_in) : 0.0;
+            double inv_out = __shfl_sync(full, inv_in, E);            // the row leaving this lane ends in lane E
+            if (!later) inv_out = 0.0;                                // only padding lies beyond the last head
+            if (!hb) inv_in = inv_out;                                // a lane without a head is inside one row
+            x0 = mul_sel(w0, inv_in, inv_out, b0);
+            x1 = mul_sel(w1, inv_in, inv_out, b1);
+            x2 = mul_sel(w2, inv_in, inv_out, b2);
+            x3 = mul_sel(w3, inv_in, inv_out, b3);
+        } else {
+            // general path: rows may start and end inside one lane
+            const double s0 = w0;
+            const double s1 = (hb & 2u) ? w1 : s0 + w1;
+            const double s2 = (hb & 4u) ? w2 : s1 + w2;
+            const double s3 = (hb & 8u) ? w3 : s2 + w3;
+            double incl = s3;                                         // segmented inclusive scan of lane tails
+#pragma unroll
+            for (uint32_t i = 0; i < 5; ++i) {
+                if (i >= nsteps) break;
+                const uint32_t d = 1u << i;
+                add_if(incl, __shfl_up_sync(full, incl, d), dist >= d);
+            }
+            double carry = __shfl_up_sync(full, incl, 1);
+            if (lane == 0) carry = 0.0;
+            const double sA = (hb & 1u) ? 0.0 : (hb & 2u) ? s0 : (hb & 4u) ? s1 : (hb & 8u) ? s2 : s3;
+            const double t_in = carry + sA;
+            const double t_in_e = __shfl_sync(full, t_in, E);
+            const double t_out = later ? t_in_e : 0.0;
+            const double pre0 = (hb & 1u) ? s0 : carry + s0;
+            const double pre1 = (hb & 3u) ? s1 : carry + s1;
+            const double pre2 = (hb & 7u) ? s2 : carry + s2;
+            const double tot3 = t_out;
+            const double tot2 = (hb & 8u) ? pre2 : tot3;
+            const double tot1 = (hb & 4u) ? pre1 : tot2;
+            const double tot0 = (hb & 2u) ? pre0 : tot1;
+            x0 = tot0 > OAR_EM_DENOM_THRESH ? w0 * fast_rcp(tot0) : 0.0;
+            x1 = tot1 > OAR_EM_DENOM_THRESH ? w1 * fast_rcp(tot1) : 0.0;
+            x2 = tot2 > OAR_EM_DENOM_THRESH ? w2 * fast_rcp(tot2) : 0.0;
+            x3 = tot3 > OAR_EM_DENOM_THRESH ? w3 * fast_rcp(tot3) : 0.0;
+        }
+
+        if (HAS_WTS) {
+            // row index of a slot inside the chunk = (number of heads at or before it) - 1
+            uint32_t incl_h = __popc(hb);
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(full, incl_h, d);
+                if ((int)lane >= d) incl_h += t;
+            }
+            const uint32_t row_base = reinterpret_cast<const uint32_t *>(rec + kRecRow)[warp];
+            const uint32_t r0 = row_base + incl_h - __popc(hb) + (hb & 1u) - 1u;
+            const uint32_t r1 = r0 + ((hb >> 1) & 1u), r2 = r1 + ((hb >> 2) & 1u), r3 = r2 + ((hb >> 3) & 1u);
+            x0 *= (double)wperm[r0];
+            x1 *= (double)wperm[r1];
+            x2 *= (double)wperm[r2];
+            x3 *= (double)wperm[r3];
+        }
+
+        // ---- M-step scatter into the transcript-sorted smem order -----------------------------
+        char *xp = reinterpret_cast<char *>(xs);
+        *reinterpret_cast<double *>(xp + (lp4.x >> 16)) = x0;
+        *reinterpret_cast<double *>(xp + (lp4.y >> 16)) = x1;
+        *reinterpret_cast<double *>(xp + (lp4.z >> 16)) = x2;
+        *reinterpret_cast<double *>(xp + (lp4.w >> 16)) = x3;
+        if (info & kInfoStray) {
+            // transcripts with fewer than kAggMin alignments in this tile: straight to global
+            const uint32_t trash = (uint32_t)kTrash * 8u;
+            if ((lp4.x >> 16) == trash && x0 != 0.0) atomicAdd(curr + table[(lp4.x & 0xFFFFu) >> 3], x0);
+            if ((lp4.y >> 16) == trash && x1 != 0.0) atomicAdd(curr + table[(lp4.y & 0xFFFFu) >> 3], x1);
+            if ((lp4.z >> 16) == trash && x2 != 0.0) atomicAdd(curr + table[(lp4.z & 0xFFFFu) >> 3], x2);
+            if ((lp4.w >> 16) == trash && x3 != 0.0) atomicAdd(curr + table[(lp4.w & 0xFFFFu) >> 3], x3);
+        }
+        __syncthreads();   // xs complete; stage s and s_prev are free again
+
+        // ---- refill stage s two tiles ahead; fetch prev[] of the next tile behind its record ----
+        const uint32_t next = tile + stride;
+        const bool has_next = next < n_tiles;
+        if (tid == 0 && next + stride < n_tiles) {
+            issue(next + stride, s, r_pending);
+            if (next + 2 * stride < n_tiles) r_pending = v.rec[next + 2 * stride];
+        }
+        double pv = 0.0;
+        uint32_t Dn = 0;
+        const uint32_t *table_n = nullptr;
+        if (has_next) {
+            mbar_wait(bar0 + 8u * (s ^ 1u), ((it + 1u) >> 1) & 1u);
+            const unsigned char *rec_n = stage_base + (s ^ 1u) * kStageBytes + 8 * kTile;
+            Dn = *reinterpret_cast<const uint32_t *>(rec_n + kRecDU);
+            table_n = reinterpret_cast<const uint32_t *>(rec_n + kRecTable);
+            if (tid < Dn) pv = prev[table_n[tid]];
+        }
+
+        // ---- phase 2: sum 8-slot units, combine equal transcripts across the warp ---------------
+        if (warp * 32u < U) {
+            const uint32_t u_txp = unit == kNoTxp ? kNoTxp : (unit & (kMaxTxps - 1u));
+            const uint32_t u_cnt = unit == kNoTxp ? 0u : (unit >> 28) + 1u;
+            double acc = 0.0;
+            const double *b = xs + tid * 9;
+#pragma unroll
+            for (uint32_t k = 0; k < 8; ++k) add_if(acc, b[k], k < u_cnt);
+            const uint32_t up = __shfl_up_sync(full, u_txp, 1);
+            const uint32_t dn = __shfl_down_sync(full, u_txp, 1);
+            const bool head = (lane == 0) || (up != u_txp);
+            const bool tail = (lane == 31) || (dn != u_txp);
+            const unsigned hmask = __ballot_sync(full, head);
+            const uint32_t dist2 = lane - (31u - __clz(hmask & (full >> (31u - lane))));
+#pragma unroll
+            for (uint32_t d = 1; d < 32; d <<= 1) add_if(acc, __shfl_up_sync(full, acc, d), dist2 >= d);
+            if (tail && u_txp != kNoTxp) atomicAdd(curr + u_txp, acc);
+        }
+
+        if (!has_next) break;
+        if (tid < Dn) s_prev[tid] = pv;
+        for (uint32_t d = tid + kThreads; d < Dn; d += kThreads) s_prev[d] = prev[table_n[d]];
+        tile = next;
+    }
 }
 
 }  // namespace tiled

@@ -232,15 +232,19 @@ template <bool AUX, bool WTS>
 static cudaError_t launch_tiled(oar_store *s, const tiled::View &v, const double *prev, double *curr,
                                 const uint32_t *wperm, const OarEmState *state, int check_done)
 {
-    static bool attr_set[16] = {false};
+    static int attr_bytes[16] = {0};
     auto kfn = tiled::em_sweep_tiled<AUX, WTS>;
-    if (!attr_set[s->device & 15]) {
-        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, tiled::kSmemBytes);
+    const tiled::Geometry g = tiled::make_geometry(s->tl.max_rec, s->tl.max_d, s->tl.max_u);
+    if (attr_bytes[s->device & 15] < (int)g.total) {
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.total);
         if (e != cudaSuccess) return e;
-        attr_set[s->device & 15] = true;
+        attr_bytes[s->device & 15] = (int)g.total;
     }
-    const uint32_t grid = std::min<uint32_t>(v.n_tiles, (uint32_t)s->sm_count * (uint32_t)s->ctas_per_sm);
-    kfn<<<grid, tiled::kThreads, tiled::kSmemBytes, s->stream>>>(v, prev, curr, wperm, state, check_done);
+    // persistent CTAs: as many per SM as shared memory allows, capped by the register budget (5)
+    int per_sm = (int)((227u * 1024u) / (g.total + 1024u));
+    per_sm = std::max(1, std::min(per_sm, s->ctas_per_sm));
+    const uint32_t grid = std::min<uint32_t>(v.n_tiles, (uint32_t)s->sm_count * (uint32_t)per_sm);
+    kfn<<<grid, tiled::kThreads, g.total, s->stream>>>(v, g, prev, curr, wperm, state, check_done);
     return cudaGetLastError();
 }
 

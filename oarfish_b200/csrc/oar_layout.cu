@@ -50,8 +50,8 @@ int build_tiled_layout(oar_store *s, uint32_t span)
     uint32_t *counters = nullptr;
     OAR_CUDA(sc.alloc(&key, N)); OAR_CUDA(sc.alloc(&idx, N));
     OAR_CUDA(sc.alloc(&key_s, N)); OAR_CUDA(sc.alloc(&srow, N));
-    OAR_CUDA(sc.alloc(&counters, 8));
-    OAR_CUDA(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 8, st));
+    OAR_CUDA(sc.alloc(&counters, 12));
+    OAR_CUDA(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 12, st));
     const int threads = 256;
     const int gridN = (int)std::min<uint64_t>((N + threads - 1) / threads, (uint64_t)s->sm_count * 32);
     row_keys<<<gridN, threads, 0, st>>>(s->d_row_ptr, s->d_txp, N, key, idx, counters);
@@ -63,7 +63,7 @@ int build_tiled_layout(oar_store *s, uint32_t span)
         OAR_CUDA(sc.alloc((char **)&tmp, tmp_bytes));
         OAR_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key, key_s, idx, srow, (int)N, 0, 32, st));
     }
-    uint32_t h_counters[8];
+    uint32_t h_counters[12];
     OAR_CUDA(cudaMemcpyAsync(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
     OAR_CUDA(cudaStreamSynchronize(st));
     const uint32_t n_tiled = N - h_counters[0];
@@ -129,6 +129,7 @@ int build_tiled_layout(oar_store *s, uint32_t span)
     t.sum_d = h_counters[5];
     t.sum_u = h_counters[6];
     t.record_bytes = (uint64_t)h_counters[7] * 16u;
+    t.max_rec = h_counters[8]; t.max_d = h_counters[9]; t.max_u = h_counters[10];
     if (n_tiles > 0) {
         OAR_CUDA(cudaMalloc(&t.records, std::max<uint64_t>(t.record_bytes, 16)));
         OAR_CUDA(cudaMemcpyAsync(t.records, records_tmp, t.record_bytes, cudaMemcpyDeviceToDevice, st));

@@ -15,6 +15,7 @@ struct TiledLayout {
     uint2 *rec = nullptr;          // per tile: {record offset (16 B granules), record bytes}
     uint4 *records = nullptr;      // per-tile records (lane descriptors, chunk info, table, units)
     uint64_t record_bytes = 0;
+    uint32_t max_rec = 0, max_d = 0, max_u = 0;   // per-tile maxima (size the sweep's shared memory)
     uint32_t *trow = nullptr;      // tile-order row -> original row (n_tiled_rows)
     uint32_t *fallback = nullptr;  // original row ids swept from the CSR
     uint32_t *wperm = nullptr;     // bootstrap weights in tile order
@@ -34,7 +35,7 @@ struct oar_store {
     uint64_t n_reads = 0, nnz = 0;
     uint32_t n_txps = 0;
     int kernel = OAR_KERNEL_ROWGROUP;
-    int ctas_per_sm = 4;  // persistent CTAs of the tiled sweep per SM
+    int ctas_per_sm = 5;  // persistent CTAs of the tiled sweep per SM (upper bound; shared memory may allow fewer)
 
     // CSR in HBM (original read order)
     uint32_t *d_row_ptr = nullptr;  // N+1

@@ -48,7 +48,8 @@ constexpr int kTile = kWarps * kChunk;    // 1024 slots
 constexpr int kThreads = kWarps * 32;     // 256
 constexpr int kAggMin = 4;                // transcripts with >= kAggMin alignments in a tile are aggregated in smem
 constexpr int kMaxUnits = kTile / 4;      // sum ceil(cnt/8) over cnt >= 4  <=  kTile/4
-constexpr int kTrash = kMaxUnits * 9;     // xs slot for padding / non-aggregated alignments (never summed)
+constexpr int kUnitStride = 10;           // doubles per 8-slot unit in xs: 80 B keeps LDS.128 conflict-free
+// padding and non-aggregated alignments write to a trash slot right after the last unit of the tile
 constexpr uint32_t kInfoStray = 8u;       // chunk_info bit 3: chunk holds alignments that RED straight to global
 constexpr uint32_t kInfoMulti = 16u;      // chunk_info bit 4: some lane holds >= 2 row heads (general path)
 constexpr uint32_t kNoTxp = 0xFFFFFFFFu;
@@ -56,11 +57,11 @@ constexpr uint32_t kMaxTxps = 1u << 28;   // unit descriptors pack (count-1) abo
 static_assert(kMaxUnits == kThreads, "one unit per thread in phase 2");
 
 // Per-tile record (variable length, 16-byte granules), one TMA bulk copy:
-//   [0,512)    lane descriptors u16[8][32]: hb(4) | dist(5) | E(5) | later(1)
+//   [0,512)    lane descriptors u16[8][32]: hb(4) | dist(5) | E(5)
 //                hb    row-head bits of the lane's 4 slots
 //                dist  lanes back to the nearest lane (<= this one) holding a head
-//                E     first later lane holding a head (where the row leaving this lane ends)
-//                later such a lane exists
+//                E     first later lane holding a head (where the row leaving this lane ends);
+//                      the lane itself if there is none (then only padding follows)
 //   [512,544)  chunk_info u32[8]: scan steps (bits 0-2) | kInfoStray | kInfoMulti
 //   [544,576)  chunk_row  u32[8]: tile-order index of the chunk's first row (bootstrap weights)
 //   [576,592)  D, U, 0, 0
@@ -68,10 +69,31 @@ static_assert(kMaxUnits == kThreads, "one unit per thread in phase 2");
 //              units u32[roundup4(U)]  : transcript id | (valid slots - 1) << 28 per 8-slot unit
 constexpr int kRecDesc = 0, kRecInfo = 512, kRecRow = 544, kRecDU = 576, kRecTable = 592;
 constexpr int kRecMax = kRecTable + 4 * kTile + 4 * kMaxUnits;   // 5712
-constexpr int kStageBytes = 4 * kTile + 4 * kTile + kRecMax;      // prob + lpos + record = 13904
 constexpr int kStages = 2;
-constexpr int kXsBytes = 8 * (kTrash + 1 + 1);                    // 18448 (16-byte multiple)
-constexpr int kSmemBytes = kStages * kStageBytes + kXsBytes + 8 * kTile + 64;
+
+// Shared-memory geometry of the sweep, sized for the store at hand (largest record, table and
+// unit count over all tiles) so that as many CTAs as possible fit on an SM.
+struct Geometry {
+    uint32_t stage_bytes;   // prob (4 KB) | lpos (4 KB) | record (max over tiles, 16 B multiple)
+    uint32_t xs_off;        // after the stages: transcript-sorted x values, kUnitStride doubles per unit (+ trash)
+    uint32_t prev_off;      // prev[] of the tile's transcripts
+    uint32_t bar_off;       // two mbarriers
+    uint32_t total;         // dynamic shared memory per CTA
+    uint32_t xs_doubles;    // doubles to clear at start
+};
+inline Geometry make_geometry(uint32_t max_rec_bytes, uint32_t max_d, uint32_t max_u)
+{
+    Geometry g;
+    const uint32_t rec = (max_rec_bytes + 15u) & ~15u;
+    g.stage_bytes = 8u * kTile + rec;
+    g.xs_off = kStages * g.stage_bytes;
+    // phase 2 reads whole warps of units: round the unit count up to 32; then the trash slot; even count
+    g.xs_doubles = ((((max_u + 31u) & ~31u) * kUnitStride + 2u) + 1u) & ~1u;
+    g.prev_off = g.xs_off + 8u * g.xs_doubles;
+    g.bar_off = g.prev_off + 8u * ((max_d + 1u) & ~1u);
+    g.total = g.bar_off + 16u;
+    return g;
+}
 
 struct View {
     uint32_t n_tiles;
@@ -151,7 +173,7 @@ struct BuildArgs {
     const uint32_t *tile_row;  // n_tiles + 1
     float *o_prob; uint32_t *o_lpos; double *o_aux; uint2 *o_rec; uint4 *o_records;
     uint32_t *o_trow;          // tile-order row -> original row
-    uint32_t *fallback; uint32_t *cursors;  // [0] fallback rows, [1] sum D, [2] sum U, [3] record granules
+    uint32_t *fallback; uint32_t *cursors;  // [0] fallback rows, [1] sum D, [2] sum U, [3] record granules, [4..6] max record bytes / D / U
 };
 
 // One CTA lays out one tile.
@@ -267,7 +289,7 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
         const int P = 31 - __clz(lanes_h & (full >> (31u - lane)));
         const unsigned later = lanes_h & ~(full >> (31u - lane));
         const uint32_t E = later ? (uint32_t)(__ffs(later) - 1) : lane;
-        const uint32_t desc = hb | ((lane - (uint32_t)P) << 4) | (E << 9) | ((later ? 1u : 0u) << 14);
+        const uint32_t desc = hb | ((lane - (uint32_t)P) << 4) | (E << 9);
         reinterpret_cast<uint16_t *>(s_rec)[kRecDesc / 2 + tid] = (uint16_t)desc;
     }
     for (uint32_t i = tid; i < (uint32_t)kTile; i += kThreads) {
@@ -279,7 +301,13 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
     // sort slots by transcript
     uint32_t keys[4], vals[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { keys[i] = s_txp[tid * 4 + i]; vals[i] = tid * 4 + i; }
+    for (int i = 0; i < 4; ++i) {
+        // feed the (stable) sort in (chunk, slot-in-lane k, lane) order: the alignments one STS of the
+        // sweep scatters for one transcript then get consecutive ranks, i.e. consecutive smem banks
+        const uint32_t j = tid * 4 + i;
+        const uint32_t slot = (j & ~127u) | ((j & 31u) << 2) | ((j >> 5) & 3u);
+        keys[i] = s_txp[slot]; vals[i] = slot;
+    }
     __syncthreads();
     Sort(tmp.sort).Sort(keys, vals);
     __syncthreads();
@@ -330,6 +358,9 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
         atomicAdd(a.cursors + 1, D);
         atomicAdd(a.cursors + 2, U);
         s_misc[2] = atomicAdd(a.cursors + 3, rec_bytes / 16u);
+        atomicMax(a.cursors + 4, rec_bytes);
+        atomicMax(a.cursors + 5, D);
+        atomicMax(a.cursors + 6, U);
         s_rec[kRecDU / 4 + 0] = D;
         s_rec[kRecDU / 4 + 1] = U;
     }
@@ -360,12 +391,12 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
             const uint32_t d = seg[i] - 1;
             const uint32_t pk = s_seg[d];
             const uint32_t start = pk & 0x7FFu, ub = pk >> 11;
-            uint32_t pos = kTrash;
-            if (ub != 0x1FFu) { const uint32_t p = ub * 8 + (r - start); pos = p + (p >> 3); }
+            uint32_t pos = U * kUnitStride;   // trash slot of this tile
+            if (ub != 0x1FFu) { const uint32_t p = ub * 8 + (r - start); pos = p + ((p >> 3) << 1); }
             else atomicOr(&s_info[vals[i] / kChunk], kInfoStray);
             s_lpos[vals[i]] = (d * 8u) | ((pos * 8u) << 16);
         } else {
-            s_lpos[vals[i]] = 0u | (((uint32_t)kTrash * 8u) << 16);
+            s_lpos[vals[i]] = 0u | ((U * kUnitStride * 8u) << 16);
         }
     }
     __syncthreads();
@@ -402,23 +433,9 @@ __device__ __forceinline__ double fast_rcp(double d)
     return r;
 }
 
-// predicated f64 arithmetic: one SASS instruction each instead of a pair of FSELs
-__device__ __forceinline__ void add_if(double &acc, double v, uint32_t p)
-{
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q add.f64 %0, %0, %1;\n\t}" : "+d"(acc) : "d"(v), "r"(p));
-}
-__device__ __forceinline__ void add_split(double &a, double &z, double v, uint32_t p)
-{   // p ? a += v : z += v
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q add.f64 %0, %0, %2;\n\t@!q add.f64 %1, %1, %2;\n\t}"
-        : "+d"(a), "+d"(z) : "d"(v), "r"(p));
-}
-__device__ __forceinline__ double mul_sel(double w, double m1, double m0, uint32_t p)
-{   // w * (p ? m1 : m0)
-    double x;
-    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %4, 0;\n\t@q mul.f64 %0, %1, %2;\n\t@!q mul.f64 %0, %1, %3;\n\t}"
-        : "=d"(x) : "d"(w), "d"(m1), "d"(m0), "r"(p));
-    return x;
-}
+// 1.0 or 0.0 from a condition, as a bit pattern: lets "add if" be a single DFMA (ptxas turns
+// predicated f64 adds into DADD + two FSELs)
+__device__ __forceinline__ double mask01(bool c) { return __hiloint2double(c ? 0x3FF00000 : 0, 0); }
 
 // --- mbarrier / TMA bulk copy (sm_90+; SASS: SYNCS, UBLKCP) -----------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -441,7 +458,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 
 // m_step (em.rs:87-133), persistent and TMA-fed.
 template <bool HAS_AUX, bool HAS_WTS>
-__global__ void __launch_bounds__(kThreads, 4) em_sweep_tiled(View v, const double *__restrict__ prev,
+__global__ void __launch_bounds__(kThreads, 5) em_sweep_tiled(View v, Geometry g, const double *__restrict__ prev,
                                                               double *__restrict__ curr,
                                                               const uint32_t *__restrict__ wperm,
                                                               const OarEmState *__restrict__ st, int check_done)
@@ -449,9 +466,10 @@ __global__ void __launch_bounds__(kThreads, 4) em_sweep_tiled(View v, const doub
     extern __shared__ __align__(128) unsigned char smem[];
     // [stage 0][stage 1][xs][s_prev][mbarriers]; a stage = prob | lpos | record
     unsigned char *stage_base = smem;
-    double *xs = reinterpret_cast<double *>(smem + kStages * kStageBytes);
-    double *s_prev = reinterpret_cast<double *>(smem + kStages * kStageBytes + kXsBytes);
-    unsigned char *bars = smem + kStages * kStageBytes + kXsBytes + 8 * kTile;
+    double *xs = reinterpret_cast<double *>(smem + g.xs_off);
+    double *s_prev = reinterpret_cast<double *>(smem + g.prev_off);
+    unsigned char *bars = smem + g.bar_off;
+    const uint32_t kStageBytes = g.stage_bytes;
 
     if (check_done && st->done) return;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -461,7 +479,7 @@ __global__ void __launch_bounds__(kThreads, 4) em_sweep_tiled(View v, const doub
     const uint32_t bar0 = smem_u32(bars), stage0 = smem_u32(stage_base);
 
     auto issue = [&](uint32_t tile, uint32_t s, uint2 r) {   // thread 0 only
-        const uint32_t bar = bar0 + 8u * s, dst = stage0 + s * (uint32_t)kStageBytes;
+        const uint32_t bar = bar0 + 8u * s, dst = stage0 + s * kStageBytes;
         mbar_expect_tx(bar, 8u * kTile + r.y);
         bulk_g2s(dst, v.prob + (size_t)tile * kTile, 4u * kTile, bar);
         bulk_g2s(dst + 4u * kTile, v.lpos + (size_t)tile * kTile, 4u * kTile, bar);
@@ -504,6 +522,12 @@ __global__ void __launch_bounds__(kThreads, 4) em_sweep_tiled(View v, const doub
         const uint32_t U = *reinterpret_cast<const uint32_t *>(rec + kRecDU + 4);
         const uint32_t *table = reinterpret_cast<const uint32_t *>(rec + kRecTable);
         const uint32_t unit = (tid < U) ? table[((D + 3u) & ~3u) + tid] : kNoTxp;
+        if (unit != kNoTxp) {   // the last unit of a transcript may be partial: clear its unused slots
+            double *b = xs + tid * kUnitStride;
+            const uint32_t cnt = (unit >> 28) + 1u;
+#pragma unroll
+            for (uint32_t k = 1; k < 8u; ++k) if (k >= cnt) b[k] = 0.0;   // predicated stores, no loop
+        }
 
         const char *sp = reinterpret_cast<const char *>(s_prev);
         double w0 = *reinterpret_cast<const double *>(sp + (lp4.x & 0xFFFFu)) * (double)p4.x;
@@ -518,38 +542,41 @@ __global__ void __launch_bounds__(kThreads, 4) em_sweep_tiled(View v, const doub
         }
 
         const unsigned full = 0xffffffffu;
-        const uint32_t hb = desc & 15u, dist = (desc >> 4) & 31u, E = (desc >> 9) & 31u, later = (desc >> 14) & 1u;
-        const uint32_t nsteps = info & 7u;
+        const uint32_t hb = desc & 15u, dist = (desc >> 4) & 31u, E = (desc >> 9) & 31u;
         double x0, x1, x2, x3;
         if (!(info & kInfoMulti)) {
-            // fast path: no lane holds more than one row head.  a = my slots before the head (they
-            // close the row entering this lane), z = my slots from the head on (they open a row).
-            const uint32_t b0 = !(hb & 1u), b1 = !(hb & 3u), b2 = !(hb & 7u), b3 = !(hb & 15u);
-            double a = 0.0, z = 0.0;
-            add_split(a, z, w0, b0);
-            add_split(a, z, w1, b1);
-            add_split(a, z, w2, b2);
-            add_split(a, z, w3, b3);
-            double incl = hb ? z : a;                                 // what this lane adds to the open row
-            if (nsteps > 0) { add_if(incl, __shfl_up_sync(full, incl, 1), dist >= 1u);
-            if (nsteps > 1) { add_if(incl, __shfl_up_sync(full, incl, 2), dist >= 2u);
-            if (nsteps > 2) { add_if(incl, __shfl_up_sync(full, incl, 4), dist >= 4u);
-            if (nsteps > 3) { add_if(incl, __shfl_up_sync(full, incl, 8), dist >= 8u);
-            if (nsteps > 4) { add_if(incl, __shfl_up_sync(full, incl, 16), dist >= 16u); } } } } }
+            // fast path: no lane holds more than one row head.  Slot i lies before that head (it
+            // closes the row entering the lane) iff hb >> (i+1) != 0; slot 3 never does.
+            //   a = slots before the head, z = slots from the head on (all four if there is none)
+            const bool c0 = (hb >> 1) != 0u, c1 = (hb >> 2) != 0u, c2 = (hb >> 3) != 0u;
+            double a = w0 * mask01(c0);
+            a = fma(w1, mask01(c1), a);
+            a = fma(w2, mask01(c2), a);
+            double z = fma(w0, mask01(!c0), w3);
+            z = fma(w1, mask01(!c1), z);
+            z = fma(w2, mask01(!c2), z);
+            // segmented inclusive scan over lanes: what each lane adds to the row open at its end
+            double incl = z;
+            incl = fma(__shfl_up_sync(full, incl, 1), mask01(dist >= 1u), incl);
+            incl = fma(__shfl_up_sync(full, incl, 2), mask01(dist >= 2u), incl);
+            incl = fma(__shfl_up_sync(full, incl, 4), mask01(dist >= 4u), incl);
+            if ((info & 7u) > 3u) {   // rows spanning more than 8 lanes (rare)
+                incl = fma(__shfl_up_sync(full, incl, 8), mask01(dist >= 8u), incl);
+                incl = fma(__shfl_up_sync(full, incl, 16), mask01(dist >= 16u), incl);
+            }
             const double carry = __shfl_up_sync(full, incl, 1);       // sum of the row entering this lane
-            const double t_in = carry + a;                            // its total, if it ends here (hb != 0);
-                                                                      // lane 0 starts a row: nobody reads its t_in
+            const double t_in = carry + a;                            // its total, if it ends here
             // reads whose denominator is <= 1e-30 contribute nothing (em.rs:115)
-            double inv_in = t_in > OAR_EM_DENOM_THRESH ? fast_rcp(t_in) : 0.0;
-            double inv_out = __shfl_sync(full, inv_in, E);            // the row leaving this lane ends in lane E
-            if (!later) inv_out = 0.0;                                // only padding lies beyond the last head
-            if (!hb) inv_in = inv_out;                                // a lane without a head is inside one row
-            x0 = mul_sel(w0, inv_in, inv_out, b0);
-            x1 = mul_sel(w1, inv_in, inv_out, b1);
-            x2 = mul_sel(w2, inv_in, inv_out, b2);
-            x3 = mul_sel(w3, inv_in, inv_out, b3);
+            const double inv_in = t_in > OAR_EM_DENOM_THRESH ? fast_rcp(t_in) : 0.0;
+            // the row leaving this lane ends in lane E (E == lane: only padding follows, w == 0)
+            const double inv_out = __shfl_sync(full, inv_in, E);
+            x0 = w0 * (c0 ? inv_in : inv_out);
+            x1 = w1 * (c1 ? inv_in : inv_out);
+            x2 = w2 * (c2 ? inv_in : inv_out);
+            x3 = w3 * inv_out;
         } else {
             // general path: rows may start and end inside one lane
+            const uint32_t nsteps = info & 7u;
             const double s0 = w0;
             const double s1 = (hb & 2u) ? w1 : s0 + w1;
             const double s2 = (hb & 4u) ? w2 : s1 + w2;
@@ -559,14 +586,13 @@ __global__ void __launch_bounds__(kThreads, 4) em_sweep_tiled(View v, const doub
             for (uint32_t i = 0; i < 5; ++i) {
                 if (i >= nsteps) break;
                 const uint32_t d = 1u << i;
-                add_if(incl, __shfl_up_sync(full, incl, d), dist >= d);
+                incl = fma(__shfl_up_sync(full, incl, d), mask01(dist >= d), incl);
             }
             double carry = __shfl_up_sync(full, incl, 1);
             if (lane == 0) carry = 0.0;
             const double sA = (hb & 1u) ? 0.0 : (hb & 2u) ? s0 : (hb & 4u) ? s1 : (hb & 8u) ? s2 : s3;
             const double t_in = carry + sA;
-            const double t_in_e = __shfl_sync(full, t_in, E);
-            const double t_out = later ? t_in_e : 0.0;
+            const double t_out = __shfl_sync(full, t_in, E);
             const double pre0 = (hb & 1u) ? s0 : carry + s0;
             const double pre1 = (hb & 3u) ? s1 : carry + s1;
             const double pre2 = (hb & 7u) ? s2 : carry + s2;
@@ -605,7 +631,7 @@ __global__ void __launch_bounds__(kThreads, 4) em_sweep_tiled(View v, const doub
         *reinterpret_cast<double *>(xp + (lp4.w >> 16)) = x3;
         if (info & kInfoStray) {
             // transcripts with fewer than kAggMin alignments in this tile: straight to global
-            const uint32_t trash = (uint32_t)kTrash * 8u;
+            const uint32_t trash = U * kUnitStride * 8u;
             if ((lp4.x >> 16) == trash && x0 != 0.0) atomicAdd(curr + table[(lp4.x & 0xFFFFu) >> 3], x0);
             if ((lp4.y >> 16) == trash && x1 != 0.0) atomicAdd(curr + table[(lp4.y & 0xFFFFu) >> 3], x1);
             if ((lp4.z >> 16) == trash && x2 != 0.0) atomicAdd(curr + table[(lp4.z & 0xFFFFu) >> 3], x2);
@@ -634,19 +660,26 @@ __global__ void __launch_bounds__(kThreads, 4) em_sweep_tiled(View v, const doub
         // ---- phase 2: sum 8-slot units, combine equal transcripts across the warp ---------------
         if (warp * 32u < U) {
             const uint32_t u_txp = unit == kNoTxp ? kNoTxp : (unit & (kMaxTxps - 1u));
-            const uint32_t u_cnt = unit == kNoTxp ? 0u : (unit >> 28) + 1u;
-            double acc = 0.0;
-            const double *b = xs + tid * 9;
-#pragma unroll
-            for (uint32_t k = 0; k < 8; ++k) add_if(acc, b[k], k < u_cnt);
+            // a unit is 8 doubles at an 80-byte stride (conflict-free LDS.128); its unused slots were cleared above
+            const double2 *b = reinterpret_cast<const double2 *>(xs + tid * kUnitStride);
+            const double2 v0 = b[0], v1 = b[1], v2 = b[2], v3 = b[3];
+            double acc = ((v0.x + v0.y) + (v1.x + v1.y)) + ((v2.x + v2.y) + (v3.x + v3.y));
             const uint32_t up = __shfl_up_sync(full, u_txp, 1);
             const uint32_t dn = __shfl_down_sync(full, u_txp, 1);
             const bool head = (lane == 0) || (up != u_txp);
             const bool tail = (lane == 31) || (dn != u_txp);
             const unsigned hmask = __ballot_sync(full, head);
             const uint32_t dist2 = lane - (31u - __clz(hmask & (full >> (31u - lane))));
-#pragma unroll
-            for (uint32_t d = 1; d < 32; d <<= 1) add_if(acc, __shfl_up_sync(full, acc, d), dist2 >= d);
+            const uint32_t maxd = __reduce_max_sync(full, dist2);     // longest run of one transcript in the warp
+            acc = fma(__shfl_up_sync(full, acc, 1), mask01(dist2 >= 1u), acc);
+            acc = fma(__shfl_up_sync(full, acc, 2), mask01(dist2 >= 2u), acc);
+            if (maxd >= 4u) {
+                acc = fma(__shfl_up_sync(full, acc, 4), mask01(dist2 >= 4u), acc);
+                if (maxd >= 8u) {
+                    acc = fma(__shfl_up_sync(full, acc, 8), mask01(dist2 >= 8u), acc);
+                    acc = fma(__shfl_up_sync(full, acc, 16), mask01(dist2 >= 16u), acc);
+                }
+            }
             if (tail && u_txp != kNoTxp) atomicAdd(curr + u_txp, acc);
         }
 

@@ -128,14 +128,22 @@ int oar_bootstrap_sample_weights(oar_store *store, uint64_t seed, uint32_t repli
 
 /*
  * Batched independent EMs over contiguous groups of reads of one store
- * (single-cell mode, single_cell.rs:91-193: one em::em(&emi,1) per cell).
+ * (single-cell mode, single_cell.rs:91-193: one em::em(&emi,1) per cell, i.e.
+ * do_em with the full transcriptome as parameter space and the N_cell/M start).
  *   cell_row_ptr  C+1 u64 over reads: cell c owns reads [cell_row_ptr[c], cell_row_ptr[c+1])
- *   out_counts    C x M f64 row-major dense, host or device (callers keep v > 0,
- *                 single_cell.rs:155-160)
+ * Output is sparse, CSR over cells (single_cell.rs:155-160 keeps only v > 0):
+ *   out_cell_ptr  C+1 u64, host or device
+ *   out_txp       transcript ids of cell c at [out_cell_ptr[c], out_cell_ptr[c+1]), ascending:
+ *                 every transcript with an alignment in the cell (all others are exactly 0)
+ *   out_val       their counts (f64; may be 0)
+ *   capacity      elements available in out_txp / out_val; the store's nnz is always enough.
+ *                 If too small: OAR_ERR_INVALID, *out_nnz = required size, out_cell_ptr filled.
+ *   out_niter     C u32 (host or device) or NULL
  */
 int oar_em_batched(oar_store *store, const uint64_t *cell_row_ptr, uint32_t n_cells,
                    uint32_t max_iter, double conv_thresh, uint32_t min_iter,
-                   double *out_counts, uint32_t *out_niter);
+                   uint64_t *out_cell_ptr, uint32_t *out_txp, double *out_val, uint64_t capacity,
+                   uint64_t *out_nnz, uint32_t *out_niter);
 
 /* Layout of the store in HBM: [0] tiled layout built, [1] tiles, [2] alignment
  * slots in tiles, [3] rows swept from the CSR instead (too long / did not fit),

@@ -535,21 +535,6 @@ extern "C" int oar_bootstrap_weights(oar_store *s, const uint32_t *weights, uint
 }
 
 // ---------------------------------------------------------------------------
-// batched per-cell EM (single-cell mode) -- first version: one EM per cell over
-// the cell's row range, sequentially on the store's stream.
-// ---------------------------------------------------------------------------
-
-extern "C" int oar_em_batched(oar_store *s, const uint64_t *cell_row_ptr, uint32_t n_cells,
-                              uint32_t max_iter, double conv_thresh, uint32_t min_iter,
-                              double *out_counts, uint32_t *out_niter)
-{
-    (void)cell_row_ptr; (void)n_cells; (void)max_iter; (void)conv_thresh; (void)min_iter;
-    (void)out_counts; (void)out_niter;
-    if (!s) return fail(OAR_ERR_INVALID, "oar_em_batched: store is null");
-    return fail(OAR_ERR_UNSUPPORTED, "oar_em_batched: not implemented in this build");
-}
-
-// ---------------------------------------------------------------------------
 // raw sweep (measurement / tests)
 // ---------------------------------------------------------------------------
 

@@ -163,6 +163,23 @@ class DeviceStore:
         check(self._lib.oar_bootstrap_sample_weights(self._h, int(seed), int(replicate), op))
         return out
 
+    def em_batched(self, cell_row_ptr, max_iter: int = 1000, conv_thresh: float = 1e-3, min_iter: int = 50):
+        """Per-cell EMs (single_cell.rs:150).  Returns (cell_ptr u64[C+1], txp u32, val f64, niter u32[C]):
+        cell c's transcripts with an alignment, ascending, and their counts."""
+        crp = np.ascontiguousarray(cell_row_ptr, dtype=np.uint64)
+        n_cells = len(crp) - 1
+        cell_ptr = np.zeros(n_cells + 1, dtype=np.uint64)
+        cap = self.nnz
+        txp = np.empty(max(cap, 1), dtype=np.uint32)
+        val = np.empty(max(cap, 1), dtype=np.float64)
+        niter = np.zeros(max(n_cells, 1), dtype=np.uint32)
+        nnz = C.c_uint64(0)
+        check(self._lib.oar_em_batched(self._h, crp.ctypes.data, n_cells, int(max_iter), float(conv_thresh), int(min_iter),
+                                       cell_ptr.ctypes.data, txp.ctypes.data, val.ctypes.data, cap, C.byref(nnz),
+                                       niter.ctypes.data))
+        n = int(nnz.value)
+        return cell_ptr, txp[:n].copy(), val[:n].copy(), niter[:n_cells]
+
     def sweep(self, prev_dev, curr_dev, weights_dev=None, sync: bool = True) -> None:
         """One raw fused E+M sweep on device buffers (torch CUDA tensors)."""
         pp, n_p, _ = _addr(prev_dev, np.dtype(np.float64), "prev")

@@ -68,3 +68,24 @@ def make_store(n_reads: int, n_txps: int, avg_aln: float, seed: int, want_truth:
 
 def make_config(name: str, **kw) -> SynthStore:
     return make_store(**CONFIGS[name], **kw)
+
+
+def make_cells(cell_reads, n_txps: int, avg_aln: float, seed: int):
+    """Concatenated store of several cells (single-cell mode): cell c has cell_reads[c] reads drawn
+    from its own abundance vector.  Returns (SynthStore, cell_row_ptr u64[C+1])."""
+    rps, txs, prs = [np.zeros(1, dtype=np.uint64)], [], []
+    cell_row_ptr = np.zeros(len(cell_reads) + 1, dtype=np.uint64)
+    off = 0
+    for c, n in enumerate(cell_reads):
+        cell_row_ptr[c + 1] = cell_row_ptr[c] + n
+        if n == 0:
+            continue
+        st = make_store(int(n), n_txps, avg_aln, seed * 1000003 + c)
+        rps.append(st.row_ptr[1:] + np.uint64(off))
+        txs.append(st.txp_id)
+        prs.append(st.prob)
+        off += st.nnz
+    row_ptr = np.concatenate(rps)
+    txp = np.concatenate(txs) if txs else np.zeros(0, np.uint32)
+    prob = np.concatenate(prs) if prs else np.zeros(0, np.float32)
+    return SynthStore(row_ptr, txp, prob, n_txps, None, None), cell_row_ptr

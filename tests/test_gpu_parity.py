@@ -217,6 +217,28 @@ def test_device_resident_inputs_and_outputs(DS, oracle_mod, tiny_store):
         assert_counts_close(out.cpu().numpy(), want)
 
 
+def test_batched_cells_match_per_cell_oracle(DS, oracle_mod):
+    """single_cell.rs:150: one em::em per cell, full transcriptome as parameter space."""
+    from oarfish_b200 import synth
+    M = 400
+    s, crp = synth.make_cells([1500, 0, 40, 3000, 1, 700], M, 5.0, seed=21)
+    with DS(s.row_ptr, s.txp_id, s.prob, M) as ds:
+        cell_ptr, txp, val, niter = ds.em_batched(crp)
+    assert len(cell_ptr) == 7 and cell_ptr[0] == 0 and cell_ptr[-1] == len(txp) == len(val)
+    for c in range(6):
+        r0, r1 = int(crp[c]), int(crp[c + 1])
+        a0, a1 = int(s.row_ptr[r0]), int(s.row_ptr[r1])
+        sub_rp = (s.row_ptr[r0:r1 + 1] - s.row_ptr[r0]).astype(np.uint64)
+        want, want_niter, _, _ = oracle_mod.do_em(sub_rp, s.txp_id[a0:a1], s.prob[a0:a1], M, min_iter=50)
+        got = np.zeros(M)
+        sl = slice(int(cell_ptr[c]), int(cell_ptr[c + 1]))
+        assert np.all(np.diff(txp[sl].astype(np.int64)) > 0)          # ascending, distinct
+        assert set(txp[sl]) == set(s.txp_id[a0:a1])                   # exactly the cell's transcripts
+        got[txp[sl]] = val[sl]
+        assert niter[c] == want_niter, c
+        assert_counts_close(got, want)
+
+
 def test_full_size_properties_c3(DS):
     """BASELINE config 3 (10M reads x 200k transcripts): size-independent properties."""
     from oarfish_b200 import synth

@@ -567,7 +567,15 @@ __global__ void __launch_bounds__(kThreads, 5) em_sweep_tiled(View v, Geometry g
             const double carry = __shfl_up_sync(full, incl, 1);       // sum of the row entering this lane
             const double t_in = carry + a;                            // its total, if it ends here
             // reads whose denominator is <= 1e-30 contribute nothing (em.rs:115)
-            const double inv_in = t_in > OAR_EM_DENOM_THRESH ? fast_rcp(t_in) : 0.0;
+            double inv_in = t_in > OAR_EM_DENOM_THRESH ? fast_rcp(t_in) : 0.0;
+            if (HAS_WTS) {
+                // bootstrap: fold the row's resampling weight into its inverse denominator.  The row whose
+                // total is t_in is the chunk's row number (heads in earlier lanes) - 1; one head per lane here.
+                const unsigned lanes_h = __ballot_sync(full, hb != 0u);
+                const uint32_t before = __popc(lanes_h & ((1u << lane) - 1u));
+                const uint32_t row_base = reinterpret_cast<const uint32_t *>(rec + kRecRow)[warp];
+                if (before) inv_in *= (double)wperm[row_base + before - 1u];
+            }
             // the row leaving this lane ends in lane E (E == lane: only padding follows, w == 0)
             const double inv_out = __shfl_sync(full, inv_in, E);
             x0 = w0 * (c0 ? inv_in : inv_out);
@@ -606,8 +614,8 @@ __global__ void __launch_bounds__(kThreads, 5) em_sweep_tiled(View v, Geometry g
             x3 = tot3 > OAR_EM_DENOM_THRESH ? w3 * fast_rcp(tot3) : 0.0;
         }
 
-        if (HAS_WTS) {
-            // row index of a slot inside the chunk = (number of heads at or before it) - 1
+        if (HAS_WTS && (info & kInfoMulti)) {
+            // general path: row index of a slot inside the chunk = (number of heads at or before it) - 1
             uint32_t incl_h = __popc(hb);
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {

@@ -145,6 +145,21 @@ int oar_em_batched(oar_store *store, const uint64_t *cell_row_ptr, uint32_t n_ce
                    uint64_t *out_cell_ptr, uint32_t *out_txp, double *out_val, uint64_t capacity,
                    uint64_t *out_nnz, uint32_t *out_niter);
 
+/*
+ * Read-level assignment probabilities with the final counts: the inner loop of
+ * write_out_prob (src/util/write_function.rs:283-332).  out_prob[j] (nnz f64, host
+ * or device) = the alignment's probability, clamped to [0,1], dropped (0) below
+ * display_thresh and renormalised over the kept ones; out_kept_or_null[r] (N u32) =
+ * alignments kept for read r.  Uses prob and the store's aux factor as the
+ * coverage probability (the reference leaves the KDE factor out of this step).
+ */
+int oar_posteriors(oar_store *store, const double *counts, double display_thresh, double *out_prob,
+                   uint32_t *out_kept_or_null);
+
+/* aux_counts::get_aux_counts (src/util/aux_counts.rs:23-50): per transcript (M u32 each,
+ * host or device) the number of alignments and the number from single-alignment reads. */
+int oar_aux_counts(oar_store *store, uint32_t *out_unique, uint32_t *out_total);
+
 /* Layout of the store in HBM: [0] tiled layout built, [1] tiles, [2] alignment
  * slots in tiles, [3] rows swept from the CSR instead (too long / did not fit),
  * [4] sum of per-tile distinct transcripts, [5] sum of per-tile 8-slot units,

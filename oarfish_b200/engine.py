@@ -180,6 +180,23 @@ class DeviceStore:
         n = int(nnz.value)
         return cell_ptr, txp[:n].copy(), val[:n].copy(), niter[:n_cells]
 
+    def posteriors(self, counts, display_thresh: float = 0.0):
+        """write_out_prob's inner loop (write_function.rs:283-332): (per-alignment probs f64[nnz], kept u32[N])."""
+        cp, n_c, _ = _addr(np.ascontiguousarray(counts, dtype=np.float64), np.dtype(np.float64), "counts")
+        if n_c != self.n_txps:
+            raise ValueError("counts must have n_txps elements")
+        out = np.zeros(max(self.nnz, 1), dtype=np.float64)
+        kept = np.zeros(max(self.n_reads, 1), dtype=np.uint32)
+        check(self._lib.oar_posteriors(self._h, cp, float(display_thresh), out.ctypes.data, kept.ctypes.data))
+        return out[:self.nnz], kept[:self.n_reads]
+
+    def aux_counts(self):
+        """aux_counts::get_aux_counts (aux_counts.rs:23-50): (unique u32[M], total u32[M])."""
+        uniq = np.zeros(self.n_txps, dtype=np.uint32)
+        tot = np.zeros(self.n_txps, dtype=np.uint32)
+        check(self._lib.oar_aux_counts(self._h, uniq.ctypes.data, tot.ctypes.data))
+        return uniq, tot
+
     def sweep(self, prev_dev, curr_dev, weights_dev=None, sync: bool = True) -> None:
         """One raw fused E+M sweep on device buffers (torch CUDA tensors)."""
         pp, n_p, _ = _addr(prev_dev, np.dtype(np.float64), "prev")

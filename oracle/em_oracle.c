@@ -154,3 +154,48 @@ void oracle_inds_to_weights(const uint64_t *inds, uint64_t n_inds, uint64_t n_ro
     memset(wts, 0, sizeof(uint32_t) * n_rows);
     for (uint64_t i = 0; i < n_inds; ++i) wts[inds[i]] += 1u;
 }
+
+/* Read-level assignment probabilities: the inner loop of write_out_prob
+ * (src/util/write_function.rs:283-332).  For every read: denom over its
+ * alignments with the FINAL counts (:286-291; note the reference leaves the KDE
+ * factor out here), nprob = clamp(c*p*cov/denom, 0, 1) (:307), kept iff
+ * nprob >= display_thresh (:309), kept values renormalised by their sum
+ * (:316-318).  out[j] = renormalised probability, 0 for dropped alignments;
+ * kept[r] = number of alignments kept for read r. */
+void oracle_posteriors(const uint64_t *row_ptr, const uint32_t *txp, const float *prob,
+                       const double *cov, uint64_t n_reads, const double *counts,
+                       double display_thresh, double *out, uint32_t *kept)
+{
+    for (uint64_t r = 0; r < n_reads; ++r) {
+        uint64_t s = row_ptr[r], e = row_ptr[r + 1];
+        double denom = 0.0;
+        for (uint64_t j = s; j < e; ++j)
+            denom += counts[txp[j]] * (double)prob[j] * (cov ? cov[j] : 1.0);
+        double denom2 = 0.0;
+        uint32_t k = 0;
+        for (uint64_t j = s; j < e; ++j) {
+            double np = (counts[txp[j]] * (double)prob[j] * (cov ? cov[j] : 1.0)) / denom;
+            /* f64::clamp propagates NaN; NaN >= thresh is false */
+            if (np < 0.0) np = 0.0; else if (np > 1.0) np = 1.0;
+            if (np >= display_thresh) { out[j] = np; denom2 += np; ++k; } else out[j] = 0.0;
+        }
+        for (uint64_t j = s; j < e; ++j) if (out[j] != 0.0 || (display_thresh <= 0.0 && k)) out[j] /= denom2;
+        if (kept) kept[r] = k;
+    }
+}
+
+/* get_aux_counts (src/util/aux_counts.rs:23-50): per transcript, the number of
+ * alignments (total) and the number of those from single-alignment reads. */
+void oracle_aux_counts(const uint64_t *row_ptr, const uint32_t *txp, uint64_t n_reads,
+                       uint32_t n_txps, uint32_t *unique, uint32_t *total)
+{
+    memset(unique, 0, sizeof(uint32_t) * n_txps);
+    memset(total, 0, sizeof(uint32_t) * n_txps);
+    for (uint64_t r = 0; r < n_reads; ++r) {
+        uint64_t s = row_ptr[r], e = row_ptr[r + 1];
+        int is_unique = (e - s) == 1;
+        for (uint64_t j = s; j < e; ++j) {
+            if (txp[j] < n_txps) { total[txp[j]] += 1; if (is_unique) unique[txp[j]] += 1; }
+        }
+    }
+}

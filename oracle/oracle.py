@@ -32,6 +32,10 @@ def lib() -> C.CDLL:
         L.oracle_get_sample_inds.argtypes = [C.c_uint64, C.c_uint64, _vp]
         L.oracle_inds_to_weights.restype = None
         L.oracle_inds_to_weights.argtypes = [_vp, C.c_uint64, C.c_uint64, _vp]
+        L.oracle_posteriors.restype = None
+        L.oracle_posteriors.argtypes = [_vp, _vp, _vp, _vp, C.c_uint64, _vp, C.c_double, _vp, _vp]
+        L.oracle_aux_counts.restype = None
+        L.oracle_aux_counts.argtypes = [_vp, _vp, C.c_uint64, C.c_uint32, _vp, _vp]
         L.port_num_threads.restype = C.c_int
         L.port_store_create.restype = _vp
         L.port_store_create.argtypes = [_vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64, C.c_uint32]
@@ -89,6 +93,23 @@ def inds_to_weights(inds, n_rows):
     w = np.zeros(n_rows, dtype=np.uint32)
     lib().oracle_inds_to_weights(_p(inds), len(inds), n_rows, _p(w))
     return w
+
+
+def posteriors(row_ptr, txp, prob, counts, display_thresh=0.0, cov=None):
+    """write_out_prob inner loop (write_function.rs:283-332)."""
+    row_ptr = _c(row_ptr, np.uint64); txp = _c(txp, np.uint32); prob = _c(prob, np.float32); cov = _c(cov, np.float64)
+    counts = _c(counts, np.float64)
+    out = np.zeros(len(txp), dtype=np.float64); kept = np.zeros(len(row_ptr) - 1, dtype=np.uint32)
+    lib().oracle_posteriors(_p(row_ptr), _p(txp), _p(prob), _p(cov), len(row_ptr) - 1, _p(counts), display_thresh, _p(out), _p(kept))
+    return out, kept
+
+
+def aux_counts(row_ptr, txp, n_txps):
+    """get_aux_counts (aux_counts.rs:23-50)."""
+    row_ptr = _c(row_ptr, np.uint64); txp = _c(txp, np.uint32)
+    u = np.zeros(n_txps, dtype=np.uint32); t = np.zeros(n_txps, dtype=np.uint32)
+    lib().oracle_aux_counts(_p(row_ptr), _p(txp), len(row_ptr) - 1, n_txps, _p(u), _p(t))
+    return u, t
 
 
 class PortStore:

@@ -239,6 +239,27 @@ def test_batched_cells_match_per_cell_oracle(DS, oracle_mod):
         assert_counts_close(got, want)
 
 
+def test_posteriors_and_aux_counts(DS, oracle_mod, small_store):
+    """write_out_prob inner loop (write_function.rs:283-332) and get_aux_counts (aux_counts.rs:23-50)."""
+    s = small_store
+    with DS(s.row_ptr, s.txp_id, s.prob, s.n_txps) as ds:
+        counts = ds.em(min_iter=1).counts
+        for thr in (0.0, 1e-3, 0.2):
+            got, kept = ds.posteriors(counts, thr)
+            want, wkept = oracle_mod.posteriors(s.row_ptr, s.txp_id, s.prob, counts, thr)
+            np.testing.assert_array_equal(kept, wkept)
+            np.testing.assert_array_equal(got == 0.0, want == 0.0)
+            np.testing.assert_allclose(got, want, rtol=1e-12, atol=0)
+            rows_with = kept > 0
+            sums = np.add.reduceat(got, s.row_ptr[:-1].astype(np.int64))
+            np.testing.assert_allclose(sums[rows_with], 1.0, rtol=1e-12)
+        u, t = ds.aux_counts()
+        wu, wt = oracle_mod.aux_counts(s.row_ptr, s.txp_id, s.n_txps)
+        np.testing.assert_array_equal(u, wu)
+        np.testing.assert_array_equal(t, wt)
+        assert t.sum() == s.nnz
+
+
 def test_full_size_properties_c3(DS):
     """BASELINE config 3 (10M reads x 200k transcripts): size-independent properties."""
     from oarfish_b200 import synth

@@ -204,3 +204,17 @@ def test_sirv_fixture_conserves_reads_per_gene(oracle_mod):
     for gene in np.unique(genes):
         m = genes == gene
         assert c[m].sum() == pytest.approx(true[m].sum(), rel=1e-9)
+
+
+def test_posteriors_and_aux_counts_known_answers(oracle_mod):
+    rows = [[(0, 1.0)], [(0, 0.5), (1, 0.5)], [(1, 1.0), (2, 0.001)], [(2, 1.0)]]
+    rp, tx, pr = csr(rows)
+    counts = np.array([3.0, 1.0, 1.0])
+    out, kept = oracle_mod.posteriors(rp, tx, pr, counts, 0.0)
+    np.testing.assert_allclose(out, [1.0, 0.75, 0.25, 1.0 / 1.001, 0.001 / 1.001, 1.0], rtol=1e-7)  # probs are f32
+    assert list(kept) == [1, 2, 2, 1]
+    out, kept = oracle_mod.posteriors(rp, tx, pr, counts, 0.01)   # drops the 0.000999 alignment, renormalises
+    np.testing.assert_allclose(out, [1.0, 0.75, 0.25, 1.0, 0.0, 1.0], rtol=1e-12)
+    assert list(kept) == [1, 2, 1, 1]
+    u, t = oracle_mod.aux_counts(rp, tx, 3)
+    assert list(u) == [1, 0, 1] and list(t) == [2, 2, 2]

@@ -632,18 +632,20 @@ __global__ void __launch_bounds__(kThreads, 5) em_sweep_tiled(View v, Geometry g
         }
 
         // ---- M-step scatter into the transcript-sorted smem order -----------------------------
+        // (padding and non-aggregated alignments carry the tile's trash offset and are not stored)
         char *xp = reinterpret_cast<char *>(xs);
-        *reinterpret_cast<double *>(xp + (lp4.x >> 16)) = x0;
-        *reinterpret_cast<double *>(xp + (lp4.y >> 16)) = x1;
-        *reinterpret_cast<double *>(xp + (lp4.z >> 16)) = x2;
-        *reinterpret_cast<double *>(xp + (lp4.w >> 16)) = x3;
+        const uint32_t trash = U * kUnitStride * 8u;
+        const uint32_t q0 = lp4.x >> 16, q1 = lp4.y >> 16, q2 = lp4.z >> 16, q3 = lp4.w >> 16;
+        if (q0 != trash) *reinterpret_cast<double *>(xp + q0) = x0;
+        if (q1 != trash) *reinterpret_cast<double *>(xp + q1) = x1;
+        if (q2 != trash) *reinterpret_cast<double *>(xp + q2) = x2;
+        if (q3 != trash) *reinterpret_cast<double *>(xp + q3) = x3;
         if (info & kInfoStray) {
             // transcripts with fewer than kAggMin alignments in this tile: straight to global
-            const uint32_t trash = U * kUnitStride * 8u;
-            if ((lp4.x >> 16) == trash && x0 != 0.0) atomicAdd(curr + table[(lp4.x & 0xFFFFu) >> 3], x0);
-            if ((lp4.y >> 16) == trash && x1 != 0.0) atomicAdd(curr + table[(lp4.y & 0xFFFFu) >> 3], x1);
-            if ((lp4.z >> 16) == trash && x2 != 0.0) atomicAdd(curr + table[(lp4.z & 0xFFFFu) >> 3], x2);
-            if ((lp4.w >> 16) == trash && x3 != 0.0) atomicAdd(curr + table[(lp4.w & 0xFFFFu) >> 3], x3);
+            if (q0 == trash && x0 != 0.0) atomicAdd(curr + table[(lp4.x & 0xFFFFu) >> 3], x0);
+            if (q1 == trash && x1 != 0.0) atomicAdd(curr + table[(lp4.y & 0xFFFFu) >> 3], x1);
+            if (q2 == trash && x2 != 0.0) atomicAdd(curr + table[(lp4.z & 0xFFFFu) >> 3], x2);
+            if (q3 == trash && x3 != 0.0) atomicAdd(curr + table[(lp4.w & 0xFFFFu) >> 3], x3);
         }
         __syncthreads();   // xs complete; stage s and s_prev are free again
 

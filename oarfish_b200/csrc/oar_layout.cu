@@ -40,7 +40,7 @@ int build_tiled_layout(oar_store *s, uint32_t span)
     free_tiled_layout(s);
     TiledLayout &t = s->tl;
     const uint32_t N = (uint32_t)s->n_reads;
-    if (span == 0 || span > (uint32_t)kTile) span = 984;
+    if (span == 0 || span > (uint32_t)kTile) span = (uint32_t)kTile - 5u * kWarps;
     t.span = span;
     if (N == 0 || s->nnz == 0) { t.ready = true; return OAR_OK; }
     if (s->n_txps >= kMaxTxps) return fail(OAR_ERR_UNSUPPORTED, "tiled layout needs n_txps < 2^28");

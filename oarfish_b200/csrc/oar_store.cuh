@@ -1,6 +1,10 @@
 // oar_store.cuh -- the store handle behind the opaque oar_store of the C ABI.
 #pragma once
 #include "oar_common.cuh"
+#ifndef OAR_TILE_WARPS
+#define OAR_TILE_WARPS 8
+#endif
+#define OAR_TILE_WARPS_DEFAULT OAR_TILE_WARPS
 
 namespace oar {
 
@@ -35,7 +39,7 @@ struct oar_store {
     uint64_t n_reads = 0, nnz = 0;
     uint32_t n_txps = 0;
     int kernel = OAR_KERNEL_ROWGROUP;
-    int ctas_per_sm = 5;  // persistent CTAs of the tiled sweep per SM (upper bound; shared memory may allow fewer)
+    int ctas_per_sm = 40 / OAR_TILE_WARPS_DEFAULT;  // persistent CTAs of the tiled sweep per SM (upper bound; shared memory may allow fewer)
 
     // CSR in HBM (original read order)
     uint32_t *d_row_ptr = nullptr;  // N+1

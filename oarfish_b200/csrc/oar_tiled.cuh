@@ -41,7 +41,10 @@
 namespace oar {
 namespace tiled {
 
-constexpr int kWarps = 8;                 // warp-chunks per tile
+#ifndef OAR_TILE_WARPS
+#define OAR_TILE_WARPS 8
+#endif
+constexpr int kWarps = OAR_TILE_WARPS;    // warp-chunks per tile
 constexpr int kChunk = 128;               // alignment slots per warp-chunk (4 per lane)
 constexpr int kChunkCap = kChunk - 1;     // rows use at most 127 slots: a padding pseudo-row always closes the chunk
 constexpr int kTile = kWarps * kChunk;    // 1024 slots
@@ -67,7 +70,8 @@ static_assert(kMaxUnits == kThreads, "one unit per thread in phase 2");
 //   [576,592)  D, U, 0, 0
 //   [592, ..)  table u32[roundup4(D)]  : distinct transcript ids
 //              units u32[roundup4(U)]  : transcript id | (valid slots - 1) << 28 per 8-slot unit
-constexpr int kRecDesc = 0, kRecInfo = 512, kRecRow = 544, kRecDU = 576, kRecTable = 592;
+constexpr int kRecDesc = 0, kRecInfo = 64 * kWarps, kRecRow = kRecInfo + 4 * kWarps, kRecDU = kRecRow + 4 * kWarps,
+              kRecTable = kRecDU + 16;
 constexpr int kRecMax = kRecTable + 4 * kTile + 4 * kMaxUnits;   // 5712
 constexpr int kStages = 2;
 
@@ -458,7 +462,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 
 // m_step (em.rs:87-133), persistent and TMA-fed.
 template <bool HAS_AUX, bool HAS_WTS>
-__global__ void __launch_bounds__(kThreads, 5) em_sweep_tiled(View v, Geometry g, const double *__restrict__ prev,
+__global__ void __launch_bounds__(kThreads, (5 * 8) / kWarps) em_sweep_tiled(View v, Geometry g, const double *__restrict__ prev,
                                                               double *__restrict__ curr,
                                                               const uint32_t *__restrict__ wperm,
                                                               const OarEmState *__restrict__ st, int check_done)

@@ -547,8 +547,12 @@ __global__ void __launch_bounds__(kThreads, (5 * 8) / kWarps) em_sweep_tiled(Vie
 
         const unsigned full = 0xffffffffu;
         const uint32_t hb = desc & 15u, dist = (desc >> 4) & 31u, E = (desc >> 9) & 31u;
+        // chunk_info is the same word for the whole warp; votes make that visible to the compiler
+        const bool multi = __any_sync(full, (info & kInfoMulti) != 0u);
+        const bool strays = __any_sync(full, (info & kInfoStray) != 0u);
+        const bool long_rows = __any_sync(full, (info & 7u) > 3u);
         double x0, x1, x2, x3;
-        if (!(info & kInfoMulti)) {
+        if (!multi) {
             // fast path: no lane holds more than one row head.  Slot i lies before that head (it
             // closes the row entering the lane) iff hb >> (i+1) != 0; slot 3 never does.
             //   a = slots before the head, z = slots from the head on (all four if there is none)
@@ -564,7 +568,7 @@ __global__ void __launch_bounds__(kThreads, (5 * 8) / kWarps) em_sweep_tiled(Vie
             incl = fma(__shfl_up_sync(full, incl, 1), mask01(dist >= 1u), incl);
             incl = fma(__shfl_up_sync(full, incl, 2), mask01(dist >= 2u), incl);
             incl = fma(__shfl_up_sync(full, incl, 4), mask01(dist >= 4u), incl);
-            if ((info & 7u) > 3u) {   // rows spanning more than 8 lanes (rare)
+            if (long_rows) {   // rows spanning more than 8 lanes (rare)
                 incl = fma(__shfl_up_sync(full, incl, 8), mask01(dist >= 8u), incl);
                 incl = fma(__shfl_up_sync(full, incl, 16), mask01(dist >= 16u), incl);
             }
@@ -618,7 +622,7 @@ __global__ void __launch_bounds__(kThreads, (5 * 8) / kWarps) em_sweep_tiled(Vie
             x3 = tot3 > OAR_EM_DENOM_THRESH ? w3 * fast_rcp(tot3) : 0.0;
         }
 
-        if (HAS_WTS && (info & kInfoMulti)) {
+        if (HAS_WTS && multi) {
             // general path: row index of a slot inside the chunk = (number of heads at or before it) - 1
             uint32_t incl_h = __popc(hb);
 #pragma unroll
@@ -644,7 +648,7 @@ __global__ void __launch_bounds__(kThreads, (5 * 8) / kWarps) em_sweep_tiled(Vie
         if (q1 != trash) *reinterpret_cast<double *>(xp + q1) = x1;
         if (q2 != trash) *reinterpret_cast<double *>(xp + q2) = x2;
         if (q3 != trash) *reinterpret_cast<double *>(xp + q3) = x3;
-        if (info & kInfoStray) {
+        if (strays) {
             // transcripts with fewer than kAggMin alignments in this tile: straight to global
             if (q0 == trash && x0 != 0.0) atomicAdd(curr + table[(lp4.x & 0xFFFFu) >> 3], x0);
             if (q1 == trash && x1 != 0.0) atomicAdd(curr + table[(lp4.y & 0xFFFFu) >> 3], x1);
@@ -672,7 +676,7 @@ __global__ void __launch_bounds__(kThreads, (5 * 8) / kWarps) em_sweep_tiled(Vie
         }
 
         // ---- phase 2: sum 8-slot units, combine equal transcripts across the warp ---------------
-        if (warp * 32u < U) {
+        if (__any_sync(full, warp * 32u < U)) {
             const uint32_t u_txp = unit == kNoTxp ? kNoTxp : (unit & (kMaxTxps - 1u));
             // a unit is 8 doubles at an 80-byte stride (conflict-free LDS.128); its unused slots were cleared above
             const double2 *b = reinterpret_cast<const double2 *>(xs + tid * kUnitStride);

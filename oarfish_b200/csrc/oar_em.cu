@@ -13,7 +13,6 @@
 #include <new>
 #include <vector>
 
-#include "oar_kernels.cuh"
 #include "oar_store.cuh"
 #include "oar_tiled.cuh"
 
@@ -220,11 +219,17 @@ extern "C" void *oar_store_stream(oar_store *s) { return s ? (void *)s->stream :
 // sweep dispatch
 // ---------------------------------------------------------------------------
 
+static const uint32_t kFoldFallbackMax = 4096;
+
 static tiled::View tiled_view(const oar_store *s)
 {
     const TiledLayout &t = s->tl;
     tiled::View v;
     v.n_tiles = t.n_tiles; v.prob = t.prob; v.lpos = t.lpos; v.aux = t.aux; v.rec = t.rec; v.records = t.records;
+    // a handful of fallback rows rides along in the tiled kernel; a long list gets its own launch
+    const bool fold = t.n_fallback <= kFoldFallbackMax;
+    v.fb_rows = t.fallback; v.n_fb = fold ? t.n_fallback : 0u;
+    v.csr_row_ptr = s->d_row_ptr; v.csr_txp = s->d_txp; v.csr_prob = s->d_prob; v.csr_aux = s->d_aux; v.csr_wts = nullptr;
     return v;
 }
 
@@ -278,7 +283,8 @@ static cudaError_t enqueue_sweep(oar_store *s, const double *prev, double *curr,
         return enqueue_rowgroup(s, nullptr, s->n_reads, prev, curr, wts, state, check_done);
     const TiledLayout &t = s->tl;
     if (t.n_tiles > 0) {
-        const tiled::View v = tiled_view(s);
+        tiled::View v = tiled_view(s);
+        v.csr_wts = wts;
         const uint32_t *wp = wts ? t.wperm : nullptr;
         cudaError_t le;
         if (s->d_aux) le = wts ? launch_tiled<true, true>(s, v, prev, curr, wp, state, check_done)
@@ -290,6 +296,7 @@ static cudaError_t enqueue_sweep(oar_store *s, const double *prev, double *curr,
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
+    if (t.n_tiles > 0 && t.n_fallback <= kFoldFallbackMax) return cudaSuccess;   // swept inside the tiled kernel
     return enqueue_rowgroup(s, t.fallback, t.n_fallback, prev, curr, wts, state, check_done);
 }
 
@@ -391,7 +398,7 @@ static int run_em(oar_store *s, const double *init_dev, uint32_t max_iter, doubl
         }
         // the launches still in flight are no-ops (done is set); they finish before the final sweep (same stream)
         // every kernel node of every graph launch is a launch of ours (those after convergence exit at once)
-        const uint64_t per_iter = 2 + ((s->kernel == OAR_KERNEL_TILED && s->tl.n_tiles > 0 && s->tl.n_fallback > 0) ? 1 : 0);
+        const uint64_t per_iter = 2 + ((s->kernel == OAR_KERNEL_TILED && s->tl.n_tiles > 0 && s->tl.n_fallback > kFoldFallbackMax) ? 1 : 0);
         s->counters[0] += launched_iters * per_iter;
     }
     double *prev = s->d_counts[sweeps & 1], *curr = s->d_counts[(sweeps + 1) & 1];

@@ -11,7 +11,7 @@ namespace kern {
 
 // boundaries (Vec<usize>, oarfish_types.rs:555) -> u32 row_ptr; flag[0] != 0 if
 // not a monotone prefix array that starts at 0 and ends at nnz.
-__global__ void narrow_validate_rowptr(const uint64_t *__restrict__ rp64, uint32_t *__restrict__ rp32,
+static __global__ void narrow_validate_rowptr(const uint64_t *__restrict__ rp64, uint32_t *__restrict__ rp32,
                                        uint64_t n_reads, uint64_t nnz, uint32_t *flag)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -27,7 +27,7 @@ __global__ void narrow_validate_rowptr(const uint64_t *__restrict__ rp64, uint32
     if (bad) atomicOr(flag, 1u);
 }
 
-__global__ void validate_txp(const uint32_t *__restrict__ txp, uint64_t nnz, uint32_t n_txps, uint32_t *flag)
+static __global__ void validate_txp(const uint32_t *__restrict__ txp, uint64_t nnz, uint32_t n_txps, uint32_t *flag)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     bool bad = false;
@@ -41,7 +41,7 @@ __global__ void validate_txp(const uint32_t *__restrict__ txp, uint64_t nnz, uin
 // ---------------------------------------------------------------------------
 
 // prev = init or avg (em.rs:160-167); curr = 0 (em.rs:158)
-__global__ void em_init(double *__restrict__ prev, double *__restrict__ curr, const double *__restrict__ init,
+static __global__ void em_init(double *__restrict__ prev, double *__restrict__ curr, const double *__restrict__ init,
                         double avg, uint32_t M)
 {
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -52,7 +52,7 @@ __global__ void em_init(double *__restrict__ prev, double *__restrict__ curr, co
 }
 
 // set very small abundances to 0 (em.rs:238-242)
-__global__ void em_threshold(double *__restrict__ prev, uint32_t M)
+static __global__ void em_threshold(double *__restrict__ prev, uint32_t M)
 {
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += stride)
@@ -63,7 +63,7 @@ __global__ void em_threshold(double *__restrict__ prev, uint32_t M)
 // (signed, starts from 0; em.rs:194-201), then "swap + fill(0)" (em.rs:204-207)
 // == zero the old prev, which is the next sweep's target.  The last CTA applies
 // the stop rule (em.rs:212 / :399) and advances niter (em.rs:218).
-__global__ void __launch_bounds__(256) em_update(double *__restrict__ prev, const double *__restrict__ curr,
+static __global__ void __launch_bounds__(256) em_update(double *__restrict__ prev, const double *__restrict__ curr,
                                                  uint32_t M, OarEmState *st)
 {
     if (st->done) return;
@@ -127,22 +127,16 @@ __global__ void __launch_bounds__(256) em_update(double *__restrict__ prev, cons
 // integer resampling weight (== visiting the row that many times,
 // oarfish_types.rs:571-598).
 template <bool HAS_AUX, bool HAS_WTS>
-__global__ void __launch_bounds__(256) em_sweep_rowgroup(const uint32_t *__restrict__ row_ptr,
-                                                         const uint32_t *__restrict__ txp,
-                                                         const float *__restrict__ prob,
-                                                         const double *__restrict__ aux,
-                                                         const uint32_t *__restrict__ wts,
-                                                         const uint32_t *__restrict__ list,
-                                                         const double *__restrict__ prev,
-                                                         double *__restrict__ curr, uint64_t n_rows,
-                                                         const OarEmState *__restrict__ st, int check_done)
+__device__ __forceinline__ void rowgroup_rows(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ txp,
+                                              const float *__restrict__ prob, const double *__restrict__ aux,
+                                              const uint32_t *__restrict__ wts, const uint32_t *__restrict__ list,
+                                              const double *__restrict__ prev, double *__restrict__ curr,
+                                              uint64_t first_group, uint64_t ngroups, uint64_t n_rows)
 {
-    if (check_done && st->done) return;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned sub = lane & 7u;
     const unsigned gmask = 0xFFu << (lane & 24u);
-    const uint64_t ngroups = ((uint64_t)gridDim.x * blockDim.x) >> 3;
-    for (uint64_t k = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; k < n_rows; k += ngroups) {
+    for (uint64_t k = first_group; k < n_rows; k += ngroups) {
         const uint64_t row = list ? (uint64_t)list[k] : k;  // fallback rows of the tiled layout come as a list
         double scale = 1.0;
         if (HAS_WTS) {
@@ -186,6 +180,23 @@ __global__ void __launch_bounds__(256) em_sweep_rowgroup(const uint32_t *__restr
     }
 }
 
+template <bool HAS_AUX, bool HAS_WTS>
+static __global__ void __launch_bounds__(256) em_sweep_rowgroup(const uint32_t *__restrict__ row_ptr,
+                                                         const uint32_t *__restrict__ txp,
+                                                         const float *__restrict__ prob,
+                                                         const double *__restrict__ aux,
+                                                         const uint32_t *__restrict__ wts,
+                                                         const uint32_t *__restrict__ list,
+                                                         const double *__restrict__ prev,
+                                                         double *__restrict__ curr, uint64_t n_rows,
+                                                         const OarEmState *__restrict__ st, int check_done)
+{
+    if (check_done && st->done) return;
+    rowgroup_rows<HAS_AUX, HAS_WTS>(row_ptr, txp, prob, aux, wts, list, prev, curr,
+                                    ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3,
+                                    ((uint64_t)gridDim.x * blockDim.x) >> 3, n_rows);
+}
+
 // ---------------------------------------------------------------------------
 // bootstrap resampling weights: histogram of N uniform draws from [0, N)
 // (bootstrap.rs:7-16; the sort there only orders the visit, the multiset is
@@ -207,7 +218,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-__global__ void __launch_bounds__(256) boot_weights_kernel(uint32_t *__restrict__ w, uint64_t n,
+static __global__ void __launch_bounds__(256) boot_weights_kernel(uint32_t *__restrict__ w, uint64_t n,
                                                            uint64_t seed, uint32_t replicate)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;

@@ -37,6 +37,7 @@
 #include <cub/cub.cuh>
 
 #include "oar_common.cuh"
+#include "oar_kernels.cuh"
 
 namespace oar {
 namespace tiled {
@@ -106,6 +107,10 @@ struct View {
     const double *aux;         // n_tiles * kTile or null
     const uint2 *rec;          // n_tiles : {record offset in 16-byte granules, record bytes}
     const uint4 *records;      // all records
+    // rows that are not tiled (longer than a chunk, or did not fit): swept from the CSR by the last CTA
+    const uint32_t *fb_rows; uint32_t n_fb;
+    const uint32_t *csr_row_ptr; const uint32_t *csr_txp; const float *csr_prob; const double *csr_aux;
+    const uint32_t *csr_wts;   // bootstrap weights in read order (fallback rows are not in tile order)
 };
 
 // ---------------------------------------------------------------------------
@@ -706,6 +711,9 @@ __global__ void __launch_bounds__(kThreads, (5 * 8) / kWarps) em_sweep_tiled(Vie
         for (uint32_t d = tid + kThreads; d < Dn; d += kThreads) s_prev[d] = prev[table_n[d]];
         tile = next;
     }
+    if (v.n_fb && blockIdx.x == gridDim.x - 1u)
+        kern::rowgroup_rows<HAS_AUX, HAS_WTS>(v.csr_row_ptr, v.csr_txp, v.csr_prob, v.csr_aux, v.csr_wts, v.fb_rows, prev, curr,
+                                              tid >> 3, kThreads >> 3, v.n_fb);
 }
 
 }  // namespace tiled

@@ -34,6 +34,14 @@ void set_error(const std::string &msg);
 int fail(int code, const std::string &msg);
 int cuda_fail(cudaError_t e, const char *what);
 
+// Stream-ordered allocation from the device's default memory pool (kept warm: freed blocks are
+// cached by the pool, so creating / destroying stores repeatedly does not pay cudaMalloc/cudaFree).
+template <typename T>
+inline cudaError_t dmalloc(T **p, size_t bytes, cudaStream_t st)
+{ return cudaMallocAsync(reinterpret_cast<void **>(p), bytes ? bytes : 16, st); }
+inline void dfree(void *p, cudaStream_t st) { if (p) cudaFreeAsync(p, st); }
+void warm_pool(int device);
+
 #define OAR_CUDA(expr)                                              \
     do {                                                            \
         cudaError_t _e = (expr);                                    \

@@ -30,6 +30,21 @@ int cuda_fail(cudaError_t e, const char *what)
 
 }  // namespace oar
 
+namespace oar {
+void warm_pool(int device)
+{
+    static bool done[64] = {false};
+    if (device < 0 || device >= 64 || done[device]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    (void)cudaGetLastError();
+    done[device] = true;
+}
+}  // namespace oar
+
 using namespace oar;
 
 // ---------------------------------------------------------------------------
@@ -65,8 +80,9 @@ extern "C" void oar_store_destroy(oar_store *s)
     if (s->stream) cudaStreamSynchronize(s->stream);
     destroy_graphs(s);
     free_tiled_layout(s);
-    cudaFree(s->d_row_ptr); cudaFree(s->d_txp); cudaFree(s->d_prob); cudaFree(s->d_aux);
-    cudaFree(s->d_counts[0]); cudaFree(s->d_counts[1]); cudaFree(s->d_state); cudaFree(s->d_weights);
+    dfree(s->d_row_ptr, s->stream); dfree(s->d_txp, s->stream); dfree(s->d_prob, s->stream); dfree(s->d_aux, s->stream);
+    dfree(s->d_counts[0], s->stream); dfree(s->d_counts[1], s->stream); dfree(s->d_state, s->stream); dfree(s->d_weights, s->stream);
+    if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->h_state) cudaFreeHost(s->h_state);
     for (auto &e : s->ev) if (e) cudaEventDestroy(e);
     for (auto &e : s->slot_ev) if (e) cudaEventDestroy(e);
@@ -96,23 +112,24 @@ extern "C" int oar_store_create(const uint64_t *row_ptr, const uint32_t *txp_id,
     s->device = device; s->n_reads = n_reads; s->nnz = nnz; s->n_txps = n_txps;
     int rc = [&]() -> int {
         OAR_CUDA(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device));
+        warm_pool(device);
         OAR_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
         for (auto &e : s->ev) OAR_CUDA(cudaEventCreate(&e));
         for (auto &e : s->slot_ev) OAR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         OAR_CUDA(cudaEventRecord(s->ev[0], s->stream));
         const size_t pad = 16;  // slack so vector loads may over-read safely
-        OAR_CUDA(cudaMalloc(&s->d_row_ptr, sizeof(uint32_t) * (n_reads + 1 + pad)));
-        OAR_CUDA(cudaMalloc(&s->d_txp, sizeof(uint32_t) * (nnz + pad)));
-        OAR_CUDA(cudaMalloc(&s->d_prob, sizeof(float) * (nnz + pad)));
-        if (aux_or_null) OAR_CUDA(cudaMalloc(&s->d_aux, sizeof(double) * (nnz + pad)));
-        OAR_CUDA(cudaMalloc(&s->d_counts[0], sizeof(double) * n_txps));
-        OAR_CUDA(cudaMalloc(&s->d_counts[1], sizeof(double) * n_txps));
-        OAR_CUDA(cudaMalloc(&s->d_state, sizeof(OarEmState) * 2));
+        OAR_CUDA(dmalloc(&s->d_row_ptr, sizeof(uint32_t) * (n_reads + 1 + pad), s->stream));
+        OAR_CUDA(dmalloc(&s->d_txp, sizeof(uint32_t) * (nnz + pad), s->stream));
+        OAR_CUDA(dmalloc(&s->d_prob, sizeof(float) * (nnz + pad), s->stream));
+        if (aux_or_null) OAR_CUDA(dmalloc(&s->d_aux, sizeof(double) * (nnz + pad), s->stream));
+        OAR_CUDA(dmalloc(&s->d_counts[0], sizeof(double) * n_txps, s->stream));
+        OAR_CUDA(dmalloc(&s->d_counts[1], sizeof(double) * n_txps, s->stream));
+        OAR_CUDA(dmalloc(&s->d_state, sizeof(OarEmState) * 2, s->stream));
         OAR_CUDA(cudaMallocHost(&s->h_state, sizeof(OarEmState) * 4));
         // stage the u64 boundaries, narrow to u32 and validate on the device
         uint64_t *d_rp64 = nullptr;
         uint32_t *d_flag = reinterpret_cast<uint32_t *>(s->d_state + 1);
-        OAR_CUDA(cudaMalloc(&d_rp64, sizeof(uint64_t) * (n_reads + 1)));
+        OAR_CUDA(dmalloc(&d_rp64, sizeof(uint64_t) * (n_reads + 1), s->stream));
         OAR_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(uint32_t) * 4, s->stream));
         OAR_CUDA(cudaMemcpyAsync(d_rp64, row_ptr, sizeof(uint64_t) * (n_reads + 1), cudaMemcpyDefault, s->stream));
         if (nnz) {
@@ -134,7 +151,7 @@ extern "C" int oar_store_create(const uint64_t *row_ptr, const uint32_t *txp_id,
         OAR_CUDA(cudaMemcpyAsync(h_flag, d_flag, sizeof(h_flag), cudaMemcpyDeviceToHost, s->stream));
         OAR_CUDA(cudaEventRecord(s->ev[1], s->stream));
         OAR_CUDA(cudaStreamSynchronize(s->stream));
-        OAR_CUDA(cudaFree(d_rp64));
+        dfree(d_rp64, s->stream);
         OAR_CUDA(cudaGetLastError());
         if (h_flag[0]) return fail(OAR_ERR_INVALID, "oar_store_create: row_ptr is not a monotone prefix ending at nnz");
         if (h_flag[1]) return fail(OAR_ERR_INVALID, "oar_store_create: txp_id out of range (>= n_txps)");
@@ -422,7 +439,7 @@ static int stage_init(oar_store *s, const double *init_or_null, double **d_init)
 {
     *d_init = nullptr;
     if (!init_or_null) return OAR_OK;
-    OAR_CUDA(cudaMalloc(d_init, sizeof(double) * s->n_txps));
+    OAR_CUDA(dmalloc(d_init, sizeof(double) * s->n_txps, s->stream));
     OAR_CUDA(cudaMemcpyAsync(*d_init, init_or_null, sizeof(double) * s->n_txps, cudaMemcpyDefault, s->stream));
     return OAR_OK;
 }
@@ -436,16 +453,16 @@ extern "C" int oar_em(oar_store *s, const double *init_or_null, uint32_t max_ite
     s->counters[0] = s->counters[1] = 0;
     double *d_init = nullptr;
     int rc = stage_init(s, init_or_null, &d_init);
-    if (rc != OAR_OK) { cudaFree(d_init); return rc; }
+    if (rc != OAR_OK) { dfree(d_init, s->stream); return rc; }
     OAR_CUDA(cudaEventRecord(s->ev[0], s->stream));
     double *res = nullptr;
     rc = run_em(s, d_init, max_iter, conv_thresh, min_iter, false, &res, out_niter, out_rel_diff, nullptr);
-    if (rc != OAR_OK) { cudaStreamSynchronize(s->stream); cudaFree(d_init); return rc; }
+    if (rc != OAR_OK) { dfree(d_init, s->stream); cudaStreamSynchronize(s->stream); return rc; }
     OAR_CUDA(cudaEventRecord(s->ev[1], s->stream));
     OAR_CUDA(cudaMemcpyAsync(out_counts, res, sizeof(double) * s->n_txps, cudaMemcpyDefault, s->stream));
     OAR_CUDA(cudaEventRecord(s->ev[2], s->stream));
     OAR_CUDA(cudaStreamSynchronize(s->stream));
-    if (d_init) OAR_CUDA(cudaFree(d_init));
+    dfree(d_init, s->stream);
     float a = 0.f, b = 0.f;
     OAR_CUDA(cudaEventElapsedTime(&a, s->ev[0], s->ev[1]));
     OAR_CUDA(cudaEventElapsedTime(&b, s->ev[1], s->ev[2]));
@@ -459,7 +476,7 @@ extern "C" int oar_em(oar_store *s, const double *init_or_null, uint32_t max_ite
 
 static int ensure_weights(oar_store *s)
 {
-    if (!s->d_weights) OAR_CUDA(cudaMalloc(&s->d_weights, sizeof(uint32_t) * (s->n_reads + 16)));
+    if (!s->d_weights) OAR_CUDA(dmalloc(&s->d_weights, sizeof(uint32_t) * (s->n_reads + 16), s->stream));
     return OAR_OK;
 }
 

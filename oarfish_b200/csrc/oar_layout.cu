@@ -16,18 +16,20 @@ namespace oar {
 void free_tiled_layout(oar_store *s)
 {
     TiledLayout &t = s->tl;
-    cudaFree(t.prob); cudaFree(t.lpos); cudaFree(t.aux); cudaFree(t.rec); cudaFree(t.records); cudaFree(t.trow);
-    cudaFree(t.fallback); cudaFree(t.wperm);
+    cudaStream_t st = s->stream;
+    dfree(t.prob, st); dfree(t.lpos, st); dfree(t.aux, st); dfree(t.rec, st); dfree(t.records, st); dfree(t.trow, st);
+    dfree(t.fallback, st); dfree(t.wperm, st);
     t = TiledLayout();
 }
 
 namespace {
 struct Scratch {
+    cudaStream_t st = nullptr;
     std::vector<void *> ptrs;
-    ~Scratch() { for (void *p : ptrs) cudaFree(p); }
+    ~Scratch() { for (void *p : ptrs) dfree(p, st); }
     template <typename T> cudaError_t alloc(T **p, size_t n)
     {
-        cudaError_t e = cudaMalloc(p, sizeof(T) * std::max<size_t>(n, 1));
+        cudaError_t e = dmalloc(p, sizeof(T) * std::max<size_t>(n, 1), st);
         if (e == cudaSuccess) ptrs.push_back(*p);
         return e;
     }
@@ -45,7 +47,7 @@ int build_tiled_layout(oar_store *s, uint32_t span)
     if (N == 0 || s->nnz == 0) { t.ready = true; return OAR_OK; }
     if (s->n_txps >= kMaxTxps) return fail(OAR_ERR_UNSUPPORTED, "tiled layout needs n_txps < 2^28");
     cudaStream_t st = s->stream;
-    Scratch sc;
+    Scratch sc; sc.st = st;
     uint32_t *key = nullptr, *idx = nullptr, *key_s = nullptr, *srow = nullptr, *slen = nullptr, *soff = nullptr;
     uint32_t *counters = nullptr;
     OAR_CUDA(sc.alloc(&key, N)); OAR_CUDA(sc.alloc(&idx, N));
@@ -98,15 +100,15 @@ int build_tiled_layout(oar_store *s, uint32_t span)
     // outputs (the variable-length records first at their worst-case size, compacted below)
     const size_t slots = (size_t)n_tiles * kTile;
     uint4 *records_tmp = nullptr;
-    OAR_CUDA(cudaMalloc(&t.fallback, sizeof(uint32_t) * std::max<uint32_t>(N, 1)));
-    OAR_CUDA(cudaMalloc(&t.trow, sizeof(uint32_t) * std::max<uint32_t>(n_tiled, 1)));
-    OAR_CUDA(cudaMalloc(&t.wperm, sizeof(uint32_t) * ((size_t)n_tiled + kChunk + 1)));
+    OAR_CUDA(dmalloc(&t.fallback, sizeof(uint32_t) * std::max<uint32_t>(N, 1), st));
+    OAR_CUDA(dmalloc(&t.trow, sizeof(uint32_t) * std::max<uint32_t>(n_tiled, 1), st));
+    OAR_CUDA(dmalloc(&t.wperm, sizeof(uint32_t) * ((size_t)n_tiled + kChunk + 1), st));
     OAR_CUDA(cudaMemsetAsync(t.wperm, 0, sizeof(uint32_t) * ((size_t)n_tiled + kChunk + 1), st));
     if (n_tiles > 0) {
-        OAR_CUDA(cudaMalloc(&t.prob, sizeof(float) * slots));
-        OAR_CUDA(cudaMalloc(&t.lpos, sizeof(uint32_t) * slots));
-        if (s->d_aux) OAR_CUDA(cudaMalloc(&t.aux, sizeof(double) * slots));
-        OAR_CUDA(cudaMalloc(&t.rec, sizeof(uint2) * n_tiles));
+        OAR_CUDA(dmalloc(&t.prob, sizeof(float) * slots, st));
+        OAR_CUDA(dmalloc(&t.lpos, sizeof(uint32_t) * slots, st));
+        if (s->d_aux) OAR_CUDA(dmalloc(&t.aux, sizeof(double) * slots, st));
+        OAR_CUDA(dmalloc(&t.rec, sizeof(uint2) * n_tiles, st));
         // a record holds at most (slots of the tile) table entries: bound the total by the real slot count
         const size_t worst = (size_t)n_tiles * (kRecTable + 16) + 4 * (size_t)total + 4 * ((size_t)total / kAggMin) + 64;
         OAR_CUDA(sc.alloc((char **)&records_tmp, worst));
@@ -131,7 +133,7 @@ int build_tiled_layout(oar_store *s, uint32_t span)
     t.record_bytes = (uint64_t)h_counters[7] * 16u;
     t.max_rec = h_counters[8]; t.max_d = h_counters[9]; t.max_u = h_counters[10];
     if (n_tiles > 0) {
-        OAR_CUDA(cudaMalloc(&t.records, std::max<uint64_t>(t.record_bytes, 16)));
+        OAR_CUDA(dmalloc(&t.records, std::max<uint64_t>(t.record_bytes, 16), st));
         OAR_CUDA(cudaMemcpyAsync(t.records, records_tmp, t.record_bytes, cudaMemcpyDeviceToDevice, st));
         OAR_CUDA(cudaStreamSynchronize(st));
     }

@@ -5,14 +5,15 @@
 
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the definitions:
 
-  N = 1   step = one complete EM (em::em_par semantics, stop rule niter > 1) on the
-          resident store; value = E+M iterations / s.  A short bootstrap leg gives
-          replicates/s at one GPU (key "bootstrap").
-  N > 1   torchrun, one process per GPU.  Rank 0 generates the store and uploads it,
-          ONE NCCL broadcast distributes it (timed, "bcast_ms"), then every rank runs
-          K bootstrap replicates of its shard (global replicate g on rank g mod N, no
-          collective on the data path).  value = total E+M iterations / s over all
-          ranks (max-over-ranks time); "bootstrap.replicates_per_sec" = N*K / time.
+  value   step = one complete EM (em::em_par semantics, stop rule niter > 1) on the store
+          resident in HBM; value = E+M iterations / s.  At N > 1 (torchrun, one process
+          per GPU) rank 0 generates the store and uploads it, ONE NCCL broadcast
+          distributes it (timed, "bcast_ms") and every rank runs the same K EMs on its
+          copy (a single EM does not shard: replicas only); value = total iterations/s
+          over all ranks with the max-over-ranks time.
+  bootstrap  the path that shards: max(K,8) replicates per rank, global replicate g on
+          rank g mod N, no collective on the data path; "bootstrap.replicates_per_sec"
+          = all replicates / max-over-ranks time, reported at every N.
   e2e     the same through the public API with HOST (pinned) buffers: store upload +
           layout + EM + download of the counts inside the timed region.
   --impl reference   the CPU restatement of the reference's rayon em_par
@@ -236,11 +237,9 @@ def run_gpu(args):
 
     def step(i):
         nonlocal launches, iters
-        if multi:
-            g = rank + i * world   # global replicate id: rank r owns r, r+G, ...
-            out, nit = ds.bootstrap(1, seed, first_replicate=g, replicate_stride=1, out=out_host.reshape(1, -1))
-        else:
-            ds.em(max_iter=1000, conv_thresh=1e-3, min_iter=1, out=out_host)
+        # every rank runs the same complete EM on its resident copy of the store (a single EM does not
+        # shard: replicas only); the sharded bootstrap path is timed separately below
+        ds.em(max_iter=1000, conv_thresh=1e-3, min_iter=1, out=out_host)
         c = ds.counters()
         launches += c["launches"]; iters += c["sweeps"]
 
@@ -281,20 +280,18 @@ def run_gpu(args):
             except Exception:
                 pass
 
-    # ---- bootstrap replicates/s -------------------------------------------------------------------
-    boot = None
-    if multi:
-        boot = {"replicates_per_sec": world * K / elapsed, "replicates": world * K, "bcast_ms": bcast_ms,
-                "store_build_ms": build_ms, "min_iter": 50}
-    else:
-        B = 2
-        ds.bootstrap(1, seed, first_replicate=1000)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        _, nit = ds.bootstrap(B, seed, first_replicate=0)
-        torch.cuda.synchronize()
-        dtb = time.perf_counter() - t0
-        boot = {"replicates_per_sec": B / dtb, "replicates": B, "niter": [int(x) for x in nit], "min_iter": 50}
+    # ---- bootstrap replicates/s: global replicate g runs on rank g mod N (no data-path collective) ----
+    B = max(K, 8)                       # replicates per rank (several, so that unequal iteration counts average out)
+    ds.bootstrap(1, seed, first_replicate=100000 + rank)     # warm-up (weights buffers, weighted graph)
+    barrier()
+    t0 = time.perf_counter()
+    _, nit = ds.bootstrap(B, seed, first_replicate=rank, replicate_stride=world)
+    boot_launches = ds.counters()["launches"]
+    barrier()
+    dtb = max_over_ranks(time.perf_counter() - t0)
+    boot_iters = sum_over_ranks(float(nit.sum() + 2 * B))
+    boot = {"replicates_per_sec": world * B / dtb, "replicates": world * B, "iterations_per_sec": boot_iters / dtb,
+            "niter_rank0": [int(x) for x in nit], "min_iter": 50, "bcast_ms": bcast_ms, "gpu_launches_rank0": int(boot_launches)}
 
     # ---- e2e: host (pinned) buffers through the public API ------------------------------------------
     e2e = None
@@ -318,7 +315,7 @@ def run_gpu(args):
         dte = elapsed + (bcast_ms + build_ms) * 1e-3
         e2e = {"value": total_iters / dte, "unit": "iterations/s",
                "h2d_bytes_per_step": store_bytes / K, "d2h_bytes_per_step": 8 * n_txps,
-               "includes": "store upload on rank 0 + NCCL broadcast + per-rank layout build (once) + K replicate EMs with counts download"}
+               "includes": "store upload on rank 0 + NCCL broadcast + per-rank layout build (once) + K EMs per rank with counts download"}
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload ----------------------
     cpu = None
@@ -334,9 +331,9 @@ def run_gpu(args):
             "steps": K, "warmup": W, "ms_per_step": 1e3 * elapsed / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload], "n_reads": n_reads, "nnz": nnz, "n_txps": n_txps,
-                       "step": ("one bootstrap replicate EM per rank (min_iter 50)" if multi else "one EM to convergence (em_par rule, min_iter 1, thr 1e-3)"),
+                       "step": "one EM to convergence per rank (em_par rule, min_iter 1, thr 1e-3); bootstrap replicates timed separately",
                        "l2": "inputs (0.66 GB/sweep) exceed the 126 MB L2; no flush needed",
-                       "parallelism": f"replicates sharded over {world} GPU(s), no data-path collective",
+                       "parallelism": f"{world} GPU(s): EM replicas for `value`, bootstrap replicates sharded g mod N; no data-path collective",
                        "layout": layout},
             "iterations_per_step": total_iters / (K * world),
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(total_launches),

@@ -6,6 +6,7 @@
 NVCC      ?= nvcc
 # the image exports CC=/opt/gcc/bin/gcc, a wrapper that cannot find libgomp.spec; use the system gcc
 HOSTCC    := $(shell [ -x /usr/bin/gcc ] && echo /usr/bin/gcc || echo gcc)
+HOSTCXX   := $(shell [ -x /usr/bin/g++ ] && echo /usr/bin/g++ || echo g++)
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wextra -Xptxas -v --expt-relaxed-constexpr
 CFLAGS    := -O3 -std=gnu11 -fPIC -Wall -Wextra -fopenmp
@@ -17,7 +18,7 @@ CU_HDRS   := $(wildcard $(CSRC)/*.cuh) include/oarfish_em.h
 
 all: product oracle
 
-product: $(LIBDIR)/liboarfish_em.so $(LIBDIR)/liboarsynth.so
+product: $(LIBDIR)/liboarfish_em.so $(LIBDIR)/liboarsynth.so $(LIBDIR)/host_mirror_test
 
 $(LIBDIR)/liboarfish_em.so: $(CU_SRCS) $(CU_HDRS)
 	@mkdir -p $(LIBDIR)
@@ -27,12 +28,16 @@ $(LIBDIR)/liboarsynth.so: $(CSRC)/synth.c
 	@mkdir -p $(LIBDIR)
 	$(HOSTCC) $(CFLAGS) -shared -o $@ $< -lm
 
+# C++ host mirror of the reference interface (include/oarfish_em.hpp) + its test driver
+$(LIBDIR)/host_mirror_test: tests/cpp/host_mirror_test.cpp include/oarfish_em.hpp include/oarfish_em.h $(LIBDIR)/liboarfish_em.so
+	$(HOSTCXX) -O2 -std=c++17 -Wall -Wextra -Iinclude -o $@ $< -L$(LIBDIR) -loarfish_em -Wl,-rpath,'$$ORIGIN'
+
 oracle: oracle/liboarfish_oracle.so
 
 oracle/liboarfish_oracle.so: oracle/em_oracle.c oracle/em_par_port.c
 	$(HOSTCC) $(CFLAGS) -shared -o $@ $^ -lm
 
 clean:
-	rm -f $(LIBDIR)/*.so $(LIBDIR)/ptxas.log oracle/*.so
+	rm -f $(LIBDIR)/*.so $(LIBDIR)/ptxas.log $(LIBDIR)/host_mirror_test oracle/*.so
 
 .PHONY: all product oracle clean

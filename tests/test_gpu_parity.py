@@ -203,6 +203,28 @@ def test_reference_interface_mirror(DS, oracle_mod, tiny_store):
     assert all(abs(r.sum() - s.n_reads) < 1e-6 * s.n_reads for r in reps)
 
 
+def test_cpp_host_mirror_matches_oracle(DS, oracle_mod, tiny_store, tmp_path):
+    """The C++ host layer (include/oarfish_em.hpp) driven like bulk.rs drives src/em.rs."""
+    import subprocess
+    s = tiny_store
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oarfish_b200", "lib", "host_mirror_test")
+    store_bin, out_bin = tmp_path / "store.bin", tmp_path / "out.bin"
+    with open(store_bin, "wb") as f:
+        f.write(np.array([s.n_reads, s.nnz, s.n_txps], dtype=np.uint64).tobytes())
+        f.write(s.row_ptr.tobytes()); f.write(s.txp_id.tobytes()); f.write(s.prob.tobytes())
+    res = subprocess.run([exe, str(store_bin), str(out_bin), "11"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr
+    out = np.fromfile(out_bin, dtype=np.float64).reshape(4, s.n_txps)
+    want50, *_ = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps, min_iter=50)
+    want1, *_ = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps, min_iter=1)
+    assert_counts_close(out[0], want50)
+    assert_counts_close(out[1], want1)
+    with DS(s.row_ptr, s.txp_id, s.prob, s.n_txps) as ds:      # same seed through the Python binding
+        ref, _ = ds.bootstrap(2, 11)
+    assert_counts_close(out[2], ref[0]); assert_counts_close(out[3], ref[1])
+
+
 def test_device_resident_inputs_and_outputs(DS, oracle_mod, tiny_store):
     import torch
     s = tiny_store

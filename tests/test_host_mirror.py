@@ -51,3 +51,14 @@ def test_model_coverage_exports_aux():
     np.testing.assert_array_equal(aux, [0.5, 0.25, 1.0])
     s2 = InMemoryAlignmentStore(AlignmentFilters(model_coverage=False))
     assert s2.csr()[3] is None
+
+
+def test_cpp_host_mirror_selfcheck():
+    """include/oarfish_em.hpp: the C++ mirror of em::em / em_par / bootstrap and of the store types."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oarfish_b200", "lib", "host_mirror_test")
+    assert os.path.exists(exe), "run `make product`"
+    res = subprocess.run([exe, "--selfcheck"], capture_output=True, text=True, timeout=60)
+    assert res.returncode == 0 and "selfcheck ok" in res.stdout

@@ -62,3 +62,20 @@ def test_cpp_host_mirror_selfcheck():
     assert os.path.exists(exe), "run `make product`"
     res = subprocess.run([exe, "--selfcheck"], capture_output=True, text=True, timeout=60)
     assert res.returncode == 0 and "selfcheck ok" in res.stdout
+
+
+def test_oarstore_roundtrip(tmp_path):
+    from oarfish_b200 import storefile, synth
+    s = synth.make_config("tiny")
+    aux = np.linspace(0.1, 1.0, s.nnz)
+    for a in (None, aux):
+        p = str(tmp_path / ("a.oarstore" if a is None else "b.oarstore"))
+        storefile.write_store(p, s.row_ptr, s.txp_id, s.prob, s.n_txps, aux=a)
+        rp, tx, pr, m, ax = storefile.read_store(p)
+        assert m == s.n_txps and np.array_equal(rp, s.row_ptr) and np.array_equal(tx, s.txp_id) and np.array_equal(pr, s.prob)
+        assert (ax is None) == (a is None) and (a is None or np.array_equal(ax, a))
+    with open(tmp_path / "bad", "wb") as f:
+        f.write(b"x" * 100)
+    import pytest
+    with pytest.raises(ValueError):
+        storefile.read_store(str(tmp_path / "bad"))

@@ -146,6 +146,21 @@ int oar_em_batched(oar_store *store, const uint64_t *cell_row_ptr, uint32_t n_ce
                    uint64_t *out_nnz, uint32_t *out_niter);
 
 /*
+ * The bulk coverage model (--model-coverage; bulk.rs:103-108) computed on the device from the resident
+ * store: add_interval histograms (src/util/oarfish_types.rs:496-537), logistic_prob
+ * (src/util/logistic_probability.rs:40-79) and normalize_read_probs
+ * (src/util/normalize_probability.rs:5-74).  The result (== InMemoryAlignmentStore.coverage_probabilities)
+ * becomes the store's aux factor, so a following oar_em / oar_bootstrap uses it (em.rs:108).
+ *   aln_start, aln_end  nnz u32 == AlnInfo.start / .end, host or device
+ *   txp_len             M u32 == TranscriptInfo.len
+ *   bin_width           --bin-width (default 100); growth_rate: --growth-rate (default 2.0)
+ *   out_aux_or_null     nnz f64 (host or device): the coverage probabilities, for the caller's records
+ */
+int oar_store_coverage_model(oar_store *store, const uint32_t *aln_start, const uint32_t *aln_end,
+                             const uint32_t *txp_len, uint32_t bin_width, double growth_rate,
+                             double *out_aux_or_null);
+
+/*
  * Read-level assignment probabilities with the final counts: the inner loop of
  * write_out_prob (src/util/write_function.rs:283-332).  out_prob[j] (nnz f64, host
  * or device) = the alignment's probability, clamped to [0,1], dropped (0) below

@@ -44,6 +44,7 @@ ABI = {
     "oar_bootstrap_weights": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_double, C.c_uint32, _vp, _vp]),
     "oar_bootstrap_sample_weights": (C.c_int, [_vp, C.c_uint64, C.c_uint32, _vp]),
     "oar_em_batched": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_double, C.c_uint32, _vp, _vp, _vp, C.c_uint64, _u64p, _vp]),
+    "oar_store_coverage_model": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint32, C.c_double, _vp]),
     "oar_posteriors": (C.c_int, [_vp, _vp, C.c_double, _vp, _vp]),
     "oar_aux_counts": (C.c_int, [_vp, _vp, _vp]),
     "oar_store_layout_info": (C.c_int, [_vp, _u64p]),

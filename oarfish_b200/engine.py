@@ -180,6 +180,18 @@ class DeviceStore:
         n = int(nnz.value)
         return cell_ptr, txp[:n].copy(), val[:n].copy(), niter[:n_cells]
 
+    def coverage_model(self, aln_start, aln_end, txp_len, bin_width: int = 100, growth_rate: float = 2.0):
+        """--model-coverage (bulk.rs:103-108): computes coverage_probabilities on the device, installs them as the
+        store's aux factor and returns them (f64[nnz])."""
+        sp, n_s, _ = _addr(np.ascontiguousarray(aln_start, dtype=np.uint32), np.dtype(np.uint32), "aln_start")
+        ep, n_e, _k = _addr(np.ascontiguousarray(aln_end, dtype=np.uint32), np.dtype(np.uint32), "aln_end")
+        lp, n_l, _k2 = _addr(np.ascontiguousarray(txp_len, dtype=np.uint32), np.dtype(np.uint32), "txp_len")
+        if n_s != self.nnz or n_e != self.nnz or n_l != self.n_txps:
+            raise ValueError("aln_start/aln_end need nnz elements, txp_len n_txps")
+        out = np.zeros(max(self.nnz, 1), dtype=np.float64)
+        check(self._lib.oar_store_coverage_model(self._h, sp, ep, lp, int(bin_width), float(growth_rate), out.ctypes.data))
+        return out[:self.nnz]
+
     def posteriors(self, counts, display_thresh: float = 0.0):
         """write_out_prob's inner loop (write_function.rs:283-332): (per-alignment probs f64[nnz], kept u32[N])."""
         cp, n_c, _ = _addr(np.ascontiguousarray(counts, dtype=np.float64), np.dtype(np.float64), "counts")

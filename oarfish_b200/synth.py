@@ -89,3 +89,15 @@ def make_cells(cell_reads, n_txps: int, avg_aln: float, seed: int):
     txp = np.concatenate(txs) if txs else np.zeros(0, np.uint32)
     prob = np.concatenate(prs) if prs else np.zeros(0, np.float32)
     return SynthStore(row_ptr, txp, prob, n_txps, None, None), cell_row_ptr
+
+
+def make_coordinates(store: SynthStore, seed: int):
+    """Synthetic transcript lengths and alignment intervals for the coverage model (AlnInfo.start/.end,
+    TranscriptInfo.len): lengths in [300, 6000], each alignment a random sub-interval covering 30-100 %."""
+    rng = np.random.default_rng(seed)
+    txp_len = rng.integers(300, 6000, size=store.n_txps, dtype=np.int64)
+    L = txp_len[store.txp_id.astype(np.int64)]
+    span = np.maximum((rng.uniform(0.3, 1.0, size=store.nnz) * L).astype(np.int64), 1)
+    start = (rng.uniform(0.0, 1.0, size=store.nnz) * (L - span + 1)).astype(np.int64)
+    end = np.minimum(start + span, L)
+    return start.astype(np.uint32), end.astype(np.uint32), txp_len.astype(np.uint32)

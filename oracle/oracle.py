@@ -36,6 +36,8 @@ def lib() -> C.CDLL:
         L.oracle_posteriors.argtypes = [_vp, _vp, _vp, _vp, C.c_uint64, _vp, C.c_double, _vp, _vp]
         L.oracle_aux_counts.restype = None
         L.oracle_aux_counts.argtypes = [_vp, _vp, C.c_uint64, C.c_uint32, _vp, _vp]
+        L.oracle_coverage_model.restype = None
+        L.oracle_coverage_model.argtypes = [_vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64, _vp, C.c_uint32, C.c_uint32, C.c_double, _vp]
         L.port_num_threads.restype = C.c_int
         L.port_store_create.restype = _vp
         L.port_store_create.argtypes = [_vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64, C.c_uint32]
@@ -110,6 +112,16 @@ def aux_counts(row_ptr, txp, n_txps):
     u = np.zeros(n_txps, dtype=np.uint32); t = np.zeros(n_txps, dtype=np.uint32)
     lib().oracle_aux_counts(_p(row_ptr), _p(txp), len(row_ptr) - 1, n_txps, _p(u), _p(t))
     return u, t
+
+
+def coverage_model(row_ptr, txp, start, end, txp_len, bin_width=100, growth_rate=2.0):
+    """--model-coverage stage (bulk.rs:103-108) -> coverage_probabilities f64[nnz]."""
+    row_ptr = _c(row_ptr, np.uint64); txp = _c(txp, np.uint32); start = _c(start, np.uint32); end = _c(end, np.uint32)
+    txp_len = _c(txp_len, np.uint32)
+    out = np.zeros(len(txp), dtype=np.float64)
+    lib().oracle_coverage_model(_p(row_ptr), _p(txp), _p(start), _p(end), len(row_ptr) - 1, len(txp), _p(txp_len), len(txp_len),
+                                bin_width, growth_rate, _p(out))
+    return out
 
 
 class PortStore:

@@ -282,6 +282,28 @@ def test_posteriors_and_aux_counts(DS, oracle_mod, small_store):
         assert t.sum() == s.nnz
 
 
+def test_coverage_model_matches_oracle(DS, oracle_mod, small_store):
+    """--model-coverage (bulk.rs:103-108) on the device, then the EM with that factor (em.rs:108)."""
+    from oarfish_b200 import synth
+    s = small_store
+    start, end, txp_len = synth.make_coordinates(s, 77)
+    want_aux = oracle_mod.coverage_model(s.row_ptr, s.txp_id, start, end, txp_len, bin_width=100, growth_rate=2.0)
+    with DS(s.row_ptr, s.txp_id, s.prob, s.n_txps) as ds:
+        aux = ds.coverage_model(start, end, txp_len, bin_width=100, growth_rate=2.0)
+        # histogram bins are summed with f64 atomics and then rounded to f32 like the reference does
+        # (oarfish_types.rs:477), so a last-bit difference can move a bin count by one f32 ulp: 1e-6 tolerance
+        np.testing.assert_allclose(aux, want_aux, rtol=1e-6, atol=1e-12)
+        sums = np.add.reduceat(aux, s.row_ptr[:-1].astype(np.int64))
+        np.testing.assert_allclose(sums, 1.0, rtol=1e-12)
+        # the EM now runs with the coverage factor: exact parity against the oracle fed the same factor
+        for kernel in KERNELS:
+            ds.set_kernel(kernel)
+            r = ds.em(min_iter=1)
+            want, niter, _, _ = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps, min_iter=1, cov=aux)
+            assert r.niter == niter
+            assert_counts_close(r.counts, want)
+
+
 def test_full_size_properties_c3(DS):
     """BASELINE config 3 (10M reads x 200k transcripts): size-independent properties."""
     from oarfish_b200 import synth

@@ -218,3 +218,29 @@ def test_posteriors_and_aux_counts_known_answers(oracle_mod):
     assert list(kept) == [1, 2, 1, 1]
     u, t = oracle_mod.aux_counts(rp, tx, 3)
     assert list(u) == [1, 0, 1] and list(t) == [2, 2, 2]
+
+
+def test_coverage_model_known_answers(oracle_mod):
+    """bulk.rs:103-108: add_interval -> logistic_prob -> normalize_read_probs on hand-computable inputs."""
+    # one transcript of 300 nt, bin width 100, one read covering it entirely: all bins equal -> logistic(0) = 0.5,
+    # a single-alignment read normalises to 1
+    rp = np.array([0, 1], dtype=np.uint64)
+    out = oracle_mod.coverage_model(rp, [0], [0], [300], [300], bin_width=100, growth_rate=2.0)
+    np.testing.assert_allclose(out, [1.0])
+    # two transcripts; read 0 hits both, reads 1..4 pile onto the first 100 nt of transcript 0 only
+    rows_t = [0, 1, 0, 0, 0, 0]
+    start = [0, 0, 0, 0, 0, 0]
+    end = [300, 300, 150, 150, 150, 150]
+    rp = np.array([0, 2, 3, 4, 5, 6], dtype=np.uint64)
+    out = oracle_mod.coverage_model(rp, rows_t, start, end, [300, 300], bin_width=100, growth_rate=2.0)
+    # transcript 0 bins: [0,100) gets 1 + 4*1 = 5, [100,200) gets 1 (end bin of the short reads is never visited),
+    # [200,300) gets 1; total_weight 5 -> +0.05 each.  Transcript 1 bins: 1,1,1 (+0.01): flat -> 0.5 everywhere.
+    c = np.array([5.05, 1.05, 1.05], dtype=np.float32).astype(np.float64)
+    exp = c.sum() / 3
+    p0 = np.clip(1 / (1 + np.exp(-2.0 * (exp - c) / exp)), 1e-8, 0.99999)
+    e_t0_full = (p0[0] + p0[1]) / 2          # bins 0,1 visited (start_bin..end_bin excludes bin 2), weights 1,1
+    e_t1_full = 0.5
+    e_t0_short = p0[0]                        # start_bin 0, end_bin 1 -> only bin 0, w = 1
+    want = [e_t0_full / (e_t0_full + e_t1_full), e_t1_full / (e_t0_full + e_t1_full), 1.0, 1.0, 1.0, 1.0]
+    np.testing.assert_allclose(out, want, rtol=1e-12)
+    assert e_t0_short > 0   # (single-alignment reads normalise to 1 whatever their coverage probability)

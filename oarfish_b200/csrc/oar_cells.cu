@@ -17,6 +17,8 @@
 #include <algorithm>
 #include <vector>
 
+#include <cstdlib>
+
 #include "oar_store.cuh"
 
 namespace oar {
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(kThreads) cell_localize(const uint32_t *__rest
             }
             for (uint32_t j = a0 + threadIdx.x; j < a1; j += kThreads) {
                 const uint32_t t = txp[j];
-                lid[j] = pre[t >> 5] + __popc(bits[t >> 5] & ((1u << (t & 31)) - 1u));
+                lid[j] = (uint32_t)d0 + pre[t >> 5] + __popc(bits[t >> 5] & ((1u << (t & 31)) - 1u));
             }
         }
         __syncthreads();
@@ -143,9 +145,9 @@ __global__ void __launch_bounds__(kThreads) cell_em(const uint32_t *__restrict__
         const uint32_t r0 = (uint32_t)cell_rows[c], r1 = (uint32_t)cell_rows[c + 1];
         const uint64_t d0 = cell_d[c];
         const uint32_t L = (uint32_t)(cell_d[c + 1] - d0);
-        double *prev = bufA + d0, *curr = bufB + d0;
+        double *prev = bufA, *curr = bufB;   // alignments carry global compact ids (cell offset + local index)
         const double avg = (double)(r1 - r0) / (double)n_txps;    // em.rs:154,165: N_cell / M (full transcriptome)
-        for (uint32_t i = threadIdx.x; i < L; i += kThreads) { prev[i] = avg; curr[i] = 0.0; }
+        for (uint32_t i = threadIdx.x; i < L; i += kThreads) { prev[d0 + i] = avg; curr[d0 + i] = 0.0; }
         __threadfence();
         __syncthreads();
         uint32_t niter = 0;
@@ -155,9 +157,9 @@ __global__ void __launch_bounds__(kThreads) cell_em(const uint32_t *__restrict__
             __syncthreads();
             double m = 0.0;
             for (uint32_t i = threadIdx.x; i < L; i += kThreads) {
-                const double pc = ld_cg(prev + i), cc = ld_cg(curr + i);
+                const double pc = ld_cg(prev + d0 + i), cc = ld_cg(curr + d0 + i);
                 if (pc > OAR_MIN_READ_THRESH) { const double rd = (cc - pc) / pc; m = rd > m ? rd : m; }   // em.rs:194-201
-                prev[i] = 0.0;                                                                               // swap + fill(0)
+                prev[d0 + i] = 0.0;                                                                          // swap + fill(0)
             }
             for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, m, o); m = t > m ? t : m; }
             if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
@@ -175,16 +177,116 @@ __global__ void __launch_bounds__(kThreads) cell_em(const uint32_t *__restrict__
             ++niter;
         }
         for (uint32_t i = threadIdx.x; i < L; i += kThreads)
-            if (ld_cg(prev + i) < OAR_MIN_READ_THRESH) prev[i] = 0.0;   // em.rs:238-242
+            if (ld_cg(prev + d0 + i) < OAR_MIN_READ_THRESH) prev[d0 + i] = 0.0;   // em.rs:238-242
         __threadfence();
         __syncthreads();
         cell_sweep<HAS_AUX>(row_ptr, lid, prob, aux, r0, r1, prev, curr);   // em.rs:245-252
         __threadfence();
         __syncthreads();
-        for (uint32_t i = threadIdx.x; i < L; i += kThreads) out_val[d0 + i] = ld_cg(curr + i);
+        for (uint32_t i = threadIdx.x; i < L; i += kThreads) out_val[d0 + i] = ld_cg(curr + d0 + i);
         if (threadIdx.x == 0) out_niter[c] = niter;
         __syncthreads();
     }
+}
+
+
+// ---- batched cells on the tiled sweep -----------------------------------------------------------
+// With (cell, transcript) pairs as the parameter space the batch is ONE block-diagonal EM: the tiled sweep
+// runs over all reads of all cells at once; only the convergence logic is per cell.
+enum : uint32_t { kRun = 0, kFinal = 1, kDone = 2 };
+struct CellState { uint32_t niter; uint32_t phase; };
+struct Chunk { uint32_t cell; uint32_t first; uint64_t begin, end; };   // a slice of one cell's id range
+
+__global__ void cells_init(const uint64_t *__restrict__ cell_rows, const uint64_t *__restrict__ cell_d, uint32_t n_cells,
+                           uint32_t n_txps, uint32_t max_iter, double *__restrict__ A, double *__restrict__ B,
+                           CellState *__restrict__ cs)
+{
+    for (uint32_t c = blockIdx.x; c < n_cells; c += gridDim.x) {
+        const uint64_t d0 = cell_d[c], d1 = cell_d[c + 1];
+        double avg = (double)(cell_rows[c + 1] - cell_rows[c]) / (double)n_txps;   // em.rs:154,165
+        if (max_iter == 0 && avg < OAR_MIN_READ_THRESH) avg = 0.0;               // no loop: threshold the start (em.rs:238)
+        for (uint64_t i = d0 + threadIdx.x; i < d1; i += blockDim.x) { A[i] = avg; B[i] = 0.0; }
+        if (threadIdx.x == 0) { cs[c].niter = 0; cs[c].phase = max_iter == 0 ? kFinal : kRun; }
+    }
+}
+
+// After a sweep prev -> curr, pass 1: per-cell max signed relative difference (em.rs:194-201), one CTA per
+// chunk of a cell's ids, combined with an atomic max on the bits of the (non-negative) f64.
+__global__ void __launch_bounds__(256) cells_reduce(const double *__restrict__ prev, const double *__restrict__ curr,
+                                                    const Chunk *__restrict__ chunks, uint32_t n_chunks,
+                                                    const CellState *__restrict__ cs, unsigned long long *__restrict__ rel_bits,
+                                                    const OarEmState *__restrict__ st)
+{
+    if (st->done) return;
+    __shared__ double s_red[8];
+    for (uint32_t k = blockIdx.x; k < n_chunks; k += gridDim.x) {
+        const Chunk ch = chunks[k];
+        if (cs[ch.cell].phase != kRun) continue;
+        double m = 0.0;
+        for (uint64_t i = ch.begin + threadIdx.x; i < ch.end; i += blockDim.x) {
+            const double pc = prev[i], cc = curr[i];
+            if (pc > OAR_MIN_READ_THRESH) { const double rd = (cc - pc) / pc; m = rd > m ? rd : m; }
+        }
+        for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, m, o); m = t > m ? t : m; }
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double b = 0.0;
+            for (int w = 0; w < 8; ++w) b = s_red[w] > b ? s_red[w] : b;
+            if (b > 0.0) atomicMax(rel_bits + ch.cell, (unsigned long long)__double_as_longlong(b));
+        }
+        __syncthreads();
+    }
+}
+
+// Pass 2: every chunk derives its cell's decision from the (read-only) old state and the reduced rel-diff --
+// stop rule and niter (em.rs:212-218, :181) -- and applies it to its ids: swap + zero; on a stop also zero the
+// small counts (em.rs:238-242) so that the next sweep is the final one; after that sweep the counts are the
+// cell's result.  The first chunk of a cell writes the new state (double buffered, so nothing races).
+__global__ void __launch_bounds__(256) cells_apply(double *__restrict__ prev, double *__restrict__ curr,
+                                                   const Chunk *__restrict__ chunks, uint32_t n_chunks, uint32_t n_cells,
+                                                   uint32_t max_iter, double thr, uint32_t min_iter,
+                                                   const CellState *__restrict__ cs_old, CellState *__restrict__ cs_new,
+                                                   unsigned long long *__restrict__ rel_bits, double *__restrict__ result,
+                                                   uint32_t *__restrict__ done_count, OarEmState *st)
+{
+    if (st->done) return;
+    for (uint32_t k = blockIdx.x; k < n_chunks; k += gridDim.x) {
+        const Chunk ch = chunks[k];
+        const CellState old = cs_old[ch.cell];
+        CellState neu = old;
+        if (old.phase == kDone) {
+            if (ch.first && threadIdx.x == 0) cs_new[ch.cell] = neu;
+            continue;                                                   // buffers are zero: the sweep adds nothing
+        }
+        if (old.phase == kFinal) {
+            for (uint64_t i = ch.begin + threadIdx.x; i < ch.end; i += blockDim.x) { result[i] = curr[i]; curr[i] = 0.0; prev[i] = 0.0; }
+            neu.phase = kDone;
+            if (ch.first && threadIdx.x == 0) {
+                cs_new[ch.cell] = neu;
+                if (atomicAdd(done_count, 1u) + 1u == n_cells) { __threadfence(); st->done = 1; }
+            }
+            continue;
+        }
+        const double rel = __longlong_as_double((long long)rel_bits[ch.cell]);
+        bool stop = rel < thr && old.niter > min_iter;                   // em.rs:212
+        if (!stop) { neu.niter = old.niter + 1; stop = neu.niter >= max_iter; }   // em.rs:218, :181
+        if (stop) neu.phase = kFinal;
+        for (uint64_t i = ch.begin + threadIdx.x; i < ch.end; i += blockDim.x) {
+            prev[i] = 0.0;                                               // swap + fill(0)
+            if (stop && curr[i] < OAR_MIN_READ_THRESH) curr[i] = 0.0;    // em.rs:238-242 on the new prev
+        }
+        if (ch.first && threadIdx.x == 0) cs_new[ch.cell] = neu;
+    }
+}
+
+// rel_bits must be zero before the next reduce; done in its own tiny pass so that no chunk of cells_apply can
+// still be reading it.
+__global__ void cells_clear_rel(unsigned long long *__restrict__ rel_bits, uint32_t n_cells, const OarEmState *st)
+{
+    if (st->done) return;
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n_cells) rel_bits[c] = 0ull;
 }
 
 }  // namespace cells
@@ -258,6 +360,85 @@ extern "C" int oar_em_batched(oar_store *s, const uint64_t *cell_row_ptr, uint32
         cells::cell_localize<false><<<grid, cells::kThreads, dyn, st>>>(s->d_row_ptr, s->d_txp, d_rows, n_cells, s->n_txps, words,
                                                                         d_scratch, d_cd, d_ctx, d_lid, use_smem);
         OAR_CUDA(cudaGetLastError());
+        // preferred: one block-diagonal EM over (cell, transcript) pairs on the tiled sweep
+        const char *ct = getenv("OAR_CELLS_TILED");
+        bool tiled_done = false;
+        if (!(ct && ct[0] == '0') && total > 0 && total < (1ull << 28)) {
+            oar_store *sub = nullptr;
+            int rc = substore_create(s, d_lid, (uint32_t)total, &sub);
+            if (rc != OAR_OK) return rc;
+            // d_lid now belongs to the sub-store
+            sc.p.erase(std::remove(sc.p.begin(), sc.p.end(), (void *)d_lid), sc.p.end());
+            struct SubGuard { oar_store *p; ~SubGuard() { oar_store_destroy(p); } } sg{sub};
+            // chunks of at most 4096 ids, never crossing a cell
+            std::vector<cells::Chunk> h_chunks;
+            for (uint32_t c = 0; c < n_cells; ++c) {
+                uint64_t b = h_cd[c]; const uint64_t e = h_cd[c + 1];
+                bool first = true;
+                do {
+                    const uint64_t e2 = std::min<uint64_t>(e, b + 4096);
+                    h_chunks.push_back(cells::Chunk{c, first ? 1u : 0u, b, e2});
+                    first = false; b = e2;
+                } while (b < e);
+            }
+            const uint32_t n_chunks = (uint32_t)h_chunks.size();
+            cells::CellState *d_cs = nullptr; uint32_t *d_done = nullptr; cells::Chunk *d_chunks = nullptr;
+            unsigned long long *d_rel = nullptr;
+            OAR_CUDA(dalloc((void **)&d_cs, sizeof(cells::CellState) * 2 * n_cells));
+            OAR_CUDA(dalloc((void **)&d_done, sizeof(uint32_t) * 4));
+            OAR_CUDA(dalloc((void **)&d_chunks, sizeof(cells::Chunk) * n_chunks));
+            OAR_CUDA(dalloc((void **)&d_rel, sizeof(unsigned long long) * n_cells));
+            OAR_CUDA(cudaMemcpyAsync(d_chunks, h_chunks.data(), sizeof(cells::Chunk) * n_chunks, cudaMemcpyHostToDevice, st));
+            OAR_CUDA(cudaMemsetAsync(d_done, 0, sizeof(uint32_t) * 4, st));
+            OAR_CUDA(cudaMemsetAsync(d_rel, 0, sizeof(unsigned long long) * n_cells, st));
+            OAR_CUDA(cudaMemsetAsync(sub->d_state, 0, sizeof(OarEmState), st));
+            const int gridc = (int)std::max<uint32_t>(1, std::min<uint32_t>(n_cells, (uint32_t)s->sm_count * 16));
+            const int gridk = (int)std::max<uint32_t>(1, std::min<uint32_t>(n_chunks, (uint32_t)s->sm_count * 8));
+            cells::cells_init<<<gridc, 128, 0, st>>>(d_rows, d_cd, n_cells, s->n_txps, max_iter, d_a, d_b, d_cs);
+            OAR_CUDA(cudaGetLastError());
+            // a CUDA graph of 16 iterations: sweep a->b, update, sweep b->a, update, ...  (cell states ping-pong)
+            cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+            OAR_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            cudaError_t e = cudaSuccess;
+            for (int it = 0; it < 16 && e == cudaSuccess; ++it) {
+                double *pv = (it & 1) ? d_b : d_a, *cr = (it & 1) ? d_a : d_b;
+                cells::CellState *cs_old = d_cs + (it & 1) * n_cells, *cs_new = d_cs + ((it + 1) & 1) * n_cells;
+                e = sweep_enqueue(sub, pv, cr, sub->d_state, 1);
+                if (e != cudaSuccess) break;
+                cells::cells_reduce<<<gridk, 256, 0, st>>>(pv, cr, d_chunks, n_chunks, cs_old, d_rel, sub->d_state);
+                cells::cells_apply<<<gridk, 256, 0, st>>>(pv, cr, d_chunks, n_chunks, n_cells, max_iter, conv_thresh, min_iter,
+                                                         cs_old, cs_new, d_rel, d_val, d_done, sub->d_state);
+                cells::cells_clear_rel<<<(n_cells + 255) / 256, 256, 0, st>>>(d_rel, n_cells, sub->d_state);
+                e = cudaGetLastError();
+            }
+            cudaError_t e2 = cudaStreamEndCapture(st, &graph);
+            if (e != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return cuda_fail(e, "cells graph capture"); }
+            if (e2 != cudaSuccess) return cuda_fail(e2, "cudaStreamEndCapture");
+            e = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate");
+            struct ExecGuard { cudaGraphExec_t x; ~ExecGuard() { cudaGraphExecDestroy(x); } } eg{exec};
+            uint64_t launched = 0;
+            for (;;) {
+                OAR_CUDA(cudaGraphLaunch(exec, st));
+                launched += 64;
+                OAR_CUDA(cudaMemcpyAsync(&sub->h_state[0], sub->d_state, sizeof(OarEmState), cudaMemcpyDeviceToHost, st));
+                OAR_CUDA(cudaStreamSynchronize(st));
+                if (sub->h_state[0].done) break;
+            }
+            s->counters[0] += launched + 3;
+            // per-cell iteration counts
+            std::vector<cells::CellState> h_cs(n_cells);
+            // 16 iterations per graph launch: the live state is back in buffer 0 (a finished batch stops updating both)
+            OAR_CUDA(cudaMemcpyAsync(h_cs.data(), d_cs, sizeof(cells::CellState) * n_cells, cudaMemcpyDeviceToHost, st));
+            OAR_CUDA(cudaStreamSynchronize(st));
+            std::vector<uint32_t> h_nit(n_cells);
+            for (uint32_t c = 0; c < n_cells; ++c) h_nit[c] = h_cs[c].niter;
+            OAR_CUDA(cudaMemcpyAsync(d_niter, h_nit.data(), sizeof(uint32_t) * n_cells, cudaMemcpyHostToDevice, st));
+            OAR_CUDA(cudaStreamSynchronize(st));
+            tiled_done = true;
+        }
+        if (!tiled_done) {
         const int grid2 = (int)std::max<uint32_t>(1, std::min<uint32_t>(n_cells, (uint32_t)s->sm_count * 4));
         if (s->d_aux)
             cells::cell_em<true><<<grid2, cells::kThreads, 0, st>>>(s->d_row_ptr, d_lid, s->d_prob, s->d_aux, d_rows, d_cd, n_cells,
@@ -267,6 +448,7 @@ extern "C" int oar_em_batched(oar_store *s, const uint64_t *cell_row_ptr, uint32
                                                                      s->n_txps, d_a, d_b, max_iter, conv_thresh, min_iter, d_val, d_niter);
         OAR_CUDA(cudaGetLastError());
         s->counters[0] += 3;
+        }
     }
     OAR_CUDA(cudaEventRecord(s->ev[1], st));
     if (total > 0) {

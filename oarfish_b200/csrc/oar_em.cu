@@ -80,16 +80,49 @@ extern "C" void oar_store_destroy(oar_store *s)
     if (s->stream) cudaStreamSynchronize(s->stream);
     destroy_graphs(s);
     free_tiled_layout(s);
-    dfree(s->d_row_ptr, s->stream); dfree(s->d_txp, s->stream); dfree(s->d_prob, s->stream); dfree(s->d_aux, s->stream);
+    if (!s->borrowed) { dfree(s->d_row_ptr, s->stream); dfree(s->d_prob, s->stream); dfree(s->d_aux, s->stream); }
+    dfree(s->d_txp, s->stream);
     dfree(s->d_counts[0], s->stream); dfree(s->d_counts[1], s->stream); dfree(s->d_state, s->stream); dfree(s->d_weights, s->stream);
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->h_state) cudaFreeHost(s->h_state);
-    for (auto &e : s->ev) if (e) cudaEventDestroy(e);
-    for (auto &e : s->slot_ev) if (e) cudaEventDestroy(e);
-    if (s->stream) cudaStreamDestroy(s->stream);
+    if (!s->borrowed) {
+        for (auto &e : s->ev) if (e) cudaEventDestroy(e);
+        for (auto &e : s->slot_ev) if (e) cudaEventDestroy(e);
+        if (s->stream) cudaStreamDestroy(s->stream);
+    }
     delete s;
     (void)cudaGetLastError();
 }
+
+namespace oar {
+int substore_create(oar_store *parent, uint32_t *d_txp, uint32_t n_txps, oar_store **out)
+{
+    *out = nullptr;
+    oar_store *s = new (std::nothrow) oar_store();
+    if (!s) return fail(OAR_ERR_OOM, "substore_create: host allocation failed");
+    s->borrowed = true;
+    s->device = parent->device; s->sm_count = parent->sm_count; s->stream = parent->stream;
+    s->n_reads = parent->n_reads; s->nnz = parent->nnz; s->n_txps = n_txps;
+    s->d_row_ptr = parent->d_row_ptr; s->d_prob = parent->d_prob; s->d_aux = parent->d_aux; s->d_txp = d_txp;
+    for (int i = 0; i < 4; ++i) s->ev[i] = parent->ev[i];
+    for (int i = 0; i < 2; ++i) s->slot_ev[i] = parent->slot_ev[i];
+    s->ctas_per_sm = parent->ctas_per_sm;
+    int rc = [&]() -> int {
+        OAR_CUDA(dmalloc(&s->d_state, sizeof(OarEmState) * 3, s->stream));
+        OAR_CUDA(cudaMemsetAsync(s->d_state, 0, sizeof(OarEmState) * 3, s->stream));
+        OAR_CUDA(cudaMallocHost(&s->h_state, sizeof(OarEmState) * 8));
+        if (parent->tl.ready) {
+            const int rc2 = build_tiled_layout(s, parent->tl.span);
+            if (rc2 == OAR_OK) s->kernel = OAR_KERNEL_TILED;
+            else if (rc2 != OAR_ERR_UNSUPPORTED) return rc2;
+        }
+        return OAR_OK;
+    }();
+    if (rc != OAR_OK) { std::string keep = g_last_error; oar_store_destroy(s); g_last_error = keep; return rc; }
+    *out = s;
+    return OAR_OK;
+}
+}  // namespace oar
 
 extern "C" int oar_store_create(const uint64_t *row_ptr, const uint32_t *txp_id, const float *prob,
                                 const double *aux_or_null, uint64_t n_reads, uint64_t nnz,
@@ -316,6 +349,11 @@ static cudaError_t enqueue_sweep(oar_store *s, const double *prev, double *curr,
     if (t.n_tiles > 0 && t.n_fallback <= kFoldFallbackMax) return cudaSuccess;   // swept inside the tiled kernel
     return enqueue_rowgroup(s, t.fallback, t.n_fallback, prev, curr, wts, state, check_done);
 }
+
+namespace oar {
+cudaError_t sweep_enqueue(oar_store *s, const double *prev, double *curr, const OarEmState *state, int check_done)
+{ return enqueue_sweep(s, prev, curr, nullptr, state, check_done); }
+}  // namespace oar
 
 // Bring the tile-order copy of the bootstrap weights up to date.
 static cudaError_t refresh_wperm(oar_store *s, const uint32_t *wts)

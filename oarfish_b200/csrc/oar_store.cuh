@@ -39,6 +39,7 @@ struct oar_store {
     uint64_t n_reads = 0, nnz = 0;
     uint32_t n_txps = 0;
     int kernel = OAR_KERNEL_ROWGROUP;
+    bool borrowed = false;  // sub-store of another store: row_ptr / prob / aux / stream / events are not owned
     int ctas_per_sm = 40 / OAR_TILE_WARPS_DEFAULT;  // persistent CTAs of the tiled sweep per SM (upper bound; shared memory may allow fewer)
 
     // CSR in HBM (original read order)
@@ -67,5 +68,10 @@ namespace oar {
 // Build s->tl from the CSR arrays already resident on s->device (enqueued on
 // s->stream, synchronises).  Returns an oar_status.
 int build_tiled_layout(oar_store *s, uint32_t span);
+// A store over the parent's reads with different transcript ids (takes ownership of d_txp): used by the
+// batched per-cell EM, where ids are (cell, transcript) pairs.  Shares the parent's stream and CSR arrays.
+int substore_create(oar_store *parent, uint32_t *d_txp, uint32_t n_txps, oar_store **out);
+// One fused E+M sweep prev -> curr on the store's stream (curr must be zero); see oar_em.cu.
+cudaError_t sweep_enqueue(oar_store *s, const double *prev, double *curr, const OarEmState *state, int check_done);
 void free_tiled_layout(oar_store *s);
 }  // namespace oar

@@ -269,7 +269,7 @@ def run_gpu(args):
         ms = ds.sweep_timed(prev, curr, reps) / reps
         alg = algorithmic_bytes(n_reads, nnz, n_txps)
         achieved = alg / (ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "em_sweep_tiled" if layout["kernel"] == 2 else "em_sweep_rowgroup",
+        roof = {"bound": "hbm", "kernel": {2: "em_sweep_tiled", 3: "em_sweep_lane"}.get(layout["kernel"], "em_sweep_rowgroup"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "us_per_launch": ms * 1e3,
                 "frac_of_nominal_8TBs": achieved / 8000.0}

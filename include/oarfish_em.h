@@ -55,7 +55,9 @@ typedef struct oar_store oar_store; /* opaque; one per alignment store per devic
 typedef enum {
     OAR_KERNEL_AUTO = 0,
     OAR_KERNEL_ROWGROUP = 1,  /* 8-lane group per read row, global f64 reductions */
-    OAR_KERNEL_TILED = 2      /* locality-sorted tiles, in-tile aggregation */
+    OAR_KERNEL_TILED = 2,     /* locality-sorted tiles of warp-chunks (4 slots per lane), in-tile aggregation;
+                                 needs the chunk layout (environment OAR_LAYOUT=chunk at store creation) */
+    OAR_KERNEL_LANE = 3       /* locality-sorted tiles, one read per lane (default layout) */
 } oar_kernel;
 
 /* ABI version: major*1000 + minor. */

@@ -11,7 +11,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_DIR = os.path.join(_HERE, "lib")
-EM_LIB_PATH = os.path.join(LIB_DIR, "liboarfish_em.so")
+# OAR_EM_LIB points at another build of the same library (kernel-tuning variants built by tests/_build_variants.sh)
+EM_LIB_PATH = os.environ.get("OAR_EM_LIB") or os.path.join(LIB_DIR, "liboarfish_em.so")
 SYNTH_LIB_PATH = os.path.join(LIB_DIR, "liboarsynth.so")
 
 OAR_OK = 0
@@ -23,6 +24,7 @@ OAR_ERR_UNSUPPORTED = -4
 KERNEL_AUTO = 0
 KERNEL_ROWGROUP = 1
 KERNEL_TILED = 2
+KERNEL_LANE = 3
 
 # every symbol include/oarfish_em.h declares: name -> (restype, argtypes)
 _u64p = C.POINTER(C.c_uint64)

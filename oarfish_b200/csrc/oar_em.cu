@@ -15,6 +15,7 @@
 
 #include "oar_store.cuh"
 #include "oar_tiled.cuh"
+#include "oar_lane.cuh"
 
 namespace oar {
 
@@ -106,14 +107,15 @@ int substore_create(oar_store *parent, uint32_t *d_txp, uint32_t n_txps, oar_sto
     s->d_row_ptr = parent->d_row_ptr; s->d_prob = parent->d_prob; s->d_aux = parent->d_aux; s->d_txp = d_txp;
     for (int i = 0; i < 4; ++i) s->ev[i] = parent->ev[i];
     for (int i = 0; i < 2; ++i) s->slot_ev[i] = parent->slot_ev[i];
-    s->ctas_per_sm = parent->ctas_per_sm;
+    s->ctas_per_sm = parent->ctas_per_sm; s->lane_ctas_per_sm = parent->lane_ctas_per_sm;
     int rc = [&]() -> int {
         OAR_CUDA(dmalloc(&s->d_state, sizeof(OarEmState) * 3, s->stream));
         OAR_CUDA(cudaMemsetAsync(s->d_state, 0, sizeof(OarEmState) * 3, s->stream));
         OAR_CUDA(cudaMallocHost(&s->h_state, sizeof(OarEmState) * 8));
         if (parent->tl.ready) {
+            s->tl.kind = parent->tl.kind;
             const int rc2 = build_tiled_layout(s, parent->tl.span);
-            if (rc2 == OAR_OK) s->kernel = OAR_KERNEL_TILED;
+            if (rc2 == OAR_OK) s->kernel = layout_kernel(s);
             else if (rc2 != OAR_ERR_UNSUPPORTED) return rc2;
         }
         return OAR_OK;
@@ -193,12 +195,14 @@ extern "C" int oar_store_create(const uint64_t *row_ptr, const uint32_t *txp_id,
             const char *env = getenv("OAR_TILED");
             if (!(env && env[0] == '0')) {
                 const char *sp = getenv("OAR_TILE_SPAN");
+                const char *lay = getenv("OAR_LAYOUT");
+                s->tl.kind = (lay && strcmp(lay, "chunk") == 0) ? 0 : 1;
                 int rc2 = build_tiled_layout(s, sp ? (uint32_t)atoi(sp) : 0u);
-                if (rc2 == OAR_OK) s->kernel = OAR_KERNEL_TILED;
+                if (rc2 == OAR_OK) s->kernel = layout_kernel(s);
                 else if (rc2 != OAR_ERR_UNSUPPORTED) return rc2;   // unsupported shape: keep the CSR kernel
             }
             const char *cps = getenv("OAR_CTAS_PER_SM");
-            if (cps && atoi(cps) > 0) s->ctas_per_sm = atoi(cps);
+            if (cps && atoi(cps) > 0) { s->ctas_per_sm = atoi(cps); s->lane_ctas_per_sm = atoi(cps); }
             OAR_CUDA(cudaEventRecord(s->ev[1], s->stream));
             OAR_CUDA(cudaStreamSynchronize(s->stream));
         }
@@ -230,11 +234,12 @@ extern "C" int oar_store_info(const oar_store *s, uint64_t *n_reads, uint64_t *n
 extern "C" int oar_store_set_kernel(oar_store *s, int kernel)
 {
     if (!s) return fail(OAR_ERR_INVALID, "oar_store_set_kernel: store is null");
-    if (kernel == OAR_KERNEL_AUTO) kernel = s->tl.ready ? OAR_KERNEL_TILED : OAR_KERNEL_ROWGROUP;
-    if (kernel != OAR_KERNEL_ROWGROUP && kernel != OAR_KERNEL_TILED)
+    if (kernel == OAR_KERNEL_AUTO) kernel = s->tl.ready ? layout_kernel(s) : OAR_KERNEL_ROWGROUP;
+    if (kernel != OAR_KERNEL_ROWGROUP && kernel != OAR_KERNEL_TILED && kernel != OAR_KERNEL_LANE)
         return fail(OAR_ERR_INVALID, "oar_store_set_kernel: unknown kernel");
-    if (kernel == OAR_KERNEL_TILED && !s->tl.ready)
-        return fail(OAR_ERR_UNSUPPORTED, "oar_store_set_kernel: tiled layout was not built (OAR_TILED=0)");
+    if (kernel != OAR_KERNEL_ROWGROUP && (!s->tl.ready || kernel != layout_kernel(s)))
+        return fail(OAR_ERR_UNSUPPORTED, "oar_store_set_kernel: the layout this kernel needs was not built "
+                                         "(OAR_TILED=0, or OAR_LAYOUT selects the other tiled layout)");
     if (kernel != s->kernel) { cudaSetDevice(s->device); cudaStreamSynchronize(s->stream); destroy_graphs(s); }
     s->kernel = kernel;
     return OAR_OK;
@@ -244,7 +249,9 @@ extern "C" int oar_store_layout_info(const oar_store *s, uint64_t out[8])
 {
     if (!s || !out) return fail(OAR_ERR_INVALID, "oar_store_layout_info: null argument");
     const TiledLayout &t = s->tl;
-    out[0] = t.ready ? 1 : 0; out[1] = t.n_tiles; out[2] = (uint64_t)t.n_tiles * tiled::kTile; out[3] = t.n_fallback;
+    out[0] = t.ready ? 1 : 0; out[1] = t.n_tiles;
+    out[2] = t.kind == 1 ? t.n_pairs : (uint64_t)t.n_tiles * tiled::kTile;   // alignment slots held in HBM
+    out[3] = t.n_fallback;
     out[4] = t.sum_d; out[5] = t.sum_u; out[6] = t.span; out[7] = (uint64_t)s->kernel;
     return OAR_OK;
 }
@@ -303,6 +310,37 @@ static cudaError_t launch_tiled(oar_store *s, const tiled::View &v, const double
     return cudaGetLastError();
 }
 
+static lane::View lane_view(const oar_store *s)
+{
+    const TiledLayout &t = s->tl;
+    lane::View v;
+    v.n_tiles = t.n_tiles; v.pairs = t.pairs; v.aux = t.aux; v.tiles = t.tiles; v.records = t.records;
+    const bool fold = t.n_fallback <= kFoldFallbackMax;
+    v.fb_rows = t.fallback; v.n_fb = fold ? t.n_fallback : 0u;
+    v.csr_row_ptr = s->d_row_ptr; v.csr_txp = s->d_txp; v.csr_prob = s->d_prob; v.csr_aux = s->d_aux; v.csr_wts = nullptr;
+    return v;
+}
+
+template <bool AUX, bool WTS>
+static cudaError_t launch_lane(oar_store *s, const lane::View &v, const double *prev, double *curr,
+                               const uint32_t *wperm, const OarEmState *state, int check_done)
+{
+    static int attr_bytes[16] = {0};
+    auto kfn = lane::em_sweep_lane<AUX, WTS>;
+    const lane::Geometry g = lane::make_geometry(s->tl.max_nnz, s->tl.max_rec, s->tl.max_d, s->tl.max_xs);
+    if (attr_bytes[s->device & 15] < (int)g.total) {
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.total);
+        if (e != cudaSuccess) return e;
+        attr_bytes[s->device & 15] = (int)g.total;
+    }
+    // persistent CTAs: as many per SM as shared memory allows, capped by the register budget
+    int per_sm = (int)((227u * 1024u) / (g.total + 1024u));
+    per_sm = std::max(1, std::min(per_sm, s->lane_ctas_per_sm));
+    const uint32_t grid = std::min<uint32_t>(v.n_tiles, (uint32_t)s->sm_count * (uint32_t)per_sm);
+    kfn<<<grid, lane::kThreads, g.total, s->stream>>>(v, g, prev, curr, wperm, state, check_done);
+    return cudaGetLastError();
+}
+
 // Row-group sweep over all rows (list == null) or over a list of row ids.
 static cudaError_t enqueue_rowgroup(oar_store *s, const uint32_t *list, uint64_t n_rows, const double *prev,
                                     double *curr, const uint32_t *wts, const OarEmState *state, int check_done)
@@ -329,10 +367,21 @@ static cudaError_t enqueue_sweep(oar_store *s, const double *prev, double *curr,
                                  const OarEmState *state, int check_done)
 {
     if (s->n_reads == 0) return cudaSuccess;
-    if (s->kernel != OAR_KERNEL_TILED)
+    if (s->kernel != OAR_KERNEL_TILED && s->kernel != OAR_KERNEL_LANE)
         return enqueue_rowgroup(s, nullptr, s->n_reads, prev, curr, wts, state, check_done);
     const TiledLayout &t = s->tl;
-    if (t.n_tiles > 0) {
+    if (t.n_tiles > 0 && s->kernel == OAR_KERNEL_LANE) {
+        lane::View v = lane_view(s);
+        v.csr_wts = wts;
+        const uint32_t *wp = wts ? t.wperm : nullptr;
+        cudaError_t le;
+        if (s->d_aux) le = wts ? launch_lane<true, true>(s, v, prev, curr, wp, state, check_done)
+                               : launch_lane<true, false>(s, v, prev, curr, wp, state, check_done);
+        else          le = wts ? launch_lane<false, true>(s, v, prev, curr, wp, state, check_done)
+                               : launch_lane<false, false>(s, v, prev, curr, wp, state, check_done);
+        if (le != cudaSuccess) return le;
+        s->counters[0] += 1;
+    } else if (t.n_tiles > 0) {
         tiled::View v = tiled_view(s);
         v.csr_wts = wts;
         const uint32_t *wp = wts ? t.wperm : nullptr;
@@ -359,7 +408,7 @@ cudaError_t sweep_enqueue(oar_store *s, const double *prev, double *curr, const 
 static cudaError_t refresh_wperm(oar_store *s, const uint32_t *wts)
 {
     const TiledLayout &t = s->tl;
-    if (s->kernel != OAR_KERNEL_TILED || t.n_tiled_rows == 0) return cudaSuccess;
+    if ((s->kernel != OAR_KERNEL_TILED && s->kernel != OAR_KERNEL_LANE) || t.n_tiled_rows == 0) return cudaSuccess;
     const int threads = 256;
     const int blocks = (int)std::min<uint64_t>((t.n_tiled_rows + threads - 1) / threads, (uint64_t)s->sm_count * 16);
     tiled::permute_weights<<<blocks, threads, 0, s->stream>>>(wts, t.trow, t.n_tiled_rows, t.wperm);
@@ -453,7 +502,7 @@ static int run_em(oar_store *s, const double *init_dev, uint32_t max_iter, doubl
         }
         // the launches still in flight are no-ops (done is set); they finish before the final sweep (same stream)
         // every kernel node of every graph launch is a launch of ours (those after convergence exit at once)
-        const uint64_t per_iter = 2 + ((s->kernel == OAR_KERNEL_TILED && s->tl.n_tiles > 0 && s->tl.n_fallback > kFoldFallbackMax) ? 1 : 0);
+        const uint64_t per_iter = 2 + ((s->kernel != OAR_KERNEL_ROWGROUP && s->tl.n_tiles > 0 && s->tl.n_fallback > kFoldFallbackMax) ? 1 : 0);
         s->counters[0] += launched_iters * per_iter;
     }
     double *prev = s->d_counts[sweeps & 1], *curr = s->d_counts[(sweeps + 1) & 1];

@@ -10,6 +10,7 @@
 
 #include "oar_store.cuh"
 #include "oar_tiled.cuh"
+#include "oar_lane.cuh"
 
 namespace oar {
 
@@ -18,8 +19,10 @@ void free_tiled_layout(oar_store *s)
     TiledLayout &t = s->tl;
     cudaStream_t st = s->stream;
     dfree(t.prob, st); dfree(t.lpos, st); dfree(t.aux, st); dfree(t.rec, st); dfree(t.records, st); dfree(t.trow, st);
-    dfree(t.fallback, st); dfree(t.wperm, st);
+    dfree(t.fallback, st); dfree(t.wperm, st); dfree(t.pairs, st); dfree(t.tiles, st);
+    const int kind = t.kind;
     t = TiledLayout();
+    t.kind = kind;
 }
 
 namespace {
@@ -36,10 +39,11 @@ struct Scratch {
 };
 }  // namespace
 
-int build_tiled_layout(oar_store *s, uint32_t span)
+static int build_chunk_layout(oar_store *s, uint32_t span)
 {
     using namespace tiled;
     free_tiled_layout(s);
+    s->tl.kind = 0;
     TiledLayout &t = s->tl;
     const uint32_t N = (uint32_t)s->n_reads;
     if (span == 0 || span > (uint32_t)kTile) span = (uint32_t)kTile - 5u * kWarps;
@@ -139,6 +143,131 @@ int build_tiled_layout(oar_store *s, uint32_t span)
     }
     t.ready = true;
     return OAR_OK;
+}
+
+// Row-per-lane layout (oar_lane.cuh): same row order and tile windows as the chunk layout, but a
+// tile's rows are re-sorted by length and stored one read per lane; no padding slots in HBM.
+static int build_lane_layout(oar_store *s, uint32_t span)
+{
+    using namespace lane;
+    free_tiled_layout(s);
+    TiledLayout &t = s->tl;
+    t.kind = 1;
+    const uint32_t N = (uint32_t)s->n_reads;
+    if (span < 128u || span > (uint32_t)kSpanMax) span = (uint32_t)kSpanDefault;
+    t.span = span;
+    if (N == 0 || s->nnz == 0) { t.ready = true; return OAR_OK; }
+    cudaStream_t st = s->stream;
+    Scratch sc; sc.st = st;
+    uint32_t *key = nullptr, *idx = nullptr, *key_s = nullptr, *srow = nullptr, *slen = nullptr, *soff = nullptr;
+    uint32_t *counters = nullptr;
+    OAR_CUDA(sc.alloc(&key, N)); OAR_CUDA(sc.alloc(&idx, N));
+    OAR_CUDA(sc.alloc(&key_s, N)); OAR_CUDA(sc.alloc(&srow, N));
+    OAR_CUDA(sc.alloc(&counters, 16));
+    OAR_CUDA(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 16, st));
+    const int threads = 256;
+    const int gridN = (int)std::min<uint64_t>((N + threads - 1) / threads, (uint64_t)s->sm_count * 32);
+    tiled::row_keys<<<gridN, threads, 0, st>>>(s->d_row_ptr, s->d_txp, N, key, idx, counters);
+    OAR_CUDA(cudaGetLastError());
+    {
+        size_t tmp_bytes = 0;
+        OAR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key, key_s, idx, srow, (int)N, 0, 32, st));
+        void *tmp = nullptr;
+        OAR_CUDA(sc.alloc((char **)&tmp, tmp_bytes));
+        OAR_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key, key_s, idx, srow, (int)N, 0, 32, st));
+    }
+    uint32_t h_counters[16];
+    OAR_CUDA(cudaMemcpyAsync(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
+    OAR_CUDA(cudaStreamSynchronize(st));
+    const uint32_t n_tiled = N - h_counters[0];
+    const uint32_t n_long = h_counters[1];
+    t.n_tiled_rows = n_tiled;
+
+    uint32_t n_tiles = 0;
+    uint32_t *tile_row = nullptr;
+    uint64_t total = 0;
+    if (n_tiled > 0) {
+        OAR_CUDA(sc.alloc(&slen, n_tiled + 1)); OAR_CUDA(sc.alloc(&soff, n_tiled + 1));
+        const int gridT = (int)std::min<uint64_t>((n_tiled + threads - 1) / threads, (uint64_t)s->sm_count * 32);
+        tiled::sorted_lens<<<gridT, threads, 0, st>>>(s->d_row_ptr, srow, n_tiled, slen);
+        OAR_CUDA(cudaGetLastError());
+        size_t tmp_bytes = 0;
+        OAR_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, slen, soff, (int)n_tiled + 1, st));
+        void *tmp = nullptr;
+        OAR_CUDA(sc.alloc((char **)&tmp, tmp_bytes));
+        OAR_CUDA(cudaMemsetAsync(slen + n_tiled, 0, sizeof(uint32_t), st));
+        OAR_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, slen, soff, (int)n_tiled + 1, st));
+        uint32_t h_total = 0;
+        OAR_CUDA(cudaMemcpyAsync(&h_total, soff + n_tiled, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        OAR_CUDA(cudaStreamSynchronize(st));
+        total = h_total;
+        n_tiles = (uint32_t)((total + span - 1) / span);
+        OAR_CUDA(sc.alloc(&tile_row, n_tiles + 1));
+        tiled::tile_row_starts<<<(n_tiles + 1 + threads - 1) / threads, threads, 0, st>>>(soff, n_tiled, span, n_tiles, tile_row);
+        OAR_CUDA(cudaGetLastError());
+    }
+    t.n_tiles = n_tiles;
+
+    OAR_CUDA(dmalloc(&t.fallback, sizeof(uint32_t) * std::max<uint32_t>(n_long, 1), st));
+    OAR_CUDA(dmalloc(&t.trow, sizeof(uint32_t) * std::max<uint32_t>(n_tiled, 1), st));
+    OAR_CUDA(dmalloc(&t.wperm, sizeof(uint32_t) * ((size_t)n_tiled + 64), st));
+    OAR_CUDA(cudaMemsetAsync(t.wperm, 0, sizeof(uint32_t) * ((size_t)n_tiled + 64), st));
+    uint4 *records_tmp = nullptr;
+    if (n_tiles > 0) {
+        // tile t starts at the even pair index >= (alignments before it) + t: at most one gap pair per tile
+        t.n_pairs = total + n_tiles + 4;
+        OAR_CUDA(dmalloc(&t.pairs, sizeof(uint2) * t.n_pairs, st));
+        OAR_CUDA(cudaMemsetAsync(t.pairs, 0, sizeof(uint2) * t.n_pairs, st));
+        if (s->d_aux) OAR_CUDA(dmalloc(&t.aux, sizeof(double) * t.n_pairs, st));
+        OAR_CUDA(dmalloc(&t.tiles, sizeof(uint4) * n_tiles, st));
+        // record bytes per transcript of a tile: <= 8 per alignment (table + singles, or table + units + pads);
+        // per group 36; per tile the header and the section roundings
+        const size_t worst = (size_t)n_tiles * 160 + 36 * ((size_t)n_tiled / 32 + n_tiles) + 8 * (size_t)total + 64;
+        OAR_CUDA(sc.alloc((char **)&records_tmp, worst));
+        static bool attr_set[64] = {false};
+        if (!attr_set[s->device & 63]) {
+            OAR_CUDA(cudaFuncSetAttribute(build_lane_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BuildSmem)));
+            attr_set[s->device & 63] = true;
+        }
+        BuildArgs a;
+        a.row_ptr = s->d_row_ptr; a.txp = s->d_txp; a.prob = s->d_prob; a.aux = s->d_aux;
+        a.srow = srow; a.soff = soff; a.tile_row = tile_row;
+        a.o_pairs = t.pairs; a.o_aux = t.aux; a.o_tiles = t.tiles; a.o_records = records_tmp; a.o_trow = t.trow;
+        a.cursors = counters + 4;
+        build_lane_tiles<<<n_tiles, kBuildThreads, sizeof(BuildSmem), st>>>(a);
+        OAR_CUDA(cudaGetLastError());
+    }
+    if (n_long > 0) {
+        const int g = (int)std::min<uint64_t>((N - n_tiled + threads - 1) / threads, (uint64_t)s->sm_count * 8);
+        tiled::collect_long_rows<<<g, threads, 0, st>>>(s->d_row_ptr, srow, n_tiled, N, t.fallback, counters + 2);
+        OAR_CUDA(cudaGetLastError());
+    }
+    OAR_CUDA(cudaMemcpyAsync(h_counters, counters, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
+    OAR_CUDA(cudaStreamSynchronize(st));
+    t.n_fallback = h_counters[2];
+    t.record_bytes = (uint64_t)h_counters[4] * 16u;
+    t.sum_d = h_counters[5]; t.sum_u = h_counters[6]; t.sum_s1 = h_counters[7];
+    t.max_rec = h_counters[8]; t.max_d = h_counters[9]; t.max_xs = h_counters[10]; t.max_nnz = h_counters[11];
+    t.sum_p = h_counters[12];
+    if (n_tiles > 0) {
+        OAR_CUDA(dmalloc(&t.records, std::max<uint64_t>(t.record_bytes, 16), st));
+        OAR_CUDA(cudaMemcpyAsync(t.records, records_tmp, t.record_bytes, cudaMemcpyDeviceToDevice, st));
+        OAR_CUDA(cudaStreamSynchronize(st));
+        const Geometry g = make_geometry(t.max_nnz, t.max_rec, t.max_d, t.max_xs);
+        if (g.total > 227u * 1024u) {
+            free_tiled_layout(s);
+            return fail(OAR_ERR_UNSUPPORTED, "lane layout: a tile does not fit shared memory");
+        }
+    }
+    t.ready = true;
+    return OAR_OK;
+}
+
+// s->tl.kind picks the layout: 1 = row-per-lane (default), 0 = warp-chunks (OAR_LAYOUT=chunk at store
+// creation; cross-checks, ablations).  Rebuilds (coverage model) and sub-stores keep the store's kind.
+int build_tiled_layout(oar_store *s, uint32_t span)
+{
+    return s->tl.kind == 0 ? build_chunk_layout(s, span) : build_lane_layout(s, span);
 }
 
 }  // namespace oar

@@ -5,12 +5,24 @@
 #define OAR_TILE_WARPS 8
 #endif
 #define OAR_TILE_WARPS_DEFAULT OAR_TILE_WARPS
+#ifndef OAR_LANE_MIN_CTAS
+#define OAR_LANE_MIN_CTAS 3
+#endif
+#define OAR_LANE_MIN_CTAS_DEFAULT OAR_LANE_MIN_CTAS
 
 namespace oar {
 
-// Locality-tiled copy of the store (see oar_tiled.cuh).
+// Locality-tiled copy of the store: kind 1 = row-per-lane tiles (oar_lane.cuh, default),
+// kind 0 = warp-chunk tiles (oar_tiled.cuh, OAR_LAYOUT=chunk).
 struct TiledLayout {
     bool ready = false;
+    int kind = 1;
+    // row-per-lane layout
+    uint2 *pairs = nullptr;        // {prob bits, lpos} per alignment, tile after tile
+    uint4 *tiles = nullptr;        // per tile: {record offset (16 B granules), record bytes, first pair, nnz}
+    uint64_t n_pairs = 0;
+    uint32_t max_nnz = 0, max_xs = 0;
+    uint64_t sum_s1 = 0, sum_p = 0;
     uint32_t n_tiles = 0, n_tiled_rows = 0, n_fallback = 0, span = 0;
     uint64_t sum_d = 0, sum_u = 0;
     float *prob = nullptr;
@@ -42,6 +54,8 @@ struct oar_store {
     bool borrowed = false;  // sub-store of another store: row_ptr / prob / aux / stream / events are not owned
     int ctas_per_sm = 40 / OAR_TILE_WARPS_DEFAULT;  // persistent CTAs of the tiled sweep per SM (upper bound; shared memory may allow fewer)
 
+    int lane_ctas_per_sm = OAR_LANE_MIN_CTAS_DEFAULT;  // same for the row-per-lane sweep (register budget of its launch bounds)
+
     // CSR in HBM (original read order)
     uint32_t *d_row_ptr = nullptr;  // N+1
     uint32_t *d_txp = nullptr;      // nnz
@@ -68,6 +82,8 @@ namespace oar {
 // Build s->tl from the CSR arrays already resident on s->device (enqueued on
 // s->stream, synchronises).  Returns an oar_status.
 int build_tiled_layout(oar_store *s, uint32_t span);
+// The sweep kernel that goes with the layout the store holds (OAR_KERNEL_LANE / OAR_KERNEL_TILED).
+inline int layout_kernel(const oar_store *s) { return s->tl.kind == 1 ? OAR_KERNEL_LANE : OAR_KERNEL_TILED; }
 // A store over the parent's reads with different transcript ids (takes ownership of d_txp): used by the
 // batched per-cell EM, where ids are (cell, transcript) pairs.  Shares the parent's stream and CSR arrays.
 int substore_create(oar_store *parent, uint32_t *d_txp, uint32_t n_txps, oar_store **out);

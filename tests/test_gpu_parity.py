@@ -3,6 +3,7 @@ oracle on the same seeded inputs.  Tolerances: transcript indexing bit-exact;
 iteration counts identical; abundances within 1e-5 relative (north_star) -- the
 tests assert the much tighter 1e-9 that f64 accumulation actually delivers, on
 counts above 1e-8 (smaller ones are compared absolutely)."""
+import contextlib
 import os
 
 import numpy as np
@@ -11,7 +12,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-KERNELS = [1, 2]  # OAR_KERNEL_ROWGROUP, OAR_KERNEL_TILED
+KERNELS = [1, 2, 3]  # OAR_KERNEL_ROWGROUP, OAR_KERNEL_TILED (chunk layout), OAR_KERNEL_LANE (default layout)
 RTOL = 1e-9
 NORTH_STAR_RTOL = 1e-5
 
@@ -36,6 +37,25 @@ def csr(rows):
     return rp, tx, pr
 
 
+@contextlib.contextmanager
+def store_for(DS, kernel, *args, **kw):
+    """A device store whose tiled layout matches `kernel` (the chunk layout is opt-in via OAR_LAYOUT)."""
+    old = os.environ.get("OAR_LAYOUT")
+    if kernel == 2:
+        os.environ["OAR_LAYOUT"] = "chunk"
+    try:
+        ds = DS(*args, **kw)
+    finally:
+        if old is None:
+            os.environ.pop("OAR_LAYOUT", None)
+        else:
+            os.environ["OAR_LAYOUT"] = old
+    with ds:
+        ds.set_kernel(kernel)
+        assert ds.layout_info()["kernel"] == kernel
+        yield ds
+
+
 @pytest.fixture(scope="module")
 def DS():
     from oarfish_b200 import DeviceStore, device_count
@@ -49,8 +69,7 @@ def DS():
 def test_em_matches_oracle(DS, oracle_mod, request, store_name, min_iter, kernel):
     s = request.getfixturevalue(store_name)
     want, niter, rel, sweeps = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps, min_iter=min_iter)
-    with DS(s.row_ptr, s.txp_id, s.prob, s.n_txps) as ds:
-        ds.set_kernel(kernel)
+    with store_for(DS, kernel, s.row_ptr, s.txp_id, s.prob, s.n_txps) as ds:
         r = ds.em(min_iter=min_iter)
         assert r.niter == niter
         assert r.rel_diff == pytest.approx(rel, rel=1e-6)
@@ -64,8 +83,7 @@ def test_em_matches_oracle(DS, oracle_mod, request, store_name, min_iter, kernel
 def test_golden_fixtures(DS, name, kernel):
     g = np.load(os.path.join(GOLD, name + ".npz"))
     rp, tx, pr, M = g["row_ptr"], g["txp_id"], g["prob"], int(g["n_txps"])
-    with DS(rp, tx, pr, M) as ds:
-        ds.set_kernel(kernel)
+    with store_for(DS, kernel, rp, tx, pr, M) as ds:
         for mi in (50, 1):
             r = ds.em(min_iter=mi)
             assert r.niter == int(g[f"niter_min{mi}"])
@@ -75,8 +93,7 @@ def test_golden_fixtures(DS, name, kernel):
         for b in range(2):
             assert nit[b] == int(g[f"boot{b}_niter"])
             assert_counts_close(out[b], g[f"boot{b}_counts"])
-    with DS(rp, tx, pr, M, aux=g["cov"]) as ds:  # --model-coverage factor (em.rs:108)
-        ds.set_kernel(kernel)
+    with store_for(DS, kernel, rp, tx, pr, M, aux=g["cov"]) as ds:  # --model-coverage factor (em.rs:108)
         r = ds.em(min_iter=50)
         assert r.niter == int(g["niter_cov"])
         assert_counts_close(r.counts, g["counts_cov"])
@@ -88,8 +105,7 @@ def test_init_abundances_and_max_iter(DS, oracle_mod, tiny_store, kernel):
     rng = np.random.default_rng(5)
     init = rng.uniform(0.0, 20.0, size=s.n_txps)
     init[::5] = 0.0
-    with DS(s.row_ptr, s.txp_id, s.prob, s.n_txps) as ds:
-        ds.set_kernel(kernel)
+    with store_for(DS, kernel, s.row_ptr, s.txp_id, s.prob, s.n_txps) as ds:
         for max_iter in (0, 1, 2, 7, 60, 1000):
             want, niter, _, sweeps = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps, init=init, max_iter=max_iter)
             r = ds.em(init=init, max_iter=max_iter)
@@ -114,8 +130,7 @@ def test_edge_shapes(DS, oracle_mod, kernel):
         rp, tx, pr = csr(rows)
         M = int(tx.max()) + 3
         want, niter, _, _ = oracle_mod.do_em(rp, tx, pr, M, min_iter=1)
-        with DS(rp, tx, pr, M) as ds:
-            ds.set_kernel(kernel)
+        with store_for(DS, kernel, rp, tx, pr, M) as ds:
             r = ds.em(min_iter=1)
             assert r.niter == niter, name
             assert_counts_close(r.counts, want)
@@ -148,8 +163,7 @@ def test_bootstrap_weights_match_index_list_oracle(DS, oracle_mod, small_store, 
     inds = oracle_mod.get_sample_inds(s.n_reads, 42)
     w = oracle_mod.inds_to_weights(inds, s.n_reads)
     want, niter, _, _ = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps, min_iter=50, inds=inds)
-    with DS(s.row_ptr, s.txp_id, s.prob, s.n_txps) as ds:
-        ds.set_kernel(kernel)
+    with store_for(DS, kernel, s.row_ptr, s.txp_id, s.prob, s.n_txps) as ds:
         out, nit = ds.bootstrap_weights(w[None, :])
         assert nit[0] == niter
         assert_counts_close(out[0], want)
@@ -296,10 +310,10 @@ def test_coverage_model_matches_oracle(DS, oracle_mod, small_store):
         sums = np.add.reduceat(aux, s.row_ptr[:-1].astype(np.int64))
         np.testing.assert_allclose(sums, 1.0, rtol=1e-12)
         # the EM now runs with the coverage factor: exact parity against the oracle fed the same factor
-        for kernel in KERNELS:
+        want, niter, _, _ = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps, min_iter=1, cov=aux)
+        for kernel in (1, ds.layout_info()["kernel"]):   # the CSR kernel and the layout's own (rebuilt with the factor)
             ds.set_kernel(kernel)
             r = ds.em(min_iter=1)
-            want, niter, _, _ = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps, min_iter=1, cov=aux)
             assert r.niter == niter
             assert_counts_close(r.counts, want)
 
@@ -310,7 +324,7 @@ def test_full_size_properties_c3(DS):
     s = synth.make_config("C3")
     with DS(s.row_ptr, s.txp_id, s.prob, s.n_txps) as ds:
         info = ds.layout_info()
-        assert info["tiled"] == 1 and info["fallback_rows"] < 0.01 * s.n_reads
+        assert info["tiled"] == 1 and info["kernel"] == 3 and info["fallback_rows"] < 0.01 * s.n_reads
         r2 = ds.em(min_iter=1)
         ds.set_kernel(1)
         r1 = ds.em(min_iter=1)

@@ -250,6 +250,7 @@ extern "C" int oar_store_layout_info(const oar_store *s, uint64_t out[8])
     if (!s || !out) return fail(OAR_ERR_INVALID, "oar_store_layout_info: null argument");
     const TiledLayout &t = s->tl;
     out[0] = t.ready ? 1 : 0; out[1] = t.n_tiles;
+    out[1] = t.kind == 1 ? t.n_groups : t.n_tiles;                           // units of work of the sweep (groups / tiles)
     out[2] = t.kind == 1 ? t.n_pairs : (uint64_t)t.n_tiles * tiled::kTile;   // alignment slots held in HBM
     out[3] = t.n_fallback;
     out[4] = t.sum_d; out[5] = t.sum_u; out[6] = t.span; out[7] = (uint64_t)s->kernel;
@@ -314,7 +315,7 @@ static lane::View lane_view(const oar_store *s)
 {
     const TiledLayout &t = s->tl;
     lane::View v;
-    v.n_tiles = t.n_tiles; v.pairs = t.pairs; v.aux = t.aux; v.tiles = t.tiles; v.records = t.records;
+    v.n_groups = t.n_groups; v.pairs = t.pairs; v.aux = t.aux; v.groups = t.groups; v.records = t.records;
     const bool fold = t.n_fallback <= kFoldFallbackMax;
     v.fb_rows = t.fallback; v.n_fb = fold ? t.n_fallback : 0u;
     v.csr_row_ptr = s->d_row_ptr; v.csr_txp = s->d_txp; v.csr_prob = s->d_prob; v.csr_aux = s->d_aux; v.csr_wts = nullptr;
@@ -328,16 +329,19 @@ static cudaError_t launch_lane(oar_store *s, const lane::View &v, const double *
     static int attr_bytes[16] = {0};
     auto kfn = lane::em_sweep_lane<AUX, WTS>;
     const lane::Geometry g = lane::make_geometry(s->tl.max_nnz, s->tl.max_rec, s->tl.max_d, s->tl.max_xs);
-    if (attr_bytes[s->device & 15] < (int)g.total) {
-        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.total);
+    const uint32_t cta_bytes = g.warp_bytes * (uint32_t)lane::kWarps;
+    if (attr_bytes[s->device & 15] < (int)cta_bytes) {
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cta_bytes);
         if (e != cudaSuccess) return e;
-        attr_bytes[s->device & 15] = (int)g.total;
+        attr_bytes[s->device & 15] = (int)cta_bytes;
     }
-    // persistent CTAs: as many per SM as shared memory allows, capped by the register budget
-    int per_sm = (int)((227u * 1024u) / (g.total + 1024u));
-    per_sm = std::max(1, std::min(per_sm, s->lane_ctas_per_sm));
-    const uint32_t grid = std::min<uint32_t>(v.n_tiles, (uint32_t)s->sm_count * (uint32_t)per_sm);
-    kfn<<<grid, lane::kThreads, g.total, s->stream>>>(v, g, prev, curr, wperm, state, check_done);
+    // persistent warps: as many CTAs per SM as shared memory allows (1 KB per CTA is reserved by the
+    // system), capped by the register budget of the launch bounds and the 32 CTA slots of an SM
+    int per_sm = (int)((227u * 1024u) / (cta_bytes + 1024u));
+    per_sm = std::max(1, std::min(std::min(per_sm, 32), s->lane_ctas_per_sm));
+    const uint32_t want = (v.n_groups + (uint32_t)lane::kWarps - 1u) / (uint32_t)lane::kWarps;
+    const uint32_t grid = std::max<uint32_t>(1u, std::min<uint32_t>(want, (uint32_t)s->sm_count * (uint32_t)per_sm));
+    kfn<<<grid, lane::kThreads, cta_bytes, s->stream>>>(v, g, prev, curr, wperm, state, check_done);
     return cudaGetLastError();
 }
 

@@ -19,7 +19,7 @@ void free_tiled_layout(oar_store *s)
     TiledLayout &t = s->tl;
     cudaStream_t st = s->stream;
     dfree(t.prob, st); dfree(t.lpos, st); dfree(t.aux, st); dfree(t.rec, st); dfree(t.records, st); dfree(t.trow, st);
-    dfree(t.fallback, st); dfree(t.wperm, st); dfree(t.pairs, st); dfree(t.tiles, st);
+    dfree(t.fallback, st); dfree(t.wperm, st); dfree(t.pairs, st); dfree(t.groups, st);
     const int kind = t.kind;
     t = TiledLayout();
     t.kind = kind;
@@ -154,7 +154,7 @@ static int build_lane_layout(oar_store *s, uint32_t span)
     TiledLayout &t = s->tl;
     t.kind = 1;
     const uint32_t N = (uint32_t)s->n_reads;
-    if (span < 128u || span > (uint32_t)kSpanMax) span = (uint32_t)kSpanDefault;
+    if (span < 256u || span > (uint32_t)kSpanMax) span = (uint32_t)kSpanDefault;
     t.span = span;
     if (N == 0 || s->nnz == 0) { t.ready = true; return OAR_OK; }
     cudaStream_t st = s->stream;
@@ -214,15 +214,15 @@ static int build_lane_layout(oar_store *s, uint32_t span)
     OAR_CUDA(cudaMemsetAsync(t.wperm, 0, sizeof(uint32_t) * ((size_t)n_tiled + 64), st));
     uint4 *records_tmp = nullptr;
     if (n_tiles > 0) {
-        // tile t starts at the even pair index >= (alignments before it) + t: at most one gap pair per tile
-        t.n_pairs = total + n_tiles + 4;
-        OAR_CUDA(dmalloc(&t.pairs, sizeof(uint2) * t.n_pairs, st));
-        OAR_CUDA(cudaMemsetAsync(t.pairs, 0, sizeof(uint2) * t.n_pairs, st));
-        if (s->d_aux) OAR_CUDA(dmalloc(&t.aux, sizeof(double) * t.n_pairs, st));
-        OAR_CUDA(dmalloc(&t.tiles, sizeof(uint4) * n_tiles, st));
-        // record bytes per transcript of a tile: <= 8 per alignment (table + singles, or table + units + pads);
-        // per group 36; per tile the header and the section roundings
-        const size_t worst = (size_t)n_tiles * 160 + 36 * ((size_t)n_tiled / 32 + n_tiles) + 8 * (size_t)total + 64;
+        // a group is closed by its 32nd row, by the alignment cap, or by the end of its tile
+        const size_t max_groups = (size_t)n_tiled / 32 + (size_t)(total / (uint64_t)(kGroupCap - kRowCap)) + n_tiles + 1;
+        const size_t max_pairs = (size_t)total + max_groups + 4;   // one pad pair per odd group
+        OAR_CUDA(dmalloc(&t.pairs, sizeof(uint2) * max_pairs, st));
+        if (s->d_aux) OAR_CUDA(dmalloc(&t.aux, sizeof(double) * max_pairs, st));
+        OAR_CUDA(dmalloc(&t.groups, sizeof(uint4) * max_groups, st));
+        // per group: header + row lengths + section roundings (80 B); per (group, transcript): a table entry and
+        // at most one item more than its alignments / 32
+        const size_t worst = 80 * max_groups + 9 * (size_t)total + 64;
         OAR_CUDA(sc.alloc((char **)&records_tmp, worst));
         static bool attr_set[64] = {false};
         if (!attr_set[s->device & 63]) {
@@ -232,7 +232,7 @@ static int build_lane_layout(oar_store *s, uint32_t span)
         BuildArgs a;
         a.row_ptr = s->d_row_ptr; a.txp = s->d_txp; a.prob = s->d_prob; a.aux = s->d_aux;
         a.srow = srow; a.soff = soff; a.tile_row = tile_row;
-        a.o_pairs = t.pairs; a.o_aux = t.aux; a.o_tiles = t.tiles; a.o_records = records_tmp; a.o_trow = t.trow;
+        a.o_pairs = t.pairs; a.o_aux = t.aux; a.o_groups = t.groups; a.o_records = records_tmp; a.o_trow = t.trow;
         a.cursors = counters + 4;
         build_lane_tiles<<<n_tiles, kBuildThreads, sizeof(BuildSmem), st>>>(a);
         OAR_CUDA(cudaGetLastError());
@@ -246,17 +246,17 @@ static int build_lane_layout(oar_store *s, uint32_t span)
     OAR_CUDA(cudaStreamSynchronize(st));
     t.n_fallback = h_counters[2];
     t.record_bytes = (uint64_t)h_counters[4] * 16u;
-    t.sum_d = h_counters[5]; t.sum_u = h_counters[6]; t.sum_s1 = h_counters[7];
-    t.max_rec = h_counters[8]; t.max_d = h_counters[9]; t.max_xs = h_counters[10]; t.max_nnz = h_counters[11];
-    t.sum_p = h_counters[12];
+    t.n_groups = h_counters[5]; t.n_pairs = h_counters[6];
+    t.sum_d = h_counters[7]; t.sum_u = h_counters[8];
+    t.max_rec = h_counters[9]; t.max_d = h_counters[10]; t.max_xs = h_counters[11]; t.max_nnz = h_counters[12];
     if (n_tiles > 0) {
         OAR_CUDA(dmalloc(&t.records, std::max<uint64_t>(t.record_bytes, 16), st));
         OAR_CUDA(cudaMemcpyAsync(t.records, records_tmp, t.record_bytes, cudaMemcpyDeviceToDevice, st));
         OAR_CUDA(cudaStreamSynchronize(st));
         const Geometry g = make_geometry(t.max_nnz, t.max_rec, t.max_d, t.max_xs);
-        if (g.total > 227u * 1024u) {
+        if ((size_t)g.warp_bytes * kWarps > 227u * 1024u) {
             free_tiled_layout(s);
-            return fail(OAR_ERR_UNSUPPORTED, "lane layout: a tile does not fit shared memory");
+            return fail(OAR_ERR_UNSUPPORTED, "lane layout: a group does not fit shared memory");
         }
     }
     t.ready = true;

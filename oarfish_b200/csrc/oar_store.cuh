@@ -6,7 +6,7 @@
 #endif
 #define OAR_TILE_WARPS_DEFAULT OAR_TILE_WARPS
 #ifndef OAR_LANE_MIN_CTAS
-#define OAR_LANE_MIN_CTAS 3
+#define OAR_LANE_MIN_CTAS 10
 #endif
 #define OAR_LANE_MIN_CTAS_DEFAULT OAR_LANE_MIN_CTAS
 
@@ -19,10 +19,10 @@ struct TiledLayout {
     int kind = 1;
     // row-per-lane layout
     uint2 *pairs = nullptr;        // {prob bits, lpos} per alignment, tile after tile
-    uint4 *tiles = nullptr;        // per tile: {record offset (16 B granules), record bytes, first pair, nnz}
-    uint64_t n_pairs = 0;
+    uint4 *groups = nullptr;       // per group: {record offset (16 B granules), record bytes, first pair, nnz}
+    uint32_t n_groups = 0;
+    uint64_t n_pairs = 0;          // pairs held (alignments + one pad per odd group)
     uint32_t max_nnz = 0, max_xs = 0;
-    uint64_t sum_s1 = 0, sum_p = 0;
     uint32_t n_tiles = 0, n_tiled_rows = 0, n_fallback = 0, span = 0;
     uint64_t sum_d = 0, sum_u = 0;
     float *prob = nullptr;

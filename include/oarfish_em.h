@@ -55,9 +55,10 @@ typedef struct oar_store oar_store; /* opaque; one per alignment store per devic
 typedef enum {
     OAR_KERNEL_AUTO = 0,
     OAR_KERNEL_ROWGROUP = 1,  /* 8-lane group per read row, global f64 reductions */
-    OAR_KERNEL_TILED = 2,     /* locality-sorted tiles of warp-chunks (4 slots per lane), in-tile aggregation;
-                                 needs the chunk layout (environment OAR_LAYOUT=chunk at store creation) */
-    OAR_KERNEL_LANE = 3       /* locality-sorted tiles, one read per lane (default layout) */
+    OAR_KERNEL_TILED = 2,     /* locality-sorted tiles of warp-chunks (4 slots per lane), in-tile aggregation
+                                 (default layout) */
+    OAR_KERNEL_LANE = 3       /* locality-sorted groups, one read per lane, warp-independent pipelines; needs
+                                 the lane layout (environment OAR_LAYOUT=lane at store creation) */
 } oar_kernel;
 
 /* ABI version: major*1000 + minor. */

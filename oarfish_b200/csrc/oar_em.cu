@@ -196,7 +196,7 @@ extern "C" int oar_store_create(const uint64_t *row_ptr, const uint32_t *txp_id,
             if (!(env && env[0] == '0')) {
                 const char *sp = getenv("OAR_TILE_SPAN");
                 const char *lay = getenv("OAR_LAYOUT");
-                s->tl.kind = (lay && strcmp(lay, "chunk") == 0) ? 0 : 1;
+                s->tl.kind = (lay && strcmp(lay, "lane") == 0) ? 1 : 0;   // default: warp-chunk tiles (fastest measured)
                 int rc2 = build_tiled_layout(s, sp ? (uint32_t)atoi(sp) : 0u);
                 if (rc2 == OAR_OK) s->kernel = layout_kernel(s);
                 else if (rc2 != OAR_ERR_UNSUPPORTED) return rc2;   // unsupported shape: keep the CSR kernel
@@ -315,7 +315,7 @@ static lane::View lane_view(const oar_store *s)
 {
     const TiledLayout &t = s->tl;
     lane::View v;
-    v.n_groups = t.n_groups; v.pairs = t.pairs; v.aux = t.aux; v.groups = t.groups; v.records = t.records;
+    v.n_groups = t.n_groups; v.blobs = t.blobs; v.groups = t.groups; v.aux = t.aux;
     const bool fold = t.n_fallback <= kFoldFallbackMax;
     v.fb_rows = t.fallback; v.n_fb = fold ? t.n_fallback : 0u;
     v.csr_row_ptr = s->d_row_ptr; v.csr_txp = s->d_txp; v.csr_prob = s->d_prob; v.csr_aux = s->d_aux; v.csr_wts = nullptr;
@@ -328,7 +328,7 @@ static cudaError_t launch_lane(oar_store *s, const lane::View &v, const double *
 {
     static int attr_bytes[16] = {0};
     auto kfn = lane::em_sweep_lane<AUX, WTS>;
-    const lane::Geometry g = lane::make_geometry(s->tl.max_nnz, s->tl.max_rec, s->tl.max_d, s->tl.max_xs);
+    const lane::Geometry g = lane::make_geometry(s->tl.max_rec, s->tl.max_d, s->tl.max_xs);
     const uint32_t cta_bytes = g.warp_bytes * (uint32_t)lane::kWarps;
     if (attr_bytes[s->device & 15] < (int)cta_bytes) {
         cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cta_bytes);

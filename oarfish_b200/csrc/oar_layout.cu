@@ -19,7 +19,7 @@ void free_tiled_layout(oar_store *s)
     TiledLayout &t = s->tl;
     cudaStream_t st = s->stream;
     dfree(t.prob, st); dfree(t.lpos, st); dfree(t.aux, st); dfree(t.rec, st); dfree(t.records, st); dfree(t.trow, st);
-    dfree(t.fallback, st); dfree(t.wperm, st); dfree(t.pairs, st); dfree(t.groups, st);
+    dfree(t.fallback, st); dfree(t.wperm, st); dfree(t.blobs, st); dfree(t.groups, st);
     const int kind = t.kind;
     t = TiledLayout();
     t.kind = kind;
@@ -212,18 +212,17 @@ static int build_lane_layout(oar_store *s, uint32_t span)
     OAR_CUDA(dmalloc(&t.trow, sizeof(uint32_t) * std::max<uint32_t>(n_tiled, 1), st));
     OAR_CUDA(dmalloc(&t.wperm, sizeof(uint32_t) * ((size_t)n_tiled + 64), st));
     OAR_CUDA(cudaMemsetAsync(t.wperm, 0, sizeof(uint32_t) * ((size_t)n_tiled + 64), st));
-    uint4 *records_tmp = nullptr;
+    uint4 *blobs_tmp = nullptr;
     if (n_tiles > 0) {
         // a group is closed by its 32nd row, by the alignment cap, or by the end of its tile
         const size_t max_groups = (size_t)n_tiled / 32 + (size_t)(total / (uint64_t)(kGroupCap - kRowCap)) + n_tiles + 1;
         const size_t max_pairs = (size_t)total + max_groups + 4;   // one pad pair per odd group
-        OAR_CUDA(dmalloc(&t.pairs, sizeof(uint2) * max_pairs, st));
         if (s->d_aux) OAR_CUDA(dmalloc(&t.aux, sizeof(double) * max_pairs, st));
-        OAR_CUDA(dmalloc(&t.groups, sizeof(uint4) * max_groups, st));
-        // per group: header + row lengths + section roundings (80 B); per (group, transcript): a table entry and
-        // at most one item more than its alignments / 32
-        const size_t worst = 80 * max_groups + 9 * (size_t)total + 64;
-        OAR_CUDA(sc.alloc((char **)&records_tmp, worst));
+        OAR_CUDA(dmalloc(&t.groups, sizeof(uint2) * max_groups, st));
+        // blob bytes: 8 per pair; per group: header + row lengths + section roundings (80 B); per (group,
+        // transcript): a table entry and at most one item more than its alignments / 16 (<= 9 per alignment)
+        const size_t worst = 8 * max_pairs + 80 * max_groups + 9 * (size_t)total + 64;
+        OAR_CUDA(sc.alloc((char **)&blobs_tmp, worst));
         static bool attr_set[64] = {false};
         if (!attr_set[s->device & 63]) {
             OAR_CUDA(cudaFuncSetAttribute(build_lane_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BuildSmem)));
@@ -232,7 +231,7 @@ static int build_lane_layout(oar_store *s, uint32_t span)
         BuildArgs a;
         a.row_ptr = s->d_row_ptr; a.txp = s->d_txp; a.prob = s->d_prob; a.aux = s->d_aux;
         a.srow = srow; a.soff = soff; a.tile_row = tile_row;
-        a.o_pairs = t.pairs; a.o_aux = t.aux; a.o_groups = t.groups; a.o_records = records_tmp; a.o_trow = t.trow;
+        a.o_aux = t.aux; a.o_groups = t.groups; a.o_blobs = blobs_tmp; a.o_trow = t.trow;
         a.cursors = counters + 4;
         build_lane_tiles<<<n_tiles, kBuildThreads, sizeof(BuildSmem), st>>>(a);
         OAR_CUDA(cudaGetLastError());
@@ -250,10 +249,11 @@ static int build_lane_layout(oar_store *s, uint32_t span)
     t.sum_d = h_counters[7]; t.sum_u = h_counters[8];
     t.max_rec = h_counters[9]; t.max_d = h_counters[10]; t.max_xs = h_counters[11]; t.max_nnz = h_counters[12];
     if (n_tiles > 0) {
-        OAR_CUDA(dmalloc(&t.records, std::max<uint64_t>(t.record_bytes, 16), st));
-        OAR_CUDA(cudaMemcpyAsync(t.records, records_tmp, t.record_bytes, cudaMemcpyDeviceToDevice, st));
+        // compact copy of the blobs (the worst-case scratch goes back to the pool)
+        OAR_CUDA(dmalloc(&t.blobs, std::max<uint64_t>(t.record_bytes, 16) + 64, st));
+        OAR_CUDA(cudaMemcpyAsync(t.blobs, blobs_tmp, t.record_bytes, cudaMemcpyDeviceToDevice, st));
         OAR_CUDA(cudaStreamSynchronize(st));
-        const Geometry g = make_geometry(t.max_nnz, t.max_rec, t.max_d, t.max_xs);
+        const Geometry g = make_geometry(t.max_rec, t.max_d, t.max_xs);
         if ((size_t)g.warp_bytes * kWarps > 227u * 1024u) {
             free_tiled_layout(s);
             return fail(OAR_ERR_UNSUPPORTED, "lane layout: a group does not fit shared memory");
@@ -263,8 +263,8 @@ static int build_lane_layout(oar_store *s, uint32_t span)
     return OAR_OK;
 }
 
-// s->tl.kind picks the layout: 1 = row-per-lane (default), 0 = warp-chunks (OAR_LAYOUT=chunk at store
-// creation; cross-checks, ablations).  Rebuilds (coverage model) and sub-stores keep the store's kind.
+// s->tl.kind picks the layout: 0 = warp-chunk tiles (default), 1 = row-per-lane groups (OAR_LAYOUT=lane at
+// store creation).  Rebuilds (coverage model) and sub-stores keep the store's kind.
 int build_tiled_layout(oar_store *s, uint32_t span)
 {
     return s->tl.kind == 0 ? build_chunk_layout(s, span) : build_lane_layout(s, span);

@@ -6,20 +6,20 @@
 #endif
 #define OAR_TILE_WARPS_DEFAULT OAR_TILE_WARPS
 #ifndef OAR_LANE_MIN_CTAS
-#define OAR_LANE_MIN_CTAS 10
+#define OAR_LANE_MIN_CTAS 6
 #endif
 #define OAR_LANE_MIN_CTAS_DEFAULT OAR_LANE_MIN_CTAS
 
 namespace oar {
 
-// Locality-tiled copy of the store: kind 1 = row-per-lane tiles (oar_lane.cuh, default),
-// kind 0 = warp-chunk tiles (oar_tiled.cuh, OAR_LAYOUT=chunk).
+// Locality-tiled copy of the store: kind 0 = warp-chunk tiles (oar_tiled.cuh, default),
+// kind 1 = row-per-lane groups (oar_lane.cuh, OAR_LAYOUT=lane at store creation).
 struct TiledLayout {
     bool ready = false;
-    int kind = 1;
+    int kind = 0;
     // row-per-lane layout
-    uint2 *pairs = nullptr;        // {prob bits, lpos} per alignment, tile after tile
-    uint4 *groups = nullptr;       // per group: {record offset (16 B granules), record bytes, first pair, nnz}
+    uint4 *blobs = nullptr;        // per group one blob: record (header, row lengths, transcript table, items) | pairs {prob bits, lpos}
+    uint2 *groups = nullptr;       // per group: {blob offset (16 B granules), blob bytes}
     uint32_t n_groups = 0;
     uint64_t n_pairs = 0;          // pairs held (alignments + one pad per odd group)
     uint32_t max_nnz = 0, max_xs = 0;

@@ -12,7 +12,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-KERNELS = [1, 2, 3]  # OAR_KERNEL_ROWGROUP, OAR_KERNEL_TILED (chunk layout), OAR_KERNEL_LANE (default layout)
+KERNELS = [1, 2, 3]  # OAR_KERNEL_ROWGROUP, OAR_KERNEL_TILED (default layout), OAR_KERNEL_LANE (OAR_LAYOUT=lane)
 RTOL = 1e-9
 NORTH_STAR_RTOL = 1e-5
 
@@ -39,10 +39,12 @@ def csr(rows):
 
 @contextlib.contextmanager
 def store_for(DS, kernel, *args, **kw):
-    """A device store whose tiled layout matches `kernel` (the chunk layout is opt-in via OAR_LAYOUT)."""
+    """A device store whose tiled layout matches `kernel` (the row-per-lane layout is opt-in via OAR_LAYOUT)."""
     old = os.environ.get("OAR_LAYOUT")
-    if kernel == 2:
-        os.environ["OAR_LAYOUT"] = "chunk"
+    if kernel == 3:
+        os.environ["OAR_LAYOUT"] = "lane"
+    elif old is not None:
+        os.environ.pop("OAR_LAYOUT")
     try:
         ds = DS(*args, **kw)
     finally:
@@ -253,12 +255,13 @@ def test_device_resident_inputs_and_outputs(DS, oracle_mod, tiny_store):
         assert_counts_close(out.cpu().numpy(), want)
 
 
-def test_batched_cells_match_per_cell_oracle(DS, oracle_mod):
+@pytest.mark.parametrize("kernel", [2, 3])
+def test_batched_cells_match_per_cell_oracle(DS, oracle_mod, kernel):
     """single_cell.rs:150: one em::em per cell, full transcriptome as parameter space."""
     from oarfish_b200 import synth
     M = 400
     s, crp = synth.make_cells([1500, 0, 40, 3000, 1, 700], M, 5.0, seed=21)
-    with DS(s.row_ptr, s.txp_id, s.prob, M) as ds:
+    with store_for(DS, kernel, s.row_ptr, s.txp_id, s.prob, M) as ds:
         cell_ptr, txp, val, niter = ds.em_batched(crp)
     assert len(cell_ptr) == 7 and cell_ptr[0] == 0 and cell_ptr[-1] == len(txp) == len(val)
     for c in range(6):
@@ -296,13 +299,14 @@ def test_posteriors_and_aux_counts(DS, oracle_mod, small_store):
         assert t.sum() == s.nnz
 
 
-def test_coverage_model_matches_oracle(DS, oracle_mod, small_store):
+@pytest.mark.parametrize("layout_kernel", [2, 3])
+def test_coverage_model_matches_oracle(DS, oracle_mod, small_store, layout_kernel):
     """--model-coverage (bulk.rs:103-108) on the device, then the EM with that factor (em.rs:108)."""
     from oarfish_b200 import synth
     s = small_store
     start, end, txp_len = synth.make_coordinates(s, 77)
     want_aux = oracle_mod.coverage_model(s.row_ptr, s.txp_id, start, end, txp_len, bin_width=100, growth_rate=2.0)
-    with DS(s.row_ptr, s.txp_id, s.prob, s.n_txps) as ds:
+    with store_for(DS, layout_kernel, s.row_ptr, s.txp_id, s.prob, s.n_txps) as ds:
         aux = ds.coverage_model(start, end, txp_len, bin_width=100, growth_rate=2.0)
         # histogram bins are summed with f64 atomics and then rounded to f32 like the reference does
         # (oarfish_types.rs:477), so a last-bit difference can move a bin count by one f32 ulp: 1e-6 tolerance
@@ -311,7 +315,7 @@ def test_coverage_model_matches_oracle(DS, oracle_mod, small_store):
         np.testing.assert_allclose(sums, 1.0, rtol=1e-12)
         # the EM now runs with the coverage factor: exact parity against the oracle fed the same factor
         want, niter, _, _ = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps, min_iter=1, cov=aux)
-        for kernel in (1, ds.layout_info()["kernel"]):   # the CSR kernel and the layout's own (rebuilt with the factor)
+        for kernel in (1, layout_kernel):   # the CSR kernel and the layout's own (rebuilt with the factor)
             ds.set_kernel(kernel)
             r = ds.em(min_iter=1)
             assert r.niter == niter
@@ -324,7 +328,7 @@ def test_full_size_properties_c3(DS):
     s = synth.make_config("C3")
     with DS(s.row_ptr, s.txp_id, s.prob, s.n_txps) as ds:
         info = ds.layout_info()
-        assert info["tiled"] == 1 and info["kernel"] == 3 and info["fallback_rows"] < 0.01 * s.n_reads
+        assert info["tiled"] == 1 and info["kernel"] == 2 and info["fallback_rows"] < 0.01 * s.n_reads
         r2 = ds.em(min_iter=1)
         ds.set_kernel(1)
         r1 = ds.em(min_iter=1)
@@ -339,3 +343,21 @@ def test_full_size_properties_c3(DS):
         r3 = ds.em(min_iter=1, init=r1.counts, max_iter=1)
         m = r1.counts > 1.0
         assert (np.abs(r3.counts[m] - r1.counts[m]) / r1.counts[m]).max() < 5e-3
+
+
+def test_full_size_lane_layout_c3(DS):
+    """The row-per-lane layout (OAR_LAYOUT=lane) on BASELINE config 3: same EM as the default tiled kernel."""
+    from oarfish_b200 import synth
+    s = synth.make_config("C3")
+    with store_for(DS, 2, s.row_ptr, s.txp_id, s.prob, s.n_txps) as ds:
+        r2 = ds.em(min_iter=1)
+    with store_for(DS, 3, s.row_ptr, s.txp_id, s.prob, s.n_txps) as ds:
+        info = ds.layout_info()
+        assert info["kernel"] == 3 and info["fallback_rows"] < 0.01 * s.n_reads
+        r3 = ds.em(min_iter=1)
+        w = ds.sample_weights(9, 0)
+    assert r3.niter == r2.niter
+    big = r2.counts > 1e-8
+    assert (np.abs(r3.counts[big] - r2.counts[big]) / r2.counts[big]).max() < 1e-8
+    assert abs(r3.counts.sum() - s.n_reads) < 1e-6 * s.n_reads
+    assert int(w.sum()) == s.n_reads

@@ -298,17 +298,25 @@ def run_gpu(args):
     if not multi:
         ds.close()
         e_iters = 0
+        parts = [0.0, 0.0, 0.0]   # create (upload + validation + layout), EM + counts download, destroy
         for i in range(1 + max(1, K // 2)):
             if i == 1:
-                torch.cuda.synchronize(); t0 = time.perf_counter(); e_iters = 0
-            with DeviceStore(s.row_ptr, s.txp_id, s.prob, n_txps, device=local_rank) as d2:
-                d2.em(max_iter=1000, conv_thresh=1e-3, min_iter=1, out=out_host)
-                e_iters += d2.counters()["sweeps"]
+                torch.cuda.synchronize(); t0 = time.perf_counter(); e_iters = 0; parts = [0.0, 0.0, 0.0]
+            ta = time.perf_counter()
+            d2 = DeviceStore(s.row_ptr, s.txp_id, s.prob, n_txps, device=local_rank)
+            tb = time.perf_counter()
+            d2.em(max_iter=1000, conv_thresh=1e-3, min_iter=1, out=out_host)
+            e_iters += d2.counters()["sweeps"]
+            tc = time.perf_counter()
+            d2.close()
+            td = time.perf_counter()
+            parts[0] += tb - ta; parts[1] += tc - tb; parts[2] += td - tc
         torch.cuda.synchronize()
         dte = time.perf_counter() - t0
         n_e = max(1, K // 2)
         e2e = {"value": e_iters / dte, "unit": "iterations/s", "h2d_bytes_per_step": store_bytes,
                "d2h_bytes_per_step": 8 * n_txps, "ms_per_step": 1e3 * dte / n_e,
+               "ms_create_em_destroy": [round(1e3 * x / n_e, 2) for x in parts],
                "includes": "pinned-host store upload + layout build + EM to convergence + counts download"}
     else:
         # the store crosses PCIe once on rank 0 and NVLink once per rank; amortise that over the K steps

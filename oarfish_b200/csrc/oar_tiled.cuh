@@ -51,14 +51,17 @@ constexpr int kChunkCap = kChunk - 1;     // rows use at most 127 slots: a paddi
 constexpr int kTile = kWarps * kChunk;    // 1024 slots
 constexpr int kThreads = kWarps * 32;     // 256
 constexpr int kAggMin = 4;                // transcripts with >= kAggMin alignments in a tile are aggregated in smem
-constexpr int kMaxUnits = kTile / 4;      // sum ceil(cnt/8) over cnt >= 4  <=  kTile/4
-constexpr int kUnitStride = 10;           // doubles per 8-slot unit in xs: 80 B keeps LDS.128 conflict-free
-// padding and non-aggregated alignments write to a trash slot right after the last unit of the tile
+constexpr int kMaxItems = kTile / 4;      // every item belongs to a transcript with >= 4 alignments and holds >= 4 of them
+// An aggregated transcript with cnt alignments in the tile owns cnt / 32 items of 32 consecutive x slots and one item
+// for the remainder, of the smallest size class (8, 16 or 32 slots) that holds it.  Items are ordered by class
+// (32s first); a class-c item sits c + 2 doubles behind its predecessor, so the 8 lanes of an LDS.128 phase hit 8
+// different 16-byte banks.  One thread sums one item and issues one RED: no cross-lane scan, no padding to clear.
+// padding and non-aggregated alignments write to a trash slot right after the last item of the tile
 constexpr uint32_t kInfoStray = 8u;       // chunk_info bit 3: chunk holds alignments that RED straight to global
 constexpr uint32_t kInfoMulti = 16u;      // chunk_info bit 4: some lane holds >= 2 row heads (general path)
 constexpr uint32_t kNoTxp = 0xFFFFFFFFu;
-constexpr uint32_t kMaxTxps = 1u << 28;   // unit descriptors pack (count-1) above bit 28
-static_assert(kMaxUnits == kThreads, "one unit per thread in phase 2");
+constexpr uint32_t kMaxTxps = 1u << 27;   // item descriptors pack (slots - 1) above bit 27
+static_assert(kMaxItems == kThreads, "one item per thread in phase 2");
 
 // Per-tile record (variable length, 16-byte granules), one TMA bulk copy:
 //   [0,512)    lane descriptors u16[8][32]: hb(4) | dist(5) | E(5)
@@ -68,32 +71,32 @@ static_assert(kMaxUnits == kThreads, "one unit per thread in phase 2");
 //                      the lane itself if there is none (then only padding follows)
 //   [512,544)  chunk_info u32[8]: scan steps (bits 0-2) | kInfoStray | kInfoMulti
 //   [544,576)  chunk_row  u32[8]: tile-order index of the chunk's first row (bootstrap weights)
-//   [576,592)  D, U, 0, 0
-//   [592, ..)  table u32[roundup4(D)]  : distinct transcript ids
-//              units u32[roundup4(U)]  : transcript id | (valid slots - 1) << 28 per 8-slot unit
+//   [576,592)  D, items, n32 | n16 << 16 (items per size class), trash x offset in bytes
+//   [592, ..)  table u32[roundup4(D)]      : distinct transcript ids
+//              items u32[roundup4(items)]  : transcript id | (slots - 1) << 27
 constexpr int kRecDesc = 0, kRecInfo = 64 * kWarps, kRecRow = kRecInfo + 4 * kWarps, kRecDU = kRecRow + 4 * kWarps,
               kRecTable = kRecDU + 16;
-constexpr int kRecMax = kRecTable + 4 * kTile + 4 * kMaxUnits;   // 5712
+constexpr int kRecMax = kRecTable + 4 * kTile + 4 * kMaxItems;   // 5712
 constexpr int kStages = 2;
 
 // Shared-memory geometry of the sweep, sized for the store at hand (largest record, table and
 // unit count over all tiles) so that as many CTAs as possible fit on an SM.
 struct Geometry {
     uint32_t stage_bytes;   // prob (4 KB) | lpos (4 KB) | record (max over tiles, 16 B multiple)
-    uint32_t xs_off;        // after the stages: transcript-sorted x values, kUnitStride doubles per unit (+ trash)
+    uint32_t xs_off;        // after the stages: transcript-sorted x values in items (+ trash)
     uint32_t prev_off;      // prev[] of the tile's transcripts
     uint32_t bar_off;       // two mbarriers
     uint32_t total;         // dynamic shared memory per CTA
     uint32_t xs_doubles;    // doubles to clear at start
 };
-inline Geometry make_geometry(uint32_t max_rec_bytes, uint32_t max_d, uint32_t max_u)
+inline Geometry make_geometry(uint32_t max_rec_bytes, uint32_t max_d, uint32_t max_x_doubles)
 {
     Geometry g;
     const uint32_t rec = (max_rec_bytes + 15u) & ~15u;
     g.stage_bytes = 8u * kTile + rec;
     g.xs_off = kStages * g.stage_bytes;
-    // phase 2 reads whole warps of units: round the unit count up to 32; then the trash slot; even count
-    g.xs_doubles = ((((max_u + 31u) & ~31u) * kUnitStride + 2u) + 1u) & ~1u;
+    // the items of the fullest tile, then the trash slot; even count
+    g.xs_doubles = (max_x_doubles + 2u + 1u) & ~1u;
     g.prev_off = g.xs_off + 8u * g.xs_doubles;
     g.bar_off = g.prev_off + 8u * ((max_d + 1u) & ~1u);
     g.total = g.bar_off + 16u;
@@ -182,7 +185,7 @@ struct BuildArgs {
     const uint32_t *tile_row;  // n_tiles + 1
     float *o_prob; uint32_t *o_lpos; double *o_aux; uint2 *o_rec; uint4 *o_records;
     uint32_t *o_trow;          // tile-order row -> original row
-    uint32_t *fallback; uint32_t *cursors;  // [0] fallback rows, [1] sum D, [2] sum U, [3] record granules, [4..6] max record bytes / D / U
+    uint32_t *fallback; uint32_t *cursors;  // [0] fallback rows, [1] sum D, [2] sum items, [3] record granules, [4..6] max record bytes / D / x doubles
 };
 
 // One CTA lays out one tile.
@@ -194,7 +197,8 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
     __shared__ uint32_t s_txp[kTile];      // slot -> transcript; later reused as sorted keys
     __shared__ uint32_t s_src[kTile];      // slot -> source alignment index in the CSR
     __shared__ uint32_t s_lpos[kTile];
-    __shared__ uint32_t s_seg[kTile + 1];  // segment -> first sorted rank; later unit base
+    __shared__ uint32_t s_seg[kTile + 1];  // segment -> first sorted rank; later start | first 32-slot item
+    __shared__ uint32_t s_seg2[kTile];     // segment -> x offset of its remainder item | n32 | stray flag
     __shared__ uint16_t s_rlen[kTile], s_rslot[kTile], s_rnew[kTile];
     __shared__ uint32_t s_heads[kWarps * 4];
     __shared__ uint32_t s_used[kWarps], s_nrow[kWarps], s_info[kWarps];
@@ -347,20 +351,27 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
     __syncthreads();
     if (tid == 0) s_seg[D] = nvalid;
     __syncthreads();
-    // units: aggregated segments get ceil(cnt/8) 8-slot units
-    uint32_t nun[4], ubase[4], U = 0, cntd[4], startd[4];
+    // items of the aggregated segments: packed per-class counts n32 | n16 << 10 | n8 << 20 (each total <= 256)
+    uint32_t pk[4], pbase[4], cntd[4], startd[4], PT = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const uint32_t d = tid * 4 + i;
-        nun[i] = 0; cntd[i] = 0; startd[i] = 0;
+        pk[i] = 0; cntd[i] = 0; startd[i] = 0;
         if (d < D) {
             startd[i] = s_seg[d];
             cntd[i] = s_seg[d + 1] - startd[i];
-            nun[i] = cntd[i] >= (uint32_t)kAggMin ? (cntd[i] + 7) >> 3 : 0;
+            if (cntd[i] >= (uint32_t)kAggMin) {
+                const uint32_t rem = cntd[i] & 31u;
+                pk[i] = (cntd[i] >> 5) + (rem > 16u ? 1u : 0u) + ((rem > 8u && rem <= 16u) ? (1u << 10) : 0u) +
+                        ((rem >= 1u && rem <= 8u) ? (1u << 20) : 0u);
+            }
         }
     }
-    Scan(tmp.scan).ExclusiveSum(nun, ubase, U);
+    Scan(tmp.scan).ExclusiveSum(pk, pbase, PT);
     __syncthreads();
+    const uint32_t N32 = PT & 0x3FFu, N16 = (PT >> 10) & 0x3FFu, N8 = PT >> 20;
+    const uint32_t U = N32 + N16 + N8;                          // items of the tile
+    const uint32_t XD = 34u * N32 + 18u * N16 + 10u * N8;       // x doubles of the tile; the trash slot sits right behind
     const uint32_t D4 = (D + 3u) & ~3u, U4 = (U + 3u) & ~3u;
     const uint32_t rec_bytes = kRecTable + 4u * D4 + 4u * U4;
     if (tid == 0) {
@@ -369,19 +380,31 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
         s_misc[2] = atomicAdd(a.cursors + 3, rec_bytes / 16u);
         atomicMax(a.cursors + 4, rec_bytes);
         atomicMax(a.cursors + 5, D);
-        atomicMax(a.cursors + 6, U);
+        atomicMax(a.cursors + 6, XD);
         s_rec[kRecDU / 4 + 0] = D;
         s_rec[kRecDU / 4 + 1] = U;
+        s_rec[kRecDU / 4 + 2] = N32 | (N16 << 16);
+        s_rec[kRecDU / 4 + 3] = XD * 8u;
     }
-    // table and unit descriptors
+    // table and item descriptors; per segment: where its alignments go
+    uint32_t sega[4], segb[4];   // start | first 32-slot item << 11 ;  x offset (doubles) of the remainder item | n32 << 12 | stray << 31
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const uint32_t d = tid * 4 + i;
+        sega[i] = segb[i] = 0;
         if (d < D) {
             const uint32_t key = s_txp[startd[i]];
             s_rec[kRecTable / 4 + d] = key;
-            for (uint32_t v = 0; v < nun[i]; ++v)
-                s_rec[kRecTable / 4 + D4 + ubase[i] + v] = key | ((min(8u, cntd[i] - 8u * v) - 1u) << 28);
+            uint32_t *items = s_rec + kRecTable / 4 + D4;
+            const uint32_t i32 = pbase[i] & 0x3FFu, i16 = (pbase[i] >> 10) & 0x3FFu, i8 = pbase[i] >> 20;
+            const uint32_t n32 = pk[i] & 0x3FFu, rem = cntd[i] & 31u;
+            if (pk[i] == 0u) { segb[i] = 1u << 31; sega[i] = startd[i]; continue; }
+            for (uint32_t v = 0; v < n32; ++v) items[i32 + v] = key | ((min(32u, cntd[i] - 32u * v) - 1u) << 27);
+            uint32_t rem_x = 0;
+            if (rem > 8u && rem <= 16u) { items[N32 + i16] = key | ((rem - 1u) << 27); rem_x = 34u * N32 + 18u * i16; }
+            else if (rem >= 1u && rem <= 8u) { items[N32 + N16 + i8] = key | ((rem - 1u) << 27); rem_x = 34u * N32 + 18u * N16 + 10u * i8; }
+            sega[i] = startd[i] | (i32 << 11);
+            segb[i] = rem_x | (n32 << 12);
         }
     }
     __syncthreads();  // everyone has read s_seg[d+1]; s_misc[2] visible
@@ -389,7 +412,7 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const uint32_t d = tid * 4 + i;
-        if (d < D) s_seg[d] = startd[i] | ((nun[i] ? ubase[i] : 0x1FFu) << 11);  // start (11 bits) | unit base (9 bits, 0x1FF = stray)
+        if (d < D) { s_seg[d] = sega[i]; s_seg2[d] = segb[i]; }
     }
     __syncthreads();
     // per sorted element: table index and position, as shared-memory byte offsets
@@ -398,14 +421,15 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
         const uint32_t r = tid * 4 + i;
         if (keys[i] != kNoTxp) {
             const uint32_t d = seg[i] - 1;
-            const uint32_t pk = s_seg[d];
-            const uint32_t start = pk & 0x7FFu, ub = pk >> 11;
-            uint32_t pos = U * kUnitStride;   // trash slot of this tile
-            if (ub != 0x1FFu) { const uint32_t p = ub * 8 + (r - start); pos = p + ((p >> 3) << 1); }
-            else atomicOr(&s_info[vals[i] / kChunk], kInfoStray);
+            const uint32_t pa = s_seg[d], pb = s_seg2[d];
+            uint32_t pos = XD;   // trash slot of this tile
+            if ((pb >> 31) == 0u) {
+                const uint32_t rr = r - (pa & 0x7FFu), n32 = (pb >> 12) & 0x3FFu;
+                pos = rr < 32u * n32 ? 34u * ((pa >> 11) + (rr >> 5)) + (rr & 31u) : (pb & 0xFFFu) + (rr - 32u * n32);
+            } else atomicOr(&s_info[vals[i] / kChunk], kInfoStray);
             s_lpos[vals[i]] = (d * 8u) | ((pos * 8u) << 16);
         } else {
-            s_lpos[vals[i]] = 0u | ((U * kUnitStride * 8u) << 16);
+            s_lpos[vals[i]] = 0u | ((XD * 8u) << 16);
         }
     }
     __syncthreads();
@@ -527,16 +551,11 @@ __global__ void __launch_bounds__(kThreads, (5 * 8) / kWarps) em_sweep_tiled(Vie
         const uint4 lp4 = *reinterpret_cast<const uint4 *>(stg + 4 * kTile + 4 * slot);
         const uint32_t desc = reinterpret_cast<const uint16_t *>(rec + kRecDesc)[tid];
         const uint32_t info = reinterpret_cast<const uint32_t *>(rec + kRecInfo)[warp];
-        const uint32_t D = *reinterpret_cast<const uint32_t *>(rec + kRecDU);
-        const uint32_t U = *reinterpret_cast<const uint32_t *>(rec + kRecDU + 4);
+        const uint4 du = *reinterpret_cast<const uint4 *>(rec + kRecDU);   // D, items, n32 | n16 << 16, trash offset
+        const uint32_t D = du.x, U = du.y;
         const uint32_t *table = reinterpret_cast<const uint32_t *>(rec + kRecTable);
-        const uint32_t unit = (tid < U) ? table[((D + 3u) & ~3u) + tid] : kNoTxp;
-        if (unit != kNoTxp) {   // the last unit of a transcript may be partial: clear its unused slots
-            double *b = xs + tid * kUnitStride;
-            const uint32_t cnt = (unit >> 28) + 1u;
-#pragma unroll
-            for (uint32_t k = 1; k < 8u; ++k) if (k >= cnt) b[k] = 0.0;   // predicated stores, no loop
-        }
+        // this thread's item (read now: the record's stage is refilled before phase 2)
+        const uint32_t item = (tid < U) ? table[((D + 3u) & ~3u) + tid] : kNoTxp;
 
         const char *sp = reinterpret_cast<const char *>(s_prev);
         double w0 = *reinterpret_cast<const double *>(sp + (lp4.x & 0xFFFFu)) * (double)p4.x;
@@ -647,7 +666,7 @@ __global__ void __launch_bounds__(kThreads, (5 * 8) / kWarps) em_sweep_tiled(Vie
         // ---- M-step scatter into the transcript-sorted smem order -----------------------------
         // (padding and non-aggregated alignments carry the tile's trash offset and are not stored)
         char *xp = reinterpret_cast<char *>(xs);
-        const uint32_t trash = U * kUnitStride * 8u;
+        const uint32_t trash = du.w;
         const uint32_t q0 = lp4.x >> 16, q1 = lp4.y >> 16, q2 = lp4.z >> 16, q3 = lp4.w >> 16;
         if (q0 != trash) *reinterpret_cast<double *>(xp + q0) = x0;
         if (q1 != trash) *reinterpret_cast<double *>(xp + q1) = x1;
@@ -680,30 +699,37 @@ __global__ void __launch_bounds__(kThreads, (5 * 8) / kWarps) em_sweep_tiled(Vie
             if (tid < Dn) pv = prev[table_n[tid]];
         }
 
-        // ---- phase 2: sum 8-slot units, combine equal transcripts across the warp ---------------
+        // ---- phase 2: one thread sums one item (<= 32 consecutive x slots of one transcript), one RED ----
         if (__any_sync(full, warp * 32u < U)) {
-            const uint32_t u_txp = unit == kNoTxp ? kNoTxp : (unit & (kMaxTxps - 1u));
-            // a unit is 8 doubles at an 80-byte stride (conflict-free LDS.128); its unused slots were cleared above
-            const double2 *b = reinterpret_cast<const double2 *>(xs + tid * kUnitStride);
-            const double2 v0 = b[0], v1 = b[1], v2 = b[2], v3 = b[3];
-            double acc = ((v0.x + v0.y) + (v1.x + v1.y)) + ((v2.x + v2.y) + (v3.x + v3.y));
-            const uint32_t up = __shfl_up_sync(full, u_txp, 1);
-            const uint32_t dn = __shfl_down_sync(full, u_txp, 1);
-            const bool head = (lane == 0) || (up != u_txp);
-            const bool tail = (lane == 31) || (dn != u_txp);
-            const unsigned hmask = __ballot_sync(full, head);
-            const uint32_t dist2 = lane - (31u - __clz(hmask & (full >> (31u - lane))));
-            const uint32_t maxd = __reduce_max_sync(full, dist2);     // longest run of one transcript in the warp
-            acc = fma(__shfl_up_sync(full, acc, 1), mask01(dist2 >= 1u), acc);
-            acc = fma(__shfl_up_sync(full, acc, 2), mask01(dist2 >= 2u), acc);
-            if (maxd >= 4u) {
-                acc = fma(__shfl_up_sync(full, acc, 4), mask01(dist2 >= 4u), acc);
-                if (maxd >= 8u) {
-                    acc = fma(__shfl_up_sync(full, acc, 8), mask01(dist2 >= 8u), acc);
-                    acc = fma(__shfl_up_sync(full, acc, 16), mask01(dist2 >= 16u), acc);
+            const uint32_t N32 = du.z & 0xFFFFu, N16 = du.z >> 16;
+            const uint32_t slots = item == kNoTxp ? 0u : (item >> 27) + 1u, npair = slots >> 1;
+            uint32_t bd = 34u * tid;   // x offset in doubles: size classes 32, 16, 8 at strides 34, 18, 10
+            if (tid >= N32) bd = 18u * tid + 16u * N32;
+            if (tid >= N32 + N16) bd = 10u * tid + 24u * N32 + 8u * N16;
+            const double2 *b = reinterpret_cast<const double2 *>(xs + bd);
+            const double2 zero = make_double2(0.0, 0.0);
+            double a0 = (slots & 1u) ? xs[bd + slots - 1u] : 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+            for (uint32_t k = 0; k < 4u; k += 2) {
+                const double2 u = k < npair ? b[k] : zero, w = k + 1u < npair ? b[k + 1u] : zero;
+                a0 += u.x; a1 += u.y; a2 += w.x; a3 += w.y;
+            }
+            if (__any_sync(full, npair > 4u)) {        // 16- and 32-slot items (they come first in the item order)
+#pragma unroll
+                for (uint32_t k = 4; k < 8u; k += 2) {
+                    const double2 u = k < npair ? b[k] : zero, w = k + 1u < npair ? b[k + 1u] : zero;
+                    a0 += u.x; a1 += u.y; a2 += w.x; a3 += w.y;
+                }
+                if (__any_sync(full, npair > 8u)) {    // 32-slot items
+#pragma unroll
+                    for (uint32_t k = 8; k < 16u; k += 2) {
+                        const double2 u = k < npair ? b[k] : zero, w = k + 1u < npair ? b[k + 1u] : zero;
+                        a0 += u.x; a1 += u.y; a2 += w.x; a3 += w.y;
+                    }
                 }
             }
-            if (tail && u_txp != kNoTxp) atomicAdd(curr + u_txp, acc);
+            const double acc = (a0 + a2) + (a1 + a3);
+            if (item != kNoTxp && acc != 0.0) atomicAdd(curr + (item & (kMaxTxps - 1u)), acc);
         }
 
         if (!has_next) break;

@@ -51,11 +51,16 @@ constexpr int kChunkCap = kChunk - 1;     // rows use at most 127 slots: a paddi
 constexpr int kTile = kWarps * kChunk;    // 1024 slots
 constexpr int kThreads = kWarps * 32;     // 256
 constexpr int kAggMin = 4;                // transcripts with >= kAggMin alignments in a tile are aggregated in smem
+#ifndef OAR_ITEM_MAX
+#define OAR_ITEM_MAX 16
+#endif
+constexpr int kItemMax = OAR_ITEM_MAX;    // x slots of the largest item size class; the classes are kItemMax, /2, /4
 constexpr int kMaxItems = kTile / 4;      // every item belongs to a transcript with >= 4 alignments and holds >= 4 of them
-// An aggregated transcript with cnt alignments in the tile owns cnt / 32 items of 32 consecutive x slots and one item
-// for the remainder, of the smallest size class (8, 16 or 32 slots) that holds it.  Items are ordered by class
-// (32s first); a class-c item sits c + 2 doubles behind its predecessor, so the 8 lanes of an LDS.128 phase hit 8
-// different 16-byte banks.  One thread sums one item and issues one RED: no cross-lane scan, no padding to clear.
+// An aggregated transcript with cnt alignments in the tile owns cnt / kItemMax items of kItemMax consecutive x slots
+// and one item for the remainder, of the smallest size class (kItemMax, /2, /4 slots) that holds it.  Items are
+// ordered by class (largest first); a class-c item sits c + 2 doubles behind its predecessor, so the 8 lanes of an
+// LDS.128 phase hit 8 different 16-byte banks.  One thread sums one item and issues one RED: no cross-lane scan, no
+// padding to clear.  (Measured on C3: 16-slot items 228 us, 32-slot items 232 us, 8-slot units + scan 244 us.)
 // padding and non-aggregated alignments write to a trash slot right after the last item of the tile
 constexpr uint32_t kInfoStray = 8u;       // chunk_info bit 3: chunk holds alignments that RED straight to global
 constexpr uint32_t kInfoMulti = 16u;      // chunk_info bit 4: some lane holds >= 2 row heads (general path)
@@ -71,7 +76,7 @@ static_assert(kMaxItems == kThreads, "one item per thread in phase 2");
 //                      the lane itself if there is none (then only padding follows)
 //   [512,544)  chunk_info u32[8]: scan steps (bits 0-2) | kInfoStray | kInfoMulti
 //   [544,576)  chunk_row  u32[8]: tile-order index of the chunk's first row (bootstrap weights)
-//   [576,592)  D, items, n32 | n16 << 16 (items per size class), trash x offset in bytes
+//   [576,592)  D, items, n0 | n1 << 16 (items of the largest and the middle size class), trash x offset in bytes
 //   [592, ..)  table u32[roundup4(D)]      : distinct transcript ids
 //              items u32[roundup4(items)]  : transcript id | (slots - 1) << 27
 constexpr int kRecDesc = 0, kRecInfo = 64 * kWarps, kRecRow = kRecInfo + 4 * kWarps, kRecDU = kRecRow + 4 * kWarps,
@@ -361,9 +366,10 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
             startd[i] = s_seg[d];
             cntd[i] = s_seg[d + 1] - startd[i];
             if (cntd[i] >= (uint32_t)kAggMin) {
-                const uint32_t rem = cntd[i] & 31u;
-                pk[i] = (cntd[i] >> 5) + (rem > 16u ? 1u : 0u) + ((rem > 8u && rem <= 16u) ? (1u << 10) : 0u) +
-                        ((rem >= 1u && rem <= 8u) ? (1u << 20) : 0u);
+                const uint32_t rem = cntd[i] % (uint32_t)kItemMax;
+                pk[i] = cntd[i] / (uint32_t)kItemMax + (rem > (uint32_t)kItemMax / 2u ? 1u : 0u) +
+                        ((rem > (uint32_t)kItemMax / 4u && rem <= (uint32_t)kItemMax / 2u) ? (1u << 10) : 0u) +
+                        ((rem >= 1u && rem <= (uint32_t)kItemMax / 4u) ? (1u << 20) : 0u);
             }
         }
     }
@@ -371,7 +377,8 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
     __syncthreads();
     const uint32_t N32 = PT & 0x3FFu, N16 = (PT >> 10) & 0x3FFu, N8 = PT >> 20;
     const uint32_t U = N32 + N16 + N8;                          // items of the tile
-    const uint32_t XD = 34u * N32 + 18u * N16 + 10u * N8;       // x doubles of the tile; the trash slot sits right behind
+    constexpr uint32_t kS0 = kItemMax + 2, kS1 = kItemMax / 2 + 2, kS2 = kItemMax / 4 + 2, kI = kItemMax;   // strides of the three classes
+    const uint32_t XD = kS0 * N32 + kS1 * N16 + kS2 * N8;       // x doubles of the tile; the trash slot sits right behind
     const uint32_t D4 = (D + 3u) & ~3u, U4 = (U + 3u) & ~3u;
     const uint32_t rec_bytes = kRecTable + 4u * D4 + 4u * U4;
     if (tid == 0) {
@@ -397,12 +404,12 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
             s_rec[kRecTable / 4 + d] = key;
             uint32_t *items = s_rec + kRecTable / 4 + D4;
             const uint32_t i32 = pbase[i] & 0x3FFu, i16 = (pbase[i] >> 10) & 0x3FFu, i8 = pbase[i] >> 20;
-            const uint32_t n32 = pk[i] & 0x3FFu, rem = cntd[i] & 31u;
+            const uint32_t n32 = pk[i] & 0x3FFu, rem = cntd[i] % kI;
             if (pk[i] == 0u) { segb[i] = 1u << 31; sega[i] = startd[i]; continue; }
-            for (uint32_t v = 0; v < n32; ++v) items[i32 + v] = key | ((min(32u, cntd[i] - 32u * v) - 1u) << 27);
+            for (uint32_t v = 0; v < n32; ++v) items[i32 + v] = key | ((min(kI, cntd[i] - kI * v) - 1u) << 27);
             uint32_t rem_x = 0;
-            if (rem > 8u && rem <= 16u) { items[N32 + i16] = key | ((rem - 1u) << 27); rem_x = 34u * N32 + 18u * i16; }
-            else if (rem >= 1u && rem <= 8u) { items[N32 + N16 + i8] = key | ((rem - 1u) << 27); rem_x = 34u * N32 + 18u * N16 + 10u * i8; }
+            if (rem > kI / 4u && rem <= kI / 2u) { items[N32 + i16] = key | ((rem - 1u) << 27); rem_x = kS0 * N32 + kS1 * i16; }
+            else if (rem >= 1u && rem <= kI / 4u) { items[N32 + N16 + i8] = key | ((rem - 1u) << 27); rem_x = kS0 * N32 + kS1 * N16 + kS2 * i8; }
             sega[i] = startd[i] | (i32 << 11);
             segb[i] = rem_x | (n32 << 12);
         }
@@ -425,7 +432,7 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
             uint32_t pos = XD;   // trash slot of this tile
             if ((pb >> 31) == 0u) {
                 const uint32_t rr = r - (pa & 0x7FFu), n32 = (pb >> 12) & 0x3FFu;
-                pos = rr < 32u * n32 ? 34u * ((pa >> 11) + (rr >> 5)) + (rr & 31u) : (pb & 0xFFFu) + (rr - 32u * n32);
+                pos = rr < kI * n32 ? kS0 * ((pa >> 11) + rr / kI) + rr % kI : (pb & 0xFFFu) + (rr - kI * n32);
             } else atomicOr(&s_info[vals[i] / kChunk], kInfoStray);
             s_lpos[vals[i]] = (d * 8u) | ((pos * 8u) << 16);
         } else {
@@ -703,26 +710,27 @@ __global__ void __launch_bounds__(kThreads, (5 * 8) / kWarps) em_sweep_tiled(Vie
         if (__any_sync(full, warp * 32u < U)) {
             const uint32_t N32 = du.z & 0xFFFFu, N16 = du.z >> 16;
             const uint32_t slots = item == kNoTxp ? 0u : (item >> 27) + 1u, npair = slots >> 1;
-            uint32_t bd = 34u * tid;   // x offset in doubles: size classes 32, 16, 8 at strides 34, 18, 10
-            if (tid >= N32) bd = 18u * tid + 16u * N32;
-            if (tid >= N32 + N16) bd = 10u * tid + 24u * N32 + 8u * N16;
+            constexpr uint32_t kS0 = kItemMax + 2, kS1 = kItemMax / 2 + 2, kS2 = kItemMax / 4 + 2, kP = kItemMax / 2;
+            uint32_t bd = kS0 * tid;   // x offset in doubles: the three size classes at strides c + 2
+            if (tid >= N32) bd = kS1 * tid + (kS0 - kS1) * N32;
+            if (tid >= N32 + N16) bd = kS2 * tid + (kS0 - kS2) * N32 + (kS1 - kS2) * N16;
             const double2 *b = reinterpret_cast<const double2 *>(xs + bd);
             const double2 zero = make_double2(0.0, 0.0);
             double a0 = (slots & 1u) ? xs[bd + slots - 1u] : 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-            for (uint32_t k = 0; k < 4u; k += 2) {
+            for (uint32_t k = 0; k < kP / 4u; k += 2) {
                 const double2 u = k < npair ? b[k] : zero, w = k + 1u < npair ? b[k + 1u] : zero;
                 a0 += u.x; a1 += u.y; a2 += w.x; a3 += w.y;
             }
-            if (__any_sync(full, npair > 4u)) {        // 16- and 32-slot items (they come first in the item order)
+            if (__any_sync(full, npair > kP / 4u)) {        // items of the two larger classes (they come first in the item order)
 #pragma unroll
-                for (uint32_t k = 4; k < 8u; k += 2) {
+                for (uint32_t k = kP / 4u; k < kP / 2u; k += 2) {
                     const double2 u = k < npair ? b[k] : zero, w = k + 1u < npair ? b[k + 1u] : zero;
                     a0 += u.x; a1 += u.y; a2 += w.x; a3 += w.y;
                 }
-                if (__any_sync(full, npair > 8u)) {    // 32-slot items
+                if (__any_sync(full, npair > kP / 2u)) {    // items of the largest class
 #pragma unroll
-                    for (uint32_t k = 8; k < 16u; k += 2) {
+                    for (uint32_t k = kP / 2u; k < kP; k += 2) {
                         const double2 u = k < npair ? b[k] : zero, w = k + 1u < npair ? b[k + 1u] : zero;
                         a0 += u.x; a1 += u.y; a2 += w.x; a3 += w.y;
                     }

@@ -180,6 +180,9 @@ def run_gpu(args):
     multi = world > 1
     if multi:
         import torch.distributed as dist
+        # stdout carries exactly one JSON line: NCCL's own banner / debug lines (NCCL_DEBUG=VERSION|INFO on some
+        # boxes) go to a file instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/oarfish_bench_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():

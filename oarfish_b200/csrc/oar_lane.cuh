@@ -46,7 +46,7 @@ namespace lane {
 #define OAR_LANE_REG_ROWS 12
 #endif
 #ifndef OAR_LANE_GROUP_CAP
-#define OAR_LANE_GROUP_CAP 320
+#define OAR_LANE_GROUP_CAP 288
 #endif
 constexpr int kWarps = OAR_LANE_WARPS;          // warps per sweep CTA (each one independent)
 constexpr int kThreads = kWarps * 32;

@@ -54,6 +54,12 @@ constexpr int kAggMin = 4;                // transcripts with >= kAggMin alignme
 #ifndef OAR_ITEM_MAX
 #define OAR_ITEM_MAX 16
 #endif
+#ifndef OAR_TILED_MIN_CTAS
+#define OAR_TILED_MIN_CTAS 5    // register budget of the two-barrier sweep: 48 registers per thread
+#endif
+#ifndef OAR_SHORT_ROW_DEFER
+#define OAR_SHORT_ROW_DEFER 1   // layout: keep rows shorter than a lane from starting and ending inside one lane
+#endif
 constexpr int kItemMax = OAR_ITEM_MAX;    // x slots of the largest item size class; the classes are kItemMax, /2, /4
 constexpr int kMaxItems = kTile / 4;      // every item belongs to a transcript with >= 4 alignments and holds >= 4 of them
 // An aggregated transcript with cnt alignments in the tile owns cnt / kItemMax items of kItemMax consecutive x slots
@@ -88,7 +94,9 @@ constexpr int kStages = 2;
 // unit count over all tiles) so that as many CTAs as possible fit on an SM.
 struct Geometry {
     uint32_t stage_bytes;   // prob (4 KB) | lpos (4 KB) | record (max over tiles, 16 B multiple)
-    uint32_t xs_off;        // after the stages: transcript-sorted x values in items (+ trash)
+    uint32_t xs_off;        // 0: transcript-sorted x values in items (+ trash) sit at the start of the window, so the
+                            // scatter addresses are the stored offsets themselves
+    uint32_t stage_off;     // the two stages
     uint32_t prev_off;      // prev[] of the tile's transcripts
     uint32_t bar_off;       // two mbarriers
     uint32_t total;         // dynamic shared memory per CTA
@@ -99,10 +107,11 @@ inline Geometry make_geometry(uint32_t max_rec_bytes, uint32_t max_d, uint32_t m
     Geometry g;
     const uint32_t rec = (max_rec_bytes + 15u) & ~15u;
     g.stage_bytes = 8u * kTile + rec;
-    g.xs_off = kStages * g.stage_bytes;
+    g.xs_off = 0;
     // the items of the fullest tile, then the trash slot; even count
     g.xs_doubles = (max_x_doubles + 2u + 1u) & ~1u;
-    g.prev_off = g.xs_off + 8u * g.xs_doubles;
+    g.stage_off = (8u * g.xs_doubles + 127u) & ~127u;
+    g.prev_off = g.stage_off + kStages * g.stage_bytes;
     g.bar_off = g.prev_off + 8u * ((max_d + 1u) & ~1u);
     g.total = g.bar_off + 16u;
     return g;
@@ -228,12 +237,12 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
         uint32_t used[kWarps], cnt[kWarps], span[kWarps];
 #pragma unroll
         for (int c = 0; c < kWarps; ++c) { used[c] = 0; cnt[c] = 0; span[c] = 0; }
-        for (uint32_t i = 0; i < nrows; ++i) {
+        // Rows shorter than a lane (4 slots) must not start and end inside one lane: two row heads in a lane
+        // send the whole chunk down the general segmented-sum path of the sweep.  The order of the rows inside a
+        // tile is free, so a short row waits until a chunk's fill position lets it cross a lane boundary
+        // ((used & 3) + len >= 4); what is still waiting at the end is placed wherever it fits.
+        auto place = [&](uint32_t i, int pick) {
             const uint32_t len = s_rlen[i];
-            int pick = -1;
-#pragma unroll
-            for (int c = 0; c < kWarps; ++c) if (pick < 0 && used[c] + len <= (uint32_t)kChunkCap) pick = c;
-            if (pick < 0) { s_rslot[i] = 0xFFFF; continue; }
 #pragma unroll
             for (int c = 0; c < kWarps; ++c) if (c == pick) {
                 s_rslot[i] = (uint16_t)(c * kChunk + used[c]);
@@ -242,6 +251,39 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
                 span[c] = max(span[c], lanes);
                 used[c] += len; cnt[c] += 1;
             }
+        };
+        auto first_fit = [&](uint32_t len, bool clean) {
+            int pick = -1;
+#pragma unroll
+            for (int c = 0; c < kWarps; ++c)
+                if (pick < 0 && used[c] + len <= (uint32_t)kChunkCap && (!clean || (used[c] & 3u) + len >= 4u)) pick = c;
+            return pick;
+        };
+        constexpr uint32_t kPend = 12;
+        uint32_t pend[kPend], np = 0;
+        for (uint32_t i = 0; i < nrows; ++i) {
+            const uint32_t len = s_rlen[i];
+            if (OAR_SHORT_ROW_DEFER && len < 4u && np < kPend) {
+                const int pc = first_fit(len, true);
+                if (pc >= 0) place(i, pc); else pend[np++] = i;
+                continue;
+            }
+            const int pick = first_fit(len, false);
+            if (pick < 0) { s_rslot[i] = 0xFFFF; continue; }
+            place(i, pick);
+            for (uint32_t k = 0; k < np;) {       // waiting short rows: does one fit cleanly now?
+                const int pc = first_fit(s_rlen[pend[k]], true);
+                if (pc < 0) { ++k; continue; }
+                place(pend[k], pc);
+                for (uint32_t m = k + 1; m < np; ++m) pend[m - 1] = pend[m];
+                --np;
+            }
+        }
+        for (uint32_t k = 0; k < np; ++k) {
+            const uint32_t i = pend[k];
+            int pick = first_fit(s_rlen[i], true);
+            if (pick < 0) pick = first_fit(s_rlen[i], false);
+            if (pick < 0) s_rslot[i] = 0xFFFF; else place(i, pick);
         }
 #pragma unroll
         for (int c = 0; c < kWarps; ++c) {
@@ -496,255 +538,458 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// --- explicit shared-space accesses ------------------------------------------
+// The sweep addresses shared memory with 32-bit shared-space addresses: with generic pointers the compiler
+// re-derives the shared window base (S2UR SR_CgaCtaId + ULEA) every iteration and cannot fold the window
+// offsets into the LDS/STS address operands.
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t r; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a)); return r; }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t r; asm volatile("{.reg .u16 h; ld.shared.u16 h, [%1]; cvt.u32.u16 %0, h;}" : "=r"(r) : "r"(a)); return r; }
+__device__ __forceinline__ uint4 lds_v4(uint32_t a)
+{ uint4 r; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a)); return r; }
+__device__ __forceinline__ float4 lds_v4f(uint32_t a)
+{ float4 r; asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a)); return r; }
+__device__ __forceinline__ double lds_f64(uint32_t a) { double r; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(a)); return r; }
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void sts_f64_if(uint32_t a, double v, bool on)
+{ asm volatile("{.reg .pred p; setp.ne.u32 p, %2, 0; @p st.shared.f64 [%0], %1;}" ::"r"(a), "d"(v), "r"((uint32_t)on) : "memory"); }
+// 0.0 unless `on`
+__device__ __forceinline__ double lds_f64_if(uint32_t a, bool on)
+{
+    double r;
+    asm volatile("{.reg .pred p; setp.ne.u32 p, %2, 0; mov.f64 %0, 0d0000000000000000; @p ld.shared.f64 %0, [%1];}"
+                 : "=d"(r) : "r"(a), "r"((uint32_t)on));
+    return r;
+}
+// {0.0, 0.0} unless `on`
+__device__ __forceinline__ double2 lds_v2f64_if(uint32_t a, bool on)
+{
+    double2 r;
+    asm volatile("{.reg .pred p; setp.ne.u32 p, %3, 0; mov.f64 %0, 0d0000000000000000; mov.f64 %1, 0d0000000000000000;"
+                 " @p ld.shared.v2.f64 {%0,%1}, [%2];}" : "=d"(r.x), "=d"(r.y) : "r"(a), "r"((uint32_t)on));
+    return r;
+}
+// warp vote on bits of a word that is the same in every lane (LOP3 with predicate output + VOTE)
+__device__ __forceinline__ bool any_bits(uint32_t v, uint32_t mask)
+{
+    uint32_t r;
+    asm volatile("{.reg .pred p, q; .reg .b32 t; and.b32 t, %1, %2; setp.ne.u32 p, t, 0; vote.sync.any.pred q, p, 0xffffffff;"
+                 " selp.u32 %0, 1, 0, q;}" : "=r"(r) : "r"(v), "r"(mask));
+    return r != 0u;
+}
+
+// ---- phase 1 of a tile: E-step in registers + M-step scatter into the transcript-sorted x array -------------
+//   bulk, rec: shared-space addresses of the tile's prob | lpos block and of its record; sp_a: prev[] of the tile's
+//   transcripts; xs_a: the x array.  Returns the thread's item and the record's DU word for phase 2.
+template <bool HAS_AUX, bool HAS_WTS>
+__device__ __forceinline__ void tile_phase1(const View &v, uint32_t tile, uint32_t bulk, uint32_t rec, uint32_t sp_a, uint32_t xs_a,
+                                            uint32_t tid, uint32_t lane, uint32_t warp, double *__restrict__ curr,
+                                            const uint32_t *__restrict__ wperm, uint32_t &item, uint4 &du)
+{
+    const unsigned full = 0xffffffffu;
+    const float4 p4 = lds_v4f(bulk + 16u * tid);                    // slots warp * kChunk + lane * 4 ..
+    const uint4 lp4 = lds_v4(bulk + 4u * kTile + 16u * tid);
+    const uint32_t desc = lds_u16(rec + kRecDesc + 2u * tid);
+    const uint32_t info = lds_u32(rec + kRecInfo + 4u * warp);
+    du = lds_v4(rec + kRecDU);   // D, items, n32 | n16 << 16, trash offset
+    const uint32_t D = du.x, U = du.y;
+    const uint32_t table_a = rec + kRecTable;
+    // this thread's item (read now: the record's stage is refilled before phase 2)
+    item = kNoTxp;
+    if (tid < U) item = lds_u32(table_a + 4u * (((D + 3u) & ~3u) + tid));
+
+    double w0 = lds_f64(sp_a + (lp4.x & 0xFFFFu)) * (double)p4.x;
+    double w1 = lds_f64(sp_a + (lp4.y & 0xFFFFu)) * (double)p4.y;
+    double w2 = lds_f64(sp_a + (lp4.z & 0xFFFFu)) * (double)p4.z;
+    double w3 = lds_f64(sp_a + (lp4.w & 0xFFFFu)) * (double)p4.w;
+    if (HAS_AUX) {
+        const double *ax = v.aux + (size_t)tile * kTile + 4u * tid;
+        const double2 q0 = *reinterpret_cast<const double2 *>(ax);
+        const double2 q1 = *reinterpret_cast<const double2 *>(ax + 2);
+        w0 *= q0.x; w1 *= q0.y; w2 *= q1.x; w3 *= q1.y;
+    }
+
+    const uint32_t hb = desc & 15u, dist = (desc >> 4) & 31u, E = (desc >> 9) & 31u;
+    // chunk_info is the same word for the whole warp; votes make that visible to the compiler
+    const bool multi = any_bits(info, kInfoMulti);
+    const bool strays = any_bits(info, kInfoStray);
+    const bool long_rows = any_bits(info, 4u);   // scan steps > 3: rows spanning more than 8 lanes
+    double x0, x1, x2, x3;
+    if (!multi) {
+        // fast path: no lane holds more than one row head.  Slot i lies before that head (it
+        // closes the row entering the lane) iff hb >> (i+1) != 0; slot 3 never does.
+        //   a = slots before the head, z = slots from the head on (all four if there is none)
+        const bool c0 = (hb >> 1) != 0u, c1 = (hb >> 2) != 0u, c2 = (hb >> 3) != 0u;
+        double a = w0 * mask01(c0);
+        a = fma(w1, mask01(c1), a);
+        a = fma(w2, mask01(c2), a);
+        double z = fma(w0, mask01(!c0), w3);
+        z = fma(w1, mask01(!c1), z);
+        z = fma(w2, mask01(!c2), z);
+        // segmented inclusive scan over lanes: what each lane adds to the row open at its end
+        double incl = z;
+        incl = fma(__shfl_up_sync(full, incl, 1), mask01(dist >= 1u), incl);
+        incl = fma(__shfl_up_sync(full, incl, 2), mask01(dist >= 2u), incl);
+        incl = fma(__shfl_up_sync(full, incl, 4), mask01(dist >= 4u), incl);
+        if (long_rows) {   // rows spanning more than 8 lanes (rare)
+            incl = fma(__shfl_up_sync(full, incl, 8), mask01(dist >= 8u), incl);
+            incl = fma(__shfl_up_sync(full, incl, 16), mask01(dist >= 16u), incl);
+        }
+        const double carry = __shfl_up_sync(full, incl, 1);       // sum of the row entering this lane
+        const double t_in = carry + a;                            // its total, if it ends here
+        // reads whose denominator is <= 1e-30 contribute nothing (em.rs:115)
+        double inv_in = t_in > OAR_EM_DENOM_THRESH ? fast_rcp(t_in) : 0.0;
+        if (HAS_WTS) {
+            // bootstrap: fold the row's resampling weight into its inverse denominator.  The row whose
+            // total is t_in is the chunk's row number (heads in earlier lanes) - 1; one head per lane here.
+            const unsigned lanes_h = __ballot_sync(full, hb != 0u);
+            const uint32_t before = __popc(lanes_h & ((1u << lane) - 1u));
+            const uint32_t row_base = lds_u32(rec + kRecRow + 4u * warp);
+            if (before) inv_in *= (double)wperm[row_base + before - 1u];
+        }
+        // the row leaving this lane ends in lane E (E == lane: only padding follows, w == 0)
+        const double inv_out = __shfl_sync(full, inv_in, E);
+        x0 = w0 * (c0 ? inv_in : inv_out);
+        x1 = w1 * (c1 ? inv_in : inv_out);
+        x2 = w2 * (c2 ? inv_in : inv_out);
+        x3 = w3 * inv_out;
+    } else {
+        // general path: rows may start and end inside one lane
+        const uint32_t nsteps = info & 7u;
+        const double s0 = w0;
+        const double s1 = (hb & 2u) ? w1 : s0 + w1;
+        const double s2 = (hb & 4u) ? w2 : s1 + w2;
+        const double s3 = (hb & 8u) ? w3 : s2 + w3;
+        double incl = s3;                                         // segmented inclusive scan of lane tails
+#pragma unroll
+        for (uint32_t i = 0; i < 5; ++i) {
+            if (i >= nsteps) break;
+            const uint32_t d = 1u << i;
+            incl = fma(__shfl_up_sync(full, incl, d), mask01(dist >= d), incl);
+        }
+        double carry = __shfl_up_sync(full, incl, 1);
+        if (lane == 0) carry = 0.0;
+        const double sA = (hb & 1u) ? 0.0 : (hb & 2u) ? s0 : (hb & 4u) ? s1 : (hb & 8u) ? s2 : s3;
+        const double t_in = carry + sA;
+        const double t_out = __shfl_sync(full, t_in, E);
+        const double pre0 = (hb & 1u) ? s0 : carry + s0;
+        const double pre1 = (hb & 3u) ? s1 : carry + s1;
+        const double pre2 = (hb & 7u) ? s2 : carry + s2;
+        const double tot3 = t_out;
+        const double tot2 = (hb & 8u) ? pre2 : tot3;
+        const double tot1 = (hb & 4u) ? pre1 : tot2;
+        const double tot0 = (hb & 2u) ? pre0 : tot1;
+        x0 = tot0 > OAR_EM_DENOM_THRESH ? w0 * fast_rcp(tot0) : 0.0;
+        x1 = tot1 > OAR_EM_DENOM_THRESH ? w1 * fast_rcp(tot1) : 0.0;
+        x2 = tot2 > OAR_EM_DENOM_THRESH ? w2 * fast_rcp(tot2) : 0.0;
+        x3 = tot3 > OAR_EM_DENOM_THRESH ? w3 * fast_rcp(tot3) : 0.0;
+    }
+
+    if (HAS_WTS && multi) {
+        // general path: row index of a slot inside the chunk = (number of heads at or before it) - 1
+        uint32_t incl_h = __popc(hb);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(full, incl_h, d);
+            if ((int)lane >= d) incl_h += t;
+        }
+        const uint32_t row_base = lds_u32(rec + kRecRow + 4u * warp);
+        const uint32_t r0 = row_base + incl_h - __popc(hb) + (hb & 1u) - 1u;
+        const uint32_t r1 = r0 + ((hb >> 1) & 1u), r2 = r1 + ((hb >> 2) & 1u), r3 = r2 + ((hb >> 3) & 1u);
+        x0 *= (double)wperm[r0];
+        x1 *= (double)wperm[r1];
+        x2 *= (double)wperm[r2];
+        x3 *= (double)wperm[r3];
+    }
+
+    // ---- M-step scatter into the transcript-sorted smem order -----------------------------
+    // (padding and non-aggregated alignments carry the tile's trash offset and are not stored)
+    const uint32_t trash = du.w;
+    const uint32_t q0 = lp4.x >> 16, q1 = lp4.y >> 16, q2 = lp4.z >> 16, q3 = lp4.w >> 16;
+#ifdef OAR_FAKE_SCATTER   // timing experiment only (wrong results): conflict-free scatter addresses
+    sts_f64_if(xs_a + 8u * lane + 256u * warp, x0, q0 != trash);
+    sts_f64_if(xs_a + 8u * lane + 256u * warp + 2048u, x1, q1 != trash);
+    sts_f64_if(xs_a + 8u * lane + 256u * warp + 4096u, x2, q2 != trash);
+    sts_f64_if(xs_a + 8u * lane + 256u * warp + 6144u, x3, q3 != trash);
+#else
+    sts_f64_if(xs_a + q0, x0, q0 != trash);
+    sts_f64_if(xs_a + q1, x1, q1 != trash);
+    sts_f64_if(xs_a + q2, x2, q2 != trash);
+    sts_f64_if(xs_a + q3, x3, q3 != trash);
+#endif
+    if (strays) {
+        // transcripts with fewer than kAggMin alignments in this tile: straight to global
+        if (q0 == trash && x0 != 0.0) atomicAdd(curr + lds_u32(table_a + ((lp4.x & 0xFFFFu) >> 1)), x0);
+        if (q1 == trash && x1 != 0.0) atomicAdd(curr + lds_u32(table_a + ((lp4.y & 0xFFFFu) >> 1)), x1);
+        if (q2 == trash && x2 != 0.0) atomicAdd(curr + lds_u32(table_a + ((lp4.z & 0xFFFFu) >> 1)), x2);
+        if (q3 == trash && x3 != 0.0) atomicAdd(curr + lds_u32(table_a + ((lp4.w & 0xFFFFu) >> 1)), x3);
+    }
+}
+
+// ---- phase 2 of a tile: one thread sums one item (<= 16 consecutive x slots of one transcript), one RED -------
+__device__ __forceinline__ void tile_phase2(uint32_t xs_a, uint32_t item, uint32_t U, uint32_t duz, uint32_t tid, uint32_t warp,
+                                            double *__restrict__ curr)
+{
+    const unsigned full = 0xffffffffu;
+    if (__any_sync(full, warp * 32u < U)) {
+        const uint32_t N32 = duz & 0xFFFFu, N16 = duz >> 16;
+        const uint32_t slots = item == kNoTxp ? 0u : (item >> 27) + 1u, npair = slots >> 1;
+        constexpr uint32_t kS0 = kItemMax + 2, kS1 = kItemMax / 2 + 2, kS2 = kItemMax / 4 + 2, kP = kItemMax / 2;
+        uint32_t bd = kS0 * tid;   // x offset in doubles: the three size classes at strides c + 2
+        if (tid >= N32) bd = kS1 * tid + (kS0 - kS1) * N32;
+        if (tid >= N32 + N16) bd = kS2 * tid + (kS0 - kS2) * N32 + (kS1 - kS2) * N16;
+        const uint32_t b = xs_a + 8u * bd;
+        double a0 = lds_f64_if(b + 8u * (slots - 1u), (slots & 1u) != 0u), a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+        for (uint32_t k = 0; k < kP / 4u; k += 2) {
+            const double2 u = lds_v2f64_if(b + 16u * k, k < npair), w = lds_v2f64_if(b + 16u * (k + 1u), k + 1u < npair);
+            a0 += u.x; a1 += u.y; a2 += w.x; a3 += w.y;
+        }
+        if (__any_sync(full, npair > kP / 4u)) {        // items of the two larger classes (they come first in the item order)
+#pragma unroll
+            for (uint32_t k = kP / 4u; k < kP / 2u; k += 2) {
+                const double2 u = lds_v2f64_if(b + 16u * k, k < npair), w = lds_v2f64_if(b + 16u * (k + 1u), k + 1u < npair);
+                a0 += u.x; a1 += u.y; a2 += w.x; a3 += w.y;
+            }
+            if (__any_sync(full, npair > kP / 2u)) {    // items of the largest class
+#pragma unroll
+                for (uint32_t k = kP / 2u; k < kP; k += 2) {
+                    const double2 u = lds_v2f64_if(b + 16u * k, k < npair), w = lds_v2f64_if(b + 16u * (k + 1u), k + 1u < npair);
+                    a0 += u.x; a1 += u.y; a2 += w.x; a3 += w.y;
+                }
+            }
+        }
+        const double acc = (a0 + a2) + (a1 + a3);
+        if (item != kNoTxp && acc != 0.0) atomicAdd(curr + (item & (kMaxTxps - 1u)), acc);
+    }
+
+}
+
 // m_step (em.rs:87-133), persistent and TMA-fed.
 template <bool HAS_AUX, bool HAS_WTS>
-__global__ void __launch_bounds__(kThreads, (5 * 8) / kWarps) em_sweep_tiled(View v, Geometry g, const double *__restrict__ prev,
+__global__ void __launch_bounds__(kThreads, (OAR_TILED_MIN_CTAS * 8) / kWarps) em_sweep_tiled(View v, Geometry g, const double *__restrict__ prev,
                                                               double *__restrict__ curr,
                                                               const uint32_t *__restrict__ wperm,
                                                               const OarEmState *__restrict__ st, int check_done)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    // [stage 0][stage 1][xs][s_prev][mbarriers]; a stage = prob | lpos | record
-    unsigned char *stage_base = smem;
-    double *xs = reinterpret_cast<double *>(smem + g.xs_off);
-    double *s_prev = reinterpret_cast<double *>(smem + g.prev_off);
-    unsigned char *bars = smem + g.bar_off;
-    const uint32_t kStageBytes = g.stage_bytes;
+    // [xs][stage 0][stage 1][s_prev][mbarriers]; a stage = prob | lpos | record
 
     if (check_done && st->done) return;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t n_tiles = v.n_tiles, stride = gridDim.x;
     const uint32_t tile0 = blockIdx.x;
     if (tile0 >= n_tiles) return;
-    const uint32_t bar0 = smem_u32(bars), stage0 = smem_u32(stage_base);
+    const uint32_t kStageBytes = g.stage_bytes;
+    uint32_t sm0;   // shared-space address of the window, computed once (a plain cvta is rematerialised every iteration)
+    asm volatile("{.reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t;}" : "=r"(sm0) : "l"(smem));
+    const uint32_t stage0 = sm0 + g.stage_off, sp_a = sm0 + g.prev_off, bar0 = sm0 + g.bar_off;
+    // xs sits at the start of the window; the plain cvta is warp-uniform to the compiler, so the scatter and the
+    // item reads address it as [offset + uniform base]
+    const uint32_t xs_a = smem_u32(smem);
 
-    auto issue = [&](uint32_t tile, uint32_t s, uint2 r) {   // thread 0 only
+    // Work between the two CTA barriers of a tile is spread over the warps: the first warps sum the items
+    // (phase 2), lane 0 of the last-but-one warp issues the TMA copies, the last warp gathers prev[].
+    const bool is_tma = tid == 32u * (kWarps - 2);
+    auto issue = [&](uint32_t tile, uint32_t s, uint2 r) {   // the TMA thread only
         const uint32_t bar = bar0 + 8u * s, dst = stage0 + s * kStageBytes;
         mbar_expect_tx(bar, 8u * kTile + r.y);
         bulk_g2s(dst, v.prob + (size_t)tile * kTile, 4u * kTile, bar);
         bulk_g2s(dst + 4u * kTile, v.lpos + (size_t)tile * kTile, 4u * kTile, bar);
         bulk_g2s(dst + 8u * kTile, v.records + r.x, r.y, bar);
     };
+    // prev[] of a tile's transcripts into s_prev, by one warp (two gathers in flight per lane)
+    auto gather_prev = [&](uint32_t rec_a) {
+        const uint32_t Dn = lds_u32(rec_a + kRecDU);
+        for (uint32_t d = lane; d < Dn; d += 64u) {
+            const uint32_t d2 = d + 32u;
+            const double p0 = prev[lds_u32(rec_a + kRecTable + 4u * d)];
+            double p1 = 0.0;
+            if (d2 < Dn) p1 = prev[lds_u32(rec_a + kRecTable + 4u * d2)];
+            sts_f64(sp_a + 8u * d, p0);
+            if (d2 < Dn) sts_f64(sp_a + 8u * d2, p1);
+        }
+    };
 
-    uint2 r_pending = make_uint2(0, 0);   // record locator of the tile two ahead (thread 0)
+    uint2 r_pending = make_uint2(0, 0);   // record locator of the tile two ahead (TMA thread)
     if (tid == 0) {
         mbar_init(bar0, 1);
         mbar_init(bar0 + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (is_tma) {
         issue(tile0, 0, v.rec[tile0]);
         if (tile0 + stride < n_tiles) issue(tile0 + stride, 1, v.rec[tile0 + stride]);
         if (tile0 + 2 * stride < n_tiles) r_pending = v.rec[tile0 + 2 * stride];
     }
-    __syncthreads();
-    // prev[] of the first tile's transcripts
-    mbar_wait(bar0, 0);
-    {
-        const unsigned char *rec = stage_base + 8 * kTile;
-        const uint32_t D = *reinterpret_cast<const uint32_t *>(rec + kRecDU);
-        const uint32_t *table = reinterpret_cast<const uint32_t *>(rec + kRecTable);
-        for (uint32_t d = tid; d < D; d += kThreads) s_prev[d] = prev[table[d]];
+    // Only the last warp waits on the stage mbarriers and gathers prev[]; the CTA barrier that follows hands the
+    // TMA-written stage on to the other warps (mbarrier completion observed by one thread + bar.sync is cumulative).
+    if (warp == kWarps - 1) {
+        mbar_wait(bar0, 0);
+        gather_prev(stage0 + 8u * kTile);
     }
 
     uint32_t tile = tile0;
     for (uint32_t it = 0;; ++it) {
         const uint32_t s = it & 1u;
-        const unsigned char *stg = stage_base + s * kStageBytes;
-        const unsigned char *rec = stg + 8 * kTile;
-        __syncthreads();   // s_prev of this tile is in place; phase 2 of the previous tile has left xs
+        const uint32_t stg = stage0 + s * kStageBytes;
+        const uint32_t rec = stg + 8u * kTile;
+        __syncthreads();   // stage s and s_prev of this tile are in place; phase 2 of the previous tile has left xs
 
-        // ---- phase 1: E-step in registers ---------------------------------------------------
-        const uint32_t slot = warp * kChunk + lane * 4;
-        const float4 p4 = *reinterpret_cast<const float4 *>(stg + 4 * slot);
-        const uint4 lp4 = *reinterpret_cast<const uint4 *>(stg + 4 * kTile + 4 * slot);
-        const uint32_t desc = reinterpret_cast<const uint16_t *>(rec + kRecDesc)[tid];
-        const uint32_t info = reinterpret_cast<const uint32_t *>(rec + kRecInfo)[warp];
-        const uint4 du = *reinterpret_cast<const uint4 *>(rec + kRecDU);   // D, items, n32 | n16 << 16, trash offset
-        const uint32_t D = du.x, U = du.y;
-        const uint32_t *table = reinterpret_cast<const uint32_t *>(rec + kRecTable);
-        // this thread's item (read now: the record's stage is refilled before phase 2)
-        const uint32_t item = (tid < U) ? table[((D + 3u) & ~3u) + tid] : kNoTxp;
-
-        const char *sp = reinterpret_cast<const char *>(s_prev);
-        double w0 = *reinterpret_cast<const double *>(sp + (lp4.x & 0xFFFFu)) * (double)p4.x;
-        double w1 = *reinterpret_cast<const double *>(sp + (lp4.y & 0xFFFFu)) * (double)p4.y;
-        double w2 = *reinterpret_cast<const double *>(sp + (lp4.z & 0xFFFFu)) * (double)p4.z;
-        double w3 = *reinterpret_cast<const double *>(sp + (lp4.w & 0xFFFFu)) * (double)p4.w;
-        if (HAS_AUX) {
-            const double *ax = v.aux + (size_t)tile * kTile + slot;
-            const double2 q0 = *reinterpret_cast<const double2 *>(ax);
-            const double2 q1 = *reinterpret_cast<const double2 *>(ax + 2);
-            w0 *= q0.x; w1 *= q0.y; w2 *= q1.x; w3 *= q1.y;
-        }
-
-        const unsigned full = 0xffffffffu;
-        const uint32_t hb = desc & 15u, dist = (desc >> 4) & 31u, E = (desc >> 9) & 31u;
-        // chunk_info is the same word for the whole warp; votes make that visible to the compiler
-        const bool multi = __any_sync(full, (info & kInfoMulti) != 0u);
-        const bool strays = __any_sync(full, (info & kInfoStray) != 0u);
-        const bool long_rows = __any_sync(full, (info & 7u) > 3u);
-        double x0, x1, x2, x3;
-        if (!multi) {
-            // fast path: no lane holds more than one row head.  Slot i lies before that head (it
-            // closes the row entering the lane) iff hb >> (i+1) != 0; slot 3 never does.
-            //   a = slots before the head, z = slots from the head on (all four if there is none)
-            const bool c0 = (hb >> 1) != 0u, c1 = (hb >> 2) != 0u, c2 = (hb >> 3) != 0u;
-            double a = w0 * mask01(c0);
-            a = fma(w1, mask01(c1), a);
-            a = fma(w2, mask01(c2), a);
-            double z = fma(w0, mask01(!c0), w3);
-            z = fma(w1, mask01(!c1), z);
-            z = fma(w2, mask01(!c2), z);
-            // segmented inclusive scan over lanes: what each lane adds to the row open at its end
-            double incl = z;
-            incl = fma(__shfl_up_sync(full, incl, 1), mask01(dist >= 1u), incl);
-            incl = fma(__shfl_up_sync(full, incl, 2), mask01(dist >= 2u), incl);
-            incl = fma(__shfl_up_sync(full, incl, 4), mask01(dist >= 4u), incl);
-            if (long_rows) {   // rows spanning more than 8 lanes (rare)
-                incl = fma(__shfl_up_sync(full, incl, 8), mask01(dist >= 8u), incl);
-                incl = fma(__shfl_up_sync(full, incl, 16), mask01(dist >= 16u), incl);
-            }
-            const double carry = __shfl_up_sync(full, incl, 1);       // sum of the row entering this lane
-            const double t_in = carry + a;                            // its total, if it ends here
-            // reads whose denominator is <= 1e-30 contribute nothing (em.rs:115)
-            double inv_in = t_in > OAR_EM_DENOM_THRESH ? fast_rcp(t_in) : 0.0;
-            if (HAS_WTS) {
-                // bootstrap: fold the row's resampling weight into its inverse denominator.  The row whose
-                // total is t_in is the chunk's row number (heads in earlier lanes) - 1; one head per lane here.
-                const unsigned lanes_h = __ballot_sync(full, hb != 0u);
-                const uint32_t before = __popc(lanes_h & ((1u << lane) - 1u));
-                const uint32_t row_base = reinterpret_cast<const uint32_t *>(rec + kRecRow)[warp];
-                if (before) inv_in *= (double)wperm[row_base + before - 1u];
-            }
-            // the row leaving this lane ends in lane E (E == lane: only padding follows, w == 0)
-            const double inv_out = __shfl_sync(full, inv_in, E);
-            x0 = w0 * (c0 ? inv_in : inv_out);
-            x1 = w1 * (c1 ? inv_in : inv_out);
-            x2 = w2 * (c2 ? inv_in : inv_out);
-            x3 = w3 * inv_out;
-        } else {
-            // general path: rows may start and end inside one lane
-            const uint32_t nsteps = info & 7u;
-            const double s0 = w0;
-            const double s1 = (hb & 2u) ? w1 : s0 + w1;
-            const double s2 = (hb & 4u) ? w2 : s1 + w2;
-            const double s3 = (hb & 8u) ? w3 : s2 + w3;
-            double incl = s3;                                         // segmented inclusive scan of lane tails
-#pragma unroll
-            for (uint32_t i = 0; i < 5; ++i) {
-                if (i >= nsteps) break;
-                const uint32_t d = 1u << i;
-                incl = fma(__shfl_up_sync(full, incl, d), mask01(dist >= d), incl);
-            }
-            double carry = __shfl_up_sync(full, incl, 1);
-            if (lane == 0) carry = 0.0;
-            const double sA = (hb & 1u) ? 0.0 : (hb & 2u) ? s0 : (hb & 4u) ? s1 : (hb & 8u) ? s2 : s3;
-            const double t_in = carry + sA;
-            const double t_out = __shfl_sync(full, t_in, E);
-            const double pre0 = (hb & 1u) ? s0 : carry + s0;
-            const double pre1 = (hb & 3u) ? s1 : carry + s1;
-            const double pre2 = (hb & 7u) ? s2 : carry + s2;
-            const double tot3 = t_out;
-            const double tot2 = (hb & 8u) ? pre2 : tot3;
-            const double tot1 = (hb & 4u) ? pre1 : tot2;
-            const double tot0 = (hb & 2u) ? pre0 : tot1;
-            x0 = tot0 > OAR_EM_DENOM_THRESH ? w0 * fast_rcp(tot0) : 0.0;
-            x1 = tot1 > OAR_EM_DENOM_THRESH ? w1 * fast_rcp(tot1) : 0.0;
-            x2 = tot2 > OAR_EM_DENOM_THRESH ? w2 * fast_rcp(tot2) : 0.0;
-            x3 = tot3 > OAR_EM_DENOM_THRESH ? w3 * fast_rcp(tot3) : 0.0;
-        }
-
-        if (HAS_WTS && multi) {
-            // general path: row index of a slot inside the chunk = (number of heads at or before it) - 1
-            uint32_t incl_h = __popc(hb);
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(full, incl_h, d);
-                if ((int)lane >= d) incl_h += t;
-            }
-            const uint32_t row_base = reinterpret_cast<const uint32_t *>(rec + kRecRow)[warp];
-            const uint32_t r0 = row_base + incl_h - __popc(hb) + (hb & 1u) - 1u;
-            const uint32_t r1 = r0 + ((hb >> 1) & 1u), r2 = r1 + ((hb >> 2) & 1u), r3 = r2 + ((hb >> 3) & 1u);
-            x0 *= (double)wperm[r0];
-            x1 *= (double)wperm[r1];
-            x2 *= (double)wperm[r2];
-            x3 *= (double)wperm[r3];
-        }
-
-        // ---- M-step scatter into the transcript-sorted smem order -----------------------------
-        // (padding and non-aggregated alignments carry the tile's trash offset and are not stored)
-        char *xp = reinterpret_cast<char *>(xs);
-        const uint32_t trash = du.w;
-        const uint32_t q0 = lp4.x >> 16, q1 = lp4.y >> 16, q2 = lp4.z >> 16, q3 = lp4.w >> 16;
-        if (q0 != trash) *reinterpret_cast<double *>(xp + q0) = x0;
-        if (q1 != trash) *reinterpret_cast<double *>(xp + q1) = x1;
-        if (q2 != trash) *reinterpret_cast<double *>(xp + q2) = x2;
-        if (q3 != trash) *reinterpret_cast<double *>(xp + q3) = x3;
-        if (strays) {
-            // transcripts with fewer than kAggMin alignments in this tile: straight to global
-            if (q0 == trash && x0 != 0.0) atomicAdd(curr + table[(lp4.x & 0xFFFFu) >> 3], x0);
-            if (q1 == trash && x1 != 0.0) atomicAdd(curr + table[(lp4.y & 0xFFFFu) >> 3], x1);
-            if (q2 == trash && x2 != 0.0) atomicAdd(curr + table[(lp4.z & 0xFFFFu) >> 3], x2);
-            if (q3 == trash && x3 != 0.0) atomicAdd(curr + table[(lp4.w & 0xFFFFu) >> 3], x3);
-        }
+        uint32_t item; uint4 du;
+        tile_phase1<HAS_AUX, HAS_WTS>(v, tile, stg, rec, sp_a, xs_a, tid, lane, warp, curr, wperm, item, du);
         __syncthreads();   // xs complete; stage s and s_prev are free again
 
-        // ---- refill stage s two tiles ahead; fetch prev[] of the next tile behind its record ----
+        // ---- refill stage s two tiles ahead; the last warp fetches prev[] of the next tile ----
         const uint32_t next = tile + stride;
         const bool has_next = next < n_tiles;
-        if (tid == 0 && next + stride < n_tiles) {
-            issue(next + stride, s, r_pending);
-            if (next + 2 * stride < n_tiles) r_pending = v.rec[next + 2 * stride];
+        if (warp >= kWarps - 2) {   // the two service warps
+            if (is_tma && next + stride < n_tiles) {
+                issue(next + stride, s, r_pending);
+                if (next + 2 * stride < n_tiles) r_pending = v.rec[next + 2 * stride];
+            }
+            if (warp == kWarps - 1 && has_next) {
+                mbar_wait(bar0 + 8u * (s ^ 1u), ((it + 1u) >> 1) & 1u);
+                gather_prev(stage0 + (s ^ 1u) * kStageBytes + 8u * kTile);
+            }
         }
-        double pv = 0.0;
-        uint32_t Dn = 0;
-        const uint32_t *table_n = nullptr;
-        if (has_next) {
-            mbar_wait(bar0 + 8u * (s ^ 1u), ((it + 1u) >> 1) & 1u);
-            const unsigned char *rec_n = stage_base + (s ^ 1u) * kStageBytes + 8 * kTile;
-            Dn = *reinterpret_cast<const uint32_t *>(rec_n + kRecDU);
-            table_n = reinterpret_cast<const uint32_t *>(rec_n + kRecTable);
-            if (tid < Dn) pv = prev[table_n[tid]];
-        }
+        __syncwarp();
 
-        // ---- phase 2: one thread sums one item (<= 32 consecutive x slots of one transcript), one RED ----
-        if (__any_sync(full, warp * 32u < U)) {
-            const uint32_t N32 = du.z & 0xFFFFu, N16 = du.z >> 16;
-            const uint32_t slots = item == kNoTxp ? 0u : (item >> 27) + 1u, npair = slots >> 1;
-            constexpr uint32_t kS0 = kItemMax + 2, kS1 = kItemMax / 2 + 2, kS2 = kItemMax / 4 + 2, kP = kItemMax / 2;
-            uint32_t bd = kS0 * tid;   // x offset in doubles: the three size classes at strides c + 2
-            if (tid >= N32) bd = kS1 * tid + (kS0 - kS1) * N32;
-            if (tid >= N32 + N16) bd = kS2 * tid + (kS0 - kS2) * N32 + (kS1 - kS2) * N16;
-            const double2 *b = reinterpret_cast<const double2 *>(xs + bd);
-            const double2 zero = make_double2(0.0, 0.0);
-            double a0 = (slots & 1u) ? xs[bd + slots - 1u] : 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll
-            for (uint32_t k = 0; k < kP / 4u; k += 2) {
-                const double2 u = k < npair ? b[k] : zero, w = k + 1u < npair ? b[k + 1u] : zero;
-                a0 += u.x; a1 += u.y; a2 += w.x; a3 += w.y;
-            }
-            if (__any_sync(full, npair > kP / 4u)) {        // items of the two larger classes (they come first in the item order)
-#pragma unroll
-                for (uint32_t k = kP / 4u; k < kP / 2u; k += 2) {
-                    const double2 u = k < npair ? b[k] : zero, w = k + 1u < npair ? b[k + 1u] : zero;
-                    a0 += u.x; a1 += u.y; a2 += w.x; a3 += w.y;
-                }
-                if (__any_sync(full, npair > kP / 2u)) {    // items of the largest class
-#pragma unroll
-                    for (uint32_t k = kP / 2u; k < kP; k += 2) {
-                        const double2 u = k < npair ? b[k] : zero, w = k + 1u < npair ? b[k + 1u] : zero;
-                        a0 += u.x; a1 += u.y; a2 += w.x; a3 += w.y;
-                    }
-                }
-            }
-            const double acc = (a0 + a2) + (a1 + a3);
-            if (item != kNoTxp && acc != 0.0) atomicAdd(curr + (item & (kMaxTxps - 1u)), acc);
-        }
+        tile_phase2(xs_a, item, du.y, du.z, tid, warp, curr);
 
         if (!has_next) break;
-        if (tid < Dn) s_prev[tid] = pv;
-        for (uint32_t d = tid + kThreads; d < Dn; d += kThreads) s_prev[d] = prev[table_n[d]];
         tile = next;
     }
+    if (v.n_fb && blockIdx.x == gridDim.x - 1u)
+        kern::rowgroup_rows<HAS_AUX, HAS_WTS>(v.csr_row_ptr, v.csr_txp, v.csr_prob, v.csr_aux, v.csr_wts, v.fb_rows, prev, curr,
+                                              tid >> 3, kThreads >> 3, v.n_fb);
+}
+
+// ---------------------------------------------------------------------------
+// Single-barrier sweep (OAR_SWEEP=1b): phase 2 of tile i-1 runs next to phase 1 of tile i.
+//
+// The two-barrier kernel above idles most of its warps between the barriers of a tile (items keep about three
+// warps busy, one gathers prev[], one issues the copies).  Here the x array and s_prev are double-buffered and
+// the ring has three stages, and one CTA barrier per tile is all that is left:
+//
+//   iteration i, after the barrier:  TMA thread   tile i+2 -> stage[(i+2)%3]
+//                                    first warps  phase 2 of tile i-1 (reads xs[(i-1)&1], items kept in registers)
+//                                    all warps    phase 1 of tile i   (reads stage[i%3], s_prev[i&1]; writes xs[i&1])
+//                                    last warp    waits for stage[(i+1)%3] (requested one iteration ago), gathers
+//                                                 prev[] of tile i+1 into s_prev[(i+1)&1]
+//
+// Every buffer written in iteration i was last read in iteration i-1, i.e. before the barrier.  The price is
+// shared memory (54 KB per CTA on C3 against 31 KB) and registers (64): 4 CTAs per SM instead of 5.
+struct Geometry1 {
+    uint32_t xs_bytes;      // one x buffer (128 B multiple); the two buffers sit at the start of the window
+    uint32_t stage_off;     // three stages: prob (4 KB) | lpos (4 KB) | record
+    uint32_t stage_bytes;
+    uint32_t prev_off;      // two s_prev buffers
+    uint32_t prev_bytes;
+    uint32_t bar_off;       // three mbarriers
+    uint32_t total;
+};
+inline Geometry1 make_geometry1(uint32_t max_rec_bytes, uint32_t max_d, uint32_t max_x_doubles)
+{
+    Geometry1 g;
+    g.xs_bytes = (8u * ((max_x_doubles + 2u + 1u) & ~1u) + 127u) & ~127u;
+    g.stage_off = 2u * g.xs_bytes;
+    g.stage_bytes = 8u * kTile + ((max_rec_bytes + 15u) & ~15u);
+    g.prev_off = g.stage_off + 3u * g.stage_bytes;
+    g.prev_bytes = 8u * ((max_d + 1u) & ~1u);
+    g.bar_off = g.prev_off + 2u * g.prev_bytes;
+    g.total = g.bar_off + 3u * 8u;
+    return g;
+}
+
+template <bool HAS_AUX, bool HAS_WTS>
+__global__ void __launch_bounds__(kThreads, (4 * 8) / kWarps) em_sweep_tiled1(View v, Geometry1 g, const double *__restrict__ prev,
+                                                               double *__restrict__ curr,
+                                                               const uint32_t *__restrict__ wperm,
+                                                               const OarEmState *__restrict__ st, int check_done)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    if (check_done && st->done) return;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t n_tiles = v.n_tiles, stride = gridDim.x;
+    const uint32_t tile0 = blockIdx.x;
+    if (tile0 >= n_tiles) return;
+    uint32_t sm0;
+    asm volatile("{.reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t;}" : "=r"(sm0) : "l"(smem));
+    const uint32_t stage0 = sm0 + g.stage_off, sp0 = sm0 + g.prev_off, bar0 = sm0 + g.bar_off;
+    const uint32_t xs0 = smem_u32(smem);   // warp-uniform to the compiler (see em_sweep_tiled)
+    const bool is_tma = tid == 32u * (kWarps - 2);
+    const bool is_gather = warp == kWarps - 1;
+
+    auto issue = [&](uint32_t tile, uint32_t slot, uint2 r) {   // the TMA thread only
+        const uint32_t bar = bar0 + 8u * slot, dst = stage0 + slot * g.stage_bytes;
+        mbar_expect_tx(bar, 8u * kTile + r.y);
+        bulk_g2s(dst, v.prob + (size_t)tile * kTile, 4u * kTile, bar);
+        bulk_g2s(dst + 4u * kTile, v.lpos + (size_t)tile * kTile, 4u * kTile, bar);
+        bulk_g2s(dst + 8u * kTile, v.records + r.x, r.y, bar);
+    };
+    auto gather_prev = [&](uint32_t rec_a, uint32_t sp_a) {   // one warp, two gathers in flight per lane
+        const uint32_t Dn = lds_u32(rec_a + kRecDU);
+        for (uint32_t d = lane; d < Dn; d += 64u) {
+            const uint32_t d2 = d + 32u;
+            const double p0 = prev[lds_u32(rec_a + kRecTable + 4u * d)];
+            double p1 = 0.0;
+            if (d2 < Dn) p1 = prev[lds_u32(rec_a + kRecTable + 4u * d2)];
+            sts_f64(sp_a + 8u * d, p0);
+            if (d2 < Dn) sts_f64(sp_a + 8u * d2, p1);
+        }
+    };
+
+    if (tid == 0) {
+#pragma unroll
+        for (uint32_t i = 0; i < 3; ++i) mbar_init(bar0 + 8u * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint2 r_pending = make_uint2(0, 0);   // record locator of the tile three ahead (TMA thread)
+    if (is_tma) {
+        issue(tile0, 0, v.rec[tile0]);
+        if (tile0 + stride < n_tiles) issue(tile0 + stride, 1, v.rec[tile0 + stride]);
+        if (tile0 + 2 * stride < n_tiles) r_pending = v.rec[tile0 + 2 * stride];
+    }
+    uint32_t spar = 0;                    // phase parity of the three stage mbarriers (gather warp)
+    if (is_gather) {
+        mbar_wait(bar0, 0); spar ^= 1u;
+        gather_prev(stage0 + 8u * kTile, sp0);
+    }
+
+    uint32_t tile = tile0;
+    uint32_t rs = 0;                      // stage of this tile = it % 3
+    uint32_t item_p = kNoTxp, U_p = 0, duz_p = 0;   // phase-2 inputs of the previous tile
+    uint32_t s_last = 0;
+    for (uint32_t it = 0;; ++it) {
+        const uint32_t s = it & 1u;
+        const uint32_t rs1 = rs == 2u ? 0u : rs + 1u, rs2 = rs1 == 2u ? 0u : rs1 + 1u;
+        const uint32_t next = tile + stride;
+        const bool has_next = next < n_tiles;
+        __syncthreads();   // tile `it` is in place (stage, s_prev); xs[s], stage[rs2], s_prev[s^1] are free
+
+        if (is_tma && next + stride < n_tiles) {
+            issue(next + stride, rs2, r_pending);
+            if (next + 2 * stride < n_tiles) r_pending = v.rec[next + 2 * stride];
+        }
+        if (it) tile_phase2(xs0 + (s ^ 1u) * g.xs_bytes, item_p, U_p, duz_p, tid, warp, curr);
+
+        uint32_t item; uint4 du;
+        const uint32_t stg = stage0 + rs * g.stage_bytes;
+        tile_phase1<HAS_AUX, HAS_WTS>(v, tile, stg, stg + 8u * kTile, sp0 + s * g.prev_bytes, xs0 + s * g.xs_bytes, tid, lane, warp,
+                                      curr, wperm, item, du);
+        item_p = item; U_p = du.y; duz_p = du.z;
+
+        if (!has_next) { s_last = s; break; }
+        if (is_gather) {
+            mbar_wait(bar0 + 8u * rs1, (spar >> rs1) & 1u); spar ^= 1u << rs1;
+            gather_prev(stage0 + rs1 * g.stage_bytes + 8u * kTile, sp0 + (s ^ 1u) * g.prev_bytes);
+        }
+        tile = next; rs = rs1;
+    }
+    __syncthreads();       // x values of the last tile
+    tile_phase2(xs0 + s_last * g.xs_bytes, item_p, U_p, duz_p, tid, warp, curr);
     if (v.n_fb && blockIdx.x == gridDim.x - 1u)
         kern::rowgroup_rows<HAS_AUX, HAS_WTS>(v.csr_row_ptr, v.csr_txp, v.csr_prob, v.csr_aux, v.csr_wts, v.fb_rows, prev, curr,
                                               tid >> 3, kThreads >> 3, v.n_fb);

@@ -18,5 +18,7 @@ for cps in [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "4").split(",
         ds.set_kernel(1); ds.sweep(prev, curr); ref = curr.cpu().numpy(); ds.set_kernel(2)
     err = (np.abs(c-ref)/np.maximum(ref,1e-300))[ref>1e-6].max()
     t=time.time(); r = ds.em(min_iter=1); wall=time.time()-t
+    li = ds.layout_info()
+    print(f"fallback {li.get('fallback_rows')} tiles {li.get('n_tiles')}", end=" | ")
     print(f"ctas/SM={cps}: {ms*1e3:.1f} us/sweep frac {bytes_alg/ms/1e6/6533.2:.3f} relerr {err:.2e} | EM niter {r.niter} {ds.timings_ms()['em']:.1f} ms -> {ds.counters()['sweeps']/wall:.0f} it/s", flush=True)
     ds.close()

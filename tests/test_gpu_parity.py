@@ -12,7 +12,9 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-KERNELS = [1, 2, 3]  # OAR_KERNEL_ROWGROUP, OAR_KERNEL_TILED (default layout), OAR_KERNEL_LANE (OAR_LAYOUT=lane)
+# OAR_KERNEL_ROWGROUP, OAR_KERNEL_TILED (default layout), OAR_KERNEL_LANE (OAR_LAYOUT=lane),
+# 4 = OAR_KERNEL_TILED with the single-barrier sweep (OAR_SWEEP=1b)
+KERNELS = [1, 2, 3, 4]
 RTOL = 1e-9
 NORTH_STAR_RTOL = 1e-5
 
@@ -39,22 +41,27 @@ def csr(rows):
 
 @contextlib.contextmanager
 def store_for(DS, kernel, *args, **kw):
-    """A device store whose tiled layout matches `kernel` (the row-per-lane layout is opt-in via OAR_LAYOUT)."""
-    old = os.environ.get("OAR_LAYOUT")
-    if kernel == 3:
-        os.environ["OAR_LAYOUT"] = "lane"
-    elif old is not None:
-        os.environ.pop("OAR_LAYOUT")
+    """A device store whose tiled layout and sweep variant match `kernel` (the row-per-lane layout is opt-in via
+    OAR_LAYOUT, the single-barrier sweep via OAR_SWEEP; both are read at store creation)."""
+    want = {"OAR_LAYOUT": "lane" if kernel == 3 else None, "OAR_SWEEP": "1b" if kernel == 4 else "2b"}
+    old = {k: os.environ.get(k) for k in want}
+    for k, val in want.items():
+        if val is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = val
     try:
         ds = DS(*args, **kw)
     finally:
-        if old is None:
-            os.environ.pop("OAR_LAYOUT", None)
-        else:
-            os.environ["OAR_LAYOUT"] = old
+        for k, val in old.items():
+            if val is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = val
+    abi_kernel = 2 if kernel == 4 else kernel
     with ds:
-        ds.set_kernel(kernel)
-        assert ds.layout_info()["kernel"] == kernel
+        ds.set_kernel(abi_kernel)
+        assert ds.layout_info()["kernel"] == abi_kernel
         yield ds
 
 

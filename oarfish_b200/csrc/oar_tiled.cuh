@@ -609,6 +609,16 @@ __device__ __forceinline__ void tile_phase1(const View &v, uint32_t tile, uint32
     }
 
     const uint32_t hb = desc & 15u, dist = (desc >> 4) & 31u, E = (desc >> 9) & 31u;
+    // bootstrap: the resampling weight of the row that ends in this lane (fast path: at most one head per lane, so
+    // that row is the chunk's row number (heads in earlier lanes) - 1).  The global load is issued here, ahead of
+    // the E-step, so that its latency is covered by the shared-memory gathers and the segmented scan.
+    uint32_t w_in = 0;
+    if (HAS_WTS) {
+        const unsigned lanes_h = __ballot_sync(full, hb != 0u);
+        const uint32_t before = __popc(lanes_h & ((1u << lane) - 1u));
+        const uint32_t row_base = lds_u32(rec + kRecRow + 4u * warp);
+        if (before) w_in = wperm[row_base + before - 1u];
+    }
     // chunk_info is the same word for the whole warp; votes make that visible to the compiler
     const bool multi = any_bits(info, kInfoMulti);
     const bool strays = any_bits(info, kInfoStray);
@@ -638,14 +648,7 @@ __device__ __forceinline__ void tile_phase1(const View &v, uint32_t tile, uint32
         const double t_in = carry + a;                            // its total, if it ends here
         // reads whose denominator is <= 1e-30 contribute nothing (em.rs:115)
         double inv_in = t_in > OAR_EM_DENOM_THRESH ? fast_rcp(t_in) : 0.0;
-        if (HAS_WTS) {
-            // bootstrap: fold the row's resampling weight into its inverse denominator.  The row whose
-            // total is t_in is the chunk's row number (heads in earlier lanes) - 1; one head per lane here.
-            const unsigned lanes_h = __ballot_sync(full, hb != 0u);
-            const uint32_t before = __popc(lanes_h & ((1u << lane) - 1u));
-            const uint32_t row_base = lds_u32(rec + kRecRow + 4u * warp);
-            if (before) inv_in *= (double)wperm[row_base + before - 1u];
-        }
+        if (HAS_WTS) inv_in *= (double)w_in;   // fold the row's resampling weight into its inverse denominator
         // the row leaving this lane ends in lane E (E == lane: only padding follows, w == 0)
         const double inv_out = __shfl_sync(full, inv_in, E);
         x0 = w0 * (c0 ? inv_in : inv_out);

@@ -57,6 +57,9 @@ constexpr int kAggMin = 4;                // transcripts with >= kAggMin alignme
 #ifndef OAR_TILED_MIN_CTAS
 #define OAR_TILED_MIN_CTAS 5    // register budget of the two-barrier sweep: 48 registers per thread
 #endif
+#ifndef OAR_SCATTER_GREEDY
+#define OAR_SCATTER_GREEDY 1    // layout: x positions chosen so that the M-step scatter spreads over the banks
+#endif
 #ifndef OAR_SHORT_ROW_DEFER
 #define OAR_SHORT_ROW_DEFER 1   // layout: keep rows shorter than a lane from starting and ending inside one lane
 #endif
@@ -464,6 +467,117 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
         if (d < D) { s_seg[d] = sega[i]; s_seg2[d] = segb[i]; }
     }
     __syncthreads();
+#if OAR_SCATTER_GREEDY
+    // Which of its transcript's x positions an alignment gets is free.  The sweep scatters the x values of slot k
+    // of the 32 lanes of a warp with one STS.64; the 16 lanes of a half-warp go through in one wavefront iff their
+    // positions fall into 16 different 8-byte banks.  A transcript's 16-slot items offer every bank residue once
+    // each, its remainder item a few of them; a serial greedy pass over the 64 half-warp groups of the tile hands
+    // every alignment a residue that is still unused in its group (starting the search at its lane, which spreads
+    // the demand evenly), if its transcript still has one to offer.  (With ranks in sort order, as before, a
+    // half-warp store took 3.1 wavefronts on C3 -- the same as positions drawn at random.)
+    uint32_t *s_state = s_txp;          // per transcript: residues on offer (bits 0-15) | free remainder slots (16-31); s_txp is dead
+    uint16_t *s_ci = s_rnew;            // per transcript: compact index of its full-item counters | partial << 15; dead since the rows were placed
+    __shared__ uint8_t s_fulluse[kTile / kItemMax][16];                 // [compact transcript][residue] -> full items used
+    if (tid == 0) s_misc[3] = 0;
+    for (uint32_t i = tid; i < (uint32_t)(kTile / kItemMax) * 16u; i += kThreads) (&s_fulluse[0][0])[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s_src[vals[i]] = keys[i] != kNoTxp ? seg[i] - 1u : kNoTxp;   // slot -> segment
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t d = tid * 4 + i;
+        if (d < D) {
+            uint32_t avail = 0, remfree = 0, ci = 0;
+            if ((segb[i] >> 31) == 0u) {
+                // q full 16-slot items, then `rem` valid slots in the remainder item -- a smaller-class item at
+                // x offset rem_x, or (rem > 8) one more 16-slot item right behind the full ones
+                const uint32_t q = cntd[i] / kI, rem = cntd[i] % kI, partial = rem > kI / 2u ? 1u : 0u;
+                const uint32_t br = partial ? (2u * ((pbase[i] & 0x3FFu) + q)) & 15u : segb[i] & 15u;
+                remfree = (1u << rem) - 1u;
+                avail = ((remfree << br) | (remfree << br >> 16)) & 0xFFFFu;   // bank residues of the remainder's slots
+                if (q) { avail = 0xFFFFu; ci = atomicAdd(&s_misc[3], 1u); }
+                ci |= partial << 15;
+            }
+            s_state[d] = avail | (remfree << 16); s_ci[d] = (uint16_t)ci;
+        }
+    }
+    __syncthreads();
+    // One warp walks the 32 scatter instructions of the tile (chunk c, slot-in-lane k); its lanes are the lanes of
+    // the sweep.  Per round every lane that still needs a position proposes the first residue at or after its lane
+    // number that its transcript offers and its half-warp has not used; the lowest lane of every (half, residue)
+    // and (transcript, residue) group goes ahead and claims it.  Deterministic: no atomics decide anything.
+    if (tid < 32u) {
+        const unsigned full = 0xffffffffu;
+        const uint32_t lane = tid, half = lane >> 4, l16 = lane & 15u;
+        for (uint32_t ck = 0; ck < (uint32_t)kWarps * 4u; ++ck) {
+            const uint32_t slot = (ck >> 2) * kChunk + 4u * lane + (ck & 3u);
+            const uint32_t d = s_src[slot];
+            bool todo = d != kNoTxp && (s_state[d] & 0xFFFFu) != 0u;   // stray transcripts have no x positions
+            uint32_t i32 = 0, q = 0, br = 0, ci = 0;
+            if (todo) {
+                const uint32_t pb = s_seg2[d], pa = s_seg[d], cw = s_ci[d];
+                i32 = pa >> 11; q = ((pb >> 12) & 0x3FFu) - (cw >> 15); ci = cw & 0x7FFFu;
+                br = (cw >> 15) ? (2u * (i32 + q)) & 15u : pb & 15u;
+            }
+            uint32_t G = 0;   // residues taken in this lane's half-warp
+            while (__any_sync(full, todo)) {
+                uint32_t rho = 0, st = 0;
+                if (todo) {
+                    st = s_state[d];
+                    const uint32_t av = st & 0xFFFFu;      // never 0 here: the transcript still owes this lane a position
+                    uint32_t cand = av & ~G;
+                    if (cand == 0u) cand = av;             // no unused residue on offer: accept a bank conflict
+                    const uint32_t rot = ((cand >> l16) | (cand << (16u - l16))) & 0xFFFFu;
+                    rho = (l16 + (uint32_t)__ffs((int)rot) - 1u) & 15u;
+                }
+                const uint32_t idle = 0x80000000u | lane;
+                const unsigned m1 = __match_any_sync(full, todo ? ((d << 4) | rho) : idle);
+                const unsigned m2 = __match_any_sync(full, todo ? ((half << 4) | rho) : idle);
+                const bool go = todo && (uint32_t)(__ffs((int)m1) - 1) == lane && (uint32_t)(__ffs((int)m2) - 1) == lane;
+                uint32_t took = 0;
+                if (go) {
+                    uint32_t m = q ? s_fulluse[ci][rho] : 0u;
+                    const uint32_t orem = (rho - br) & 15u;
+                    uint32_t clear = 0;
+                    if (m < q) {                               // item m of the transcript's full items
+                        const uint32_t o = (rho - 2u * (i32 + m)) & 15u;   // item base = 18 * (i32 + m) doubles
+                        s_src[slot] = d | ((kI * m + o) << 16);
+                        s_fulluse[ci][rho] = (uint8_t)(++m);
+                    } else {                                   // the remainder item (its slot of this residue is free)
+                        s_src[slot] = d | ((kI * q + orem) << 16);
+                        clear = 1u << (16u + orem);
+                        st &= ~clear;
+                    }
+                    if (m >= q && !((st >> (16u + orem)) & 1u)) clear |= 1u << rho;   // residue no longer on offer
+                    if (clear) atomicAnd(&s_state[d], ~clear);   // lanes of other residues may update the same word
+                    todo = false;
+                    took = 1u << (rho + 16u * half);
+                }
+                __syncwarp();
+                G |= (__reduce_or_sync(full, took) >> (16u * half)) & 0xFFFFu;
+            }
+        }
+    }
+    __syncthreads();
+    // per slot: table index and position, as shared-memory byte offsets
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t slot = tid * 4 + i;
+        const uint32_t dj = s_src[slot];
+        if (dj != kNoTxp) {
+            const uint32_t d = dj & 0xFFFFu;
+            const uint32_t pa = s_seg[d], pb = s_seg2[d];
+            uint32_t pos = XD;   // trash slot of this tile
+            if ((pb >> 31) == 0u) {
+                const uint32_t j = dj >> 16, n32 = (pb >> 12) & 0x3FFu;
+                pos = j < kI * n32 ? kS0 * ((pa >> 11) + j / kI) + j % kI : (pb & 0xFFFu) + (j - kI * n32);
+            } else atomicOr(&s_info[slot / kChunk], kInfoStray);
+            s_lpos[slot] = (d * 8u) | ((pos * 8u) << 16);
+        } else {
+            s_lpos[slot] = 0u | ((XD * 8u) << 16);
+        }
+    }
+#else
     // per sorted element: table index and position, as shared-memory byte offsets
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -481,6 +595,7 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
             s_lpos[vals[i]] = 0u | ((XD * 8u) << 16);
         }
     }
+#endif
     __syncthreads();
     for (uint32_t i = tid; i < (uint32_t)kTile; i += kThreads) a.o_lpos[(size_t)tile * kTile + i] = s_lpos[i];
     if (tid < kWarps) s_rec[kRecInfo / 4 + tid] = s_info[tid];

@@ -106,8 +106,8 @@ static int build_chunk_layout(oar_store *s, uint32_t span)
     uint4 *records_tmp = nullptr;
     OAR_CUDA(dmalloc(&t.fallback, sizeof(uint32_t) * std::max<uint32_t>(N, 1), st));
     OAR_CUDA(dmalloc(&t.trow, sizeof(uint32_t) * std::max<uint32_t>(n_tiled, 1), st));
-    OAR_CUDA(dmalloc(&t.wperm, sizeof(uint32_t) * ((size_t)n_tiled + kChunk + 1), st));
-    OAR_CUDA(cudaMemsetAsync(t.wperm, 0, sizeof(uint32_t) * ((size_t)n_tiled + kChunk + 1), st));
+    OAR_CUDA(dmalloc(&t.wperm, sizeof(uint32_t) * ((size_t)n_tiled + kChunk + 257), st));
+    OAR_CUDA(cudaMemsetAsync(t.wperm, 0, sizeof(uint32_t) * ((size_t)n_tiled + kChunk + 257), st));
     if (n_tiles > 0) {
         OAR_CUDA(dmalloc(&t.prob, sizeof(float) * slots, st));
         OAR_CUDA(dmalloc(&t.lpos, sizeof(uint32_t) * slots, st));

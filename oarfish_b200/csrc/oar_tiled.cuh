@@ -692,6 +692,17 @@ __device__ __forceinline__ bool any_bits(uint32_t v, uint32_t mask)
     return r != 0u;
 }
 
+// bootstrap: pull the weights of a tile's rows (tile order, starting at row `row0`) into L1 one tile ahead, so that the
+// per-lane loads of phase 1 hit it.  Eight 128-byte lines cover 256 rows (C3: ~123 rows per tile); a load whose
+// result is never used does not stall anybody.
+__device__ __forceinline__ void weights_touch(const uint32_t *__restrict__ w, uint32_t lane)
+{
+    if (lane < 8u) {
+        uint32_t sink;
+        asm volatile("ld.global.nc.L1::evict_last.u32 %0, [%1];" : "=r"(sink) : "l"(w + 32u * lane));
+    }
+}
+
 // ---- phase 1 of a tile: E-step in registers + M-step scatter into the transcript-sorted x array -------------
 //   bulk, rec: shared-space addresses of the tile's prob | lpos block and of its record; sp_a: prev[] of the tile's
 //   transcripts; xs_a: the x array.  Returns the thread's item and the record's DU word for phase 2.
@@ -926,6 +937,7 @@ __global__ void __launch_bounds__(kThreads, (OAR_TILED_MIN_CTAS * 8) / kWarps) e
             sts_f64(sp_a + 8u * d, p0);
             if (d2 < Dn) sts_f64(sp_a + 8u * d2, p1);
         }
+        if (HAS_WTS) weights_touch(wperm + lds_u32(rec_a + kRecRow), lane);
     };
 
     uint2 r_pending = make_uint2(0, 0);   // record locator of the tile two ahead (TMA thread)
@@ -1056,6 +1068,7 @@ __global__ void __launch_bounds__(kThreads, (4 * 8) / kWarps) em_sweep_tiled1(Vi
             sts_f64(sp_a + 8u * d, p0);
             if (d2 < Dn) sts_f64(sp_a + 8u * d2, p1);
         }
+        if (HAS_WTS) weights_touch(wperm + lds_u32(rec_a + kRecRow), lane);
     };
 
     if (tid == 0) {

@@ -1,0 +1,14 @@
+"""Dev script: steady-state bootstrap-weighted sweeps on a config (for ncu: -k regex:em_sweep_tiled -s 40 -c 1)."""
+import sys, numpy as np, torch
+sys.path.insert(0, "/root/repo")
+from oarfish_b200 import synth, DeviceStore
+s = synth.make_config(sys.argv[1] if len(sys.argv) > 1 else "C3")
+M = s.n_txps
+ds = DeviceStore(s.row_ptr, s.txp_id, s.prob, M)
+prev = torch.full((M,), s.n_reads / M, dtype=torch.float64, device="cuda")
+curr = torch.zeros(M, dtype=torch.float64, device="cuda")
+r = ds.em(min_iter=1, max_iter=30)
+prev.copy_(torch.from_numpy(r.counts))
+wts = torch.from_numpy(ds.sample_weights(7, 0).astype(np.int32)).cuda()
+ds.sweep_timed(prev, curr, 6, wts)
+print(ds.sweep_timed(prev, curr, 20, wts) / 20 * 1e3, "us (weighted)")

@@ -76,6 +76,7 @@ constexpr uint32_t kInfoMulti = 16u;      // chunk_info bit 4: some lane holds >
 constexpr uint32_t kNoTxp = 0xFFFFFFFFu;
 constexpr uint32_t kMaxTxps = 1u << 27;   // item descriptors pack (slots - 1) above bit 27
 static_assert(kMaxItems == kThreads, "one item per thread in phase 2");
+static_assert(!OAR_SCATTER_GREEDY || kItemMax == 16, "the bank-aware x positions assume 16-slot items at a stride of 18 doubles: one slot per 8-byte bank residue");
 
 // Per-tile record (variable length, 16-byte granules), one TMA bulk copy:
 //   [0,512)    lane descriptors u16[8][32]: hb(4) | dist(5) | E(5)

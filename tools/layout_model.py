@@ -1,0 +1,263 @@
+#!/usr/bin/env python
+"""CPU model of the chunk layout's shared-memory bank behaviour (no GPU needed).
+
+Restates what build_tiles (oarfish_b200/csrc/oar_tiled.cuh) does to a store -- rows sorted by smallest transcript,
+tiles of `span` alignments, first-fit packing into 8 warp-chunks of 127 slots, items of 16/8/4 x slots at strides
+18/10/6 doubles -- and counts the wavefronts the sweep's shared-memory instructions need per tile:
+
+  scatter  STS.64 of slot k of the 32 lanes of a warp: per half-warp, max number of positions in one 8-byte bank
+  gather   LDS.64 of prev[table index]: per half-warp, max number of DISTINCT table entries in one bank
+
+for several ways of handing out x positions / table indices.  Used to choose the heuristics before spending GPU time.
+usage: python tools/layout_model.py [n_reads] [n_txps] [avg] [max_tiles]
+"""
+import sys
+import numpy as np
+
+sys.path.insert(0, __file__.rsplit("/", 2)[0])
+from oarfish_b200 import synth
+
+SPAN, CHUNK, CAP, NW, IMAX = 984, 128, 127, 8, 16
+
+
+def tiles_of(store, max_tiles):
+    rp = store.row_ptr.astype(np.int64); tx = store.txp_id
+    lens = np.diff(rp)
+    mn = np.minimum.reduceat(tx, rp[:-1])
+    order = np.argsort(mn, kind="stable")
+    off = np.concatenate([[0], np.cumsum(lens[order])])
+    n_tiles = int((off[-1] + SPAN - 1) // SPAN)
+    starts = np.searchsorted(off[:-1], np.arange(n_tiles + 1) * SPAN, side="left")
+    pick = np.linspace(0, n_tiles - 1, min(max_tiles, n_tiles)).astype(int)
+    for t in pick:
+        rows = order[starts[t]:starts[t + 1]]
+        yield [np.sort(tx[rp[r]:rp[r + 1]]) for r in rows]
+
+
+def pack(rows):
+    """slot -> transcript (or -1), first fit; short rows wait for a lane-crossing position (as build_tiles)."""
+    used = [0] * NW
+    slots = -np.ones(NW * CHUNK, dtype=np.int64)
+    pend = []
+
+    def fit(n, clean):
+        for c in range(NW):
+            if used[c] + n <= CAP and (not clean or (used[c] & 3) + n >= 4):
+                return c
+        return -1
+
+    def place(r, c):
+        slots[c * CHUNK + used[c]: c * CHUNK + used[c] + len(r)] = r
+        used[c] += len(r)
+
+    for r in rows:
+        if len(r) < 4:
+            c = fit(len(r), True)
+            if c >= 0: place(r, c)
+            else: pend.append(r)
+            continue
+        c = fit(len(r), False)
+        if c < 0: continue
+        place(r, c)
+        k = 0
+        while k < len(pend):
+            c2 = fit(len(pend[k]), True)
+            if c2 >= 0: place(pend.pop(k), c2)
+            else: k += 1
+    for r in pend:
+        c = fit(len(r), True)
+        if c < 0: c = fit(len(r), False)
+        if c >= 0: place(r, c)
+    return slots
+
+
+def items_of(slots):
+    """per transcript: (count, list of (x offset, n valid) items) in the build's class order."""
+    t, cnt = np.unique(slots[slots >= 0], return_counts=True)
+    agg = [(int(a), int(b)) for a, b in zip(t, cnt) if b >= 4]
+    n0 = sum(c // IMAX + (1 if c % IMAX > IMAX // 2 else 0) for _, c in agg)
+    n1 = sum(1 for _, c in agg if IMAX // 4 < c % IMAX <= IMAX // 2)
+    i0 = i1 = i2 = 0
+    out = {}
+    for tr, c in agg:
+        q, rem = divmod(c, IMAX)
+        its = [((i0 + v) * 18, IMAX) for v in range(q)]
+        i0 += q
+        if rem > IMAX // 2: its.append((i0 * 18, rem)); i0 += 1
+        elif rem > IMAX // 4: its.append((n0 * 18 + i1 * 10, rem)); i1 += 1
+        elif rem >= 1: its.append((n0 * 18 + n1 * 10 + i2 * 6, rem)); i2 += 1
+        out[tr] = its
+    return out, list(t)
+
+
+def groups():
+    for c in range(NW):
+        for k in range(4):
+            for h in range(2):
+                yield [c * CHUNK + 4 * (16 * h + l) + k for l in range(16)]
+
+
+def scatter_sorted(slots, items):
+    """positions in (transcript; chunk, k, lane) sort order -- the layout before the bank-aware assignment."""
+    pos = {}
+    nxt = {tr: 0 for tr in items}
+    flat = {tr: [x + o for x, n in its for o in range(n)] for tr, its in items.items()}
+    for g in groups():
+        pass
+    order = sorted((s for s in range(NW * CHUNK) if slots[s] in items),
+                   key=lambda s: (slots[s], s // CHUNK, s % 4, (s % CHUNK) // 4))
+    for s in order:
+        tr = slots[s]; pos[s] = flat[tr][nxt[tr]]; nxt[tr] += 1
+    return pos
+
+
+def scatter_greedy(slots, items, mode="lane"):
+    """the greedy of build_tiles; mode: 'lane' start the residue search at the lane number (current),
+    'scarce' = lanes whose transcript offers the fewest residues choose first, then 'lane'."""
+    free = {tr: {} for tr in items}          # residue -> list of positions still free
+    for tr, its in items.items():
+        for x, n in its:
+            for o in range(n):
+                free[tr].setdefault((x + o) & 15, []).append(x + o)
+    pos = {}
+    for g in groups():
+        G = set()
+        lanes = [(l, s) for l, s in enumerate(g) if slots[s] in items]
+        if mode == "scarce":
+            lanes.sort(key=lambda ls: (len(free[slots[ls[1]]]), ls[0]))
+        for l, s in lanes:
+            av = free[slots[s]]
+            cand = [r for r in av if r not in G] or list(av)
+            rho = min(cand, key=lambda r: (r - l) & 15)
+            G.add(rho)
+            pos[s] = av[rho].pop(0)
+            if not av[rho]: del av[rho]
+    return pos
+
+
+def scatter_wavefronts(pos):
+    w = 0
+    for g in groups():
+        banks = {}
+        for s in g:
+            if s in pos: banks[pos[s] & 15] = banks.get(pos[s] & 15, 0) + 1
+        w += max(banks.values()) if banks else 0
+    return w
+
+
+def gather_wavefronts(slots, index):
+    w = 0
+    for g in groups():
+        banks = {}
+        for s in g:
+            d = index.get(slots[s], 0)
+            banks.setdefault(d & 15, set()).add(d)
+        w += max(len(v) for v in banks.values())
+    return w
+
+
+def table_coloured(slots, table):
+    """table order chosen so that transcripts read by the same half-warp instruction sit in different banks:
+    greedy over transcripts by decreasing count, each takes the residue with the least co-occurrence weight."""
+    co = {}
+    for g in groups():
+        ts = {slots[s] for s in g if slots[s] >= 0}
+        for a in ts:
+            for b in ts:
+                if a != b: co.setdefault(a, {}); co[a][b] = co[a].get(b, 0) + 1
+    cnt = {t: int((slots == t).sum()) for t in table}
+    res_of, load = {}, [0] * 16
+    for t in sorted(table, key=lambda t: -cnt[t]):
+        cost = [sum(wt for b, wt in co.get(t, {}).items() if res_of.get(b) == r) for r in range(16)]
+        r = min(range(16), key=lambda r: (cost[r], load[r]))
+        res_of[t] = r; load[r] += 1
+    # residue r, j-th transcript with that residue -> index r + 16 j (the table gets holes up to 16 * max load)
+    seen = [0] * 16; index = {}
+    for t in sorted(table, key=lambda t: -cnt[t]):
+        r = res_of[t]; index[t] = r + 16 * seen[r]; seen[r] += 1
+    return index, 16 * max(load)
+
+
+def main():
+    n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 400000
+    n_txps = int(sys.argv[2]) if len(sys.argv) > 2 else 8000
+    avg = float(sys.argv[3]) if len(sys.argv) > 3 else 8.0
+    max_tiles = int(sys.argv[4]) if len(sys.argv) > 4 else 150
+    st = synth.make_store(n_reads, n_txps, avg, 3)
+    acc = {}
+    nt = 0
+    for rows in tiles_of(st, max_tiles):
+        slots = pack(rows)
+        items, table = items_of(slots)
+        nt += 1
+        for name, pos in (("scatter sorted", scatter_sorted(slots, items)), ("scatter greedy/lane", scatter_greedy(slots, items, "lane")),
+                          ("scatter greedy/scarce", scatter_greedy(slots, items, "scarce"))):
+            acc[name] = acc.get(name, 0) + scatter_wavefronts(pos)
+        acc["gather id order"] = acc.get("gather id order", 0) + gather_wavefronts(slots, {t: i for i, t in enumerate(table)})
+        idx, size = table_coloured(slots, table)
+        acc["gather coloured"] = acc.get("gather coloured", 0) + gather_wavefronts(slots, idx)
+        acc["table size id"] = acc.get("table size id", 0) + len(table)
+        acc["table size coloured"] = acc.get("table size coloured", 0) + size
+    print(f"{nt} tiles; per tile (64 half-warp instructions each, ideal 64):")
+    for k, v in acc.items():
+        print(f"  {k:24s} {v / nt:8.1f}")
+
+
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "matching"):
+    main()
+
+
+def scatter_matching(slots, items):
+    """per half-warp group a maximum bipartite matching lanes <-> bank residues (augmenting paths) on what the
+    transcripts still offer: the best a group-by-group assignment can do (bound for the greedy)."""
+    free = {tr: {} for tr in items}
+    for tr, its in items.items():
+        for x, n in its:
+            for o in range(n):
+                free[tr].setdefault((x + o) & 15, []).append(x + o)
+    pos = {}
+    for g in groups():
+        lanes = [s for s in g if slots[s] in items]
+        # capacities: a transcript offers residue r len(free[tr][r]) times; lanes of one transcript share them
+        match_r = {}          # residue -> lane slot
+        def try_lane(s, seen):
+            tr = slots[s]
+            for r in sorted(free[tr], key=lambda r: -len(free[tr][r])):
+                if r in seen: continue
+                # supply check: lanes of the same transcript already holding r
+                held = sum(1 for rr, ss in match_r.items() if rr == r and slots[ss] == tr)
+                if held >= len(free[tr][r]): continue
+                seen.add(r)
+                if r not in match_r or try_lane(match_r[r], seen):
+                    match_r[r] = s
+                    return True
+            return False
+        unmatched = []
+        for s in sorted(lanes, key=lambda s: len(free[slots[s]])):
+            if not try_lane(s, set()): unmatched.append(s)
+        for r, s in match_r.items():
+            pos[s] = free[slots[s]][r].pop(0)
+            if not free[slots[s]][r]: del free[slots[s]][r]
+        for s in unmatched:   # conflict: take the residue the transcript has most of
+            av = free[slots[s]]
+            r = max(av, key=lambda r: len(av[r]))
+            pos[s] = av[r].pop(0)
+            if not av[r]: del av[r]
+    return pos
+
+
+def main2():
+    n_reads = int(sys.argv[2]) if len(sys.argv) > 2 else 400000
+    st = synth.make_store(n_reads, n_reads // 50, 8.0, 3)
+    acc = {}; nt = 0
+    for rows in tiles_of(st, int(sys.argv[3]) if len(sys.argv) > 3 else 60):
+        slots = pack(rows); items, table = items_of(slots); nt += 1
+        for name, pos in (("scatter greedy/lane", scatter_greedy(slots, items, "lane")), ("scatter greedy/scarce", scatter_greedy(slots, items, "scarce")),
+                          ("scatter matching", scatter_matching(slots, items))):
+            acc[name] = acc.get(name, 0) + scatter_wavefronts(pos)
+    for k, v in acc.items():
+        print(f"  {k:24s} {v / nt:8.1f}")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "matching":
+    main2()

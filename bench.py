@@ -288,13 +288,19 @@ def run_gpu(args):
     ds.bootstrap(1, seed, first_replicate=100000 + rank)     # warm-up (weights buffers, weighted graph)
     barrier()
     t0 = time.perf_counter()
-    _, nit = ds.bootstrap(B, seed, first_replicate=rank, replicate_stride=world)
+    if args.boot_schedule == "dynamic" and multi:
+        # opt-in: ranks pull global replicate ids from a shared counter (oarfish_b200.dist.ReplicateQueue)
+        from oarfish_b200 import dist as odist
+        _ids, res = odist.run_replicates_dynamic(lambda g: ds.bootstrap(1, seed, first_replicate=g)[1], world * B)
+        nit = np.concatenate(res) if res else np.zeros(0, dtype=np.uint32)
+    else:
+        _, nit = ds.bootstrap(B, seed, first_replicate=rank, replicate_stride=world)
     boot_launches = ds.counters()["launches"]
     barrier()
     dtb = max_over_ranks(time.perf_counter() - t0)
-    boot_iters = sum_over_ranks(float(nit.sum() + 2 * B))
+    boot_iters = sum_over_ranks(float(nit.sum() + 2 * len(nit)))
     boot = {"replicates_per_sec": world * B / dtb, "replicates": world * B, "iterations_per_sec": boot_iters / dtb,
-            "niter_rank0": [int(x) for x in nit], "min_iter": 50, "bcast_ms": bcast_ms, "gpu_launches_rank0": int(boot_launches)}
+            "niter_rank0": [int(x) for x in nit], "min_iter": 50, "schedule": args.boot_schedule if multi else "static", "bcast_ms": bcast_ms, "gpu_launches_rank0": int(boot_launches)}
 
     # ---- e2e: host (pinned) buffers through the public API ------------------------------------------
     e2e = None
@@ -365,6 +371,8 @@ def main():
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--boot-schedule", default="static", choices=["static", "dynamic"],
+                    help="bootstrap leg at N > 1: replicate g on rank g mod N (default) or pulled from a shared counter")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

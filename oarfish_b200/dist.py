@@ -87,3 +87,74 @@ def gather_replicates(local: "np.ndarray", num_boot: int, world: int, rank: int,
         if idx:
             out[idx] = np.asarray(sh).reshape(len(idx), n_txps)
     return out
+
+
+# ---------------------------------------------------------------------------
+# Dynamic replicate scheduling (opt-in)
+# ---------------------------------------------------------------------------
+# Replicates differ in length (486..1000 EM iterations on C3), so the static g mod G split leaves ranks idle at the end
+# (8 GPUs: 7.1x one GPU).  Because a replicate's weights depend only on (seed, g), WHICH rank runs it is free: ranks can
+# pull the next global replicate id from a shared counter instead.  The counter lives in the process group's key-value
+# store (TCPStore.add is atomic); one round trip per replicate (~0.1 ms against ~100 ms of EM), still no collective on
+# the EM data path.
+
+_queue_serial = 0
+
+
+class ReplicateQueue:
+    """Shared work queue over the global replicate ids 0 .. num_boot-1 (collective constructor: every rank must create
+    its queues in the same order)."""
+
+    def __init__(self, num_boot: int, store=None):
+        global _queue_serial
+        import torch.distributed as dist
+
+        if store is None:
+            from torch.distributed import distributed_c10d as c10d
+            store = c10d._get_default_store()
+        self._store = store
+        self._num_boot = int(num_boot)
+        self._key = f"oarfish_b200/replicate_queue/{_queue_serial}"
+        _queue_serial += 1
+        if dist.get_rank() == 0:
+            store.add(self._key, 0)      # create the counter before anybody pulls from it
+        dist.barrier()
+
+    def next(self) -> Optional[int]:
+        """The next replicate id nobody has taken yet, or None when all are handed out."""
+        g = int(self._store.add(self._key, 1)) - 1
+        return g if g < self._num_boot else None
+
+
+def run_replicates_dynamic(run_one, num_boot: int, store=None) -> Tuple[List[int], list]:
+    """Pull replicate ids from a ReplicateQueue until it is empty; `run_one(g)` computes global replicate g.
+    Returns (ids this rank ran, their results in the same order)."""
+    q = ReplicateQueue(num_boot, store)
+    ids, results = [], []
+    while True:
+        g = q.next()
+        if g is None:
+            break
+        ids.append(g)
+        results.append(run_one(g))
+    return ids, results
+
+
+def gather_replicates_by_id(ids: List[int], local: "np.ndarray", num_boot: int, rank: int, n_txps: int) -> Optional[np.ndarray]:
+    """Reassemble [replicate][transcript] on rank 0 when every rank ran an arbitrary subset `ids` (rows of `local`)."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size()
+    shards = [None] * world if rank == 0 else None
+    dist.gather_object((list(ids), np.ascontiguousarray(local)), shards, dst=0)
+    if rank != 0:
+        return None
+    out = np.full((num_boot, n_txps), np.nan, dtype=np.float64)
+    seen = []
+    for sh_ids, sh in shards:
+        if sh_ids:
+            out[sh_ids] = np.asarray(sh).reshape(len(sh_ids), n_txps)
+            seen += sh_ids
+    if sorted(seen) != list(range(num_boot)):
+        raise RuntimeError("replicate queue: the ranks did not cover every replicate exactly once")
+    return out

@@ -203,7 +203,7 @@ def main():
         print(f"  {k:24s} {v / nt:8.1f}")
 
 
-if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "matching"):
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] in ("matching", "heuristics")):
     main()
 
 
@@ -261,3 +261,76 @@ def main2():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "matching":
     main2()
+
+
+def scatter_greedy2(slots, items, augment=True, by_supply=True):
+    """scarce-first greedy; constrained lanes take the free residue their transcript has most of; a lane left without a
+    free residue may displace one already-placed lane of the group whose transcript can move elsewhere (one-step
+    augmentation)."""
+    free = {tr: {} for tr in items}
+    for tr, its in items.items():
+        for x, n in its:
+            for o in range(n):
+                free[tr].setdefault((x + o) & 15, []).append(x + o)
+    pos = {}
+    for g in groups():
+        lanes = [(l, s) for l, s in enumerate(g) if slots[s] in items]
+        lanes.sort(key=lambda ls: (len(free[slots[ls[1]]]), ls[0]))
+        taken = {}     # residue -> slot
+        held = {}      # (tr, residue) -> count reserved in this group
+        def offers(tr, r):
+            return r in free[tr] and len(free[tr][r]) > held.get((tr, r), 0)
+        todo_conf = []
+        for l, s in lanes:
+            tr = slots[s]
+            cand = [r for r in free[tr] if r not in taken and offers(tr, r)]
+            if cand:
+                if by_supply and len(free[tr]) < 16:
+                    r = max(cand, key=lambda r: (len(free[tr][r]), -((r - l) & 15)))
+                else:
+                    r = min(cand, key=lambda r: (r - l) & 15)
+                taken[r] = s; held[(tr, r)] = held.get((tr, r), 0) + 1
+                continue
+            moved = False
+            if augment:
+                for r in list(free[tr]):
+                    if not offers(tr, r) or r not in taken: continue
+                    s2 = taken[r]; tr2 = slots[s2]
+                    alt = [r2 for r2 in free[tr2] if r2 not in taken and offers(tr2, r2)]
+                    if alt:
+                        r2 = alt[0]
+                        held[(tr2, r)] -= 1; taken[r2] = s2; held[(tr2, r2)] = held.get((tr2, r2), 0) + 1
+                        taken[r] = s; held[(tr, r)] = held.get((tr, r), 0) + 1
+                        moved = True
+                        break
+            if not moved: todo_conf.append(s)
+        for r, s in taken.items():
+            tr = slots[s]; pos[s] = free[tr][r].pop(0)
+            if not free[tr][r]: del free[tr][r]
+        for s in todo_conf:
+            av = free[slots[s]]
+            r = max(av, key=lambda r: len(av[r]))
+            pos[s] = av[r].pop(0)
+            if not av[r]: del av[r]
+    return pos
+
+
+def main3():
+    n_reads = int(sys.argv[2]) if len(sys.argv) > 2 else 400000
+    st = synth.make_store(n_reads, n_reads // 50, 8.0, 3)
+    acc = {}; nt = 0
+    for rows in tiles_of(st, int(sys.argv[3]) if len(sys.argv) > 3 else 60):
+        slots = pack(rows); items, table = items_of(slots); nt += 1
+        for name, pos in (("greedy/lane (shipped)", scatter_greedy(slots, items, "lane")),
+                          ("scarce first", scatter_greedy(slots, items, "scarce")),
+                          ("scarce + by supply", scatter_greedy2(slots, items, augment=False)),
+                          ("scarce + by supply + 1-step augment", scatter_greedy2(slots, items, augment=True)),
+                          ("scarce + 1-step augment", scatter_greedy2(slots, items, augment=True, by_supply=False)),
+                          ("matching", scatter_matching(slots, items))):
+            acc[name] = acc.get(name, 0) + scatter_wavefronts(pos)
+    for k, v in acc.items():
+        print(f"  {k:40s} {v / nt:8.1f}")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "heuristics":
+    main3()

@@ -60,6 +60,9 @@ constexpr int kAggMin = 4;                // transcripts with >= kAggMin alignme
 #ifndef OAR_SCATTER_GREEDY
 #define OAR_SCATTER_GREEDY 1    // layout: x positions chosen so that the M-step scatter spreads over the banks
 #endif
+#ifndef OAR_GREEDY_SCARCE
+#define OAR_GREEDY_SCARCE 0     // layout: scarce-first / by-supply refinement of the x position greedy (unmeasured)
+#endif
 #ifndef OAR_SHORT_ROW_DEFER
 #define OAR_SHORT_ROW_DEFER 1   // layout: keep rows shorter than a lane from starting and ending inside one lane
 #endif
@@ -478,7 +481,7 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
     // half-warp store took 3.1 wavefronts on C3 -- the same as positions drawn at random.)
     uint32_t *s_state = s_txp;          // per transcript: residues on offer (bits 0-15) | free remainder slots (16-31); s_txp is dead
     uint16_t *s_ci = s_rnew;            // per transcript: compact index of its full-item counters | partial << 15; dead since the rows were placed
-    __shared__ uint8_t s_fulluse[kTile / kItemMax][16];                 // [compact transcript][residue] -> full items used
+    __shared__ __align__(16) uint8_t s_fulluse[kTile / kItemMax][16];                 // [compact transcript][residue] -> full items used
     if (tid == 0) s_misc[3] = 0;
     for (uint32_t i = tid; i < (uint32_t)(kTile / kItemMax) * 16u; i += kThreads) (&s_fulluse[0][0])[i] = 0;
 #pragma unroll
@@ -523,18 +526,42 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
             uint32_t G = 0;   // residues taken in this lane's half-warp
             while (__any_sync(full, todo)) {
                 uint32_t rho = 0, st = 0;
-                if (todo) {
+                bool prop = todo;                          // does this lane propose in this round?
+#if OAR_GREEDY_SCARCE
+                // (prepared for round 2, off by default: tools/layout_model.py puts it at 72.7 wavefronts per tile against
+                // 88.9.)  Lanes whose transcript no longer offers every residue choose first, and among the unused
+                // residues they take the one their transcript has most left of.
+                if (todo) st = s_state[d];
+                const bool cons = todo && (st & 0xFFFFu) != 0xFFFFu;
+                prop = todo && (cons || !__any_sync(full, cons));
+#endif
+                if (prop) {
                     st = s_state[d];
                     const uint32_t av = st & 0xFFFFu;      // never 0 here: the transcript still owes this lane a position
                     uint32_t cand = av & ~G;
                     if (cand == 0u) cand = av;             // no unused residue on offer: accept a bank conflict
                     const uint32_t rot = ((cand >> l16) | (cand << (16u - l16))) & 0xFFFFu;
                     rho = (l16 + (uint32_t)__ffs((int)rot) - 1u) & 15u;
+#if OAR_GREEDY_SCARCE
+                    if (av != 0xFFFFu && q) {
+                        const uint4 fu = *reinterpret_cast<const uint4 *>(&s_fulluse[ci][0]);
+                        const uint32_t fw[4] = {fu.x, fu.y, fu.z, fu.w};
+                        uint32_t best = 0;
+#pragma unroll
+                        for (uint32_t r = 0; r < 16u; ++r) {
+                            const uint32_t used_r = (fw[r >> 2] >> (8u * (r & 3u))) & 0xFFu;
+                            const uint32_t left = (q > used_r ? q - used_r : 0u) + ((st >> (16u + ((r - br) & 15u))) & 1u);
+                            const uint32_t key = ((cand >> r) & 1u) ? (left << 8) | ((15u - ((r - l16) & 15u)) << 4) | r | 0x80000000u : 0u;
+                            best = key > best ? key : best;
+                        }
+                        rho = best & 15u;
+                    }
+#endif
                 }
                 const uint32_t idle = 0x80000000u | lane;
-                const unsigned m1 = __match_any_sync(full, todo ? ((d << 4) | rho) : idle);
-                const unsigned m2 = __match_any_sync(full, todo ? ((half << 4) | rho) : idle);
-                const bool go = todo && (uint32_t)(__ffs((int)m1) - 1) == lane && (uint32_t)(__ffs((int)m2) - 1) == lane;
+                const unsigned m1 = __match_any_sync(full, prop ? ((d << 4) | rho) : idle);
+                const unsigned m2 = __match_any_sync(full, prop ? ((half << 4) | rho) : idle);
+                const bool go = prop && (uint32_t)(__ffs((int)m1) - 1) == lane && (uint32_t)(__ffs((int)m2) - 1) == lane;
                 uint32_t took = 0;
                 if (go) {
                     uint32_t m = q ? s_fulluse[ci][rho] : 0u;

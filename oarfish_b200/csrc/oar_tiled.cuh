@@ -12,11 +12,12 @@
 //     table is gathered once into shared memory, alignments store a 16-bit
 //     table offset instead of the 32-bit id;
 //   * the M-step scatter goes through shared memory: every alignment also
-//     stores `pos`, its position in the tile's transcript-sorted order, x_j =
-//     w_j/denom is written to xs[pos] and 8-slot units of xs are summed
-//     contiguously, then combined across a warp and flushed with ONE f64 RED
-//     per (warp, transcript) instead of one per alignment.  No shared-memory
-//     atomics (f64 smem atomics are CAS loops on sm_100a).
+//     stores `pos`, one of its transcript's x positions in the tile (chosen at
+//     layout time so that the 16 lanes of a half-warp store into 16 different
+//     banks), x_j = w_j/denom is written to xs[pos]; a transcript's positions
+//     form ITEMS of <= 16 consecutive slots, one thread sums one item and
+//     flushes it with ONE f64 RED instead of one per alignment.  No shared-
+//     memory atomics (f64 smem atomics are CAS loops on sm_100a).
 //   * rows never straddle a 128-slot warp-chunk, so the per-row denominator
 //     (em.rs:98-112) is a segmented warp scan in registers, driven by a
 //     precomputed 16-bit descriptor per lane.
@@ -25,14 +26,17 @@
 // and a two-stage ring of shared-memory buffers is filled by TMA bulk copies
 // (cp.async.bulk, completion on an mbarrier), issued two tiles ahead by one
 // thread, so HBM latency never sits on the compute path and no registers are
-// spent on prefetching.
+// spent on prefetching.  One warp alone waits on the mbarriers and gathers
+// prev[]; the CTA barrier hands the stage on to the others.  em_sweep_tiled has
+// two CTA barriers per tile, em_sweep_tiled1 (OAR_SWEEP=1b) one.
 //
 // Per alignment the HBM stream is 4 B (prob f32) + 4 B (table offset u16 | pos
 // u16), the same 8 B as CSR's txp_id + prob; row structure costs 2 B per lane
 // (4 slots) instead of a 4-byte row_ptr entry per row.
 //
 // Rows longer than a warp-chunk, or that do not fit their tile, are listed in
-// `fallback_rows` and swept by em_sweep_rowgroup from the original CSR.
+// `fallback_rows` and swept from the original CSR by the last CTA of the sweep
+// (a long list gets its own em_sweep_rowgroup launch).
 #pragma once
 #include <cub/cub.cuh>
 

@@ -201,8 +201,8 @@ extern "C" int oar_store_create(const uint64_t *row_ptr, const uint32_t *txp_id,
                 if (rc2 == OAR_OK) s->kernel = layout_kernel(s);
                 else if (rc2 != OAR_ERR_UNSUPPORTED) return rc2;   // unsupported shape: keep the CSR kernel
             }
-            const char *sw = getenv("OAR_SWEEP");   // "1b": single-barrier tiled sweep, "2b": two barriers per tile
-            if (sw) s->sweep_1b = strcmp(sw, "1b") == 0 ? 1 : 0;
+            const char *sw = getenv("OAR_SWEEP");   // "2b": two barriers per tile (default), "1b": single barrier, "1c": same with deeper rings (unmeasured)
+            if (sw) s->sweep_1b = strcmp(sw, "1b") == 0 ? 1 : strcmp(sw, "1c") == 0 ? 2 : 0;
             const char *cps = getenv("OAR_CTAS_PER_SM");
             if (cps && atoi(cps) > 0) { s->ctas_per_sm = atoi(cps); s->lane_ctas_per_sm = atoi(cps); }
             OAR_CUDA(cudaEventRecord(s->ev[1], s->stream));
@@ -333,6 +333,26 @@ static cudaError_t launch_tiled1(oar_store *s, const tiled::View &v, const doubl
     return cudaGetLastError();
 }
 
+// single-barrier sweep with deeper rings (OAR_SWEEP=1c; prepared for round 2, not yet run on a GPU)
+template <bool AUX, bool WTS>
+static cudaError_t launch_tiled2(oar_store *s, const tiled::View &v, const double *prev, double *curr,
+                                 const uint32_t *wperm, const OarEmState *state, int check_done)
+{
+    static int attr_bytes[16] = {0};
+    auto kfn = tiled::em_sweep_tiled2<AUX, WTS>;
+    const tiled::Geometry2 g = tiled::make_geometry2(s->tl.max_rec, s->tl.max_d, s->tl.max_u);
+    if (attr_bytes[s->device & 15] < (int)g.total) {
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.total);
+        if (e != cudaSuccess) return e;
+        attr_bytes[s->device & 15] = (int)g.total;
+    }
+    int per_sm = (int)((227u * 1024u) / (g.total + 1024u));
+    per_sm = std::max(1, std::min(per_sm, std::min(s->ctas_per_sm, 32 / tiled::kWarps)));   // register budget: 4 CTAs
+    const uint32_t grid = std::min<uint32_t>(v.n_tiles, (uint32_t)s->sm_count * (uint32_t)per_sm);
+    kfn<<<grid, tiled::kThreads, g.total, s->stream>>>(v, g, prev, curr, wperm, state, check_done);
+    return cudaGetLastError();
+}
+
 static lane::View lane_view(const oar_store *s)
 {
     const TiledLayout &t = s->tl;
@@ -412,7 +432,12 @@ static cudaError_t enqueue_sweep(oar_store *s, const double *prev, double *curr,
         v.csr_wts = wts;
         const uint32_t *wp = wts ? t.wperm : nullptr;
         cudaError_t le;
-        if (s->sweep_1b) {
+        if (s->sweep_1b == 2) {
+            if (s->d_aux) le = wts ? launch_tiled2<true, true>(s, v, prev, curr, wp, state, check_done)
+                                   : launch_tiled2<true, false>(s, v, prev, curr, wp, state, check_done);
+            else          le = wts ? launch_tiled2<false, true>(s, v, prev, curr, wp, state, check_done)
+                                   : launch_tiled2<false, false>(s, v, prev, curr, wp, state, check_done);
+        } else if (s->sweep_1b) {
             if (s->d_aux) le = wts ? launch_tiled1<true, true>(s, v, prev, curr, wp, state, check_done)
                                    : launch_tiled1<true, false>(s, v, prev, curr, wp, state, check_done);
             else          le = wts ? launch_tiled1<false, true>(s, v, prev, curr, wp, state, check_done)

@@ -52,7 +52,7 @@ struct oar_store {
     uint32_t n_txps = 0;
     int kernel = OAR_KERNEL_ROWGROUP;
     bool borrowed = false;  // sub-store of another store: row_ptr / prob / aux / stream / events are not owned
-    int sweep_1b = 0;   // tiled sweep variant: 0 = two CTA barriers per tile (em_sweep_tiled), 1 = one (em_sweep_tiled1, OAR_SWEEP=1b)
+    int sweep_1b = 0;   // tiled sweep variant: 0 = two CTA barriers per tile (em_sweep_tiled), 1 = one (em_sweep_tiled1, OAR_SWEEP=1b), 2 = one, deeper rings (em_sweep_tiled2, OAR_SWEEP=1c)
     int ctas_per_sm = 40 / OAR_TILE_WARPS_DEFAULT;  // persistent CTAs of the tiled sweep per SM (upper bound; shared memory may allow fewer)
 
     int lane_ctas_per_sm = OAR_LANE_MIN_CTAS_DEFAULT;  // same for the row-per-lane sweep (register budget of its launch bounds)

@@ -1158,5 +1158,141 @@ __global__ void __launch_bounds__(kThreads, (4 * 8) / kWarps) em_sweep_tiled1(Vi
                                               tid >> 3, kThreads >> 3, v.n_fb);
 }
 
+// ---------------------------------------------------------------------------
+// Single-barrier sweep with deeper rings (OAR_SWEEP=1c) -- PREPARED FOR ROUND 2, NOT YET RUN ON A GPU.
+//
+// ncu on em_sweep_tiled1 shows its gather warp polling ~75 times per tile for a stage requested one iteration
+// earlier: at 4 CTAs/SM an iteration (1.4 us) is about one HBM round trip, so the kernel is bound by prefetch depth.
+// A fourth unified stage does not fit next to the second x buffer, but a tile's record is small (1.3 KB on C3):
+// here the records travel in their own ring of four slots (requested three tiles ahead, needed two iterations
+// later by the gather warp) and the prob | lpos blocks in a ring of three (requested two tiles ahead).
+//
+//   iteration i, after the barrier:  TMA thread   bulk of tile i+2 -> bulk[(i+2)%3], record of tile i+3 -> rec[(i+3)%4]
+//                                    first warps  phase 2 of tile i-1
+//                                    all warps    phase 1 of tile i   (bulk[i%3], rec[i%4], s_prev[i&1] -> xs[i&1])
+//                                    last warp    waits for rec[(i+1)%4], gathers prev[] of tile i+1 into s_prev[(i+1)&1],
+//                                                 waits for bulk[(i+1)%3]
+struct Geometry2 {
+    uint32_t xs_bytes, bulk_off, rec_off, rec_bytes, prev_off, prev_bytes, bar_off, total;
+};
+inline Geometry2 make_geometry2(uint32_t max_rec_bytes, uint32_t max_d, uint32_t max_x_doubles)
+{
+    Geometry2 g;
+    g.xs_bytes = (8u * ((max_x_doubles + 2u + 1u) & ~1u) + 127u) & ~127u;
+    g.bulk_off = 2u * g.xs_bytes;
+    g.rec_off = g.bulk_off + 3u * 8u * kTile;
+    g.rec_bytes = (max_rec_bytes + 15u) & ~15u;
+    g.prev_off = g.rec_off + 4u * g.rec_bytes;
+    g.prev_bytes = 8u * ((max_d + 1u) & ~1u);
+    g.bar_off = g.prev_off + 2u * g.prev_bytes;
+    g.total = g.bar_off + 7u * 8u;   // mbarriers: bulk[3], rec[4]
+    return g;
+}
+
+template <bool HAS_AUX, bool HAS_WTS>
+__global__ void __launch_bounds__(kThreads, (4 * 8) / kWarps) em_sweep_tiled2(View v, Geometry2 g, const double *__restrict__ prev,
+                                                               double *__restrict__ curr,
+                                                               const uint32_t *__restrict__ wperm,
+                                                               const OarEmState *__restrict__ st, int check_done)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    if (check_done && st->done) return;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t n_tiles = v.n_tiles, stride = gridDim.x;
+    const uint32_t tile0 = blockIdx.x;
+    if (tile0 >= n_tiles) return;
+    uint32_t sm0;
+    asm volatile("{.reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t;}" : "=r"(sm0) : "l"(smem));
+    const uint32_t bulk0 = sm0 + g.bulk_off, rec0 = sm0 + g.rec_off, sp0 = sm0 + g.prev_off, bar0 = sm0 + g.bar_off;
+    const uint32_t xs0 = smem_u32(smem);   // warp-uniform to the compiler (see em_sweep_tiled)
+    const bool is_tma = tid == 32u * (kWarps - 2);
+    const bool is_gather = warp == kWarps - 1;
+
+    auto issue_bulk = [&](uint32_t tile, uint32_t b) {   // the TMA thread only
+        const uint32_t bar = bar0 + 8u * b, dst = bulk0 + b * (8u * kTile);
+        mbar_expect_tx(bar, 8u * kTile);
+        bulk_g2s(dst, v.prob + (size_t)tile * kTile, 4u * kTile, bar);
+        bulk_g2s(dst + 4u * kTile, v.lpos + (size_t)tile * kTile, 4u * kTile, bar);
+    };
+    auto issue_rec = [&](uint2 r, uint32_t slot) {
+        const uint32_t bar = bar0 + 24u + 8u * slot;
+        mbar_expect_tx(bar, r.y);
+        bulk_g2s(rec0 + slot * g.rec_bytes, v.records + r.x, r.y, bar);
+    };
+    auto gather_prev = [&](uint32_t rec_a, uint32_t sp_a) {   // one warp, two gathers in flight per lane
+        const uint32_t Dn = lds_u32(rec_a + kRecDU);
+        for (uint32_t d = lane; d < Dn; d += 64u) {
+            const uint32_t d2 = d + 32u;
+            const double p0 = prev[lds_u32(rec_a + kRecTable + 4u * d)];
+            double p1 = 0.0;
+            if (d2 < Dn) p1 = prev[lds_u32(rec_a + kRecTable + 4u * d2)];
+            sts_f64(sp_a + 8u * d, p0);
+            if (d2 < Dn) sts_f64(sp_a + 8u * d2, p1);
+        }
+        if (HAS_WTS) weights_touch(wperm + lds_u32(rec_a + kRecRow), lane);
+    };
+
+    if (tid == 0) {
+#pragma unroll
+        for (uint32_t i = 0; i < 7; ++i) mbar_init(bar0 + 8u * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint2 r_pending = make_uint2(0, 0);   // record locator of the tile three ahead of the current one (TMA thread)
+    if (is_tma) {
+        issue_rec(v.rec[tile0], 0);
+        issue_bulk(tile0, 0);
+        if (tile0 + stride < n_tiles) { issue_rec(v.rec[tile0 + stride], 1); issue_bulk(tile0 + stride, 1); }
+        if (tile0 + 2 * stride < n_tiles) issue_rec(v.rec[tile0 + 2 * stride], 2);
+        if (tile0 + 3 * stride < n_tiles) r_pending = v.rec[tile0 + 3 * stride];
+    }
+    uint32_t rpar = 0, bpar = 0;          // phase parities of the record / bulk mbarriers (gather warp)
+    if (is_gather) {
+        mbar_wait(bar0 + 24u, 0); rpar ^= 1u;
+        gather_prev(rec0, sp0);
+        mbar_wait(bar0, 0); bpar ^= 1u;
+    }
+
+    uint32_t tile = tile0;
+    uint32_t bs = 0, rs = 0;              // bulk stage = it % 3, record slot = it % 4 of this tile
+    uint32_t item_p = kNoTxp, U_p = 0, duz_p = 0;   // phase-2 inputs of the previous tile
+    uint32_t s_last = 0;
+    for (uint32_t it = 0;; ++it) {
+        const uint32_t s = it & 1u;
+        const uint32_t bs1 = bs == 2u ? 0u : bs + 1u, bs2 = bs1 == 2u ? 0u : bs1 + 1u;
+        const uint32_t rs1 = (rs + 1u) & 3u, rs3 = (rs + 3u) & 3u;
+        const uint32_t next = tile + stride;
+        const bool has_next = next < n_tiles;
+        __syncthreads();   // tile `it` is in place; xs[s], bulk[bs2], rec[rs3], s_prev[s^1] are free
+
+        if (is_tma) {
+            if (next + stride < n_tiles) issue_bulk(next + stride, bs2);
+            if (next + 2 * stride < n_tiles) {
+                issue_rec(r_pending, rs3);
+                if (next + 3 * stride < n_tiles) r_pending = v.rec[next + 3 * stride];
+            }
+        }
+        if (it) tile_phase2(xs0 + (s ^ 1u) * g.xs_bytes, item_p, U_p, duz_p, tid, warp, curr);
+
+        uint32_t item; uint4 du;
+        tile_phase1<HAS_AUX, HAS_WTS>(v, tile, bulk0 + bs * (8u * kTile), rec0 + rs * g.rec_bytes, sp0 + s * g.prev_bytes,
+                                      xs0 + s * g.xs_bytes, tid, lane, warp, curr, wperm, item, du);
+        item_p = item; U_p = du.y; duz_p = du.z;
+
+        if (!has_next) { s_last = s; break; }
+        if (is_gather) {
+            mbar_wait(bar0 + 24u + 8u * rs1, (rpar >> rs1) & 1u); rpar ^= 1u << rs1;
+            gather_prev(rec0 + rs1 * g.rec_bytes, sp0 + (s ^ 1u) * g.prev_bytes);
+            mbar_wait(bar0 + 8u * bs1, (bpar >> bs1) & 1u); bpar ^= 1u << bs1;
+        }
+        tile = next; bs = bs1; rs = rs1;
+    }
+    __syncthreads();       // x values of the last tile
+    tile_phase2(xs0 + s_last * g.xs_bytes, item_p, U_p, duz_p, tid, warp, curr);
+    if (v.n_fb && blockIdx.x == gridDim.x - 1u)
+        kern::rowgroup_rows<HAS_AUX, HAS_WTS>(v.csr_row_ptr, v.csr_txp, v.csr_prob, v.csr_aux, v.csr_wts, v.fb_rows, prev, curr,
+                                              tid >> 3, kThreads >> 3, v.n_fb);
+}
+
 }  // namespace tiled
 }  // namespace oar

@@ -15,6 +15,8 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 # OAR_KERNEL_ROWGROUP, OAR_KERNEL_TILED (default layout), OAR_KERNEL_LANE (OAR_LAYOUT=lane),
 # 4 = OAR_KERNEL_TILED with the single-barrier sweep (OAR_SWEEP=1b)
 KERNELS = [1, 2, 3, 4]
+if os.environ.get("OAR_TEST_EXPERIMENTAL"):
+    KERNELS.append(5)   # OAR_KERNEL_TILED with OAR_SWEEP=1c (deeper rings; prepared, not part of the default suite yet)
 RTOL = 1e-9
 NORTH_STAR_RTOL = 1e-5
 
@@ -43,7 +45,7 @@ def csr(rows):
 def store_for(DS, kernel, *args, **kw):
     """A device store whose tiled layout and sweep variant match `kernel` (the row-per-lane layout is opt-in via
     OAR_LAYOUT, the single-barrier sweep via OAR_SWEEP; both are read at store creation)."""
-    want = {"OAR_LAYOUT": "lane" if kernel == 3 else None, "OAR_SWEEP": "1b" if kernel == 4 else "2b"}
+    want = {"OAR_LAYOUT": "lane" if kernel == 3 else None, "OAR_SWEEP": {4: "1b", 5: "1c"}.get(kernel, "2b")}
     old = {k: os.environ.get(k) for k in want}
     for k, val in want.items():
         if val is None:
@@ -58,7 +60,7 @@ def store_for(DS, kernel, *args, **kw):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = val
-    abi_kernel = 2 if kernel == 4 else kernel
+    abi_kernel = 2 if kernel in (4, 5) else kernel
     with ds:
         ds.set_kernel(abi_kernel)
         assert ds.layout_info()["kernel"] == abi_kernel

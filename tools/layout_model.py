@@ -203,7 +203,7 @@ def main():
         print(f"  {k:24s} {v / nt:8.1f}")
 
 
-if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] in ("matching", "heuristics")):
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] in ("matching", "heuristics", "table")):
     main()
 
 
@@ -334,3 +334,43 @@ def main3():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "heuristics":
     main3()
+
+
+def table_online(slots, table):
+    """online colouring: walk the half-warp groups in order; a transcript seen for the first time takes the residue
+    that no other transcript of that group holds (ties: the least loaded residue)."""
+    res_of, load = {}, [0] * 16
+    for g in groups():
+        ts = []
+        for s in g:
+            t = slots[s]
+            if t >= 0 and t not in ts: ts.append(t)
+        held = {res_of[t] for t in ts if t in res_of}
+        for t in ts:
+            if t in res_of: continue
+            r = min(range(16), key=lambda r: (r in held, load[r]))
+            res_of[t] = r; load[r] += 1; held.add(r)
+    seen = [0] * 16; index = {}
+    for t in table:
+        r = res_of.get(t, 0); index[t] = r + 16 * seen[r]; seen[r] += 1
+    return index, 16 * max(max(load), 1)
+
+
+def main4():
+    n_reads = int(sys.argv[2]) if len(sys.argv) > 2 else 400000
+    st = synth.make_store(n_reads, n_reads // 50, 8.0, 3)
+    acc = {}; nt = 0
+    for rows in tiles_of(st, int(sys.argv[3]) if len(sys.argv) > 3 else 60):
+        slots = pack(rows); items, table = items_of(slots); nt += 1
+        acc["gather id order"] = acc.get("gather id order", 0) + gather_wavefronts(slots, {t: i for i, t in enumerate(table)})
+        for name, fn in (("gather coloured (co-occurrence)", table_coloured), ("gather coloured (online)", table_online)):
+            idx, size = fn(slots, table)
+            acc[name] = acc.get(name, 0) + gather_wavefronts(slots, idx)
+            acc[name + " table size"] = acc.get(name + " table size", 0) + size
+        acc["table size id"] = acc.get("table size id", 0) + len(table)
+    for k, v in acc.items():
+        print(f"  {k:48s} {v / nt:8.1f}")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "table":
+    main4()

@@ -145,6 +145,7 @@ extern "C" int oar_store_create(const uint64_t *row_ptr, const uint32_t *txp_id,
     oar_store *s = new (std::nothrow) oar_store();
     if (!s) return fail(OAR_ERR_OOM, "oar_store_create: host allocation failed");
     s->device = device; s->n_reads = n_reads; s->nnz = nnz; s->n_txps = n_txps;
+    cudaStream_t copy_stream = nullptr;
     int rc = [&]() -> int {
         OAR_CUDA(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device));
         warm_pool(device);
@@ -167,14 +168,28 @@ extern "C" int oar_store_create(const uint64_t *row_ptr, const uint32_t *txp_id,
         OAR_CUDA(dmalloc(&d_rp64, sizeof(uint64_t) * (n_reads + 1), s->stream));
         OAR_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(uint32_t) * 4, s->stream));
         OAR_CUDA(cudaMemcpyAsync(d_rp64, row_ptr, sizeof(uint64_t) * (n_reads + 1), cudaMemcpyDefault, s->stream));
-        if (nnz) {
-            OAR_CUDA(cudaMemcpyAsync(s->d_txp, txp_id, sizeof(uint32_t) * nnz, cudaMemcpyDefault, s->stream));
-            OAR_CUDA(cudaMemcpyAsync(s->d_prob, prob, sizeof(float) * nnz, cudaMemcpyDefault, s->stream));
-            if (aux_or_null)
-                OAR_CUDA(cudaMemcpyAsync(s->d_aux, aux_or_null, sizeof(double) * nnz, cudaMemcpyDefault, s->stream));
-        }
+        // OAR_UPLOAD_OVERLAP=1 (prepared for round 2, off by default, not yet run on a GPU): prob / aux are not needed
+        // before build_tiles, so they are uploaded on a second stream behind txp_id while validation, row keys and the
+        // sort run on the first; the layout build waits for s->prob_ready right before the tiles are written.
+        const char *ov = getenv("OAR_UPLOAD_OVERLAP");
+        const bool overlap = ov && ov[0] == '1' && nnz > 0;
+        if (nnz) OAR_CUDA(cudaMemcpyAsync(s->d_txp, txp_id, sizeof(uint32_t) * nnz, cudaMemcpyDefault, s->stream));
         OAR_CUDA(cudaMemsetAsync(s->d_txp + nnz, 0, sizeof(uint32_t) * pad, s->stream));
-        OAR_CUDA(cudaMemsetAsync(s->d_prob + nnz, 0, sizeof(float) * pad, s->stream));
+        cudaStream_t up = s->stream;
+        if (overlap) {
+            OAR_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+            OAR_CUDA(cudaEventCreateWithFlags(&s->prob_ready, cudaEventDisableTiming));
+            OAR_CUDA(cudaEventRecord(s->prob_ready, s->stream));           // allocations and the txp_id copy are in order
+            OAR_CUDA(cudaStreamWaitEvent(copy_stream, s->prob_ready, 0));
+            up = copy_stream;
+        }
+        if (nnz) {
+            OAR_CUDA(cudaMemcpyAsync(s->d_prob, prob, sizeof(float) * nnz, cudaMemcpyDefault, up));
+            if (aux_or_null)
+                OAR_CUDA(cudaMemcpyAsync(s->d_aux, aux_or_null, sizeof(double) * nnz, cudaMemcpyDefault, up));
+        }
+        OAR_CUDA(cudaMemsetAsync(s->d_prob + nnz, 0, sizeof(float) * pad, up));
+        if (overlap) OAR_CUDA(cudaEventRecord(s->prob_ready, copy_stream));
         {
             const int threads = 256;
             const int blocks = (int)std::min<uint64_t>((n_reads + threads) / threads, (uint64_t)s->sm_count * 16);
@@ -205,6 +220,7 @@ extern "C" int oar_store_create(const uint64_t *row_ptr, const uint32_t *txp_id,
             if (sw) s->sweep_1b = strcmp(sw, "1b") == 0 ? 1 : strcmp(sw, "1c") == 0 ? 2 : 0;
             const char *cps = getenv("OAR_CTAS_PER_SM");
             if (cps && atoi(cps) > 0) { s->ctas_per_sm = atoi(cps); s->lane_ctas_per_sm = atoi(cps); }
+            if (s->prob_ready) OAR_CUDA(cudaStreamWaitEvent(s->stream, s->prob_ready, 0));   // no layout was built: wait here
             OAR_CUDA(cudaEventRecord(s->ev[1], s->stream));
             OAR_CUDA(cudaStreamSynchronize(s->stream));
         }
@@ -213,6 +229,8 @@ extern "C" int oar_store_create(const uint64_t *row_ptr, const uint32_t *txp_id,
         s->timings[0] = ms;
         return OAR_OK;
     }();
+    if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }   // also on the error paths: d_prob is about to be freed
+    if (s->prob_ready) { cudaEventDestroy(s->prob_ready); s->prob_ready = nullptr; }
     if (rc != OAR_OK) {
         std::string keep = g_last_error;
         oar_store_destroy(s);

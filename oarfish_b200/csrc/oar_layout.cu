@@ -121,6 +121,7 @@ static int build_chunk_layout(oar_store *s, uint32_t span)
         a.srow = srow; a.tile_row = tile_row;
         a.o_prob = t.prob; a.o_lpos = t.lpos; a.o_aux = t.aux; a.o_rec = t.rec; a.o_records = records_tmp;
         a.o_trow = t.trow; a.fallback = t.fallback; a.cursors = counters + 4;
+        if (s->prob_ready) OAR_CUDA(cudaStreamWaitEvent(st, s->prob_ready, 0));   // prob / aux uploaded on a second stream
         build_tiles<<<n_tiles, kThreads, 0, st>>>(a);
         OAR_CUDA(cudaGetLastError());
     }
@@ -233,6 +234,7 @@ static int build_lane_layout(oar_store *s, uint32_t span)
         a.srow = srow; a.soff = soff; a.tile_row = tile_row;
         a.o_aux = t.aux; a.o_groups = t.groups; a.o_blobs = blobs_tmp; a.o_trow = t.trow;
         a.cursors = counters + 4;
+        if (s->prob_ready) OAR_CUDA(cudaStreamWaitEvent(st, s->prob_ready, 0));
         build_lane_tiles<<<n_tiles, kBuildThreads, sizeof(BuildSmem), st>>>(a);
         OAR_CUDA(cudaGetLastError());
     }

@@ -72,6 +72,7 @@ struct oar_store {
     uint32_t *d_weights = nullptr;  // N, bootstrap weights of the current replicate (read order)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t slot_ev[2] = {nullptr, nullptr};
+    cudaEvent_t prob_ready = nullptr;   // during oar_store_create with OAR_UPLOAD_OVERLAP=1: prob / aux have arrived (second stream)
 
     oar::GraphSlot graphs[2];  // [0] unweighted, [1] weighted
 

@@ -20,9 +20,17 @@ all: product oracle
 
 product: $(LIBDIR)/liboarfish_em.so $(LIBDIR)/liboarsynth.so $(LIBDIR)/host_mirror_test
 
-$(LIBDIR)/liboarfish_em.so: $(CU_SRCS) $(CU_HDRS)
-	@mkdir -p $(LIBDIR)
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(CU_SRCS) 2> $(LIBDIR)/ptxas.log || (cat $(LIBDIR)/ptxas.log; exit 1)
+# one object per translation unit, so that `make -j` compiles them side by side
+OBJDIR    := $(LIBDIR)/obj
+CU_OBJS   := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU_SRCS))
+
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(CU_HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) $(EXTRA_NVFLAGS) -c -o $@ $< 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; exit 1)
+
+$(LIBDIR)/liboarfish_em.so: $(CU_OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(CU_OBJS)
+	@cat $(OBJDIR)/*.ptxas.log > $(LIBDIR)/ptxas.log
 
 $(LIBDIR)/liboarsynth.so: $(CSRC)/synth.c
 	@mkdir -p $(LIBDIR)
@@ -38,6 +46,6 @@ oracle/liboarfish_oracle.so: oracle/em_oracle.c oracle/em_par_port.c oracle/cove
 	$(HOSTCC) $(CFLAGS) -shared -o $@ $^ -lm
 
 clean:
-	rm -f $(LIBDIR)/*.so $(LIBDIR)/ptxas.log $(LIBDIR)/host_mirror_test oracle/*.so
+	rm -rf $(OBJDIR) $(LIBDIR)/*.so $(LIBDIR)/ptxas.log $(LIBDIR)/host_mirror_test oracle/*.so
 
 .PHONY: all product oracle clean

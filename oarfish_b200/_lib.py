@@ -11,7 +11,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_DIR = os.path.join(_HERE, "lib")
-# OAR_EM_LIB points at another build of the same library (kernel-tuning variants built by tests/_build_variants.sh)
+# OAR_EM_LIB points at another build of the same library (kernel-tuning variants built by tools/dev/build_variants.sh)
 EM_LIB_PATH = os.environ.get("OAR_EM_LIB") or os.path.join(LIB_DIR, "liboarfish_em.so")
 SYNTH_LIB_PATH = os.path.join(LIB_DIR, "liboarsynth.so")
 

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <new>
 #include <vector>
 
@@ -77,20 +78,34 @@ extern "C" int oar_device_count(void)
 extern "C" void oar_store_destroy(oar_store *s)
 {
     if (!s) return;
+    const bool trace = getenv("OAR_TRACE") != nullptr;
+    double t[8]; int nt = 0;
+    auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    t[nt++] = now();
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    t[nt++] = now();
     destroy_graphs(s);
+    t[nt++] = now();
     free_tiled_layout(s);
     if (!s->borrowed) { dfree(s->d_row_ptr, s->stream); dfree(s->d_prob, s->stream); dfree(s->d_aux, s->stream); }
     dfree(s->d_txp, s->stream);
     dfree(s->d_counts[0], s->stream); dfree(s->d_counts[1], s->stream); dfree(s->d_state, s->stream); dfree(s->d_weights, s->stream);
+    t[nt++] = now();
     if (s->stream) cudaStreamSynchronize(s->stream);
+    t[nt++] = now();
     if (s->h_state) cudaFreeHost(s->h_state);
+    t[nt++] = now();
     if (!s->borrowed) {
         for (auto &e : s->ev) if (e) cudaEventDestroy(e);
         for (auto &e : s->slot_ev) if (e) cudaEventDestroy(e);
+        t[nt++] = now();
         if (s->stream) cudaStreamDestroy(s->stream);
-    }
+    } else t[nt++] = now();
+    t[nt++] = now();
+    if (trace)
+        fprintf(stderr, "[oar] destroy: sync %.2f graphs %.2f free-async %.2f sync %.2f freehost %.2f events %.2f stream %.2f ms\n",
+                t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4], t[6] - t[5], t[7] - t[6]);
     delete s;
     (void)cudaGetLastError();
 }
@@ -217,7 +232,7 @@ extern "C" int oar_store_create(const uint64_t *row_ptr, const uint32_t *txp_id,
                 else if (rc2 != OAR_ERR_UNSUPPORTED) return rc2;   // unsupported shape: keep the CSR kernel
             }
             const char *sw = getenv("OAR_SWEEP");   // "2b": two barriers per tile (default), "1b": single barrier, "1c": same with deeper rings (unmeasured)
-            if (sw) s->sweep_1b = strcmp(sw, "1b") == 0 ? 1 : strcmp(sw, "1c") == 0 ? 2 : 0;
+            if (sw) s->sweep_1b = strcmp(sw, "1b") == 0 ? 1 : strcmp(sw, "1c") == 0 ? 2 : strcmp(sw, "3") == 0 ? 3 : 0;
             const char *cps = getenv("OAR_CTAS_PER_SM");
             if (cps && atoi(cps) > 0) { s->ctas_per_sm = atoi(cps); s->lane_ctas_per_sm = atoi(cps); }
             if (s->prob_ready) OAR_CUDA(cudaStreamWaitEvent(s->stream, s->prob_ready, 0));   // no layout was built: wait here
@@ -371,6 +386,26 @@ static cudaError_t launch_tiled2(oar_store *s, const tiled::View &v, const doubl
     return cudaGetLastError();
 }
 
+// streaming single-barrier sweep (OAR_SWEEP=3): prob | lpos by LDG.128, records by TMA, prev[] by cp.async
+template <bool AUX, bool WTS>
+static cudaError_t launch_tiled3(oar_store *s, const tiled::View &v, const double *prev, double *curr,
+                                 const uint32_t *wperm, const OarEmState *state, int check_done)
+{
+    static int attr_bytes[16] = {0};
+    auto kfn = tiled::em_sweep_tiled3<AUX, WTS>;
+    const tiled::Geometry3 g = tiled::make_geometry3(s->tl.max_rec, s->tl.max_d, s->tl.max_u);
+    if (attr_bytes[s->device & 15] < (int)g.total) {
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.total);
+        if (e != cudaSuccess) return e;
+        attr_bytes[s->device & 15] = (int)g.total;
+    }
+    int per_sm = (int)((227u * 1024u) / (g.total + 1024u));
+    per_sm = std::max(1, std::min(per_sm, s->ctas_per_sm));
+    const uint32_t grid = std::min<uint32_t>(v.n_tiles, (uint32_t)s->sm_count * (uint32_t)per_sm);
+    kfn<<<grid, tiled::kThreads, g.total, s->stream>>>(v, g, prev, curr, wperm, state, check_done);
+    return cudaGetLastError();
+}
+
 static lane::View lane_view(const oar_store *s)
 {
     const TiledLayout &t = s->tl;
@@ -450,7 +485,12 @@ static cudaError_t enqueue_sweep(oar_store *s, const double *prev, double *curr,
         v.csr_wts = wts;
         const uint32_t *wp = wts ? t.wperm : nullptr;
         cudaError_t le;
-        if (s->sweep_1b == 2) {
+        if (s->sweep_1b == 3) {
+            if (s->d_aux) le = wts ? launch_tiled3<true, true>(s, v, prev, curr, wp, state, check_done)
+                                   : launch_tiled3<true, false>(s, v, prev, curr, wp, state, check_done);
+            else          le = wts ? launch_tiled3<false, true>(s, v, prev, curr, wp, state, check_done)
+                                   : launch_tiled3<false, false>(s, v, prev, curr, wp, state, check_done);
+        } else if (s->sweep_1b == 2) {
             if (s->d_aux) le = wts ? launch_tiled2<true, true>(s, v, prev, curr, wp, state, check_done)
                                    : launch_tiled2<true, false>(s, v, prev, curr, wp, state, check_done);
             else          le = wts ? launch_tiled2<false, true>(s, v, prev, curr, wp, state, check_done)

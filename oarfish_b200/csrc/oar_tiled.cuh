@@ -64,9 +64,6 @@ constexpr int kAggMin = 4;                // transcripts with >= kAggMin alignme
 #ifndef OAR_SCATTER_GREEDY
 #define OAR_SCATTER_GREEDY 1    // layout: x positions chosen so that the M-step scatter spreads over the banks
 #endif
-#ifndef OAR_GREEDY_SCARCE
-#define OAR_GREEDY_SCARCE 0     // layout: scarce-first / by-supply refinement of the x position greedy (unmeasured)
-#endif
 #ifndef OAR_SHORT_ROW_DEFER
 #define OAR_SHORT_ROW_DEFER 1   // layout: keep rows shorter than a lane from starting and ending inside one lane
 #endif
@@ -531,14 +528,6 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
             while (__any_sync(full, todo)) {
                 uint32_t rho = 0, st = 0;
                 bool prop = todo;                          // does this lane propose in this round?
-#if OAR_GREEDY_SCARCE
-                // (prepared for round 2, off by default: tools/layout_model.py puts it at 72.7 wavefronts per tile against
-                // 88.9.)  Lanes whose transcript no longer offers every residue choose first, and among the unused
-                // residues they take the one their transcript has most left of.
-                if (todo) st = s_state[d];
-                const bool cons = todo && (st & 0xFFFFu) != 0xFFFFu;
-                prop = todo && (cons || !__any_sync(full, cons));
-#endif
                 if (prop) {
                     st = s_state[d];
                     const uint32_t av = st & 0xFFFFu;      // never 0 here: the transcript still owes this lane a position
@@ -546,21 +535,6 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
                     if (cand == 0u) cand = av;             // no unused residue on offer: accept a bank conflict
                     const uint32_t rot = ((cand >> l16) | (cand << (16u - l16))) & 0xFFFFu;
                     rho = (l16 + (uint32_t)__ffs((int)rot) - 1u) & 15u;
-#if OAR_GREEDY_SCARCE
-                    if (av != 0xFFFFu && q) {
-                        const uint4 fu = *reinterpret_cast<const uint4 *>(&s_fulluse[ci][0]);
-                        const uint32_t fw[4] = {fu.x, fu.y, fu.z, fu.w};
-                        uint32_t best = 0;
-#pragma unroll
-                        for (uint32_t r = 0; r < 16u; ++r) {
-                            const uint32_t used_r = (fw[r >> 2] >> (8u * (r & 3u))) & 0xFFu;
-                            const uint32_t left = (q > used_r ? q - used_r : 0u) + ((st >> (16u + ((r - br) & 15u))) & 1u);
-                            const uint32_t key = ((cand >> r) & 1u) ? (left << 8) | ((15u - ((r - l16) & 15u)) << 4) | r | 0x80000000u : 0u;
-                            best = key > best ? key : best;
-                        }
-                        rho = best & 15u;
-                    }
-#endif
                 }
                 const uint32_t idle = 0x80000000u | lane;
                 const unsigned m1 = __match_any_sync(full, prop ? ((d << 4) | rho) : idle);
@@ -738,22 +712,16 @@ __device__ __forceinline__ void weights_touch(const uint32_t *__restrict__ w, ui
 // ---- phase 1 of a tile: E-step in registers + M-step scatter into the transcript-sorted x array -------------
 //   bulk, rec: shared-space addresses of the tile's prob | lpos block and of its record; sp_a: prev[] of the tile's
 //   transcripts; xs_a: the x array.  Returns the thread's item and the record's DU word for phase 2.
+//   The thread's four slots (prob, lpos) come in registers: p4 / lp4 = slots warp * kChunk + lane * 4 ...
 template <bool HAS_AUX, bool HAS_WTS>
-__device__ __forceinline__ void tile_phase1(const View &v, uint32_t tile, uint32_t bulk, uint32_t rec, uint32_t sp_a, uint32_t xs_a,
-                                            uint32_t tid, uint32_t lane, uint32_t warp, double *__restrict__ curr,
-                                            const uint32_t *__restrict__ wperm, uint32_t &item, uint4 &du)
+__device__ __forceinline__ void tile_phase1_core(const View &v, uint32_t tile, const float4 p4, const uint4 lp4, uint32_t rec, uint32_t sp_a,
+                                                 uint32_t xs_a, uint32_t trash, uint32_t tid, uint32_t lane, uint32_t warp,
+                                                 double *__restrict__ curr, const uint32_t *__restrict__ wperm)
 {
     const unsigned full = 0xffffffffu;
-    const float4 p4 = lds_v4f(bulk + 16u * tid);                    // slots warp * kChunk + lane * 4 ..
-    const uint4 lp4 = lds_v4(bulk + 4u * kTile + 16u * tid);
     const uint32_t desc = lds_u16(rec + kRecDesc + 2u * tid);
     const uint32_t info = lds_u32(rec + kRecInfo + 4u * warp);
-    du = lds_v4(rec + kRecDU);   // D, items, n32 | n16 << 16, trash offset
-    const uint32_t D = du.x, U = du.y;
     const uint32_t table_a = rec + kRecTable;
-    // this thread's item (read now: the record's stage is refilled before phase 2)
-    item = kNoTxp;
-    if (tid < U) item = lds_u32(table_a + 4u * (((D + 3u) & ~3u) + tid));
 
     double w0 = lds_f64(sp_a + (lp4.x & 0xFFFFu)) * (double)p4.x;
     double w1 = lds_f64(sp_a + (lp4.y & 0xFFFFu)) * (double)p4.y;
@@ -864,7 +832,6 @@ __device__ __forceinline__ void tile_phase1(const View &v, uint32_t tile, uint32
 
     // ---- M-step scatter into the transcript-sorted smem order -----------------------------
     // (padding and non-aggregated alignments carry the tile's trash offset and are not stored)
-    const uint32_t trash = du.w;
     const uint32_t q0 = lp4.x >> 16, q1 = lp4.y >> 16, q2 = lp4.z >> 16, q3 = lp4.w >> 16;
 #ifdef OAR_FAKE_SCATTER   // timing experiment only (wrong results): conflict-free scatter addresses
     sts_f64_if(xs_a + 8u * lane + 256u * warp, x0, q0 != trash);
@@ -884,6 +851,21 @@ __device__ __forceinline__ void tile_phase1(const View &v, uint32_t tile, uint32
         if (q2 == trash && x2 != 0.0) atomicAdd(curr + lds_u32(table_a + ((lp4.z & 0xFFFFu) >> 1)), x2);
         if (q3 == trash && x3 != 0.0) atomicAdd(curr + lds_u32(table_a + ((lp4.w & 0xFFFFu) >> 1)), x3);
     }
+}
+
+// phase 1 with the tile's prob | lpos block staged in shared memory (`bulk`); also returns the thread's item and the
+// record's DU word for phase 2 (read now: the record's stage is refilled before phase 2).
+template <bool HAS_AUX, bool HAS_WTS>
+__device__ __forceinline__ void tile_phase1(const View &v, uint32_t tile, uint32_t bulk, uint32_t rec, uint32_t sp_a, uint32_t xs_a,
+                                            uint32_t tid, uint32_t lane, uint32_t warp, double *__restrict__ curr,
+                                            const uint32_t *__restrict__ wperm, uint32_t &item, uint4 &du)
+{
+    const float4 p4 = lds_v4f(bulk + 16u * tid);
+    const uint4 lp4 = lds_v4(bulk + 4u * kTile + 16u * tid);
+    du = lds_v4(rec + kRecDU);   // D, items, n32 | n16 << 16, trash offset
+    item = kNoTxp;
+    if (tid < du.y) item = lds_u32(rec + kRecTable + 4u * (((du.x + 3u) & ~3u) + tid));
+    tile_phase1_core<HAS_AUX, HAS_WTS>(v, tile, p4, lp4, rec, sp_a, xs_a, du.w, tid, lane, warp, curr, wperm);
 }
 
 // ---- phase 2 of a tile: one thread sums one item (<= 16 consecutive x slots of one transcript), one RED -------
@@ -923,6 +905,43 @@ __device__ __forceinline__ void tile_phase2(uint32_t xs_a, uint32_t item, uint32
         if (item != kNoTxp && acc != 0.0) atomicAdd(curr + (item & (kMaxTxps - 1u)), acc);
     }
 
+}
+
+// ---- phase 2, lane-parallel (OAR_P2Q): every lane sums up to FOUR consecutive x slots of one item; the four (two, one)
+// lanes of a 16- (8-, 4-) slot item combine with shuffles and the first one issues the RED.  The thread-per-item
+// version above keeps ~3 warps busy with ~100 instructions each while the other warps of the CTA wait at the barrier
+// (profiles/: 43 % of a CTA's time); here the same work is spread over all warps, ~45 instructions per 32 lanes.
+// Items of the 16-slot class sit 18 doubles apart, so the 8 lanes of an LDS.128 wavefront (2 items x 4 lanes at
+// 32-byte steps) still hit 8 different 16-byte banks.
+#ifndef OAR_P2Q
+#define OAR_P2Q 1
+#endif
+__device__ __forceinline__ void tile_phase2q(uint32_t xs_a, uint32_t rec, uint32_t D, uint32_t U, uint32_t duz, uint32_t tid,
+                                             double *__restrict__ curr)
+{
+    static_assert(kItemMax == 16, "lane-parallel phase 2: item classes 16 / 8 / 4 at strides 18 / 10 / 6 doubles");
+    const unsigned full = 0xffffffffu;
+    const uint32_t N16 = duz & 0xFFFFu, N8 = duz >> 16;
+    const uint32_t L16 = 4u * N16, L8 = L16 + 2u * N8, LT = L8 + (U - N16 - N8);   // lanes of the three classes
+    const uint32_t items_a = rec + kRecTable + 4u * ((D + 3u) & ~3u);
+    for (uint32_t L = tid; (L & ~31u) < LT; L += (uint32_t)kThreads) {             // warp-uniform trip count
+        uint32_t item, part, bd;
+        if (L < L16) { item = L >> 2; part = L & 3u; bd = 18u * item + 4u * part; }
+        else if (L < L8) { const uint32_t l = L - L16; item = N16 + (l >> 1); part = l & 1u; bd = 18u * N16 + 10u * (l >> 1) + 4u * part; }
+        else { const uint32_t l = L - L8; item = N16 + N8 + l; part = 0u; bd = 18u * N16 + 10u * N8 + 6u * l; }
+        uint32_t desc = kNoTxp;
+        if (L < LT) desc = lds_u32(items_a + 4u * item);
+        const int slots = desc == kNoTxp ? 0 : (int)(desc >> 27) + 1;
+        const int v = min(max(slots - 4 * (int)part, 0), 4);                         // valid slots of this lane's four
+        const uint32_t b = xs_a + 8u * bd;
+        const double2 u = lds_v2f64_if(b, v >= 2), w = lds_v2f64_if(b + 16u, v >= 4);
+        const double o = lds_f64_if(b + 8u * (uint32_t)(v - 1), (v & 1) != 0);
+        const double s0 = ((u.x + u.y) + (w.x + w.y)) + o;
+        const double s1 = s0 + __shfl_xor_sync(full, s0, 1);
+        const double s2 = s1 + __shfl_xor_sync(full, s1, 2);
+        const double tot = L < L16 ? s2 : (L < L8 ? s1 : s0);
+        if (part == 0u && desc != kNoTxp && tot != 0.0) atomicAdd(curr + (desc & (kMaxTxps - 1u)), tot);
+    }
 }
 
 // m_step (em.rs:87-133), persistent and TMA-fed.
@@ -1289,6 +1308,195 @@ __global__ void __launch_bounds__(kThreads, (4 * 8) / kWarps) em_sweep_tiled2(Vi
     }
     __syncthreads();       // x values of the last tile
     tile_phase2(xs0 + s_last * g.xs_bytes, item_p, U_p, duz_p, tid, warp, curr);
+    if (v.n_fb && blockIdx.x == gridDim.x - 1u)
+        kern::rowgroup_rows<HAS_AUX, HAS_WTS>(v.csr_row_ptr, v.csr_txp, v.csr_prob, v.csr_aux, v.csr_wts, v.fb_rows, prev, curr,
+                                              tid >> 3, kThreads >> 3, v.n_fb);
+}
+
+// ---------------------------------------------------------------------------
+// Streaming single-barrier sweep (OAR_SWEEP=3).
+//
+// What the profile of em_sweep_tiled says (profiles/r1_tiled_sweep_ncu_full_summary.csv, source page): 43 % of a CTA's
+// time is the window between its two barriers in which three warps sum the items and one waits ~700 cycles for the
+// prev[] gather to come back from L2, and the shared-memory data pipe is 75 % busy -- 128 of its ~476 wavefronts per
+// tile are the 8 KB prob | lpos block going into shared memory by TMA and straight out again by LDS.128.  Here
+//   * the prob | lpos block never touches shared memory: every thread reads its own 2 x 16 B with coalesced
+//     LDG.128 (L1 no-allocate) at the END of the previous tile's phase 1, when the registers they land in are dead;
+//     the latency hides behind the barrier and phase 2.  One thread prefetches the blocks into L2 kL2Ahead tiles
+//     ahead (cp.async.bulk.prefetch.L2), so those loads are L2 hits;
+//   * only the small per-tile records travel by TMA, in a ring of kRing slots requested kRecAhead tiles ahead;
+//   * the prev[] gather of tile i+1 is issued by one warp as 8-byte cp.async (LDGSTS: global -> shared, no register,
+//     no wait) at the START of iteration i and completes under that warp's own phase 1;
+//   * x array and s_prev are double-buffered and phase 2 of tile i-1 runs inside iteration i: ONE CTA barrier per tile.
+// Shared memory per CTA on C3: 2 x 10.5 KB x arrays + 8 x 1.4 KB records + 2 x 1 KB prev -- less than the staged kernels,
+// so registers (48 at 5 CTAs/SM) are what bounds the occupancy.
+//
+//   iteration i, after the barrier:  TMA thread   record of tile i+kRecAhead -> rec[(i+kRecAhead)%kRing], L2 prefetch of the
+//                                                 prob | lpos blocks of tile i+kL2Ahead
+//                                    gather warp  waits for rec[(i+1)%kRing] (requested kRecAhead-1 iterations ago), issues the
+//                                                 cp.async gather of tile i+1's prev[] into s_prev[(i+1)&1]
+//                                    first warps  phase 2 of tile i-1 (x values in xs[(i-1)&1], items in rec[(i-1)%kRing])
+//                                    all warps    phase 1 of tile i (registers, rec[i%kRing], s_prev[i&1] -> xs[i&1]), then the
+//                                                 LDG.128 of tile i+1's slots
+// Every buffer written in iteration i was last read in iteration i-1, i.e. before the barrier.
+constexpr uint32_t kRing = 8;        // record slots (power of two)
+#ifndef OAR_REC_AHEAD
+#define OAR_REC_AHEAD 5
+#endif
+#ifndef OAR_L2_AHEAD
+#define OAR_L2_AHEAD 3
+#endif
+constexpr uint32_t kRecAhead = OAR_REC_AHEAD, kL2Ahead = OAR_L2_AHEAD;
+static_assert(kRecAhead + 2u <= kRing && kRecAhead >= 2u, "slots of tiles i-1 .. i+kRecAhead-1 are live while tile i+kRecAhead is requested");
+struct Geometry3 {
+    uint32_t xs_bytes;      // one x buffer (128 B multiple); the two buffers sit at the start of the window
+    uint32_t rec_off, rec_bytes;    // kRing record slots
+    uint32_t prev_off, prev_bytes;  // two s_prev buffers
+    uint32_t bar_off;       // kRing mbarriers
+    uint32_t total;
+};
+inline Geometry3 make_geometry3(uint32_t max_rec_bytes, uint32_t max_d, uint32_t max_x_doubles)
+{
+    Geometry3 g;
+    g.xs_bytes = (8u * ((max_x_doubles + 2u + 1u) & ~1u) + 127u) & ~127u;
+    g.rec_off = 2u * g.xs_bytes;
+    g.rec_bytes = (max_rec_bytes + 15u) & ~15u;
+    g.prev_off = g.rec_off + kRing * g.rec_bytes;
+    g.prev_bytes = 8u * ((max_d + 1u) & ~1u);
+    g.bar_off = g.prev_off + 2u * g.prev_bytes;
+    g.total = g.bar_off + kRing * 8u;
+    return g;
+}
+
+__device__ __forceinline__ float4 ldg_stream_v4f(const float *p)
+{ float4 r; asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p)); return r; }
+__device__ __forceinline__ uint4 ldg_stream_v4(const uint32_t *p)
+{ uint4 r; asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p)); return r; }
+__device__ __forceinline__ void l2_prefetch(const void *p, uint32_t bytes)
+{ asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void cp_async_8(uint32_t dst, const void *src)
+{ asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <bool HAS_AUX, bool HAS_WTS>
+__global__ void __launch_bounds__(kThreads, (OAR_TILED_MIN_CTAS * 8) / kWarps) em_sweep_tiled3(View v, Geometry3 g, const double *__restrict__ prev,
+                                                               double *__restrict__ curr,
+                                                               const uint32_t *__restrict__ wperm,
+                                                               const OarEmState *__restrict__ st, int check_done)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    if (check_done && st->done) return;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t n_tiles = v.n_tiles, stride = gridDim.x;
+    const uint32_t tile0 = blockIdx.x;
+    if (tile0 >= n_tiles) return;
+    uint32_t sm0;
+    asm volatile("{.reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t;}" : "=r"(sm0) : "l"(smem));
+    const uint32_t rec0 = sm0 + g.rec_off, sp0 = sm0 + g.prev_off, bar0 = sm0 + g.bar_off;
+    const uint32_t xs0 = smem_u32(smem);   // warp-uniform to the compiler (see em_sweep_tiled)
+    const bool is_tma = tid == 32u * (kWarps - 2);
+    const bool is_gather = warp == kWarps - 1;
+
+    auto issue_rec = [&](uint2 r, uint32_t slot) {   // the TMA thread only
+        const uint32_t bar = bar0 + 8u * slot;
+        mbar_expect_tx(bar, r.y);
+        bulk_g2s(rec0 + slot * g.rec_bytes, v.records + r.x, r.y, bar);
+    };
+    // prev[] of a tile's transcripts, global -> shared without a register in between; completion: cp_async_wait_all()
+    auto gather_prev_async = [&](uint32_t rec_a, uint32_t sp_a) {
+        const uint32_t Dn = lds_u32(rec_a + kRecDU);
+        for (uint32_t d = lane; d < Dn; d += 32u) cp_async_8(sp_a + 8u * d, prev + lds_u32(rec_a + kRecTable + 4u * d));
+        if (HAS_WTS) weights_touch(wperm + lds_u32(rec_a + kRecRow), lane);
+    };
+
+    if (tid == 0) {
+#pragma unroll
+        for (uint32_t i = 0; i < kRing; ++i) mbar_init(bar0 + 8u * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint2 r_pending = make_uint2(0, 0);   // record locator of the tile to request next (TMA thread)
+    if (is_tma) {
+#pragma unroll
+        for (uint32_t k = 0; k < kRecAhead; ++k)
+            if (tile0 + k * stride < n_tiles) issue_rec(v.rec[tile0 + k * stride], k);
+        if (tile0 + kRecAhead * stride < n_tiles) r_pending = v.rec[tile0 + kRecAhead * stride];
+#pragma unroll
+        for (uint32_t k = 1; k < kL2Ahead; ++k)
+            if (tile0 + k * stride < n_tiles) {
+                l2_prefetch(v.prob + (size_t)(tile0 + k * stride) * kTile, 4u * kTile);
+                l2_prefetch(v.lpos + (size_t)(tile0 + k * stride) * kTile, 4u * kTile);
+            }
+    }
+    float4 p4 = ldg_stream_v4f(v.prob + (size_t)tile0 * kTile + 4u * tid);
+    uint4 lp4 = ldg_stream_v4(v.lpos + (size_t)tile0 * kTile + 4u * tid);
+    if (is_gather) {
+        mbar_wait(bar0, 0);
+        gather_prev_async(rec0, sp0);
+        cp_async_wait_all();
+    }
+
+    uint32_t tile = tile0;
+    uint32_t s_last = 0, rec_last = rec0;
+    for (uint32_t it = 0;; ++it) {
+        const uint32_t s = it & 1u;
+        const uint32_t rec = rec0 + (it & (kRing - 1u)) * g.rec_bytes;
+        const uint32_t next = tile + stride;
+        const bool has_next = next < n_tiles;
+        __syncthreads();   // tile `it` is in place (record, s_prev[s]); xs[s], s_prev[s^1] and rec[(it+kRecAhead)%kRing] are free
+
+        if (warp >= kWarps - 2) {   // the two service warps
+            if (is_tma) {
+                const uint32_t ta = tile + kRecAhead * stride;
+                if (ta < n_tiles) {
+                    issue_rec(r_pending, (it + kRecAhead) & (kRing - 1u));
+                    if (ta + stride < n_tiles) r_pending = v.rec[ta + stride];
+                }
+                const uint32_t tp = tile + kL2Ahead * stride;
+                if (tp < n_tiles) {
+                    l2_prefetch(v.prob + (size_t)tp * kTile, 4u * kTile);
+                    l2_prefetch(v.lpos + (size_t)tp * kTile, 4u * kTile);
+                }
+            }
+            if (is_gather && has_next) {
+                const uint32_t j = it + 1u;
+                mbar_wait(bar0 + 8u * (j & (kRing - 1u)), (j / kRing) & 1u);
+                gather_prev_async(rec0 + (j & (kRing - 1u)) * g.rec_bytes, sp0 + (s ^ 1u) * g.prev_bytes);
+            }
+            __syncwarp();
+        }
+        if (it) {   // phase 2 of the previous tile: its record is still in the ring
+            const uint32_t rec_p = rec0 + ((it - 1u) & (kRing - 1u)) * g.rec_bytes;
+            const uint4 du_p = lds_v4(rec_p + kRecDU);
+#if OAR_P2Q
+            tile_phase2q(xs0 + (s ^ 1u) * g.xs_bytes, rec_p, du_p.x, du_p.y, du_p.z, tid, curr);
+#else
+            uint32_t item_p = kNoTxp;
+            if (tid < du_p.y) item_p = lds_u32(rec_p + kRecTable + 4u * (((du_p.x + 3u) & ~3u) + tid));
+            tile_phase2(xs0 + (s ^ 1u) * g.xs_bytes, item_p, du_p.y, du_p.z, tid, warp, curr);
+#endif
+        }
+        const uint32_t trash = lds_u32(rec + kRecDU + 12u);
+        tile_phase1_core<HAS_AUX, HAS_WTS>(v, tile, p4, lp4, rec, sp0 + s * g.prev_bytes, xs0 + s * g.xs_bytes, trash, tid, lane, warp,
+                                           curr, wperm);
+        if (!has_next) { s_last = s; rec_last = rec; break; }
+        // the next tile's slots: issued now, needed after the barrier and phase 2
+        p4 = ldg_stream_v4f(v.prob + (size_t)next * kTile + 4u * tid);
+        lp4 = ldg_stream_v4(v.lpos + (size_t)next * kTile + 4u * tid);
+        if (is_gather) cp_async_wait_all();   // s_prev of the next tile has landed (issued before this warp's phase 1)
+        tile = next;
+    }
+    __syncthreads();       // x values of the last tile
+    {
+        const uint4 du_p = lds_v4(rec_last + kRecDU);
+#if OAR_P2Q
+        tile_phase2q(xs0 + s_last * g.xs_bytes, rec_last, du_p.x, du_p.y, du_p.z, tid, curr);
+#else
+        uint32_t item_p = kNoTxp;
+        if (tid < du_p.y) item_p = lds_u32(rec_last + kRecTable + 4u * (((du_p.x + 3u) & ~3u) + tid));
+        tile_phase2(xs0 + s_last * g.xs_bytes, item_p, du_p.y, du_p.z, tid, warp, curr);
+#endif
+    }
     if (v.n_fb && blockIdx.x == gridDim.x - 1u)
         kern::rowgroup_rows<HAS_AUX, HAS_WTS>(v.csr_row_ptr, v.csr_txp, v.csr_prob, v.csr_aux, v.csr_wts, v.fb_rows, prev, curr,
                                               tid >> 3, kThreads >> 3, v.n_fb);

@@ -54,6 +54,9 @@ typedef struct {
 } port_store_t;
 
 int port_num_threads(void) { return omp_get_max_threads(); }
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm of bench.py sets the pool size explicitly
+   (the rayon pool of em_par / bootstrap is sized by the caller as well: em.rs:324-327, :299-302). */
+void port_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 port_store_t *port_store_create(const uint64_t *row_ptr, const uint32_t *txp, const float *prob,
                                 const double *cov_or_null, uint64_t n_reads, uint64_t nnz,
@@ -238,9 +241,26 @@ static uint32_t do_em_inds(const port_store_t *s, int model_coverage, const uint
 }
 
 /* bootstrap, em.rs:292-314: num_boot replicates on a pool of nthreads. */
+static void port_bootstrap_impl(const port_store_t *s, int model_coverage, uint32_t num_boot, uint64_t seed,
+                                uint32_t max_iter, double conv_thresh, int nthreads,
+                                double *out, uint32_t *out_niter, double *out_em_seconds);
+
 void port_bootstrap(const port_store_t *s, int model_coverage, uint32_t num_boot, uint64_t seed,
                     uint32_t max_iter, double conv_thresh, int nthreads,
                     double *out /* num_boot x M */, uint32_t *out_niter /* num_boot or NULL */)
+{ port_bootstrap_impl(s, model_coverage, num_boot, seed, max_iter, conv_thresh, nthreads, out, out_niter, NULL); }
+
+/* Same, and reports per replicate the seconds spent in do_em alone (without drawing and sorting the sample): a bounded
+   benchmark sample caps max_iter, which would otherwise overweight the per-replicate set-up a full run amortises
+   over hundreds of sweeps. */
+void port_bootstrap_timed(const port_store_t *s, int model_coverage, uint32_t num_boot, uint64_t seed,
+                          uint32_t max_iter, double conv_thresh, int nthreads,
+                          double *out, uint32_t *out_niter, double *out_em_seconds /* num_boot */)
+{ port_bootstrap_impl(s, model_coverage, num_boot, seed, max_iter, conv_thresh, nthreads, out, out_niter, out_em_seconds); }
+
+static void port_bootstrap_impl(const port_store_t *s, int model_coverage, uint32_t num_boot, uint64_t seed,
+                                uint32_t max_iter, double conv_thresh, int nthreads,
+                                double *out, uint32_t *out_niter, double *out_em_seconds)
 {
     if (nthreads <= 0) nthreads = omp_get_max_threads();
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
@@ -254,8 +274,10 @@ void port_bootstrap(const port_store_t *s, int model_coverage, uint32_t num_boot
             inds[i] = (uint64_t)(m >> 64);
         }
         radix_sort_u64(inds, tmp, n, n ? n - 1 : 0);     /* bootstrap.rs:14 */
+        const double t0 = omp_get_wtime();
         uint32_t it = do_em_inds(s, model_coverage, inds, n, max_iter, conv_thresh,
                                  out + (uint64_t)b * s->n_txps);
+        if (out_em_seconds) out_em_seconds[b] = omp_get_wtime() - t0;
         if (out_niter) out_niter[b] = it;
         free(inds); free(tmp);
     }

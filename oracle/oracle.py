@@ -39,6 +39,8 @@ def lib() -> C.CDLL:
         L.oracle_coverage_model.restype = None
         L.oracle_coverage_model.argtypes = [_vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64, _vp, C.c_uint32, C.c_uint32, C.c_double, _vp]
         L.port_num_threads.restype = C.c_int
+        L.port_set_num_threads.restype = None
+        L.port_set_num_threads.argtypes = [C.c_int]
         L.port_store_create.restype = _vp
         L.port_store_create.argtypes = [_vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64, C.c_uint32]
         L.port_store_destroy.restype = None
@@ -47,6 +49,8 @@ def lib() -> C.CDLL:
         L.port_em_par.argtypes = [_vp, C.c_int, _vp, C.c_uint32, C.c_double, _vp, _vp, _vp]
         L.port_bootstrap.restype = None
         L.port_bootstrap.argtypes = [_vp, C.c_int, C.c_uint32, C.c_uint64, C.c_uint32, C.c_double, C.c_int, _vp, _vp]
+        L.port_bootstrap_timed.restype = None
+        L.port_bootstrap_timed.argtypes = [_vp, C.c_int, C.c_uint32, C.c_uint64, C.c_uint32, C.c_double, C.c_int, _vp, _vp, _vp]
         _lib = L
     return _lib
 
@@ -149,6 +153,15 @@ class PortStore:
                              _p(out), _p(niter))
         return out, niter[:num_boot]
 
+    def bootstrap_timed(self, num_boot, seed, max_iter=1000, conv_thresh=1e-3, nthreads=0):
+        """bootstrap() that also returns the seconds each replicate spent inside do_em (sample drawing and sorting excluded)."""
+        out = np.zeros((num_boot, self.n_txps), dtype=np.float64)
+        niter = np.zeros(max(num_boot, 1), dtype=np.uint32)
+        secs = np.zeros(max(num_boot, 1), dtype=np.float64)
+        lib().port_bootstrap_timed(self._h, int(self.model_coverage), num_boot, seed, max_iter, conv_thresh, nthreads,
+                                   _p(out), _p(niter), _p(secs))
+        return out, niter[:num_boot], secs[:num_boot]
+
     def close(self):
         if self._h:
             lib().port_store_destroy(self._h)
@@ -163,3 +176,9 @@ class PortStore:
 
 def num_threads() -> int:
     return int(lib().port_num_threads())
+
+
+def set_num_threads(n: int) -> int:
+    """Size the OpenMP pool explicitly (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    lib().port_set_num_threads(int(n))
+    return num_threads()

@@ -14,9 +14,8 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 # OAR_KERNEL_ROWGROUP, OAR_KERNEL_TILED (default layout), OAR_KERNEL_LANE (OAR_LAYOUT=lane),
 # 4 = OAR_KERNEL_TILED with the single-barrier sweep (OAR_SWEEP=1b)
-KERNELS = [1, 2, 3, 4]
-if os.environ.get("OAR_TEST_EXPERIMENTAL"):
-    KERNELS.append(5)   # OAR_KERNEL_TILED with OAR_SWEEP=1c (deeper rings; prepared, not part of the default suite yet)
+# 5 = OAR_SWEEP=1c (single barrier, deeper rings), 6 = OAR_SWEEP=3 (streaming single-barrier sweep)
+KERNELS = [1, 2, 3, 4, 5, 6]
 RTOL = 1e-9
 NORTH_STAR_RTOL = 1e-5
 
@@ -45,7 +44,7 @@ def csr(rows):
 def store_for(DS, kernel, *args, **kw):
     """A device store whose tiled layout and sweep variant match `kernel` (the row-per-lane layout is opt-in via
     OAR_LAYOUT, the single-barrier sweep via OAR_SWEEP; both are read at store creation)."""
-    want = {"OAR_LAYOUT": "lane" if kernel == 3 else None, "OAR_SWEEP": {4: "1b", 5: "1c"}.get(kernel, "2b")}
+    want = {"OAR_LAYOUT": "lane" if kernel == 3 else None, "OAR_SWEEP": {4: "1b", 5: "1c", 6: "3"}.get(kernel, "2b")}
     old = {k: os.environ.get(k) for k in want}
     for k, val in want.items():
         if val is None:
@@ -60,7 +59,7 @@ def store_for(DS, kernel, *args, **kw):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = val
-    abi_kernel = 2 if kernel in (4, 5) else kernel
+    abi_kernel = 2 if kernel in (4, 5, 6) else kernel
     with ds:
         ds.set_kernel(abi_kernel)
         assert ds.layout_info()["kernel"] == abi_kernel
@@ -329,6 +328,78 @@ def test_coverage_model_matches_oracle(DS, oracle_mod, small_store, layout_kerne
             r = ds.em(min_iter=1)
             assert r.niter == niter
             assert_counts_close(r.counts, want)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE configs C2 and C3 at full size against the CPU oracle (em.rs:144-255, :320-447)
+# ---------------------------------------------------------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def c2_store():
+    from oarfish_b200 import synth
+    return synth.make_config("C2")
+
+
+@pytest.fixture(scope="module")
+def c3_store():
+    from oarfish_b200 import synth
+    return synth.make_config("C3")
+
+
+@pytest.mark.parametrize("min_iter", [50, 1])
+def test_c2_converged_em_matches_oracle(DS, oracle_mod, c2_store, min_iter):
+    """BASELINE config 2 (1M reads x 50k transcripts) to convergence at 1e-3: the sequential oracle's do_em
+    (em::em rule, min_iter 50) and the em_par rule (min_iter 1) -- same niter, counts within 1e-9."""
+    s = c2_store
+    want, niter, rel, sweeps = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps, min_iter=min_iter)
+    with DS(s.row_ptr, s.txp_id, s.prob, s.n_txps) as ds:
+        assert ds.layout_info()["kernel"] == 2
+        r = ds.em(min_iter=min_iter)
+        assert r.niter == niter
+        assert r.rel_diff == pytest.approx(rel, rel=1e-6)
+        assert_counts_close(r.counts, want)
+        assert ds.counters()["sweeps"] == sweeps + 1
+
+
+def test_c3_fixed_iterations_match_sequential_oracle(DS, oracle_mod, c3_store):
+    """BASELINE config 3 (10M reads x 200k transcripts): ten loop sweeps + threshold + final sweep against the
+    sequential oracle (0.4 s per sweep on one core), and one bootstrap replicate with device-drawn weights
+    against do_em(wts=...) (em.rs:273-290) at the same iteration cap."""
+    s = c3_store
+    want, niter, _, sweeps = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps, min_iter=1, max_iter=10)
+    with DS(s.row_ptr, s.txp_id, s.prob, s.n_txps) as ds:
+        r = ds.em(min_iter=1, max_iter=10)
+        assert r.niter == niter == 10
+        assert_counts_close(r.counts, want)
+        assert ds.counters()["sweeps"] == sweeps + 1
+        w = ds.sample_weights(4, 0)
+        assert int(w.sum()) == s.n_reads
+        wantb, nb, _, _ = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps, min_iter=50, max_iter=10, wts=w)
+        out, nit = ds.bootstrap_weights(w[None, :], max_iter=10, min_iter=50)
+        assert nit[0] == nb == 10
+        assert_counts_close(out[0], wantb)
+        # the seeded entry point draws the same weights itself
+        out2, nit2 = ds.bootstrap(1, 4, max_iter=10)
+        assert nit2[0] == 10
+        assert_counts_close(out2[0], wantb)
+
+
+def test_c3_converged_em_matches_em_par_port(DS, oracle_mod, c3_store):
+    """BASELINE config 3 to convergence against the multi-threaded restatement of em_par (oracle/em_par_port.c,
+    em.rs:320-447): identical niter, counts within 1e-9 (north_star allows 1e-5)."""
+    s = c3_store
+    ps = oracle_mod.PortStore(s.row_ptr, s.txp_id, s.prob, s.n_txps)
+    try:
+        want, niter, rel, sweeps = ps.em_par(max_iter=1000, conv_thresh=1e-3)
+    finally:
+        ps.close()
+    with DS(s.row_ptr, s.txp_id, s.prob, s.n_txps) as ds:
+        r = ds.em(min_iter=1)
+        assert r.niter == niter
+        assert r.rel_diff == pytest.approx(rel, rel=1e-6)
+        assert_counts_close(r.counts, want)
+        assert_counts_close(r.counts, want, rtol=NORTH_STAR_RTOL)
+        assert abs(r.counts.sum() - s.n_reads) < 1e-6 * s.n_reads
 
 
 def test_full_size_properties_c3(DS):

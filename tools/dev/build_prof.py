@@ -1,6 +1,6 @@
 """Dev script: wall time of DeviceStore creation from pinned host buffers (upload + validation + layout build)."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oarfish_b200 import synth, DeviceStore
 s = synth.make_config(sys.argv[1] if len(sys.argv) > 1 else "C3", pinned=True)
 for i in range(int(sys.argv[2]) if len(sys.argv) > 2 else 3):

@@ -1,8 +1,8 @@
 #!/bin/bash
 # Dev helper: builds tuning variants of liboarfish_em.so into oarfish_b200/lib/variants/ (git-ignored, travels with gpurun).
-# usage: tests/_build_variants.sh name "-DOAR_LANE_THREADS=128 -DOAR_LANE_MIN_CTAS=6" [name2 "flags2" ...]
+# usage: tools/dev/build_variants.sh name "-DOAR_LANE_THREADS=128 -DOAR_LANE_MIN_CTAS=6" [name2 "flags2" ...]
 set -e
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p oarfish_b200/lib/variants
 while [ $# -ge 2 ]; do
   name=$1; flags=$2; shift 2

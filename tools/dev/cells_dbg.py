@@ -1,5 +1,5 @@
 import sys, time, numpy as np, torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))))
 from oarfish_b200 import synth, DeviceStore
 n_cells, reads, M = 296, 50000, 200000
 s, crp = synth.make_cells([reads] * n_cells, M, 6.0, seed=5)

@@ -1,7 +1,7 @@
 """Dev script: where an end-to-end step (create from pinned host buffers -> EM -> counts on host -> destroy) spends its time."""
 import os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oarfish_b200 import synth, DeviceStore
 s = synth.make_config(sys.argv[1] if len(sys.argv) > 1 else "C3", pinned=True)
 out = np.empty(s.n_txps)

@@ -1,5 +1,5 @@
 """Dev script (not a test): row-per-lane sweep against the CSR kernel on small and edge stores, then C3 timing.
-Usage: python tests/_lane_check.py [check|time] [config] [ctas list]"""
+Usage: python tools/dev/lane_check.py [check|time] [config] [ctas list]"""
 import os
 import sys
 import time

@@ -1,5 +1,5 @@
 import sys, time, os, numpy as np, torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))))
 from oarfish_b200 import synth, DeviceStore
 cfg = sys.argv[1] if len(sys.argv) > 1 else "C3"
 s = synth.make_config(cfg); M = s.n_txps

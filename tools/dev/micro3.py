@@ -1,5 +1,5 @@
 import sys, time, os, numpy as np, torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))))
 from oarfish_b200 import synth, DeviceStore
 s = synth.make_config("C3"); M = s.n_txps
 ds = DeviceStore(s.row_ptr, s.txp_id, s.prob, M)

@@ -1,6 +1,6 @@
 """Dev script for ncu: a handful of raw sweeps on a config (no EM driver, so every matching launch is a full sweep)."""
 import os, sys, numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oarfish_b200 import synth, DeviceStore
 s = synth.make_config(sys.argv[1] if len(sys.argv) > 1 else "C3")
 M = s.n_txps

@@ -1,5 +1,5 @@
 import sys, numpy as np
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))))
 from oarfish_b200 import synth, DeviceStore
 s = synth.make_store(6000, 700, 6.0, 33)
 ds = DeviceStore(s.row_ptr, s.txp_id, s.prob, s.n_txps)

@@ -16,7 +16,6 @@
 
 #include "oar_store.cuh"
 #include "oar_tiled.cuh"
-#include "oar_lane.cuh"
 
 namespace oar {
 
@@ -30,21 +29,6 @@ int cuda_fail(cudaError_t e, const char *what)
     return e == cudaErrorMemoryAllocation ? OAR_ERR_OOM : OAR_ERR_CUDA;
 }
 
-}  // namespace oar
-
-namespace oar {
-void warm_pool(int device)
-{
-    static bool done[64] = {false};
-    if (device < 0 || device >= 64 || done[device]) return;
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        uint64_t thr = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
-    (void)cudaGetLastError();
-    done[device] = true;
-}
 }  // namespace oar
 
 using namespace oar;
@@ -78,34 +62,24 @@ extern "C" int oar_device_count(void)
 extern "C" void oar_store_destroy(oar_store *s)
 {
     if (!s) return;
-    const bool trace = getenv("OAR_TRACE") != nullptr;
-    double t[8]; int nt = 0;
-    auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
-    t[nt++] = now();
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    t[nt++] = now();
     destroy_graphs(s);
-    t[nt++] = now();
     free_tiled_layout(s);
     if (!s->borrowed) { dfree(s->d_row_ptr, s->stream); dfree(s->d_prob, s->stream); dfree(s->d_aux, s->stream); }
     dfree(s->d_txp, s->stream);
     dfree(s->d_counts[0], s->stream); dfree(s->d_counts[1], s->stream); dfree(s->d_state, s->stream); dfree(s->d_weights, s->stream);
-    t[nt++] = now();
     if (s->stream) cudaStreamSynchronize(s->stream);
-    t[nt++] = now();
-    if (s->h_state) cudaFreeHost(s->h_state);
-    t[nt++] = now();
-    if (!s->borrowed) {
-        for (auto &e : s->ev) if (e) cudaEventDestroy(e);
-        for (auto &e : s->slot_ev) if (e) cudaEventDestroy(e);
-        t[nt++] = now();
-        if (s->stream) cudaStreamDestroy(s->stream);
-    } else t[nt++] = now();
-    t[nt++] = now();
-    if (trace)
-        fprintf(stderr, "[oar] destroy: sync %.2f graphs %.2f free-async %.2f sync %.2f freehost %.2f events %.2f stream %.2f ms\n",
-                t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4], t[6] - t[5], t[7] - t[6]);
+    // stream, events and the pinned state block go back to the device context's pools (cudaFreeHost / cudaStreamDestroy
+    // synchronise the whole context: 0.8-400 ms per store on the GPU box)
+    if (s->ctx) {
+        ctx_give_host_state(s->ctx, s->h_state);
+        if (!s->borrowed) {
+            for (auto &e : s->ev) ctx_give_event(s->ctx, true, e);
+            for (auto &e : s->slot_ev) ctx_give_event(s->ctx, false, e);
+            ctx_give_stream(s->ctx, s->stream);
+        }
+    }
     delete s;
     (void)cudaGetLastError();
 }
@@ -117,22 +91,74 @@ int substore_create(oar_store *parent, uint32_t *d_txp, uint32_t n_txps, oar_sto
     oar_store *s = new (std::nothrow) oar_store();
     if (!s) return fail(OAR_ERR_OOM, "substore_create: host allocation failed");
     s->borrowed = true;
-    s->device = parent->device; s->sm_count = parent->sm_count; s->stream = parent->stream;
+    s->device = parent->device; s->sm_count = parent->sm_count; s->stream = parent->stream; s->ctx = parent->ctx;
     s->n_reads = parent->n_reads; s->nnz = parent->nnz; s->n_txps = n_txps;
     s->d_row_ptr = parent->d_row_ptr; s->d_prob = parent->d_prob; s->d_aux = parent->d_aux; s->d_txp = d_txp;
     for (int i = 0; i < 4; ++i) s->ev[i] = parent->ev[i];
     for (int i = 0; i < 2; ++i) s->slot_ev[i] = parent->slot_ev[i];
-    s->ctas_per_sm = parent->ctas_per_sm; s->lane_ctas_per_sm = parent->lane_ctas_per_sm; s->sweep_1b = parent->sweep_1b;
+    s->ctas_per_sm = parent->ctas_per_sm; s->sweep_1b = parent->sweep_1b;
     int rc = [&]() -> int {
         OAR_CUDA(dmalloc(&s->d_state, sizeof(OarEmState) * 3, s->stream));
         OAR_CUDA(cudaMemsetAsync(s->d_state, 0, sizeof(OarEmState) * 3, s->stream));
-        OAR_CUDA(cudaMallocHost(&s->h_state, sizeof(OarEmState) * 8));
+        OAR_CUDA(ctx_take_host_state(s->ctx, &s->h_state));
         if (parent->tl.ready) {
-            s->tl.kind = parent->tl.kind;
             const int rc2 = build_tiled_layout(s, parent->tl.span);
-            if (rc2 == OAR_OK) s->kernel = layout_kernel(s);
+            if (rc2 == OAR_OK) s->kernel = OAR_KERNEL_TILED;
             else if (rc2 != OAR_ERR_UNSUPPORTED) return rc2;
         }
+        return OAR_OK;
+    }();
+    if (rc != OAR_OK) { std::string keep = g_last_error; oar_store_destroy(s); g_last_error = keep; return rc; }
+    *out = s;
+    return OAR_OK;
+}
+}  // namespace oar
+
+namespace oar {
+// Shared tail of store creation: the CSR arrays are resident (d_row_ptr u32, d_txp, d_prob, d_aux); build the tiled
+// layout and read the tuning environment.
+static int finish_store(oar_store *s)
+{
+    // OAR_TILED=0 keeps only the CSR (row-group kernel); OAR_TILE_SPAN tunes the tile fill
+    const char *env = getenv("OAR_TILED");
+    if (!(env && env[0] == '0')) {
+        const char *sp = getenv("OAR_TILE_SPAN");
+        int rc2 = build_tiled_layout(s, sp ? (uint32_t)atoi(sp) : 0u);
+        if (rc2 == OAR_OK) s->kernel = OAR_KERNEL_TILED;
+        else if (rc2 != OAR_ERR_UNSUPPORTED) return rc2;   // unsupported shape: keep the CSR kernel
+    }
+    const char *sw = getenv("OAR_SWEEP");   // sweep variant of the tiled layout (development switch)
+    if (sw) s->sweep_1b = strcmp(sw, "1b") == 0 ? 1 : strcmp(sw, "1c") == 0 ? 2 : strcmp(sw, "3") == 0 ? 3 : strcmp(sw, "2e") == 0 ? 4 : 0;
+    const char *cps = getenv("OAR_CTAS_PER_SM");
+    if (cps && atoi(cps) > 0) s->ctas_per_sm = atoi(cps);
+    return OAR_OK;
+}
+
+// Handle + stream + events + pinned state from the device context; EM work buffers.
+static int new_store(int device, uint64_t n_reads, uint64_t nnz, uint32_t n_txps, const char *who, oar_store **out)
+{
+    *out = nullptr;
+    if (n_txps == 0) return fail(OAR_ERR_INVALID, std::string(who) + ": n_txps must be > 0");
+    if (nnz >= 0xFFFFFFF0ull || n_reads >= 0xFFFFFFF0ull)
+        return fail(OAR_ERR_UNSUPPORTED, std::string(who) + ": stores with >= 2^32 alignments or reads are not supported");
+    int ndev = 0;
+    OAR_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(OAR_ERR_INVALID, std::string(who) + ": bad device index");
+    cudaError_t ce = cudaSuccess;
+    DeviceCtx *ctx = device_ctx(device, &ce);
+    if (!ctx) return cuda_fail(ce, "device context");
+    oar_store *s = new (std::nothrow) oar_store();
+    if (!s) return fail(OAR_ERR_OOM, std::string(who) + ": host allocation failed");
+    s->device = device; s->ctx = ctx; s->sm_count = ctx->sm_count;
+    s->n_reads = n_reads; s->nnz = nnz; s->n_txps = n_txps;
+    int rc = [&]() -> int {
+        OAR_CUDA(ctx_take_stream(ctx, &s->stream));
+        for (auto &e : s->ev) OAR_CUDA(ctx_take_event(ctx, true, &e));
+        for (auto &e : s->slot_ev) OAR_CUDA(ctx_take_event(ctx, false, &e));
+        OAR_CUDA(ctx_take_host_state(ctx, &s->h_state));
+        OAR_CUDA(dmalloc(&s->d_counts[0], sizeof(double) * n_txps, s->stream));
+        OAR_CUDA(dmalloc(&s->d_counts[1], sizeof(double) * n_txps, s->stream));
+        OAR_CUDA(dmalloc(&s->d_state, sizeof(OarEmState) * 2, s->stream));
         return OAR_OK;
     }();
     if (rc != OAR_OK) { std::string keep = g_last_error; oar_store_destroy(s); g_last_error = keep; return rc; }
@@ -149,62 +175,30 @@ extern "C" int oar_store_create(const uint64_t *row_ptr, const uint32_t *txp_id,
     *out = nullptr;
     if (!row_ptr) return fail(OAR_ERR_INVALID, "oar_store_create: row_ptr is null");
     if (nnz > 0 && (!txp_id || !prob)) return fail(OAR_ERR_INVALID, "oar_store_create: txp_id/prob is null");
-    if (n_txps == 0) return fail(OAR_ERR_INVALID, "oar_store_create: n_txps must be > 0");
-    if (nnz >= 0xFFFFFFF0ull || n_reads >= 0xFFFFFFF0ull)
-        return fail(OAR_ERR_UNSUPPORTED, "oar_store_create: stores with >= 2^32 alignments or reads are not supported");
-    int ndev = 0;
-    OAR_CUDA(cudaGetDeviceCount(&ndev));
-    if (device < 0 || device >= ndev) return fail(OAR_ERR_INVALID, "oar_store_create: bad device index");
-    OAR_CUDA(cudaSetDevice(device));
-
-    oar_store *s = new (std::nothrow) oar_store();
-    if (!s) return fail(OAR_ERR_OOM, "oar_store_create: host allocation failed");
-    s->device = device; s->n_reads = n_reads; s->nnz = nnz; s->n_txps = n_txps;
-    cudaStream_t copy_stream = nullptr;
-    int rc = [&]() -> int {
-        OAR_CUDA(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device));
-        warm_pool(device);
-        OAR_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-        for (auto &e : s->ev) OAR_CUDA(cudaEventCreate(&e));
-        for (auto &e : s->slot_ev) OAR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    oar_store *s = nullptr;
+    int rc = new_store(device, n_reads, nnz, n_txps, "oar_store_create", &s);
+    if (rc != OAR_OK) return rc;
+    rc = [&]() -> int {
         OAR_CUDA(cudaEventRecord(s->ev[0], s->stream));
         const size_t pad = 16;  // slack so vector loads may over-read safely
         OAR_CUDA(dmalloc(&s->d_row_ptr, sizeof(uint32_t) * (n_reads + 1 + pad), s->stream));
         OAR_CUDA(dmalloc(&s->d_txp, sizeof(uint32_t) * (nnz + pad), s->stream));
         OAR_CUDA(dmalloc(&s->d_prob, sizeof(float) * (nnz + pad), s->stream));
         if (aux_or_null) OAR_CUDA(dmalloc(&s->d_aux, sizeof(double) * (nnz + pad), s->stream));
-        OAR_CUDA(dmalloc(&s->d_counts[0], sizeof(double) * n_txps, s->stream));
-        OAR_CUDA(dmalloc(&s->d_counts[1], sizeof(double) * n_txps, s->stream));
-        OAR_CUDA(dmalloc(&s->d_state, sizeof(OarEmState) * 2, s->stream));
-        OAR_CUDA(cudaMallocHost(&s->h_state, sizeof(OarEmState) * 4));
         // stage the u64 boundaries, narrow to u32 and validate on the device
         uint64_t *d_rp64 = nullptr;
         uint32_t *d_flag = reinterpret_cast<uint32_t *>(s->d_state + 1);
         OAR_CUDA(dmalloc(&d_rp64, sizeof(uint64_t) * (n_reads + 1), s->stream));
         OAR_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(uint32_t) * 4, s->stream));
         OAR_CUDA(cudaMemcpyAsync(d_rp64, row_ptr, sizeof(uint64_t) * (n_reads + 1), cudaMemcpyDefault, s->stream));
-        // OAR_UPLOAD_OVERLAP=1 (prepared for round 2, off by default, not yet run on a GPU): prob / aux are not needed
-        // before build_tiles, so they are uploaded on a second stream behind txp_id while validation, row keys and the
-        // sort run on the first; the layout build waits for s->prob_ready right before the tiles are written.
-        const char *ov = getenv("OAR_UPLOAD_OVERLAP");
-        const bool overlap = ov && ov[0] == '1' && nnz > 0;
-        if (nnz) OAR_CUDA(cudaMemcpyAsync(s->d_txp, txp_id, sizeof(uint32_t) * nnz, cudaMemcpyDefault, s->stream));
-        OAR_CUDA(cudaMemsetAsync(s->d_txp + nnz, 0, sizeof(uint32_t) * pad, s->stream));
-        cudaStream_t up = s->stream;
-        if (overlap) {
-            OAR_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-            OAR_CUDA(cudaEventCreateWithFlags(&s->prob_ready, cudaEventDisableTiming));
-            OAR_CUDA(cudaEventRecord(s->prob_ready, s->stream));           // allocations and the txp_id copy are in order
-            OAR_CUDA(cudaStreamWaitEvent(copy_stream, s->prob_ready, 0));
-            up = copy_stream;
-        }
         if (nnz) {
-            OAR_CUDA(cudaMemcpyAsync(s->d_prob, prob, sizeof(float) * nnz, cudaMemcpyDefault, up));
+            OAR_CUDA(cudaMemcpyAsync(s->d_txp, txp_id, sizeof(uint32_t) * nnz, cudaMemcpyDefault, s->stream));
+            OAR_CUDA(cudaMemcpyAsync(s->d_prob, prob, sizeof(float) * nnz, cudaMemcpyDefault, s->stream));
             if (aux_or_null)
-                OAR_CUDA(cudaMemcpyAsync(s->d_aux, aux_or_null, sizeof(double) * nnz, cudaMemcpyDefault, up));
+                OAR_CUDA(cudaMemcpyAsync(s->d_aux, aux_or_null, sizeof(double) * nnz, cudaMemcpyDefault, s->stream));
         }
-        OAR_CUDA(cudaMemsetAsync(s->d_prob + nnz, 0, sizeof(float) * pad, up));
-        if (overlap) OAR_CUDA(cudaEventRecord(s->prob_ready, copy_stream));
+        OAR_CUDA(cudaMemsetAsync(s->d_txp + nnz, 0, sizeof(uint32_t) * pad, s->stream));
+        OAR_CUDA(cudaMemsetAsync(s->d_prob + nnz, 0, sizeof(float) * pad, s->stream));
         {
             const int threads = 256;
             const int blocks = (int)std::min<uint64_t>((n_reads + threads) / threads, (uint64_t)s->sm_count * 16);
@@ -212,40 +206,22 @@ extern "C" int oar_store_create(const uint64_t *row_ptr, const uint32_t *txp_id,
             const int blocks2 = (int)std::max<uint64_t>(1, std::min<uint64_t>((nnz + threads - 1) / threads, (uint64_t)s->sm_count * 16));
             kern::validate_txp<<<blocks2, threads, 0, s->stream>>>(s->d_txp, nnz, n_txps, d_flag + 1);
         }
-        uint32_t h_flag[4] = {0, 0, 0, 0};
-        OAR_CUDA(cudaMemcpyAsync(h_flag, d_flag, sizeof(h_flag), cudaMemcpyDeviceToHost, s->stream));
-        OAR_CUDA(cudaEventRecord(s->ev[1], s->stream));
+        uint32_t *h_flag = reinterpret_cast<uint32_t *>(&s->h_state[kHostStateSlots - 1]);   // pinned: the copy does not stage
+        OAR_CUDA(cudaMemcpyAsync(h_flag, d_flag, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, s->stream));
         OAR_CUDA(cudaStreamSynchronize(s->stream));
         dfree(d_rp64, s->stream);
         OAR_CUDA(cudaGetLastError());
         if (h_flag[0]) return fail(OAR_ERR_INVALID, "oar_store_create: row_ptr is not a monotone prefix ending at nnz");
         if (h_flag[1]) return fail(OAR_ERR_INVALID, "oar_store_create: txp_id out of range (>= n_txps)");
-        {
-            // OAR_TILED=0 keeps only the CSR (row-group kernel); OAR_TILE_SPAN tunes the tile fill
-            const char *env = getenv("OAR_TILED");
-            if (!(env && env[0] == '0')) {
-                const char *sp = getenv("OAR_TILE_SPAN");
-                const char *lay = getenv("OAR_LAYOUT");
-                s->tl.kind = (lay && strcmp(lay, "lane") == 0) ? 1 : 0;   // default: warp-chunk tiles (fastest measured)
-                int rc2 = build_tiled_layout(s, sp ? (uint32_t)atoi(sp) : 0u);
-                if (rc2 == OAR_OK) s->kernel = layout_kernel(s);
-                else if (rc2 != OAR_ERR_UNSUPPORTED) return rc2;   // unsupported shape: keep the CSR kernel
-            }
-            const char *sw = getenv("OAR_SWEEP");   // "2b": two barriers per tile (default), "1b": single barrier, "1c": same with deeper rings (unmeasured)
-            if (sw) s->sweep_1b = strcmp(sw, "1b") == 0 ? 1 : strcmp(sw, "1c") == 0 ? 2 : strcmp(sw, "3") == 0 ? 3 : 0;
-            const char *cps = getenv("OAR_CTAS_PER_SM");
-            if (cps && atoi(cps) > 0) { s->ctas_per_sm = atoi(cps); s->lane_ctas_per_sm = atoi(cps); }
-            if (s->prob_ready) OAR_CUDA(cudaStreamWaitEvent(s->stream, s->prob_ready, 0));   // no layout was built: wait here
-            OAR_CUDA(cudaEventRecord(s->ev[1], s->stream));
-            OAR_CUDA(cudaStreamSynchronize(s->stream));
-        }
+        int rc2 = finish_store(s);
+        if (rc2 != OAR_OK) return rc2;
+        OAR_CUDA(cudaEventRecord(s->ev[1], s->stream));
+        OAR_CUDA(cudaStreamSynchronize(s->stream));
         float ms = 0.f;
         OAR_CUDA(cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]));
         s->timings[0] = ms;
         return OAR_OK;
     }();
-    if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }   // also on the error paths: d_prob is about to be freed
-    if (s->prob_ready) { cudaEventDestroy(s->prob_ready); s->prob_ready = nullptr; }
     if (rc != OAR_OK) {
         std::string keep = g_last_error;
         oar_store_destroy(s);
@@ -269,12 +245,11 @@ extern "C" int oar_store_info(const oar_store *s, uint64_t *n_reads, uint64_t *n
 extern "C" int oar_store_set_kernel(oar_store *s, int kernel)
 {
     if (!s) return fail(OAR_ERR_INVALID, "oar_store_set_kernel: store is null");
-    if (kernel == OAR_KERNEL_AUTO) kernel = s->tl.ready ? layout_kernel(s) : OAR_KERNEL_ROWGROUP;
-    if (kernel != OAR_KERNEL_ROWGROUP && kernel != OAR_KERNEL_TILED && kernel != OAR_KERNEL_LANE)
+    if (kernel == OAR_KERNEL_AUTO) kernel = s->tl.ready ? OAR_KERNEL_TILED : OAR_KERNEL_ROWGROUP;
+    if (kernel != OAR_KERNEL_ROWGROUP && kernel != OAR_KERNEL_TILED)
         return fail(OAR_ERR_INVALID, "oar_store_set_kernel: unknown kernel");
-    if (kernel != OAR_KERNEL_ROWGROUP && (!s->tl.ready || kernel != layout_kernel(s)))
-        return fail(OAR_ERR_UNSUPPORTED, "oar_store_set_kernel: the layout this kernel needs was not built "
-                                         "(OAR_TILED=0, or OAR_LAYOUT selects the other tiled layout)");
+    if (kernel == OAR_KERNEL_TILED && !s->tl.ready)
+        return fail(OAR_ERR_UNSUPPORTED, "oar_store_set_kernel: the tiled layout was not built (OAR_TILED=0, or a store shape it does not support)");
     if (kernel != s->kernel) { cudaSetDevice(s->device); cudaStreamSynchronize(s->stream); destroy_graphs(s); }
     s->kernel = kernel;
     return OAR_OK;
@@ -285,8 +260,7 @@ extern "C" int oar_store_layout_info(const oar_store *s, uint64_t out[8])
     if (!s || !out) return fail(OAR_ERR_INVALID, "oar_store_layout_info: null argument");
     const TiledLayout &t = s->tl;
     out[0] = t.ready ? 1 : 0; out[1] = t.n_tiles;
-    out[1] = t.kind == 1 ? t.n_groups : t.n_tiles;                           // units of work of the sweep (groups / tiles)
-    out[2] = t.kind == 1 ? t.n_pairs : (uint64_t)t.n_tiles * tiled::kTile;   // alignment slots held in HBM
+    out[2] = (uint64_t)t.n_tiles * tiled::kTile;   // alignment slots held in HBM
     out[3] = t.n_fallback;
     out[4] = t.sum_d; out[5] = t.sum_u; out[6] = t.span; out[7] = (uint64_t)s->kernel;
     return OAR_OK;
@@ -406,37 +380,23 @@ static cudaError_t launch_tiled3(oar_store *s, const tiled::View &v, const doubl
     return cudaGetLastError();
 }
 
-static lane::View lane_view(const oar_store *s)
-{
-    const TiledLayout &t = s->tl;
-    lane::View v;
-    v.n_groups = t.n_groups; v.blobs = t.blobs; v.groups = t.groups; v.aux = t.aux;
-    const bool fold = t.n_fallback <= kFoldFallbackMax;
-    v.fb_rows = t.fallback; v.n_fb = fold ? t.n_fallback : 0u;
-    v.csr_row_ptr = s->d_row_ptr; v.csr_txp = s->d_txp; v.csr_prob = s->d_prob; v.csr_aux = s->d_aux; v.csr_wts = nullptr;
-    return v;
-}
-
+// two-barrier sweep with the early cp.async gather (OAR_SWEEP=2e)
 template <bool AUX, bool WTS>
-static cudaError_t launch_lane(oar_store *s, const lane::View &v, const double *prev, double *curr,
-                               const uint32_t *wperm, const OarEmState *state, int check_done)
+static cudaError_t launch_tiled_eg(oar_store *s, const tiled::View &v, const double *prev, double *curr,
+                                   const uint32_t *wperm, const OarEmState *state, int check_done)
 {
     static int attr_bytes[16] = {0};
-    auto kfn = lane::em_sweep_lane<AUX, WTS>;
-    const lane::Geometry g = lane::make_geometry(s->tl.max_rec, s->tl.max_d, s->tl.max_xs);
-    const uint32_t cta_bytes = g.warp_bytes * (uint32_t)lane::kWarps;
-    if (attr_bytes[s->device & 15] < (int)cta_bytes) {
-        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cta_bytes);
+    auto kfn = tiled::em_sweep_tiled_eg<AUX, WTS>;
+    const tiled::GeometryE g = tiled::make_geometry_e(s->tl.max_rec, s->tl.max_d, s->tl.max_u);
+    if (attr_bytes[s->device & 15] < (int)g.total) {
+        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.total);
         if (e != cudaSuccess) return e;
-        attr_bytes[s->device & 15] = (int)cta_bytes;
+        attr_bytes[s->device & 15] = (int)g.total;
     }
-    // persistent warps: as many CTAs per SM as shared memory allows (1 KB per CTA is reserved by the
-    // system), capped by the register budget of the launch bounds and the 32 CTA slots of an SM
-    int per_sm = (int)((227u * 1024u) / (cta_bytes + 1024u));
-    per_sm = std::max(1, std::min(std::min(per_sm, 32), s->lane_ctas_per_sm));
-    const uint32_t want = (v.n_groups + (uint32_t)lane::kWarps - 1u) / (uint32_t)lane::kWarps;
-    const uint32_t grid = std::max<uint32_t>(1u, std::min<uint32_t>(want, (uint32_t)s->sm_count * (uint32_t)per_sm));
-    kfn<<<grid, lane::kThreads, cta_bytes, s->stream>>>(v, g, prev, curr, wperm, state, check_done);
+    int per_sm = (int)((227u * 1024u) / (g.total + 1024u));
+    per_sm = std::max(1, std::min(per_sm, s->ctas_per_sm));
+    const uint32_t grid = std::min<uint32_t>(v.n_tiles, (uint32_t)s->sm_count * (uint32_t)per_sm);
+    kfn<<<grid, tiled::kThreads, g.total, s->stream>>>(v, g, prev, curr, wperm, state, check_done);
     return cudaGetLastError();
 }
 
@@ -466,26 +426,20 @@ static cudaError_t enqueue_sweep(oar_store *s, const double *prev, double *curr,
                                  const OarEmState *state, int check_done)
 {
     if (s->n_reads == 0) return cudaSuccess;
-    if (s->kernel != OAR_KERNEL_TILED && s->kernel != OAR_KERNEL_LANE)
+    if (s->kernel != OAR_KERNEL_TILED)
         return enqueue_rowgroup(s, nullptr, s->n_reads, prev, curr, wts, state, check_done);
     const TiledLayout &t = s->tl;
-    if (t.n_tiles > 0 && s->kernel == OAR_KERNEL_LANE) {
-        lane::View v = lane_view(s);
-        v.csr_wts = wts;
-        const uint32_t *wp = wts ? t.wperm : nullptr;
-        cudaError_t le;
-        if (s->d_aux) le = wts ? launch_lane<true, true>(s, v, prev, curr, wp, state, check_done)
-                               : launch_lane<true, false>(s, v, prev, curr, wp, state, check_done);
-        else          le = wts ? launch_lane<false, true>(s, v, prev, curr, wp, state, check_done)
-                               : launch_lane<false, false>(s, v, prev, curr, wp, state, check_done);
-        if (le != cudaSuccess) return le;
-        s->counters[0] += 1;
-    } else if (t.n_tiles > 0) {
+    if (t.n_tiles > 0) {
         tiled::View v = tiled_view(s);
         v.csr_wts = wts;
         const uint32_t *wp = wts ? t.wperm : nullptr;
         cudaError_t le;
-        if (s->sweep_1b == 3) {
+        if (s->sweep_1b == 4) {
+            if (s->d_aux) le = wts ? launch_tiled_eg<true, true>(s, v, prev, curr, wp, state, check_done)
+                                   : launch_tiled_eg<true, false>(s, v, prev, curr, wp, state, check_done);
+            else          le = wts ? launch_tiled_eg<false, true>(s, v, prev, curr, wp, state, check_done)
+                                   : launch_tiled_eg<false, false>(s, v, prev, curr, wp, state, check_done);
+        } else if (s->sweep_1b == 3) {
             if (s->d_aux) le = wts ? launch_tiled3<true, true>(s, v, prev, curr, wp, state, check_done)
                                    : launch_tiled3<true, false>(s, v, prev, curr, wp, state, check_done);
             else          le = wts ? launch_tiled3<false, true>(s, v, prev, curr, wp, state, check_done)
@@ -524,7 +478,7 @@ cudaError_t sweep_enqueue(oar_store *s, const double *prev, double *curr, const 
 static cudaError_t refresh_wperm(oar_store *s, const uint32_t *wts)
 {
     const TiledLayout &t = s->tl;
-    if ((s->kernel != OAR_KERNEL_TILED && s->kernel != OAR_KERNEL_LANE) || t.n_tiled_rows == 0) return cudaSuccess;
+    if (s->kernel != OAR_KERNEL_TILED || t.n_tiled_rows == 0) return cudaSuccess;
     const int threads = 256;
     const int blocks = (int)std::min<uint64_t>((t.n_tiled_rows + threads - 1) / threads, (uint64_t)s->sm_count * 16);
     tiled::permute_weights<<<blocks, threads, 0, s->stream>>>(wts, t.trow, t.n_tiled_rows, t.wperm);

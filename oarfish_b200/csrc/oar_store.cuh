@@ -1,28 +1,17 @@
 // oar_store.cuh -- the store handle behind the opaque oar_store of the C ABI.
 #pragma once
 #include "oar_common.cuh"
+#include "oar_ctx.cuh"
 #ifndef OAR_TILE_WARPS
 #define OAR_TILE_WARPS 8
 #endif
 #define OAR_TILE_WARPS_DEFAULT OAR_TILE_WARPS
-#ifndef OAR_LANE_MIN_CTAS
-#define OAR_LANE_MIN_CTAS 6
-#endif
-#define OAR_LANE_MIN_CTAS_DEFAULT OAR_LANE_MIN_CTAS
 
 namespace oar {
 
-// Locality-tiled copy of the store: kind 0 = warp-chunk tiles (oar_tiled.cuh, default),
-// kind 1 = row-per-lane groups (oar_lane.cuh, OAR_LAYOUT=lane at store creation).
+// Locality-tiled copy of the store (oar_tiled.cuh): tiles of warp-chunks.
 struct TiledLayout {
     bool ready = false;
-    int kind = 0;
-    // row-per-lane layout
-    uint4 *blobs = nullptr;        // per group one blob: record (header, row lengths, transcript table, items) | pairs {prob bits, lpos}
-    uint2 *groups = nullptr;       // per group: {blob offset (16 B granules), blob bytes}
-    uint32_t n_groups = 0;
-    uint64_t n_pairs = 0;          // pairs held (alignments + one pad per odd group)
-    uint32_t max_nnz = 0, max_xs = 0;
     uint32_t n_tiles = 0, n_tiled_rows = 0, n_fallback = 0, span = 0;
     uint64_t sum_d = 0, sum_u = 0;
     float *prob = nullptr;
@@ -47,6 +36,7 @@ struct GraphSlot {
 struct oar_store {
     int device = 0;
     int sm_count = 148;
+    oar::DeviceCtx *ctx = nullptr;  // per-device pools the stream, events and pinned state below come from
     cudaStream_t stream = nullptr;
     uint64_t n_reads = 0, nnz = 0;
     uint32_t n_txps = 0;
@@ -54,8 +44,6 @@ struct oar_store {
     bool borrowed = false;  // sub-store of another store: row_ptr / prob / aux / stream / events are not owned
     int sweep_1b = 0;   // tiled sweep variant: 0 = two CTA barriers per tile (em_sweep_tiled), 1 = one (em_sweep_tiled1, OAR_SWEEP=1b), 2 = one, deeper rings (em_sweep_tiled2, OAR_SWEEP=1c)
     int ctas_per_sm = 40 / OAR_TILE_WARPS_DEFAULT;  // persistent CTAs of the tiled sweep per SM (upper bound; shared memory may allow fewer)
-
-    int lane_ctas_per_sm = OAR_LANE_MIN_CTAS_DEFAULT;  // same for the row-per-lane sweep (register budget of its launch bounds)
 
     // CSR in HBM (original read order)
     uint32_t *d_row_ptr = nullptr;  // N+1
@@ -68,11 +56,10 @@ struct oar_store {
     // EM work buffers
     double *d_counts[2] = {nullptr, nullptr};
     OarEmState *d_state = nullptr;
-    OarEmState *h_state = nullptr;  // pinned, 4 slots
+    OarEmState *h_state = nullptr;  // pinned, oar::kHostStateSlots slots (from the context's pool)
     uint32_t *d_weights = nullptr;  // N, bootstrap weights of the current replicate (read order)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t slot_ev[2] = {nullptr, nullptr};
-    cudaEvent_t prob_ready = nullptr;   // during oar_store_create with OAR_UPLOAD_OVERLAP=1: prob / aux have arrived (second stream)
 
     oar::GraphSlot graphs[2];  // [0] unweighted, [1] weighted
 
@@ -84,8 +71,6 @@ namespace oar {
 // Build s->tl from the CSR arrays already resident on s->device (enqueued on
 // s->stream, synchronises).  Returns an oar_status.
 int build_tiled_layout(oar_store *s, uint32_t span);
-// The sweep kernel that goes with the layout the store holds (OAR_KERNEL_LANE / OAR_KERNEL_TILED).
-inline int layout_kernel(const oar_store *s) { return s->tl.kind == 1 ? OAR_KERNEL_LANE : OAR_KERNEL_TILED; }
 // A store over the parent's reads with different transcript ids (takes ownership of d_txp): used by the
 // batched per-cell EM, where ids are (cell, transcript) pairs.  Shares the parent's stream and CSR arrays.
 int substore_create(oar_store *parent, uint32_t *d_txp, uint32_t n_txps, oar_store **out);

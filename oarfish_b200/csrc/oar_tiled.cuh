@@ -1502,5 +1502,116 @@ __global__ void __launch_bounds__(kThreads, (OAR_TILED_MIN_CTAS * 8) / kWarps) e
                                               tid >> 3, kThreads >> 3, v.n_fb);
 }
 
+// ---------------------------------------------------------------------------
+// Two-barrier sweep with an EARLY prev[] gather (OAR_SWEEP=2e).
+//
+// em_sweep_tiled's window between the second barrier of a tile and the first barrier of the next one is as long as
+// its slower occupant: the item warps (phase 2) or the gather warp, which waits for the stage's TMA copy, loads the
+// table ids, gathers prev[] from L2 (~700 cycles) and stores it.  ncu puts the gather slightly ahead (the five idle
+// warps wait ~650 sample units per tile, phase 2 takes ~440).  Here the gather of tile i+1 is issued at the START of
+// tile i's phase 1 as 8-byte cp.async copies (LDGSTS: no register, no wait) into a second s_prev buffer and has landed
+// long before the second barrier; the ring has three stages, requested three tiles ahead, so the record of tile i+1
+// is in shared memory by then.  The window shrinks to phase 2 alone.
+struct GeometryE {
+    uint32_t stage_bytes, stage_off, prev_off, prev_bytes, bar_off, total;
+};
+inline GeometryE make_geometry_e(uint32_t max_rec_bytes, uint32_t max_d, uint32_t max_x_doubles)
+{
+    GeometryE g;
+    g.stage_bytes = 8u * kTile + ((max_rec_bytes + 15u) & ~15u);
+    g.stage_off = (8u * ((max_x_doubles + 2u + 1u) & ~1u) + 127u) & ~127u;
+    g.prev_off = g.stage_off + 3u * g.stage_bytes;
+    g.prev_bytes = 8u * ((max_d + 1u) & ~1u);
+    g.bar_off = g.prev_off + 2u * g.prev_bytes;
+    g.total = g.bar_off + 3u * 8u;
+    return g;
+}
+
+template <bool HAS_AUX, bool HAS_WTS>
+__global__ void __launch_bounds__(kThreads, (OAR_TILED_MIN_CTAS * 8) / kWarps) em_sweep_tiled_eg(View v, GeometryE g, const double *__restrict__ prev,
+                                                                 double *__restrict__ curr,
+                                                                 const uint32_t *__restrict__ wperm,
+                                                                 const OarEmState *__restrict__ st, int check_done)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    // [xs][stage 0][stage 1][stage 2][s_prev 0][s_prev 1][mbarriers]; a stage = prob | lpos | record
+    if (check_done && st->done) return;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t n_tiles = v.n_tiles, stride = gridDim.x;
+    const uint32_t tile0 = blockIdx.x;
+    if (tile0 >= n_tiles) return;
+    uint32_t sm0;
+    asm volatile("{.reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t;}" : "=r"(sm0) : "l"(smem));
+    const uint32_t stage0 = sm0 + g.stage_off, sp0 = sm0 + g.prev_off, bar0 = sm0 + g.bar_off;
+    const uint32_t xs_a = smem_u32(smem);
+    const bool is_tma = tid == 32u * (kWarps - 2);
+    const bool is_gather = warp == kWarps - 1;
+
+    auto issue = [&](uint32_t tile, uint32_t slot, uint2 r) {   // the TMA thread only
+        const uint32_t bar = bar0 + 8u * slot, dst = stage0 + slot * g.stage_bytes;
+        mbar_expect_tx(bar, 8u * kTile + r.y);
+        bulk_g2s(dst, v.prob + (size_t)tile * kTile, 4u * kTile, bar);
+        bulk_g2s(dst + 4u * kTile, v.lpos + (size_t)tile * kTile, 4u * kTile, bar);
+        bulk_g2s(dst + 8u * kTile, v.records + r.x, r.y, bar);
+    };
+    auto gather_prev_async = [&](uint32_t rec_a, uint32_t sp_a) {
+        const uint32_t Dn = lds_u32(rec_a + kRecDU);
+        for (uint32_t d = lane; d < Dn; d += 32u) cp_async_8(sp_a + 8u * d, prev + lds_u32(rec_a + kRecTable + 4u * d));
+        if (HAS_WTS) weights_touch(wperm + lds_u32(rec_a + kRecRow), lane);
+    };
+
+    if (tid == 0) {
+#pragma unroll
+        for (uint32_t i = 0; i < 3; ++i) mbar_init(bar0 + 8u * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint2 r_pending = make_uint2(0, 0);   // record locator of the tile three ahead (TMA thread)
+    if (is_tma) {
+        issue(tile0, 0, v.rec[tile0]);
+        if (tile0 + stride < n_tiles) issue(tile0 + stride, 1, v.rec[tile0 + stride]);
+        if (tile0 + 2 * stride < n_tiles) issue(tile0 + 2 * stride, 2, v.rec[tile0 + 2 * stride]);
+        if (tile0 + 3 * stride < n_tiles) r_pending = v.rec[tile0 + 3 * stride];
+    }
+    uint32_t spar = 0;                    // phase parities of the three stage mbarriers (gather warp)
+    if (is_gather) {
+        mbar_wait(bar0, 0); spar ^= 1u;
+        gather_prev_async(stage0 + 8u * kTile, sp0);
+        cp_async_wait_all();
+    }
+
+    uint32_t tile = tile0;
+    uint32_t rs = 0;                      // stage of this tile = it % 3
+    for (uint32_t it = 0;; ++it) {
+        const uint32_t s = it & 1u;
+        const uint32_t rs1 = rs == 2u ? 0u : rs + 1u;
+        const uint32_t stg = stage0 + rs * g.stage_bytes;
+        const uint32_t next = tile + stride;
+        const bool has_next = next < n_tiles;
+        __syncthreads();   // stage rs and s_prev[s] of this tile are in place; phase 2 of the previous tile has left xs
+
+        if (is_gather && has_next) {   // stage rs1 was requested a whole iteration ago: no polling to speak of
+            mbar_wait(bar0 + 8u * rs1, (spar >> rs1) & 1u); spar ^= 1u << rs1;
+            gather_prev_async(stage0 + rs1 * g.stage_bytes + 8u * kTile, sp0 + (s ^ 1u) * g.prev_bytes);
+        }
+        uint32_t item; uint4 du;
+        tile_phase1<HAS_AUX, HAS_WTS>(v, tile, stg, stg + 8u * kTile, sp0 + s * g.prev_bytes, xs_a, tid, lane, warp, curr, wperm, item, du);
+        if (is_gather) cp_async_wait_all();
+        __syncthreads();   // xs complete; stage rs is free again; s_prev[s^1] of the next tile is in place
+
+        if (is_tma && next + 2u * stride < n_tiles) {
+            issue(next + 2u * stride, rs, r_pending);
+            if (next + 3u * stride < n_tiles) r_pending = v.rec[next + 3u * stride];
+        }
+        tile_phase2(xs_a, item, du.y, du.z, tid, warp, curr);
+
+        if (!has_next) break;
+        tile = next; rs = rs1;
+    }
+    if (v.n_fb && blockIdx.x == gridDim.x - 1u)
+        kern::rowgroup_rows<HAS_AUX, HAS_WTS>(v.csr_row_ptr, v.csr_txp, v.csr_prob, v.csr_aux, v.csr_wts, v.fb_rows, prev, curr,
+                                              tid >> 3, kThreads >> 3, v.n_fb);
+}
+
 }  // namespace tiled
 }  // namespace oar

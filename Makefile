@@ -38,7 +38,7 @@ $(LIBDIR)/liboarsynth.so: $(CSRC)/synth.c
 
 # C++ host mirror of the reference interface (include/oarfish_em.hpp) + its test driver
 $(LIBDIR)/host_mirror_test: tests/cpp/host_mirror_test.cpp include/oarfish_em.hpp include/oarfish_em.h $(LIBDIR)/liboarfish_em.so
-	$(HOSTCXX) -O2 -std=c++17 -Wall -Wextra -Iinclude -o $@ $< -L$(LIBDIR) -loarfish_em -Wl,-rpath,'$$ORIGIN'
+	$(HOSTCXX) -O2 -std=c++17 -Wall -Wextra -Iinclude -o $@ $< -L$(LIBDIR) -loarfish_em -pthread -Wl,-rpath,'$$ORIGIN'
 
 oracle: oracle/liboarfish_oracle.so
 

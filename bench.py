@@ -187,6 +187,47 @@ def run_reference(args):
 # GPU arm
 # ---------------------------------------------------------------------------------------------
 
+C5_READS, C5_TXPS, C5_AVG, C5_SEED = 50_000, 200_000, 6.0, 5
+
+
+def c5_block(args, rank, world, local_rank, barrier, max_over_ranks, sum_over_ranks):
+    """BASELINE config 5 scaled to --c5-cells cells x 50k reads x 200k transcripts (the full 5k cells are 1.5 G alignments:
+    minutes of host-side generation): one em::em per cell (single_cell.rs:150) batched per rank; cells are independent
+    units, rank r owns a contiguous range (strong scaling, no collective).  Timed per rank: upload of the rank's rows
+    from pinned host memory + layout + all EMs + sparse results to the host; cells/s = all cells / max-over-ranks time."""
+    import torch
+    from oarfish_b200 import DeviceStore, synth
+    n_total = args.c5_cells
+    c0, c1 = rank * n_total // world, (rank + 1) * n_total // world
+    st, crp = synth.make_cells([C5_READS] * (c1 - c0), C5_TXPS, C5_AVG, C5_SEED * 7919 + c0)
+    if c1 > c0:   # untimed warm-up on the first cell (module load, pool growth)
+        r1 = int(crp[1]); a1 = int(st.row_ptr[r1])
+        with DeviceStore(st.row_ptr[:r1 + 1].copy(), st.txp_id[:a1].copy(), st.prob[:a1].copy(), C5_TXPS, device=local_rank) as w:
+            w.em_batched(crp[:2].copy(), conv_thresh=THR)
+    barrier()
+    t0 = time.perf_counter()
+    em_ms, nit, launches = 0.0, np.zeros(0, np.uint32), 0
+    if c1 > c0:
+        with DeviceStore(st.row_ptr, st.txp_id, st.prob, C5_TXPS, device=local_rank) as d5:
+            _, _, _, nit = d5.em_batched(crp, conv_thresh=THR)
+            em_ms = d5.timings_ms()["em"]
+            launches = d5.counters()["launches"]
+    torch.cuda.synchronize()
+    dt_local = time.perf_counter() - t0
+    barrier()
+    dt = max_over_ranks(dt_local)
+    em_ms = max_over_ranks(em_ms)
+    iters = sum_over_ranks(float(nit.astype(np.float64).sum() + 2 * len(nit)))
+    nnz = sum_over_ranks(float(st.nnz))
+    launches = sum_over_ranks(float(launches))
+    niter_max = max_over_ranks(float(nit.max()) if len(nit) else 0.0)
+    return {"workload": f"config 5 scaled: {n_total} cells x {C5_READS} reads x {C5_TXPS} transcripts, avg {C5_AVG:g} aln/read, one em::em per cell (do_em rule, thr {THR})",
+            "cells": n_total, "n_gpus": world, "cells_per_sec": n_total / dt, "ms": 1e3 * dt, "em_ms_max_rank": em_ms,
+            "nnz": int(nnz), "cell_iterations": int(iters), "niter_mean": iters / max(n_total, 1) - 2, "niter_max": int(niter_max),
+            "gpu_launches": int(launches),
+            "includes": "per rank: upload of its cells' rows (pinned host) + layout + all per-cell EMs + sparse counts to the host"}
+
+
 def run_gpu(args):
     import torch
     from oarfish_b200 import DeviceStore
@@ -302,7 +343,7 @@ def run_gpu(args):
         prev.clamp_(min=1e-3)
         curr = torch.zeros(n_txps, dtype=torch.float64, device=dev)
         wts = torch.from_numpy(ds.sample_weights(SEED, 0).view(np.int32)).to(dev)
-        kname = {2: "em_sweep_tiled", 3: "em_sweep_lane"}.get(layout["kernel"], "em_sweep_rowgroup")
+        kname = {2: "em_sweep_tiled"}.get(layout["kernel"], "em_sweep_rowgroup")
         traffic = None
         tr = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tr):
@@ -419,6 +460,11 @@ def run_gpu(args):
                   "us_per_sweep": ms2 * 1e3, "roofline_frac": alg2 / (ms2 * 1e-3) / 1e9 / peak,
                   "note": "53 MB per sweep fits the 126 MB L2: back-to-back sweeps are L2-resident, the fraction is against the HBM peak all the same"}
 
+    # ---- BASELINE config 5, scaled (single-cell mode): per-cell EMs batched, cells sharded over the ranks ---------------
+    c5 = None
+    if not args.no_c5:
+        c5 = c5_block(args, rank, world, local_rank, barrier, max_over_ranks, sum_over_ranks)
+
     if rank == 0:
         line = {
             "metric": "em_iterations_per_sec", "value": value, "unit": "iterations/s", "n_gpus": world,
@@ -434,7 +480,7 @@ def run_gpu(args):
             "replicates_per_sec": n_timed / elapsed, "iterations_per_replicate": total_iters / max(n_timed, 1),
             "roofline": roof, "roofline_plain_em": roof_plain, "em_single_gpu": em_single,
             "cpu_baseline": cpu, "cpu_baseline_em_par": cpu_par, "e2e": e2e, "e2e_single_em": e2e_single,
-            "gpu_launches": int(total_launches), "c2": c2, "clocks": clocks,
+            "gpu_launches": int(total_launches), "c2": c2, "c5": c5, "clocks": clocks,
             "store_build_ms": build_ms, "bcast_ms": bcast_ms if multi else None,
         }
         print(json.dumps(line), flush=True)
@@ -456,6 +502,8 @@ def main():
                     help="at N > 1: ranks pull replicate ids from a shared counter (default) or replicate g runs on rank g mod N")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c2", action="store_true")
+    ap.add_argument("--no-c5", action="store_true")
+    ap.add_argument("--c5-cells", type=int, default=256, help="cells of the scaled config-5 sub-record (in total, sharded over the ranks)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

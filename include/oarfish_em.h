@@ -26,7 +26,9 @@
  *     Pointers documented "host or device" are resolved with CUDA unified
  *     addressing (cudaMemcpyDefault).
  *   - a handle is used by one host thread at a time; distinct handles are
- *     independent.  Device memory is owned by the handle.
+ *     independent and may be created, used and destroyed concurrently from
+ *     different host threads (the single-cell driver calls em::em from a pool
+ *     of workers, single_cell.rs:91-193).  Device memory is owned by the handle.
  *   - transcript indexing is bit-exact: out[i] is the count of header reference
  *     id i, exactly as em::em returns Vec<f64> indexed by ref_id.
  *   - there is no CPU fallback: without a CUDA device every compute entry point
@@ -55,10 +57,8 @@ typedef struct oar_store oar_store; /* opaque; one per alignment store per devic
 typedef enum {
     OAR_KERNEL_AUTO = 0,
     OAR_KERNEL_ROWGROUP = 1,  /* 8-lane group per read row, global f64 reductions */
-    OAR_KERNEL_TILED = 2,     /* locality-sorted tiles of warp-chunks (4 slots per lane), in-tile aggregation
-                                 (default layout) */
-    OAR_KERNEL_LANE = 3       /* locality-sorted groups, one read per lane, warp-independent pipelines; needs
-                                 the lane layout (environment OAR_LAYOUT=lane at store creation) */
+    OAR_KERNEL_TILED = 2      /* locality-sorted tiles of warp-chunks (4 slots per lane), in-tile aggregation
+                                 (default) */
 } oar_kernel;
 
 /* ABI version: major*1000 + minor. */
@@ -120,7 +120,9 @@ int oar_bootstrap(oar_store *store, uint32_t num_boot, uint64_t seed, uint32_t f
                   double *out, uint32_t *out_niter);
 
 /* Same, with caller-supplied integer read weights (R x N u32, host or device):
- * weights[r*N + i] = number of times read i appears in replicate r's sample. */
+ * weights[r*N + i] = number of times read i appears in replicate r's sample.  The tiled sweep carries
+ * a weight as 16 bits: a weight above 65535 fails with OAR_ERR_UNSUPPORTED (OAR_KERNEL_ROWGROUP has
+ * no such limit). */
 int oar_bootstrap_weights(oar_store *store, const uint32_t *weights, uint32_t n_replicates,
                           uint32_t max_iter, double conv_thresh, uint32_t min_iter,
                           double *out, uint32_t *out_niter);
@@ -149,6 +151,50 @@ int oar_em_batched(oar_store *store, const uint64_t *cell_row_ptr, uint32_t n_ce
                    uint64_t *out_nnz, uint32_t *out_niter);
 
 /*
+ * ---- all GPUs of the box behind one call from one host thread ---------------------------------
+ * em::bootstrap(em_info, num_boot, nthreads) (src/em.rs:292-314) builds its own pool and fans the
+ * replicates out internally; so does the single-cell driver with cells (src/single_cell.rs:91-193).
+ * The entry points below give a caller the same shape: the library runs one host thread per
+ * device.  All pointers are HOST pointers here.
+ */
+typedef struct oar_multi oar_multi; /* opaque: one resident copy of a store on each of `devices` */
+
+/*
+ * Upload the store once to devices[0] (as oar_store_create), copy the validated CSR device-to-device
+ * (NVLink peer copies) to the other devices; every device builds its own layout.  No collective on
+ * the data path afterwards.
+ */
+int oar_multi_create(const uint64_t *row_ptr, const uint32_t *txp_id, const float *prob,
+                     const double *aux_or_null, uint64_t n_reads, uint64_t nnz, uint32_t n_txps,
+                     const int *devices, int n_devices, oar_multi **out);
+void oar_multi_destroy(oar_multi *m);
+/* The store on devices[i] (for oar_em, oar_posteriors, ... on one device); owned by the handle. */
+oar_store *oar_multi_store(oar_multi *m, int i);
+/* n_devices; out_ms: [0] upload + layout on devices[0], [1] peer copies + layouts on the others (wall);
+ * out_last_per_device (n_devices u32): units each device ran in the last oar_multi_bootstrap.  Any may be NULL. */
+int oar_multi_info(const oar_multi *m, int *n_devices, double out_ms[2], uint32_t *out_last_per_device);
+
+/*
+ * em::bootstrap (src/em.rs:292-314) over all devices of the handle: replicate g in [0, num_boot) is
+ * the same (seed, g) replicate oar_bootstrap computes, so out (num_boot x M, row g = replicate g) does
+ * not depend on the number of devices.  Devices pull replicate ids from a shared counter.
+ */
+int oar_multi_bootstrap(oar_multi *m, uint32_t num_boot, uint64_t seed, uint32_t max_iter,
+                        double conv_thresh, double *out, uint32_t *out_niter);
+
+/*
+ * oar_em_batched over several devices (single_cell.rs:91-193): cells are split into contiguous ranges
+ * balanced on alignments, every device receives only its cells' rows, results come back as one CSR over
+ * all cells (same layout and meaning as oar_em_batched).  out_cells_per_device: n_devices u32 or NULL.
+ */
+int oar_em_batched_multi(const uint64_t *row_ptr, const uint32_t *txp_id, const float *prob,
+                         const double *aux_or_null, uint64_t n_reads, uint64_t nnz, uint32_t n_txps,
+                         const uint64_t *cell_row_ptr, uint32_t n_cells, const int *devices, int n_devices,
+                         uint32_t max_iter, double conv_thresh, uint32_t min_iter,
+                         uint64_t *out_cell_ptr, uint32_t *out_txp, double *out_val, uint64_t capacity,
+                         uint64_t *out_nnz, uint32_t *out_niter, uint32_t *out_cells_per_device);
+
+/*
  * The bulk coverage model (--model-coverage; bulk.rs:103-108) computed on the device from the resident
  * store: add_interval histograms (src/util/oarfish_types.rs:496-537), logistic_prob
  * (src/util/logistic_probability.rs:40-79) and normalize_read_probs
@@ -162,6 +208,14 @@ int oar_em_batched(oar_store *store, const uint64_t *cell_row_ptr, uint32_t n_ce
 int oar_store_coverage_model(oar_store *store, const uint32_t *aln_start, const uint32_t *aln_end,
                              const uint32_t *txp_len, uint32_t bin_width, double growth_rate,
                              double *out_aux_or_null);
+
+/*
+ * The same stage with the binomial bin model the single-cell driver uses per cell (single_cell.rs:132-137):
+ * binomial_continuous_prob / binomial_probability (src/util/binomial_probability.rs:180-224, :7-178; ln_gamma as in
+ * statrs 0.18) in place of logistic_prob; histograms and normalize_read_probs as above.
+ */
+int oar_store_coverage_model_binomial(oar_store *store, const uint32_t *aln_start, const uint32_t *aln_end,
+                                      const uint32_t *txp_len, uint32_t bin_width, double *out_aux_or_null);
 
 /*
  * Read-level assignment probabilities with the final counts: the inner loop of

@@ -64,6 +64,19 @@ public:
     std::vector<double> coverage_probabilities;
 
     explicit InMemoryAlignmentStore(AlignmentFilters fo = {}) : filter_opts(fo), boundaries_{0} {}
+    // copies share no device state: the copy uploads its own store on first use
+    InMemoryAlignmentStore(const InMemoryAlignmentStore &o)
+        : filter_opts(o.filter_opts), alignments(o.alignments), as_probabilities(o.as_probabilities),
+          coverage_probabilities(o.coverage_probabilities), boundaries_(o.boundaries_) {}
+    InMemoryAlignmentStore &operator=(const InMemoryAlignmentStore &o)
+    {
+        if (this != &o) {
+            filter_opts = o.filter_opts; alignments = o.alignments; as_probabilities = o.as_probabilities;
+            coverage_probabilities = o.coverage_probabilities; boundaries_ = o.boundaries_;
+            invalidate_device();
+        }
+        return *this;
+    }
 
     // add_filtered_group, oarfish_types.rs:718-738: empty groups are dropped
     bool add_filtered_group(const std::vector<AlnInfo> &alns, const std::vector<float> &as_probs)
@@ -81,11 +94,31 @@ public:
     size_t total_len() const { return alignments.size(); }         // :740-742
     const std::vector<size_t> &boundaries() const { return boundaries_; }
 
-    // the device copy (created on first use, reused by em then bootstrap like bulk.rs:155-179)
+    // the device copy (created on first use, reused by em then bootstrap like bulk.rs:155-179).  It is a snapshot:
+    // after changing alignments / as_probabilities / coverage_probabilities / filter_opts in place (the reference's
+    // normalize_read_probs replaces coverage_probabilities once the store is built) call invalidate_device().
     oar_store *device_store(uint32_t n_txps, int device) const
     {
-        if (!device_ || device_txps_ != n_txps || device_id_ != device) upload(n_txps, device);
+        if (!device_ || device_txps_ != n_txps || device_id_ != device || device_nnz_ != alignments.size() ||
+            device_cov_ != filter_opts.model_coverage)
+            upload(n_txps, device);
         return device_.get();
+    }
+    void invalidate_device() const { device_.reset(); multi_.reset(); }
+    // one copy per device for em::bootstrap's fan-out (oar_multi_*)
+    oar_multi *multi_store(uint32_t n_txps, const std::vector<int> &devices) const
+    {
+        if (!multi_ || multi_txps_ != n_txps || multi_devices_ != devices || multi_nnz_ != alignments.size() ||
+            multi_cov_ != filter_opts.model_coverage) {
+            Flat f = flatten();
+            oar_multi *h = nullptr;
+            detail::check(oar_multi_create(f.row_ptr.data(), f.txp_id.data(), as_probabilities.data(), f.aux, len(), total_len(),
+                                           n_txps, devices.data(), (int)devices.size(), &h),
+                          "oar_multi_create");
+            multi_.reset(h);
+            multi_txps_ = n_txps; multi_devices_ = devices; multi_nnz_ = alignments.size(); multi_cov_ = filter_opts.model_coverage;
+        }
+        return multi_.get();
     }
 
 private:
@@ -93,22 +126,39 @@ private:
     mutable std::unique_ptr<oar_store, detail::StoreDeleter> device_;
     mutable uint32_t device_txps_ = 0;
     mutable int device_id_ = -1;
+    mutable size_t device_nnz_ = 0;
+    mutable bool device_cov_ = false;
+    struct MultiDeleter { void operator()(oar_multi *m) const { oar_multi_destroy(m); } };
+    mutable std::unique_ptr<oar_multi, MultiDeleter> multi_;
+    mutable uint32_t multi_txps_ = 0;
+    mutable std::vector<int> multi_devices_;
+    mutable size_t multi_nnz_ = 0;
+    mutable bool multi_cov_ = false;
 
     // flatten exactly as the EM reads the store (em.rs:97-131): boundaries -> row_ptr u64,
     // AlnInfo.ref_id -> txp_id, as_probabilities -> prob, coverage_probabilities -> aux iff model_coverage
+    struct Flat { std::vector<uint64_t> row_ptr; std::vector<uint32_t> txp_id; const double *aux; };
+    Flat flatten() const
+    {
+        Flat f;
+        f.row_ptr.assign(boundaries_.begin(), boundaries_.end());
+        f.txp_id.resize(alignments.size());
+        for (size_t j = 0; j < alignments.size(); ++j) f.txp_id[j] = alignments[j].ref_id;
+        f.aux = filter_opts.model_coverage ? coverage_probabilities.data() : nullptr;
+        return f;
+    }
     void upload(uint32_t n_txps, int device) const
     {
-        std::vector<uint64_t> row_ptr(boundaries_.begin(), boundaries_.end());
-        std::vector<uint32_t> txp_id(alignments.size());
-        for (size_t j = 0; j < alignments.size(); ++j) txp_id[j] = alignments[j].ref_id;
-        const double *aux = filter_opts.model_coverage ? coverage_probabilities.data() : nullptr;
+        Flat f = flatten();
         oar_store *h = nullptr;
-        detail::check(oar_store_create(row_ptr.data(), txp_id.data(), as_probabilities.data(), aux, len(), total_len(),
+        detail::check(oar_store_create(f.row_ptr.data(), f.txp_id.data(), as_probabilities.data(), f.aux, len(), total_len(),
                                        n_txps, device, &h),
                       "oar_store_create");
         device_.reset(h);
         device_txps_ = n_txps;
         device_id_ = device;
+        device_nnz_ = alignments.size();
+        device_cov_ = filter_opts.model_coverage;
     }
 };
 
@@ -122,6 +172,7 @@ struct EMInfo {
     // kde_model (em.rs:173-178): the density factor comes from the un-vendored `kders` crate; fold it into
     // coverage_probabilities and set filter_opts.model_coverage.
     int device = 0;
+    std::vector<int> devices;   // em::bootstrap fans out over these (empty: `device` only)
 };
 
 namespace detail {
@@ -150,11 +201,17 @@ inline std::vector<std::vector<double>> bootstrap(const EMInfo &em_info, uint32_
                                                   std::optional<uint64_t> seed = std::nullopt)
 {
     const uint32_t m = (uint32_t)em_info.txp_info->size();
-    oar_store *st = em_info.eq_map->device_store(m, em_info.device);
     const uint64_t sd = seed ? *seed : ((uint64_t)std::random_device{}() << 32) ^ std::random_device{}();
     std::vector<double> flat((size_t)num_boot * m);
-    detail::check(oar_bootstrap(st, num_boot, sd, 0, 1, em_info.max_iter, em_info.convergence_thresh, flat.data(), nullptr),
-                  "oar_bootstrap");
+    if (em_info.devices.size() > 1) {   // the pool of em.rs:296-300, with devices in place of threads
+        oar_multi *mt = em_info.eq_map->multi_store(m, em_info.devices);
+        detail::check(oar_multi_bootstrap(mt, num_boot, sd, em_info.max_iter, em_info.convergence_thresh, flat.data(), nullptr),
+                      "oar_multi_bootstrap");
+    } else {
+        oar_store *st = em_info.eq_map->device_store(m, em_info.devices.empty() ? em_info.device : em_info.devices[0]);
+        detail::check(oar_bootstrap(st, num_boot, sd, 0, 1, em_info.max_iter, em_info.convergence_thresh, flat.data(), nullptr),
+                      "oar_bootstrap");
+    }
     std::vector<std::vector<double>> out(num_boot);
     for (uint32_t b = 0; b < num_boot; ++b) out[b].assign(flat.begin() + (size_t)b * m, flat.begin() + (size_t)(b + 1) * m);
     return out;

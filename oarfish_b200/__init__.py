@@ -6,7 +6,7 @@ em.py mirrors the reference's interface; engine.py wraps the ABI handle.
 """
 from .em import (ALN_INFO_DTYPE, AlignmentFilters, EMInfo, InMemoryAlignmentStore, TranscriptInfo, bootstrap, em,
                  em_par)
-from .engine import DeviceStore, EMResult, device_count
+from .engine import DeviceStore, EMResult, MultiStore, device_count, em_batched_multi
 
 __all__ = ["ALN_INFO_DTYPE", "AlignmentFilters", "EMInfo", "InMemoryAlignmentStore", "TranscriptInfo", "bootstrap",
-           "em", "em_par", "DeviceStore", "EMResult", "device_count"]
+           "em", "em_par", "DeviceStore", "EMResult", "MultiStore", "device_count", "em_batched_multi"]

@@ -24,7 +24,6 @@ OAR_ERR_UNSUPPORTED = -4
 KERNEL_AUTO = 0
 KERNEL_ROWGROUP = 1
 KERNEL_TILED = 2
-KERNEL_LANE = 3
 
 # every symbol include/oarfish_em.h declares: name -> (restype, argtypes)
 _u64p = C.POINTER(C.c_uint64)
@@ -47,6 +46,7 @@ ABI = {
     "oar_bootstrap_sample_weights": (C.c_int, [_vp, C.c_uint64, C.c_uint32, _vp]),
     "oar_em_batched": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_double, C.c_uint32, _vp, _vp, _vp, C.c_uint64, _u64p, _vp]),
     "oar_store_coverage_model": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint32, C.c_double, _vp]),
+    "oar_store_coverage_model_binomial": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint32, _vp]),
     "oar_posteriors": (C.c_int, [_vp, _vp, C.c_double, _vp, _vp]),
     "oar_aux_counts": (C.c_int, [_vp, _vp, _vp]),
     "oar_store_layout_info": (C.c_int, [_vp, _u64p]),
@@ -55,6 +55,13 @@ ABI = {
     "oar_sweep": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int]),
     "oar_sweep_timed": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.POINTER(C.c_float)]),
     "oar_store_stream": (_vp, [_vp]),
+    "oar_multi_create": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64, C.c_uint32, _vp, C.c_int, C.POINTER(_vp)]),
+    "oar_multi_destroy": (None, [_vp]),
+    "oar_multi_store": (_vp, [_vp, C.c_int]),
+    "oar_multi_info": (C.c_int, [_vp, C.POINTER(C.c_int), _f64p, _vp]),
+    "oar_multi_bootstrap": (C.c_int, [_vp, C.c_uint32, C.c_uint64, C.c_uint32, C.c_double, _vp, _vp]),
+    "oar_em_batched_multi": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64, C.c_uint32, _vp, C.c_uint32, _vp, C.c_int,
+                                        C.c_uint32, C.c_double, C.c_uint32, _vp, _vp, _vp, C.c_uint64, _u64p, _vp, _vp]),
 }
 
 _em_lib = None

@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(256) cells_apply(double *__restrict__ prev, do
             neu.phase = kDone;
             if (ch.first && threadIdx.x == 0) {
                 cs_new[ch.cell] = neu;
-                if (atomicAdd(done_count, 1u) + 1u == n_cells) { __threadfence(); st->done = 1; }
+                atomicAdd(done_count, 1u);   // published as st->done by cells_clear_rel: CTAs of THIS launch still test st->done
             }
             continue;
         }
@@ -280,13 +280,51 @@ __global__ void __launch_bounds__(256) cells_apply(double *__restrict__ prev, do
     }
 }
 
+// The tiles the next graph launch sweeps: those with a cell that has not delivered its result yet.  One CTA walks
+// the tiles in order (the list stays ascending: neighbouring tiles keep sharing transcripts in L2).
+__global__ void __launch_bounds__(1024) cells_active_tiles(const uint2 *__restrict__ ranges, uint32_t n_tiles,
+                                                           const CellState *__restrict__ cs, uint32_t *__restrict__ list,
+                                                           uint32_t *__restrict__ n_active, const OarEmState *st)
+{
+    if (st->done) return;
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_run;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_tiles; base += blockDim.x) {
+        const uint32_t t = base + threadIdx.x;
+        bool active = false;
+        if (t < n_tiles) {
+            const uint2 r = ranges[t];
+            for (uint32_t c = r.x; c <= r.y && !active && r.x != 0xFFFFFFFFu; ++c) active = cs[c].phase != kDone;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, active);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+        for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) { const uint32_t v = s_warp[w]; if (w < warp) before += v; total += v; }
+        const uint32_t run = s_run;
+        if (active) list[run + before + __popc(m & ((1u << lane) - 1u))] = t;
+        __syncthreads();
+        if (threadIdx.x == 0) s_run = run + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_active = s_run;
+}
+
 // rel_bits must be zero before the next reduce; done in its own tiny pass so that no chunk of cells_apply can
 // still be reading it.
-__global__ void cells_clear_rel(unsigned long long *__restrict__ rel_bits, uint32_t n_cells, const OarEmState *st)
+// Also publishes the end of the batch: once every cell has delivered its result (done_count, incremented by
+// cells_apply) st->done is set HERE, in the launch after cells_apply -- set inside cells_apply, a CTA of the same
+// launch that starts later would return at its `if (st->done)` test before copying its chunk of a result.
+__global__ void cells_clear_rel(unsigned long long *__restrict__ rel_bits, uint32_t n_cells, const uint32_t *__restrict__ done_count,
+                                OarEmState *st)
 {
     if (st->done) return;
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < n_cells) rel_bits[c] = 0ull;
+    if (c == 0 && *done_count == n_cells) st->done = 1;
 }
 
 }  // namespace cells
@@ -303,9 +341,10 @@ extern "C" int oar_em_batched(oar_store *s, const uint64_t *cell_row_ptr, uint32
     OAR_CUDA(cudaSetDevice(s->device));
     cudaStream_t st = s->stream;
     s->counters[0] = s->counters[1] = 0;
-    struct Scratch { std::vector<void *> p; ~Scratch() { for (void *q : p) cudaFree(q); } } sc;
+    // stream-ordered allocations from the device's pool (kept warm by the device context): no cudaMalloc / cudaFree per call
+    struct Scratch { cudaStream_t st; std::vector<void *> p; ~Scratch() { for (void *q : p) dfree(q, st); } } sc{st, {}};
     auto dalloc = [&](void **ptr, size_t bytes) -> cudaError_t {
-        cudaError_t e = cudaMalloc(ptr, std::max<size_t>(bytes, 16)); if (e == cudaSuccess) sc.p.push_back(*ptr); return e; };
+        cudaError_t e = dmalloc(ptr, std::max<size_t>(bytes, 16), st); if (e == cudaSuccess) sc.p.push_back(*ptr); return e; };
     uint64_t *d_rows = nullptr, *d_cd = nullptr;
     OAR_CUDA(dalloc((void **)&d_rows, sizeof(uint64_t) * ((size_t)n_cells + 1)));
     OAR_CUDA(dalloc((void **)&d_cd, sizeof(uint64_t) * ((size_t)n_cells + 1)));
@@ -355,6 +394,7 @@ extern "C" int oar_em_batched(oar_store *s, const uint64_t *cell_row_ptr, uint32
     OAR_CUDA(dalloc((void **)&d_a, sizeof(double) * total));
     OAR_CUDA(dalloc((void **)&d_b, sizeof(double) * total));
     OAR_CUDA(dalloc((void **)&d_val, sizeof(double) * total));
+    OAR_CUDA(cudaMemsetAsync(d_val, 0, sizeof(double) * std::max<uint64_t>(total, 2), st));
     OAR_CUDA(dalloc((void **)&d_niter, sizeof(uint32_t) * std::max<uint32_t>(n_cells, 1)));
     if (n_cells > 0) {
         cells::cell_localize<false><<<grid, cells::kThreads, dyn, st>>>(s->d_row_ptr, s->d_txp, d_rows, n_cells, s->n_txps, words,
@@ -365,10 +405,10 @@ extern "C" int oar_em_batched(oar_store *s, const uint64_t *cell_row_ptr, uint32
         bool tiled_done = false;
         if (!(ct && ct[0] == '0') && total > 0 && total < (1ull << 28)) {
             oar_store *sub = nullptr;
+            // d_lid belongs to the sub-store from here on (substore_create frees it when it fails)
+            sc.p.erase(std::remove(sc.p.begin(), sc.p.end(), (void *)d_lid), sc.p.end());
             int rc = substore_create(s, d_lid, (uint32_t)total, &sub);
             if (rc != OAR_OK) return rc;
-            // d_lid now belongs to the sub-store
-            sc.p.erase(std::remove(sc.p.begin(), sc.p.end(), (void *)d_lid), sc.p.end());
             struct SubGuard { oar_store *p; ~SubGuard() { oar_store_destroy(p); } } sg{sub};
             // chunks of at most 4096 ids, never crossing a cell
             std::vector<cells::Chunk> h_chunks;
@@ -392,6 +432,16 @@ extern "C" int oar_em_batched(oar_store *s, const uint64_t *cell_row_ptr, uint32
             OAR_CUDA(cudaMemsetAsync(d_done, 0, sizeof(uint32_t) * 4, st));
             OAR_CUDA(cudaMemsetAsync(d_rel, 0, sizeof(unsigned long long) * n_cells, st));
             OAR_CUDA(cudaMemsetAsync(sub->d_state, 0, sizeof(OarEmState), st));
+            // tiles whose cells have all delivered are dropped from the sweep: per tile its range of cells (once), and at
+            // the head of every graph launch the list of tiles that still have a live cell
+            const uint32_t nt = sub->tl.n_tiles;
+            uint2 *d_ranges = nullptr; uint32_t *d_list = nullptr, *d_nact = nullptr;
+            OAR_CUDA(dalloc((void **)&d_ranges, sizeof(uint2) * std::max<uint32_t>(nt, 1)));
+            OAR_CUDA(dalloc((void **)&d_list, sizeof(uint32_t) * std::max<uint32_t>(nt, 1)));
+            OAR_CUDA(dalloc((void **)&d_nact, sizeof(uint32_t) * 4));
+            OAR_CUDA(cudaMemsetAsync(d_nact, 0, sizeof(uint32_t) * 4, st));
+            const bool listed = sub->kernel == OAR_KERNEL_TILED && nt > 0;
+            if (listed) OAR_CUDA(tile_group_ranges_enqueue(sub, d_rows, n_cells, d_ranges));
             const int gridc = (int)std::max<uint32_t>(1, std::min<uint32_t>(n_cells, (uint32_t)s->sm_count * 16));
             const int gridk = (int)std::max<uint32_t>(1, std::min<uint32_t>(n_chunks, (uint32_t)s->sm_count * 8));
             cells::cells_init<<<gridc, 128, 0, st>>>(d_rows, d_cd, n_cells, s->n_txps, max_iter, d_a, d_b, d_cs);
@@ -400,15 +450,19 @@ extern "C" int oar_em_batched(oar_store *s, const uint64_t *cell_row_ptr, uint32
             cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
             OAR_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
             cudaError_t e = cudaSuccess;
+            if (listed) {
+                cells::cells_active_tiles<<<1, 1024, 0, st>>>(d_ranges, nt, d_cs, d_list, d_nact, sub->d_state);
+                e = cudaGetLastError();
+            }
             for (int it = 0; it < 16 && e == cudaSuccess; ++it) {
                 double *pv = (it & 1) ? d_b : d_a, *cr = (it & 1) ? d_a : d_b;
                 cells::CellState *cs_old = d_cs + (it & 1) * n_cells, *cs_new = d_cs + ((it + 1) & 1) * n_cells;
-                e = sweep_enqueue(sub, pv, cr, sub->d_state, 1);
+                e = listed ? sweep_enqueue_list(sub, pv, cr, sub->d_state, 1, d_list, d_nact) : sweep_enqueue(sub, pv, cr, sub->d_state, 1);
                 if (e != cudaSuccess) break;
                 cells::cells_reduce<<<gridk, 256, 0, st>>>(pv, cr, d_chunks, n_chunks, cs_old, d_rel, sub->d_state);
                 cells::cells_apply<<<gridk, 256, 0, st>>>(pv, cr, d_chunks, n_chunks, n_cells, max_iter, conv_thresh, min_iter,
                                                          cs_old, cs_new, d_rel, d_val, d_done, sub->d_state);
-                cells::cells_clear_rel<<<(n_cells + 255) / 256, 256, 0, st>>>(d_rel, n_cells, sub->d_state);
+                cells::cells_clear_rel<<<(n_cells + 255) / 256, 256, 0, st>>>(d_rel, n_cells, d_done, sub->d_state);
                 e = cudaGetLastError();
             }
             cudaError_t e2 = cudaStreamEndCapture(st, &graph);
@@ -418,15 +472,24 @@ extern "C" int oar_em_batched(oar_store *s, const uint64_t *cell_row_ptr, uint32
             cudaGraphDestroy(graph);
             if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate");
             struct ExecGuard { cudaGraphExec_t x; ~ExecGuard() { cudaGraphExecDestroy(x); } } eg{exec};
+            // two graph launches in flight; the state copied after each is polled (launches after the end are no-ops)
             uint64_t launched = 0;
-            for (;;) {
-                OAR_CUDA(cudaGraphLaunch(exec, st));
-                launched += 64;
-                OAR_CUDA(cudaMemcpyAsync(&sub->h_state[0], sub->d_state, sizeof(OarEmState), cudaMemcpyDeviceToHost, st));
-                OAR_CUDA(cudaStreamSynchronize(st));
-                if (sub->h_state[0].done) break;
+            int inflight = 0, head = 0;
+            for (bool done = false; !done;) {
+                while (inflight < 2) {
+                    const int slot = (head + inflight) & 1;
+                    OAR_CUDA(cudaGraphLaunch(exec, st));
+                    launched += 64 + (listed ? 1 : 0);
+                    OAR_CUDA(cudaMemcpyAsync(&sub->h_state[slot], sub->d_state, sizeof(OarEmState), cudaMemcpyDeviceToHost, st));
+                    OAR_CUDA(cudaEventRecord(sub->slot_ev[slot], st));
+                    ++inflight;
+                }
+                OAR_CUDA(cudaEventSynchronize(sub->slot_ev[head]));
+                done = sub->h_state[head].done != 0;
+                head ^= 1; --inflight;
             }
-            s->counters[0] += launched + 3;
+            OAR_CUDA(cudaStreamSynchronize(st));
+            s->counters[0] += launched + 4;
             // per-cell iteration counts
             std::vector<cells::CellState> h_cs(n_cells);
             // 16 iterations per graph launch: the live state is back in buffer 0 (a finished batch stops updating both)

@@ -70,6 +70,66 @@ __global__ void logistic(uint32_t n_txps, const uint32_t *__restrict__ bin_off, 
     }
 }
 
+// statrs 0.18 ln_gamma (Lanczos, g = 10.900511, 11 coefficients), branch x >= 0.5: the function the reference calls
+// (binomial_probability.rs:4); restated so that the device follows the reference's arithmetic rather than CUDA's lgamma
+__device__ __forceinline__ double statrs_ln_gamma(double x)
+{
+    const double dk[11] = {
+        2.48574089138753565546e-5, 1.05142378581721974210, -3.45687097222016235469, 4.51227709466894823700,
+        -2.98285225323576655721, 1.05639711577126713077, -1.95428773191645869583e-1, 1.70970543404441224307e-2,
+        -5.71926117404305781283e-4, 4.63399473359905636708e-6, -2.71994908488607703910e-9 };
+    double sum = dk[0];
+#pragma unroll
+    for (int k = 1; k < 11; ++k) sum += dk[k] / (x + (double)k - 1.0);
+    return log(sum) + 0.6207822376352452223455184457816472122518527279025978 +
+           (x - 0.5) * log((x - 0.5 + 10.900511) / 2.718281828459045235360287471352662497757);
+}
+
+// binomial_continuous_prob + binomial_probability (binomial_probability.rs:180-224, :7-178): the coverage model of the
+// single-cell driver (single_cell.rs:132-137).  One thread per transcript, bins in order: the f32 sums of the
+// reference (count_sum, sum_vec) keep their summation order.
+__global__ void binomial(uint32_t n_txps, const uint32_t *__restrict__ txp_len, const uint32_t *__restrict__ bin_off,
+                         const double *__restrict__ bins, const double *__restrict__ tw, double *__restrict__ cov_prob)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_txps) return;
+    const uint32_t o = bin_off[t], n = bin_off[t + 1] - o;
+    if (n == 0) return;
+    const double min_cov = tw[t] / 100.0, zero_thresh = 1e-20, max_scale = 709.0;
+    const float tlen = (float)(double)txp_len[t];
+    const float bwf = (float)round((double)txp_len[t] / (double)n);
+    float count_sum = 0.0f, max_count = nanf("");
+    double rate = 0.0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const float c = (float)(bins[o + i] + min_cov);
+        const float len = fminf(((float)i + 1.0f) * bwf, tlen) - (float)i * bwf;
+        rate += (double)c / (double)len;
+        count_sum += c;
+        max_count = fmaxf(max_count, c);
+    }
+    if (count_sum == 0.0f || rate == 0.0) { for (uint32_t i = 0; i < n; ++i) cov_prob[o + i] = 0.0; return; }
+    float sum_vec = 0.0f;
+    for (uint32_t i = 0; i < n; ++i) {
+        const float c = (float)(bins[o + i] + min_cov);
+        sum_vec += c == max_count ? (float)max_scale : (float)(((double)c * max_scale) / (double)max_count);
+    }
+    const double ln1 = statrs_ln_gamma((double)sum_vec + 1.0);
+    double total = 0.0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const float c = (float)(bins[o + i] + min_cov);
+        const float len = fminf(((float)i + 1.0f) * bwf, tlen) - (float)i * bwf;
+        const double prob = (c == 0.0f || len == 0.0f) ? 0.0 : (double)c / ((double)len * rate);
+        const float m = c == max_count ? (float)max_scale : (float)(((double)c * max_scale) / (double)max_count);
+        const float rest = sum_vec - m;
+        const double den = statrs_ln_gamma((double)m + 1.0) + statrs_ln_gamma((double)rest + 1.0);
+        const double num2 = (prob > zero_thresh ? log(prob) : log(zero_thresh)) * (double)m;
+        const double num3 = ((1.0 - prob) > zero_thresh ? log(1.0 - prob) : log(zero_thresh)) * (double)rest;
+        const double res = exp(ln1 - den + num2 + num3);
+        cov_prob[o + i] = res; total += res;
+    }
+    for (uint32_t i = 0; i < n; ++i) cov_prob[o + i] /= total;
+}
+
 __device__ __forceinline__ double aln_cov(const double *__restrict__ cp, uint32_t nb, double sa, double ea, double tlen, double bl)
 {   // normalize_probability.rs:19-60
     const uint32_t sb = (uint32_t)(sa / bl);
@@ -118,9 +178,10 @@ __global__ void __launch_bounds__(256) normalize(const uint32_t *__restrict__ ro
 
 using namespace oar;
 
-extern "C" int oar_store_coverage_model(oar_store *s, const uint32_t *aln_start, const uint32_t *aln_end,
-                                        const uint32_t *txp_len, uint32_t bin_width, double growth_rate,
-                                        double *out_aux_or_null)
+enum CovModel { kCovLogistic = 0, kCovBinomial = 1 };
+
+static int coverage_model_impl(oar_store *s, const uint32_t *aln_start, const uint32_t *aln_end, const uint32_t *txp_len,
+                               uint32_t bin_width, CovModel model, double growth_rate, double *out_aux_or_null)
 {
     if (!s || !txp_len || (s->nnz && (!aln_start || !aln_end))) return fail(OAR_ERR_INVALID, "oar_store_coverage_model: null argument");
     if (bin_width == 0) return fail(OAR_ERR_UNSUPPORTED, "oar_store_coverage_model: bin width 0 is not implemented (logistic_probability.rs:55)");
@@ -166,7 +227,8 @@ extern "C" int oar_store_coverage_model(oar_store *s, const uint32_t *aln_start,
         cov::add_intervals<<<blocks, threads, 0, st>>>(s->d_txp, d_start, d_end, s->nnz, d_len, d_off, d_bins, d_tw);
         OAR_CUDA(cudaGetLastError());
     }
-    cov::logistic<<<(M + threads - 1) / threads, threads, 0, st>>>(M, d_off, d_bins, d_tw, growth_rate, d_cp);
+    if (model == kCovBinomial) cov::binomial<<<(M + threads - 1) / threads, threads, 0, st>>>(M, d_len, d_off, d_bins, d_tw, d_cp);
+    else cov::logistic<<<(M + threads - 1) / threads, threads, 0, st>>>(M, d_off, d_bins, d_tw, growth_rate, d_cp);
     OAR_CUDA(cudaGetLastError());
     if (!s->d_aux) OAR_CUDA(dmalloc(&s->d_aux, sizeof(double) * (s->nnz + 16), st));
     if (s->n_reads) {
@@ -181,9 +243,24 @@ extern "C" int oar_store_coverage_model(oar_store *s, const uint32_t *aln_start,
     // the store now carries the coverage factor: rebuild the tiled copy (it embeds aux) and drop stale graphs
     for (auto &g : s->graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
     if (s->tl.ready) {
-        const int rc = build_tiled_layout(s, s->tl.span);
-        if (rc != OAR_OK && rc != OAR_ERR_UNSUPPORTED) return rc;
-        if (rc == OAR_ERR_UNSUPPORTED) s->kernel = OAR_KERNEL_ROWGROUP;
+        const uint32_t span = s->tl.span;
+        s->kernel = OAR_KERNEL_ROWGROUP;          // whatever happens below, the store stays usable through the CSR kernel
+        const int rc = build_tiled_layout(s, span);
+        if (rc == OAR_OK) s->kernel = OAR_KERNEL_TILED;
+        else if (rc != OAR_ERR_UNSUPPORTED) return rc;
     }
     return OAR_OK;
+}
+
+extern "C" int oar_store_coverage_model(oar_store *s, const uint32_t *aln_start, const uint32_t *aln_end,
+                                        const uint32_t *txp_len, uint32_t bin_width, double growth_rate,
+                                        double *out_aux_or_null)
+{
+    return coverage_model_impl(s, aln_start, aln_end, txp_len, bin_width, kCovLogistic, growth_rate, out_aux_or_null);
+}
+
+extern "C" int oar_store_coverage_model_binomial(oar_store *s, const uint32_t *aln_start, const uint32_t *aln_end,
+                                                 const uint32_t *txp_len, uint32_t bin_width, double *out_aux_or_null)
+{
+    return coverage_model_impl(s, aln_start, aln_end, txp_len, bin_width, kCovBinomial, 0.0, out_aux_or_null);
 }

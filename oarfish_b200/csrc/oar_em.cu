@@ -96,7 +96,7 @@ int substore_create(oar_store *parent, uint32_t *d_txp, uint32_t n_txps, oar_sto
     s->d_row_ptr = parent->d_row_ptr; s->d_prob = parent->d_prob; s->d_aux = parent->d_aux; s->d_txp = d_txp;
     for (int i = 0; i < 4; ++i) s->ev[i] = parent->ev[i];
     for (int i = 0; i < 2; ++i) s->slot_ev[i] = parent->slot_ev[i];
-    s->ctas_per_sm = parent->ctas_per_sm; s->sweep_1b = parent->sweep_1b;
+    s->ctas_per_sm = parent->ctas_per_sm;
     int rc = [&]() -> int {
         OAR_CUDA(dmalloc(&s->d_state, sizeof(OarEmState) * 3, s->stream));
         OAR_CUDA(cudaMemsetAsync(s->d_state, 0, sizeof(OarEmState) * 3, s->stream));
@@ -127,8 +127,6 @@ static int finish_store(oar_store *s)
         if (rc2 == OAR_OK) s->kernel = OAR_KERNEL_TILED;
         else if (rc2 != OAR_ERR_UNSUPPORTED) return rc2;   // unsupported shape: keep the CSR kernel
     }
-    const char *sw = getenv("OAR_SWEEP");   // sweep variant of the tiled layout (development switch)
-    if (sw) s->sweep_1b = strcmp(sw, "1b") == 0 ? 1 : strcmp(sw, "1c") == 0 ? 2 : strcmp(sw, "3") == 0 ? 3 : strcmp(sw, "2e") == 0 ? 4 : 0;
     const char *cps = getenv("OAR_CTAS_PER_SM");
     if (cps && atoi(cps) > 0) s->ctas_per_sm = atoi(cps);
     return OAR_OK;
@@ -167,9 +165,10 @@ static int new_store(int device, uint64_t n_reads, uint64_t nnz, uint32_t n_txps
 }
 }  // namespace oar
 
-extern "C" int oar_store_create(const uint64_t *row_ptr, const uint32_t *txp_id, const float *prob,
-                                const double *aux_or_null, uint64_t n_reads, uint64_t nnz,
-                                uint32_t n_txps, int device, oar_store **out)
+namespace oar {
+// oar_store_create with the boundaries of a slice: row_ptr[0] == row_base, the slice's alignments start at txp_id[0].
+int store_create_slice(const uint64_t *row_ptr, uint64_t row_base, const uint32_t *txp_id, const float *prob,
+                       const double *aux_or_null, uint64_t n_reads, uint64_t nnz, uint32_t n_txps, int device, oar_store **out)
 {
     if (!out) return fail(OAR_ERR_INVALID, "oar_store_create: out is null");
     *out = nullptr;
@@ -202,7 +201,7 @@ extern "C" int oar_store_create(const uint64_t *row_ptr, const uint32_t *txp_id,
         {
             const int threads = 256;
             const int blocks = (int)std::min<uint64_t>((n_reads + threads) / threads, (uint64_t)s->sm_count * 16);
-            kern::narrow_validate_rowptr<<<blocks, threads, 0, s->stream>>>(d_rp64, s->d_row_ptr, n_reads, nnz, d_flag);
+            kern::narrow_validate_rowptr<<<blocks, threads, 0, s->stream>>>(d_rp64, s->d_row_ptr, n_reads, nnz, row_base, d_flag);
             const int blocks2 = (int)std::max<uint64_t>(1, std::min<uint64_t>((nnz + threads - 1) / threads, (uint64_t)s->sm_count * 16));
             kern::validate_txp<<<blocks2, threads, 0, s->stream>>>(s->d_txp, nnz, n_txps, d_flag + 1);
         }
@@ -230,6 +229,57 @@ extern "C" int oar_store_create(const uint64_t *row_ptr, const uint32_t *txp_id,
     }
     *out = s;
     return OAR_OK;
+}
+
+// A copy of `src` (its CSR as uploaded and validated) on another device: device-to-device over NVLink when the two
+// devices are peers (cudaMemcpyPeerAsync; staged through the host otherwise), then this device's own tiled layout.
+int store_clone(const oar_store *src, int device, oar_store **out)
+{
+    if (!src || !out) return fail(OAR_ERR_INVALID, "store_clone: null argument");
+    *out = nullptr;
+    oar_store *s = nullptr;
+    int rc = new_store(device, src->n_reads, src->nnz, src->n_txps, "store_clone", &s);
+    if (rc != OAR_OK) return rc;
+    rc = [&]() -> int {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, device, src->device) == cudaSuccess && can) {
+            cudaError_t pe = cudaDeviceEnablePeerAccess(src->device, 0);
+            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(pe, "cudaDeviceEnablePeerAccess");
+            (void)cudaGetLastError();
+        }
+        OAR_CUDA(cudaEventRecord(s->ev[0], s->stream));
+        const size_t pad = 16, N = src->n_reads, nnz = src->nnz;
+        OAR_CUDA(dmalloc(&s->d_row_ptr, sizeof(uint32_t) * (N + 1 + pad), s->stream));
+        OAR_CUDA(dmalloc(&s->d_txp, sizeof(uint32_t) * (nnz + pad), s->stream));
+        OAR_CUDA(dmalloc(&s->d_prob, sizeof(float) * (nnz + pad), s->stream));
+        if (src->d_aux) OAR_CUDA(dmalloc(&s->d_aux, sizeof(double) * (nnz + pad), s->stream));
+        OAR_CUDA(cudaMemsetAsync(s->d_state, 0, sizeof(OarEmState) * 2, s->stream));
+        OAR_CUDA(cudaMemcpyPeerAsync(s->d_row_ptr, device, src->d_row_ptr, src->device, sizeof(uint32_t) * (N + 1), s->stream));
+        OAR_CUDA(cudaMemcpyPeerAsync(s->d_txp, device, src->d_txp, src->device, sizeof(uint32_t) * (nnz + pad), s->stream));
+        OAR_CUDA(cudaMemcpyPeerAsync(s->d_prob, device, src->d_prob, src->device, sizeof(float) * (nnz + pad), s->stream));
+        if (src->d_aux) OAR_CUDA(cudaMemcpyPeerAsync(s->d_aux, device, src->d_aux, src->device, sizeof(double) * nnz, s->stream));
+        OAR_CUDA(cudaEventRecord(s->ev[2], s->stream));
+        int rc2 = finish_store(s);
+        if (rc2 != OAR_OK) return rc2;
+        OAR_CUDA(cudaEventRecord(s->ev[1], s->stream));
+        OAR_CUDA(cudaStreamSynchronize(s->stream));
+        float ms = 0.f, ms_copy = 0.f;
+        OAR_CUDA(cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]));
+        OAR_CUDA(cudaEventElapsedTime(&ms_copy, s->ev[0], s->ev[2]));
+        s->timings[0] = ms; s->timings[3] = ms_copy;
+        return OAR_OK;
+    }();
+    if (rc != OAR_OK) { std::string keep = g_last_error; oar_store_destroy(s); g_last_error = keep; return rc; }
+    *out = s;
+    return OAR_OK;
+}
+}  // namespace oar
+
+extern "C" int oar_store_create(const uint64_t *row_ptr, const uint32_t *txp_id, const float *prob,
+                                const double *aux_or_null, uint64_t n_reads, uint64_t nnz,
+                                uint32_t n_txps, int device, oar_store **out)
+{
+    return store_create_slice(row_ptr, 0, txp_id, prob, aux_or_null, n_reads, nnz, n_txps, device, out);
 }
 
 extern "C" int oar_store_info(const oar_store *s, uint64_t *n_reads, uint64_t *nnz, uint32_t *n_txps, int *device)
@@ -286,13 +336,14 @@ extern "C" void *oar_store_stream(oar_store *s) { return s ? (void *)s->stream :
 // sweep dispatch
 // ---------------------------------------------------------------------------
 
-static const uint32_t kFoldFallbackMax = 4096;
+static const uint32_t kFoldFallbackMax = 65536;   // fallback rows swept inside the tiled kernel (spread over all its CTAs); longer lists get their own launch
 
 static tiled::View tiled_view(const oar_store *s)
 {
     const TiledLayout &t = s->tl;
     tiled::View v;
-    v.n_tiles = t.n_tiles; v.prob = t.prob; v.lpos = t.lpos; v.aux = t.aux; v.rec = t.rec; v.records = t.records;
+    v.n_tiles = t.n_tiles; v.prob = t.prob; v.lpos = t.lpos; v.aux = t.aux; v.rec = t.rec; v.records = t.records; v.wlane = t.wlane;
+    v.tile_list = nullptr; v.n_active = nullptr;
     // a handful of fallback rows rides along in the tiled kernel; a long list gets its own launch
     const bool fold = t.n_fallback <= kFoldFallbackMax;
     v.fb_rows = t.fallback; v.n_fb = fold ? t.n_fallback : 0u;
@@ -300,99 +351,15 @@ static tiled::View tiled_view(const oar_store *s)
     return v;
 }
 
-template <bool AUX, bool WTS>
+template <bool AUX, bool WTS, bool LIST = false>
 static cudaError_t launch_tiled(oar_store *s, const tiled::View &v, const double *prev, double *curr,
                                 const uint32_t *wperm, const OarEmState *state, int check_done)
 {
-    static int attr_bytes[16] = {0};
-    auto kfn = tiled::em_sweep_tiled<AUX, WTS>;
-    const tiled::Geometry g = tiled::make_geometry(s->tl.max_rec, s->tl.max_d, s->tl.max_u);
-    if (attr_bytes[s->device & 15] < (int)g.total) {
-        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.total);
-        if (e != cudaSuccess) return e;
-        attr_bytes[s->device & 15] = (int)g.total;
-    }
+    auto kfn = tiled::em_sweep_tiled<AUX, WTS, LIST>;
+    const tiled::Geometry g = tiled::make_geometry(s->tl.max_rec, s->tl.max_d, s->tl.max_u, WTS);
+    cudaError_t ae = ctx_ensure_smem(s->ctx, reinterpret_cast<const void *>(kfn), (int)g.total);
+    if (ae != cudaSuccess) return ae;
     // persistent CTAs: as many per SM as shared memory allows, capped by the register budget (5)
-    int per_sm = (int)((227u * 1024u) / (g.total + 1024u));
-    per_sm = std::max(1, std::min(per_sm, s->ctas_per_sm));
-    const uint32_t grid = std::min<uint32_t>(v.n_tiles, (uint32_t)s->sm_count * (uint32_t)per_sm);
-    kfn<<<grid, tiled::kThreads, g.total, s->stream>>>(v, g, prev, curr, wperm, state, check_done);
-    return cudaGetLastError();
-}
-
-// single-barrier variant of the tiled sweep (OAR_SWEEP=1b)
-template <bool AUX, bool WTS>
-static cudaError_t launch_tiled1(oar_store *s, const tiled::View &v, const double *prev, double *curr,
-                                 const uint32_t *wperm, const OarEmState *state, int check_done)
-{
-    static int attr_bytes[16] = {0};
-    auto kfn = tiled::em_sweep_tiled1<AUX, WTS>;
-    const tiled::Geometry1 g = tiled::make_geometry1(s->tl.max_rec, s->tl.max_d, s->tl.max_u);
-    if (attr_bytes[s->device & 15] < (int)g.total) {
-        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.total);
-        if (e != cudaSuccess) return e;
-        attr_bytes[s->device & 15] = (int)g.total;
-    }
-    int per_sm = (int)((227u * 1024u) / (g.total + 1024u));
-    per_sm = std::max(1, std::min(per_sm, std::min(s->ctas_per_sm, 32 / tiled::kWarps)));   // register budget: 4 CTAs
-    const uint32_t grid = std::min<uint32_t>(v.n_tiles, (uint32_t)s->sm_count * (uint32_t)per_sm);
-    kfn<<<grid, tiled::kThreads, g.total, s->stream>>>(v, g, prev, curr, wperm, state, check_done);
-    return cudaGetLastError();
-}
-
-// single-barrier sweep with deeper rings (OAR_SWEEP=1c; prepared for round 2, not yet run on a GPU)
-template <bool AUX, bool WTS>
-static cudaError_t launch_tiled2(oar_store *s, const tiled::View &v, const double *prev, double *curr,
-                                 const uint32_t *wperm, const OarEmState *state, int check_done)
-{
-    static int attr_bytes[16] = {0};
-    auto kfn = tiled::em_sweep_tiled2<AUX, WTS>;
-    const tiled::Geometry2 g = tiled::make_geometry2(s->tl.max_rec, s->tl.max_d, s->tl.max_u);
-    if (attr_bytes[s->device & 15] < (int)g.total) {
-        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.total);
-        if (e != cudaSuccess) return e;
-        attr_bytes[s->device & 15] = (int)g.total;
-    }
-    int per_sm = (int)((227u * 1024u) / (g.total + 1024u));
-    per_sm = std::max(1, std::min(per_sm, std::min(s->ctas_per_sm, 32 / tiled::kWarps)));   // register budget: 4 CTAs
-    const uint32_t grid = std::min<uint32_t>(v.n_tiles, (uint32_t)s->sm_count * (uint32_t)per_sm);
-    kfn<<<grid, tiled::kThreads, g.total, s->stream>>>(v, g, prev, curr, wperm, state, check_done);
-    return cudaGetLastError();
-}
-
-// streaming single-barrier sweep (OAR_SWEEP=3): prob | lpos by LDG.128, records by TMA, prev[] by cp.async
-template <bool AUX, bool WTS>
-static cudaError_t launch_tiled3(oar_store *s, const tiled::View &v, const double *prev, double *curr,
-                                 const uint32_t *wperm, const OarEmState *state, int check_done)
-{
-    static int attr_bytes[16] = {0};
-    auto kfn = tiled::em_sweep_tiled3<AUX, WTS>;
-    const tiled::Geometry3 g = tiled::make_geometry3(s->tl.max_rec, s->tl.max_d, s->tl.max_u);
-    if (attr_bytes[s->device & 15] < (int)g.total) {
-        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.total);
-        if (e != cudaSuccess) return e;
-        attr_bytes[s->device & 15] = (int)g.total;
-    }
-    int per_sm = (int)((227u * 1024u) / (g.total + 1024u));
-    per_sm = std::max(1, std::min(per_sm, s->ctas_per_sm));
-    const uint32_t grid = std::min<uint32_t>(v.n_tiles, (uint32_t)s->sm_count * (uint32_t)per_sm);
-    kfn<<<grid, tiled::kThreads, g.total, s->stream>>>(v, g, prev, curr, wperm, state, check_done);
-    return cudaGetLastError();
-}
-
-// two-barrier sweep with the early cp.async gather (OAR_SWEEP=2e)
-template <bool AUX, bool WTS>
-static cudaError_t launch_tiled_eg(oar_store *s, const tiled::View &v, const double *prev, double *curr,
-                                   const uint32_t *wperm, const OarEmState *state, int check_done)
-{
-    static int attr_bytes[16] = {0};
-    auto kfn = tiled::em_sweep_tiled_eg<AUX, WTS>;
-    const tiled::GeometryE g = tiled::make_geometry_e(s->tl.max_rec, s->tl.max_d, s->tl.max_u);
-    if (attr_bytes[s->device & 15] < (int)g.total) {
-        cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.total);
-        if (e != cudaSuccess) return e;
-        attr_bytes[s->device & 15] = (int)g.total;
-    }
     int per_sm = (int)((227u * 1024u) / (g.total + 1024u));
     per_sm = std::max(1, std::min(per_sm, s->ctas_per_sm));
     const uint32_t grid = std::min<uint32_t>(v.n_tiles, (uint32_t)s->sm_count * (uint32_t)per_sm);
@@ -426,7 +393,7 @@ static cudaError_t enqueue_sweep(oar_store *s, const double *prev, double *curr,
                                  const OarEmState *state, int check_done)
 {
     if (s->n_reads == 0) return cudaSuccess;
-    if (s->kernel != OAR_KERNEL_TILED)
+    if (s->kernel != OAR_KERNEL_TILED || !s->tl.ready)   // no layout (OAR_TILED=0, unsupported shape, failed rebuild): the CSR kernel
         return enqueue_rowgroup(s, nullptr, s->n_reads, prev, curr, wts, state, check_done);
     const TiledLayout &t = s->tl;
     if (t.n_tiles > 0) {
@@ -434,32 +401,10 @@ static cudaError_t enqueue_sweep(oar_store *s, const double *prev, double *curr,
         v.csr_wts = wts;
         const uint32_t *wp = wts ? t.wperm : nullptr;
         cudaError_t le;
-        if (s->sweep_1b == 4) {
-            if (s->d_aux) le = wts ? launch_tiled_eg<true, true>(s, v, prev, curr, wp, state, check_done)
-                                   : launch_tiled_eg<true, false>(s, v, prev, curr, wp, state, check_done);
-            else          le = wts ? launch_tiled_eg<false, true>(s, v, prev, curr, wp, state, check_done)
-                                   : launch_tiled_eg<false, false>(s, v, prev, curr, wp, state, check_done);
-        } else if (s->sweep_1b == 3) {
-            if (s->d_aux) le = wts ? launch_tiled3<true, true>(s, v, prev, curr, wp, state, check_done)
-                                   : launch_tiled3<true, false>(s, v, prev, curr, wp, state, check_done);
-            else          le = wts ? launch_tiled3<false, true>(s, v, prev, curr, wp, state, check_done)
-                                   : launch_tiled3<false, false>(s, v, prev, curr, wp, state, check_done);
-        } else if (s->sweep_1b == 2) {
-            if (s->d_aux) le = wts ? launch_tiled2<true, true>(s, v, prev, curr, wp, state, check_done)
-                                   : launch_tiled2<true, false>(s, v, prev, curr, wp, state, check_done);
-            else          le = wts ? launch_tiled2<false, true>(s, v, prev, curr, wp, state, check_done)
-                                   : launch_tiled2<false, false>(s, v, prev, curr, wp, state, check_done);
-        } else if (s->sweep_1b) {
-            if (s->d_aux) le = wts ? launch_tiled1<true, true>(s, v, prev, curr, wp, state, check_done)
-                                   : launch_tiled1<true, false>(s, v, prev, curr, wp, state, check_done);
-            else          le = wts ? launch_tiled1<false, true>(s, v, prev, curr, wp, state, check_done)
-                                   : launch_tiled1<false, false>(s, v, prev, curr, wp, state, check_done);
-        } else {
-            if (s->d_aux) le = wts ? launch_tiled<true, true>(s, v, prev, curr, wp, state, check_done)
-                                   : launch_tiled<true, false>(s, v, prev, curr, wp, state, check_done);
-            else          le = wts ? launch_tiled<false, true>(s, v, prev, curr, wp, state, check_done)
-                                   : launch_tiled<false, false>(s, v, prev, curr, wp, state, check_done);
-        }
+        if (s->d_aux) le = wts ? launch_tiled<true, true>(s, v, prev, curr, wp, state, check_done)
+                               : launch_tiled<true, false>(s, v, prev, curr, wp, state, check_done);
+        else          le = wts ? launch_tiled<false, true>(s, v, prev, curr, wp, state, check_done)
+                               : launch_tiled<false, false>(s, v, prev, curr, wp, state, check_done);
         if (le != cudaSuccess) return le;
         s->counters[0] += 1;
         cudaError_t e = cudaGetLastError();
@@ -472,9 +417,40 @@ static cudaError_t enqueue_sweep(oar_store *s, const double *prev, double *curr,
 namespace oar {
 cudaError_t sweep_enqueue(oar_store *s, const double *prev, double *curr, const OarEmState *state, int check_done)
 { return enqueue_sweep(s, prev, curr, nullptr, state, check_done); }
+
+// The same sweep over the tiles listed in tile_list[0 .. *n_active) (device memory) only; rows outside the tiled
+// layout are swept every time.  Needs the tiled layout.
+cudaError_t sweep_enqueue_list(oar_store *s, const double *prev, double *curr, const OarEmState *state, int check_done,
+                               const uint32_t *tile_list, const uint32_t *n_active)
+{
+    const TiledLayout &t = s->tl;
+    if (s->kernel != OAR_KERNEL_TILED || !t.ready || t.n_tiles == 0) return enqueue_sweep(s, prev, curr, nullptr, state, check_done);
+    tiled::View v = tiled_view(s);
+    v.tile_list = tile_list; v.n_active = n_active;
+    cudaError_t le = s->d_aux ? launch_tiled<true, false, true>(s, v, prev, curr, nullptr, state, check_done)
+                              : launch_tiled<false, false, true>(s, v, prev, curr, nullptr, state, check_done);
+    if (le != cudaSuccess) return le;
+    s->counters[0] += 1;
+    if (t.n_fallback <= kFoldFallbackMax) return cudaSuccess;
+    return enqueue_rowgroup(s, t.fallback, t.n_fallback, prev, curr, nullptr, state, check_done);
+}
 }  // namespace oar
 
-// Bring the tile-order copy of the bootstrap weights up to date.
+// device word set by tiled::lane_weights when a weight does not fit 16 bits (next to the validation flags of store creation)
+static uint32_t *weight_flag(oar_store *s) { return reinterpret_cast<uint32_t *>(s->d_state + 1) + 2; }
+
+// 0 if the weights staged since the last reset fit the tiled sweep; enqueues nothing when the CSR kernel is active
+static int check_weight_flag(oar_store *s, const char *who)
+{
+    if (s->kernel != OAR_KERNEL_TILED || s->tl.n_tiles == 0) return OAR_OK;
+    uint32_t *h = reinterpret_cast<uint32_t *>(&s->h_state[oar::kHostStateSlots - 1]);
+    OAR_CUDA(cudaMemcpyAsync(h, weight_flag(s), sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    OAR_CUDA(cudaStreamSynchronize(s->stream));
+    if (*h) return fail(OAR_ERR_UNSUPPORTED, std::string(who) + ": a read weight above 65535 does not fit the tiled sweep (OAR_TILED=0 selects the CSR kernel)");
+    return OAR_OK;
+}
+
+// Bring the tile-order copies of the bootstrap weights up to date.
 static cudaError_t refresh_wperm(oar_store *s, const uint32_t *wts)
 {
     const TiledLayout &t = s->tl;
@@ -482,6 +458,15 @@ static cudaError_t refresh_wperm(oar_store *s, const uint32_t *wts)
     const int threads = 256;
     const int blocks = (int)std::min<uint64_t>((t.n_tiled_rows + threads - 1) / threads, (uint64_t)s->sm_count * 16);
     tiled::permute_weights<<<blocks, threads, 0, s->stream>>>(wts, t.trow, t.n_tiled_rows, t.wperm);
+    s->counters[0] += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || t.n_tiles == 0) return e;
+    if (!s->tl.wlane) {
+        e = dmalloc(&s->tl.wlane, sizeof(uint16_t) * (size_t)t.n_tiles * tiled::kThreads, s->stream);
+        if (e != cudaSuccess) return e;
+    }
+    const int blocks2 = (int)std::min<uint32_t>(t.n_tiles, (uint32_t)s->sm_count * 8);
+    tiled::lane_weights<<<blocks2, tiled::kThreads, 0, s->stream>>>(t.rec, t.records, t.wperm, t.n_tiles, s->tl.wlane, weight_flag(s));
     s->counters[0] += 1;
     return cudaGetLastError();
 }
@@ -673,6 +658,7 @@ static int bootstrap_impl(oar_store *s, const uint32_t *weights_or_null, uint32_
     s->counters[0] = s->counters[1] = 0;
     int rc = ensure_weights(s);
     if (rc != OAR_OK) return rc;
+    OAR_CUDA(cudaMemsetAsync(weight_flag(s), 0, sizeof(uint32_t), s->stream));
     OAR_CUDA(cudaEventRecord(s->ev[0], s->stream));
     for (uint32_t b = 0; b < n_rep; ++b) {
         if (weights_or_null) {
@@ -695,7 +681,7 @@ static int bootstrap_impl(oar_store *s, const uint32_t *weights_or_null, uint32_
     float a = 0.f;
     OAR_CUDA(cudaEventElapsedTime(&a, s->ev[0], s->ev[1]));
     s->timings[1] = a; s->timings[2] = 0; s->timings[3] = 0;
-    return OAR_OK;
+    return check_weight_flag(s, "oar_bootstrap");
 }
 
 extern "C" int oar_bootstrap(oar_store *s, uint32_t num_boot, uint64_t seed, uint32_t first_replicate,
@@ -725,8 +711,12 @@ extern "C" int oar_sweep(oar_store *s, const double *prev_dev, double *curr_dev,
     if (!s || !prev_dev || !curr_dev) return fail(OAR_ERR_INVALID, "oar_sweep: null argument");
     OAR_CUDA(cudaSetDevice(s->device));
     OAR_CUDA(cudaMemsetAsync(curr_dev, 0, sizeof(double) * s->n_txps, s->stream));
-    if (weights_or_null) OAR_CUDA(refresh_wperm(s, weights_or_null));
+    if (weights_or_null) {
+        OAR_CUDA(cudaMemsetAsync(weight_flag(s), 0, sizeof(uint32_t), s->stream));
+        OAR_CUDA(refresh_wperm(s, weights_or_null));
+    }
     OAR_CUDA(enqueue_sweep(s, prev_dev, curr_dev, weights_or_null, s->d_state, 0));
+    if (weights_or_null && sync) return check_weight_flag(s, "oar_sweep");
     if (sync) OAR_CUDA(cudaStreamSynchronize(s->stream));
     return OAR_OK;
 }
@@ -737,12 +727,15 @@ extern "C" int oar_sweep_timed(oar_store *s, const double *prev_dev, double *cur
     if (!s || !prev_dev || !curr_dev || !out_ms_total || reps <= 0)
         return fail(OAR_ERR_INVALID, "oar_sweep_timed: bad argument");
     OAR_CUDA(cudaSetDevice(s->device));
-    if (weights_or_null) OAR_CUDA(refresh_wperm(s, weights_or_null));
+    if (weights_or_null) {
+        OAR_CUDA(cudaMemsetAsync(weight_flag(s), 0, sizeof(uint32_t), s->stream));
+        OAR_CUDA(refresh_wperm(s, weights_or_null));
+    }
     OAR_CUDA(cudaMemsetAsync(curr_dev, 0, sizeof(double) * s->n_txps, s->stream));
     OAR_CUDA(cudaEventRecord(s->ev[0], s->stream));
     for (int i = 0; i < reps; ++i) OAR_CUDA(enqueue_sweep(s, prev_dev, curr_dev, weights_or_null, s->d_state, 0));
     OAR_CUDA(cudaEventRecord(s->ev[1], s->stream));
     OAR_CUDA(cudaStreamSynchronize(s->stream));
     OAR_CUDA(cudaEventElapsedTime(out_ms_total, s->ev[0], s->ev[1]));
-    return OAR_OK;
+    return weights_or_null ? check_weight_flag(s, "oar_sweep_timed") : OAR_OK;
 }

@@ -11,16 +11,18 @@ namespace kern {
 
 // boundaries (Vec<usize>, oarfish_types.rs:555) -> u32 row_ptr; flag[0] != 0 if
 // not a monotone prefix array that starts at 0 and ends at nnz.
+// `base` = value of the first boundary (0 for a whole store; a slice of a larger store -- one device's cells in
+// oar_em_batched_multi -- starts at its first alignment's offset): it is subtracted while narrowing.
 static __global__ void narrow_validate_rowptr(const uint64_t *__restrict__ rp64, uint32_t *__restrict__ rp32,
-                                       uint64_t n_reads, uint64_t nnz, uint32_t *flag)
+                                       uint64_t n_reads, uint64_t nnz, uint64_t base, uint32_t *flag)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     bool bad = false;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n_reads; i += stride) {
-        const uint64_t v = rp64[i];
+        const uint64_t v = rp64[i] - base;
         if (i == 0 && v != 0) bad = true;
         if (i == n_reads && v != nnz) bad = true;
-        if (i < n_reads && rp64[i + 1] < v) bad = true;
+        if (i < n_reads && rp64[i + 1] - base < v) bad = true;
         if (v > nnz) bad = true;
         rp32[i] = (uint32_t)v;
     }

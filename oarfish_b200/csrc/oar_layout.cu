@@ -18,7 +18,7 @@ void free_tiled_layout(oar_store *s)
     TiledLayout &t = s->tl;
     cudaStream_t st = s->stream;
     dfree(t.prob, st); dfree(t.lpos, st); dfree(t.aux, st); dfree(t.rec, st); dfree(t.records, st); dfree(t.trow, st);
-    dfree(t.fallback, st); dfree(t.wperm, st);
+    dfree(t.fallback, st); dfree(t.wperm, st); dfree(t.wlane, st);
     t = TiledLayout();
 }
 
@@ -139,6 +139,42 @@ static int build_chunk_layout(oar_store *s, uint32_t span)
     }
     t.ready = true;
     return OAR_OK;
+}
+
+namespace {
+// per tile: the smallest and the largest group (cell) among its rows; groups are contiguous row ranges given by
+// group_rows[0 .. n_groups] (original row numbers).  One warp per tile.
+__global__ void tile_group_ranges(const uint2 *__restrict__ rec, const uint4 *__restrict__ records, const uint32_t *__restrict__ trow,
+                                  uint32_t n_tiles, uint32_t n_tiled_rows, const uint64_t *__restrict__ group_rows, uint32_t n_groups,
+                                  uint2 *__restrict__ out)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < n_tiles; tile += warps) {
+        auto first_row = [&](uint32_t t) {   // tile-order index of the tile's first row: chunk_row[0] of its record
+            return reinterpret_cast<const uint32_t *>(reinterpret_cast<const unsigned char *>(records + rec[t].x) + tiled::kRecRow)[0];
+        };
+        const uint32_t b = first_row(tile), e = tile + 1 < n_tiles ? first_row(tile + 1) : n_tiled_rows;
+        uint32_t lo = 0xFFFFFFFFu, hi = 0;
+        for (uint32_t k = b + lane; k < e; k += 32u) {
+            const uint64_t row = trow[k];
+            uint32_t l = 0, h = n_groups;   // last group whose first row is <= row
+            while (h - l > 1) { const uint32_t m = l + (h - l) / 2; if (group_rows[m] <= row) l = m; else h = m; }
+            lo = min(lo, l); hi = max(hi, l);
+        }
+        lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
+        if (lane == 0) out[tile] = make_uint2(lo, hi);
+    }
+}
+}  // namespace
+
+cudaError_t tile_group_ranges_enqueue(oar_store *s, const uint64_t *d_group_rows, uint32_t n_groups, uint2 *d_out)
+{
+    const TiledLayout &t = s->tl;
+    if (!t.ready || t.n_tiles == 0 || n_groups == 0) return cudaSuccess;
+    const int blocks = (int)std::min<uint32_t>((t.n_tiles + 7) / 8, (uint32_t)s->sm_count * 8);
+    tile_group_ranges<<<blocks, 256, 0, s->stream>>>(t.rec, t.records, t.trow, t.n_tiles, t.n_tiled_rows, d_group_rows, n_groups, d_out);
+    return cudaGetLastError();
 }
 
 // Rebuilds (coverage model) and sub-stores go through the same entry point.

@@ -24,6 +24,7 @@ struct TiledLayout {
     uint32_t *trow = nullptr;      // tile-order row -> original row (n_tiled_rows)
     uint32_t *fallback = nullptr;  // original row ids swept from the CSR
     uint32_t *wperm = nullptr;     // bootstrap weights in tile order
+    uint16_t *wlane = nullptr;     // bootstrap weight per lane of every tile (tiled::lane_weights); allocated with the first replicate
 };
 
 struct GraphSlot {
@@ -42,7 +43,6 @@ struct oar_store {
     uint32_t n_txps = 0;
     int kernel = OAR_KERNEL_ROWGROUP;
     bool borrowed = false;  // sub-store of another store: row_ptr / prob / aux / stream / events are not owned
-    int sweep_1b = 0;   // tiled sweep variant: 0 = two CTA barriers per tile (em_sweep_tiled), 1 = one (em_sweep_tiled1, OAR_SWEEP=1b), 2 = one, deeper rings (em_sweep_tiled2, OAR_SWEEP=1c)
     int ctas_per_sm = 40 / OAR_TILE_WARPS_DEFAULT;  // persistent CTAs of the tiled sweep per SM (upper bound; shared memory may allow fewer)
 
     // CSR in HBM (original read order)
@@ -76,5 +76,17 @@ int build_tiled_layout(oar_store *s, uint32_t span);
 int substore_create(oar_store *parent, uint32_t *d_txp, uint32_t n_txps, oar_store **out);
 // One fused E+M sweep prev -> curr on the store's stream (curr must be zero); see oar_em.cu.
 cudaError_t sweep_enqueue(oar_store *s, const double *prev, double *curr, const OarEmState *state, int check_done);
+// The same over the tiles in tile_list[0 .. *n_active) only (both in device memory; the batched per-cell EM drops the
+// tiles of converged cells).
+cudaError_t sweep_enqueue_list(oar_store *s, const double *prev, double *curr, const OarEmState *state, int check_done,
+                               const uint32_t *tile_list, const uint32_t *n_active);
+// d_out[tile] = {smallest, largest} group among the tile's rows, groups being the contiguous row ranges
+// d_group_rows[0 .. n_groups] (cells of the batched per-cell EM)
+cudaError_t tile_group_ranges_enqueue(oar_store *s, const uint64_t *d_group_rows, uint32_t n_groups, uint2 *d_out);
 void free_tiled_layout(oar_store *s);
+// oar_store_create for a slice of a larger store (row_ptr[0] == row_base; txp_id / prob / aux start at the slice's first alignment)
+int store_create_slice(const uint64_t *row_ptr, uint64_t row_base, const uint32_t *txp_id, const float *prob,
+                       const double *aux_or_null, uint64_t n_reads, uint64_t nnz, uint32_t n_txps, int device, oar_store **out);
+// a copy of `src` on another device (peer copy of the validated CSR + that device's own layout)
+int store_clone(const oar_store *src, int device, oar_store **out);
 }  // namespace oar

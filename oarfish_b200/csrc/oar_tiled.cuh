@@ -27,16 +27,17 @@
 // (cp.async.bulk, completion on an mbarrier), issued two tiles ahead by one
 // thread, so HBM latency never sits on the compute path and no registers are
 // spent on prefetching.  One warp alone waits on the mbarriers and gathers
-// prev[]; the CTA barrier hands the stage on to the others.  em_sweep_tiled has
-// two CTA barriers per tile, em_sweep_tiled1 (OAR_SWEEP=1b) one.
+// prev[]; the CTA barrier hands the stage on to the others (two CTA barriers per
+// tile; the single-barrier and streaming variants tried in rounds 1 and 2 were
+// slower, profiles/experiments/).
 //
 // Per alignment the HBM stream is 4 B (prob f32) + 4 B (table offset u16 | pos
 // u16), the same 8 B as CSR's txp_id + prob; row structure costs 2 B per lane
 // (4 slots) instead of a 4-byte row_ptr entry per row.
 //
 // Rows longer than a warp-chunk, or that do not fit their tile, are listed in
-// `fallback_rows` and swept from the original CSR by the last CTA of the sweep
-// (a long list gets its own em_sweep_rowgroup launch).
+// `fallback_rows` and swept from the original CSR, every CTA of the sweep taking
+// its share (a very long list gets its own em_sweep_rowgroup launch).
 #pragma once
 #include <cub/cub.cuh>
 
@@ -63,6 +64,12 @@ constexpr int kAggMin = 4;                // transcripts with >= kAggMin alignme
 #endif
 #ifndef OAR_SCATTER_GREEDY
 #define OAR_SCATTER_GREEDY 1    // layout: x positions chosen so that the M-step scatter spreads over the banks
+#endif
+#ifndef OAR_GREEDY_SCARCE
+#define OAR_GREEDY_SCARCE 1     // layout: in the x position greedy the lane whose transcript offers the fewest residues wins a contested bank
+#endif
+#ifndef OAR_SCAN_COND
+#define OAR_SCAN_COND 1         // sweep: the 4-lane step of the segmented scan only in chunks that hold a row spanning more than 4 lanes
 #endif
 #ifndef OAR_SHORT_ROW_DEFER
 #define OAR_SHORT_ROW_DEFER 1   // layout: keep rows shorter than a lane from starting and ending inside one lane
@@ -101,7 +108,8 @@ constexpr int kStages = 2;
 // Shared-memory geometry of the sweep, sized for the store at hand (largest record, table and
 // unit count over all tiles) so that as many CTAs as possible fit on an SM.
 struct Geometry {
-    uint32_t stage_bytes;   // prob (4 KB) | lpos (4 KB) | record (max over tiles, 16 B multiple)
+    uint32_t stage_bytes;   // prob (4 KB) | lpos (4 KB) | record (max over tiles, 16 B multiple) [| lane weights u16[256]]
+    uint32_t w_off;         // offset of the lane weights inside a stage (bootstrap only)
     uint32_t xs_off;        // 0: transcript-sorted x values in items (+ trash) sit at the start of the window, so the
                             // scatter addresses are the stored offsets themselves
     uint32_t stage_off;     // the two stages
@@ -110,11 +118,12 @@ struct Geometry {
     uint32_t total;         // dynamic shared memory per CTA
     uint32_t xs_doubles;    // doubles to clear at start
 };
-inline Geometry make_geometry(uint32_t max_rec_bytes, uint32_t max_d, uint32_t max_x_doubles)
+inline Geometry make_geometry(uint32_t max_rec_bytes, uint32_t max_d, uint32_t max_x_doubles, bool weighted)
 {
     Geometry g;
     const uint32_t rec = (max_rec_bytes + 15u) & ~15u;
-    g.stage_bytes = 8u * kTile + rec;
+    g.w_off = 8u * kTile + rec;
+    g.stage_bytes = g.w_off + (weighted ? 2u * kThreads : 0u);
     g.xs_off = 0;
     // the items of the fullest tile, then the trash slot; even count
     g.xs_doubles = (max_x_doubles + 2u + 1u) & ~1u;
@@ -132,7 +141,9 @@ struct View {
     const double *aux;         // n_tiles * kTile or null
     const uint2 *rec;          // n_tiles : {record offset in 16-byte granules, record bytes}
     const uint4 *records;      // all records
-    // rows that are not tiled (longer than a chunk, or did not fit): swept from the CSR by the last CTA
+    const uint16_t *wlane;     // n_tiles * kThreads: bootstrap weight of the row that ends in each lane (lane_weights) or null
+    const uint32_t *tile_list; const uint32_t *n_active;   // LIST sweeps: the tiles to walk and how many (device memory)
+    // rows that are not tiled (longer than a chunk, or did not fit): swept from the CSR, spread over all CTAs
     const uint32_t *fb_rows; uint32_t n_fb;
     const uint32_t *csr_row_ptr; const uint32_t *csr_txp; const float *csr_prob; const double *csr_aux;
     const uint32_t *csr_wts;   // bootstrap weights in read order (fallback rows are not in tile order)
@@ -526,11 +537,12 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
             }
             uint32_t G = 0;   // residues taken in this lane's half-warp
             while (__any_sync(full, todo)) {
-                uint32_t rho = 0, st = 0;
+                uint32_t rho = 0, st = 0, key = 0xFFFF0000u | lane;
                 bool prop = todo;                          // does this lane propose in this round?
                 if (prop) {
                     st = s_state[d];
                     const uint32_t av = st & 0xFFFFu;      // never 0 here: the transcript still owes this lane a position
+                    key = ((OAR_GREEDY_SCARCE ? (uint32_t)__popc(av) : 0u) << 5) | lane;   // scarce first: the fewer residues on offer, the higher the priority
                     uint32_t cand = av & ~G;
                     if (cand == 0u) cand = av;             // no unused residue on offer: accept a bank conflict
                     const uint32_t rot = ((cand >> l16) | (cand << (16u - l16))) & 0xFFFFu;
@@ -539,7 +551,10 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
                 const uint32_t idle = 0x80000000u | lane;
                 const unsigned m1 = __match_any_sync(full, prop ? ((d << 4) | rho) : idle);
                 const unsigned m2 = __match_any_sync(full, prop ? ((half << 4) | rho) : idle);
-                const bool go = prop && (uint32_t)(__ffs((int)m1) - 1) == lane && (uint32_t)(__ffs((int)m2) - 1) == lane;
+                // one winner per (transcript, residue) and per (half-warp, residue): the lane whose transcript has the
+                // fewest residues left on offer (model, tools/layout_model.py: 89 -> 80 scatter wavefronts per tile);
+                // the lane with the smallest key of the warp wins both of its groups, so every round places someone
+                const bool go = prop && __reduce_min_sync(m1, key) == key && __reduce_min_sync(m2, key) == key;
                 uint32_t took = 0;
                 if (go) {
                     uint32_t m = q ? s_fulluse[ci][rho] : 0u;
@@ -621,6 +636,30 @@ static __global__ void permute_weights(const uint32_t *__restrict__ w, const uin
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) wperm[k] = w[trow[k]];
 }
 
+// Bootstrap weights per LANE of every tile: the weight of the row that ends in the lane (fast path of the sweep: at
+// most one row head per lane, so that row is number (lanes with a head before this one) - 1 of its chunk).  The sweep
+// gets them with the tile's TMA copies and reads one u16 per thread instead of deriving the row index (ballot, popc,
+// chunk base) and loading the weight from global memory inside the E-step.  Chunks on the general path (two heads in
+// a lane) read wperm as before.  Weights above 65535 do not fit: flag[0] is set and the caller reports an error.
+static __global__ void __launch_bounds__(kThreads) lane_weights(const uint2 *__restrict__ rec, const uint4 *__restrict__ records,
+                                                                const uint32_t *__restrict__ wperm, uint32_t n_tiles,
+                                                                uint16_t *__restrict__ wlane, uint32_t *__restrict__ flag)
+{
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    bool over = false;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const unsigned char *r = reinterpret_cast<const unsigned char *>(records + rec[tile].x);
+        const uint32_t desc = reinterpret_cast<const uint16_t *>(r + kRecDesc)[tid];
+        const uint32_t row_base = reinterpret_cast<const uint32_t *>(r + kRecRow)[warp];
+        const unsigned lanes_h = __ballot_sync(0xffffffffu, (desc & 15u) != 0u);
+        const uint32_t before = __popc(lanes_h & ((1u << lane) - 1u));
+        uint32_t w = before ? wperm[row_base + before - 1u] : 0u;
+        if (w > 0xFFFFu) { over = true; w = 0xFFFFu; }
+        wlane[(size_t)tile * kThreads + tid] = (uint16_t)w;
+    }
+    if (over) atomicOr(flag, 1u);
+}
+
 // ---------------------------------------------------------------------------
 // the sweep
 // ---------------------------------------------------------------------------
@@ -698,24 +737,13 @@ __device__ __forceinline__ bool any_bits(uint32_t v, uint32_t mask)
     return r != 0u;
 }
 
-// bootstrap: pull the weights of a tile's rows (tile order, starting at row `row0`) into L1 one tile ahead, so that the
-// per-lane loads of phase 1 hit it.  Eight 128-byte lines cover 256 rows (C3: ~123 rows per tile); a load whose
-// result is never used does not stall anybody.
-__device__ __forceinline__ void weights_touch(const uint32_t *__restrict__ w, uint32_t lane)
-{
-    if (lane < 8u) {
-        uint32_t sink;
-        asm volatile("ld.global.nc.L1::evict_last.u32 %0, [%1];" : "=r"(sink) : "l"(w + 32u * lane));
-    }
-}
-
 // ---- phase 1 of a tile: E-step in registers + M-step scatter into the transcript-sorted x array -------------
 //   bulk, rec: shared-space addresses of the tile's prob | lpos block and of its record; sp_a: prev[] of the tile's
 //   transcripts; xs_a: the x array.  Returns the thread's item and the record's DU word for phase 2.
 //   The thread's four slots (prob, lpos) come in registers: p4 / lp4 = slots warp * kChunk + lane * 4 ...
 template <bool HAS_AUX, bool HAS_WTS>
 __device__ __forceinline__ void tile_phase1_core(const View &v, uint32_t tile, const float4 p4, const uint4 lp4, uint32_t rec, uint32_t sp_a,
-                                                 uint32_t xs_a, uint32_t trash, uint32_t tid, uint32_t lane, uint32_t warp,
+                                                 uint32_t xs_a, uint32_t trash, uint32_t w_in, uint32_t tid, uint32_t lane, uint32_t warp,
                                                  double *__restrict__ curr, const uint32_t *__restrict__ wperm)
 {
     const unsigned full = 0xffffffffu;
@@ -735,20 +763,13 @@ __device__ __forceinline__ void tile_phase1_core(const View &v, uint32_t tile, c
     }
 
     const uint32_t hb = desc & 15u, dist = (desc >> 4) & 31u, E = (desc >> 9) & 31u;
-    // bootstrap: the resampling weight of the row that ends in this lane (fast path: at most one head per lane, so
-    // that row is the chunk's row number (heads in earlier lanes) - 1).  The global load is issued here, ahead of
-    // the E-step, so that its latency is covered by the shared-memory gathers and the segmented scan.
-    uint32_t w_in = 0;
-    if (HAS_WTS) {
-        const unsigned lanes_h = __ballot_sync(full, hb != 0u);
-        const uint32_t before = __popc(lanes_h & ((1u << lane) - 1u));
-        const uint32_t row_base = lds_u32(rec + kRecRow + 4u * warp);
-        if (before) w_in = wperm[row_base + before - 1u];
-    }
+    // bootstrap: w_in = the resampling weight of the row that ends in this lane (fast path; staged with the tile,
+    // see lane_weights)
     // chunk_info is the same word for the whole warp; votes make that visible to the compiler
     const bool multi = any_bits(info, kInfoMulti);
     const bool strays = any_bits(info, kInfoStray);
     const bool long_rows = any_bits(info, 4u);   // scan steps > 3: rows spanning more than 8 lanes
+    const bool mid_rows = !OAR_SCAN_COND || __any_sync(full, (info & 7u) >= 3u);   // scan steps > 2
     double x0, x1, x2, x3;
     if (!multi) {
         // fast path: no lane holds more than one row head.  Slot i lies before that head (it
@@ -765,7 +786,7 @@ __device__ __forceinline__ void tile_phase1_core(const View &v, uint32_t tile, c
         double incl = z;
         incl = fma(__shfl_up_sync(full, incl, 1), mask01(dist >= 1u), incl);
         incl = fma(__shfl_up_sync(full, incl, 2), mask01(dist >= 2u), incl);
-        incl = fma(__shfl_up_sync(full, incl, 4), mask01(dist >= 4u), incl);
+        if (mid_rows) incl = fma(__shfl_up_sync(full, incl, 4), mask01(dist >= 4u), incl);   // rows spanning more than 4 lanes (a third of the chunks on C3)
         if (long_rows) {   // rows spanning more than 8 lanes (rare)
             incl = fma(__shfl_up_sync(full, incl, 8), mask01(dist >= 8u), incl);
             incl = fma(__shfl_up_sync(full, incl, 16), mask01(dist >= 16u), incl);
@@ -856,7 +877,7 @@ __device__ __forceinline__ void tile_phase1_core(const View &v, uint32_t tile, c
 // phase 1 with the tile's prob | lpos block staged in shared memory (`bulk`); also returns the thread's item and the
 // record's DU word for phase 2 (read now: the record's stage is refilled before phase 2).
 template <bool HAS_AUX, bool HAS_WTS>
-__device__ __forceinline__ void tile_phase1(const View &v, uint32_t tile, uint32_t bulk, uint32_t rec, uint32_t sp_a, uint32_t xs_a,
+__device__ __forceinline__ void tile_phase1(const View &v, uint32_t tile, uint32_t bulk, uint32_t rec, uint32_t wl_a, uint32_t sp_a, uint32_t xs_a,
                                             uint32_t tid, uint32_t lane, uint32_t warp, double *__restrict__ curr,
                                             const uint32_t *__restrict__ wperm, uint32_t &item, uint4 &du)
 {
@@ -865,7 +886,9 @@ __device__ __forceinline__ void tile_phase1(const View &v, uint32_t tile, uint32
     du = lds_v4(rec + kRecDU);   // D, items, n32 | n16 << 16, trash offset
     item = kNoTxp;
     if (tid < du.y) item = lds_u32(rec + kRecTable + 4u * (((du.x + 3u) & ~3u) + tid));
-    tile_phase1_core<HAS_AUX, HAS_WTS>(v, tile, p4, lp4, rec, sp_a, xs_a, du.w, tid, lane, warp, curr, wperm);
+    uint32_t w_in = 0;
+    if (HAS_WTS) w_in = lds_u16(wl_a + 2u * tid);
+    tile_phase1_core<HAS_AUX, HAS_WTS>(v, tile, p4, lp4, rec, sp_a, xs_a, du.w, w_in, tid, lane, warp, curr, wperm);
 }
 
 // ---- phase 2 of a tile: one thread sums one item (<= 16 consecutive x slots of one transcript), one RED -------
@@ -907,45 +930,10 @@ __device__ __forceinline__ void tile_phase2(uint32_t xs_a, uint32_t item, uint32
 
 }
 
-// ---- phase 2, lane-parallel (OAR_P2Q): every lane sums up to FOUR consecutive x slots of one item; the four (two, one)
-// lanes of a 16- (8-, 4-) slot item combine with shuffles and the first one issues the RED.  The thread-per-item
-// version above keeps ~3 warps busy with ~100 instructions each while the other warps of the CTA wait at the barrier
-// (profiles/: 43 % of a CTA's time); here the same work is spread over all warps, ~45 instructions per 32 lanes.
-// Items of the 16-slot class sit 18 doubles apart, so the 8 lanes of an LDS.128 wavefront (2 items x 4 lanes at
-// 32-byte steps) still hit 8 different 16-byte banks.
-#ifndef OAR_P2Q
-#define OAR_P2Q 1
-#endif
-__device__ __forceinline__ void tile_phase2q(uint32_t xs_a, uint32_t rec, uint32_t D, uint32_t U, uint32_t duz, uint32_t tid,
-                                             double *__restrict__ curr)
-{
-    static_assert(kItemMax == 16, "lane-parallel phase 2: item classes 16 / 8 / 4 at strides 18 / 10 / 6 doubles");
-    const unsigned full = 0xffffffffu;
-    const uint32_t N16 = duz & 0xFFFFu, N8 = duz >> 16;
-    const uint32_t L16 = 4u * N16, L8 = L16 + 2u * N8, LT = L8 + (U - N16 - N8);   // lanes of the three classes
-    const uint32_t items_a = rec + kRecTable + 4u * ((D + 3u) & ~3u);
-    for (uint32_t L = tid; (L & ~31u) < LT; L += (uint32_t)kThreads) {             // warp-uniform trip count
-        uint32_t item, part, bd;
-        if (L < L16) { item = L >> 2; part = L & 3u; bd = 18u * item + 4u * part; }
-        else if (L < L8) { const uint32_t l = L - L16; item = N16 + (l >> 1); part = l & 1u; bd = 18u * N16 + 10u * (l >> 1) + 4u * part; }
-        else { const uint32_t l = L - L8; item = N16 + N8 + l; part = 0u; bd = 18u * N16 + 10u * N8 + 6u * l; }
-        uint32_t desc = kNoTxp;
-        if (L < LT) desc = lds_u32(items_a + 4u * item);
-        const int slots = desc == kNoTxp ? 0 : (int)(desc >> 27) + 1;
-        const int v = min(max(slots - 4 * (int)part, 0), 4);                         // valid slots of this lane's four
-        const uint32_t b = xs_a + 8u * bd;
-        const double2 u = lds_v2f64_if(b, v >= 2), w = lds_v2f64_if(b + 16u, v >= 4);
-        const double o = lds_f64_if(b + 8u * (uint32_t)(v - 1), (v & 1) != 0);
-        const double s0 = ((u.x + u.y) + (w.x + w.y)) + o;
-        const double s1 = s0 + __shfl_xor_sync(full, s0, 1);
-        const double s2 = s1 + __shfl_xor_sync(full, s1, 2);
-        const double tot = L < L16 ? s2 : (L < L8 ? s1 : s0);
-        if (part == 0u && desc != kNoTxp && tot != 0.0) atomicAdd(curr + (desc & (kMaxTxps - 1u)), tot);
-    }
-}
-
 // m_step (em.rs:87-133), persistent and TMA-fed.
-template <bool HAS_AUX, bool HAS_WTS>
+// LIST: the sweep walks v.tile_list[0 .. *v.n_active) instead of all tiles (batched per-cell EM: tiles whose cells
+// have all converged are dropped from the list between graph launches, oar_cells.cu).
+template <bool HAS_AUX, bool HAS_WTS, bool LIST = false>
 __global__ void __launch_bounds__(kThreads, (OAR_TILED_MIN_CTAS * 8) / kWarps) em_sweep_tiled(View v, Geometry g, const double *__restrict__ prev,
                                                               double *__restrict__ curr,
                                                               const uint32_t *__restrict__ wperm,
@@ -956,9 +944,17 @@ __global__ void __launch_bounds__(kThreads, (OAR_TILED_MIN_CTAS * 8) / kWarps) e
 
     if (check_done && st->done) return;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t n_tiles = v.n_tiles, stride = gridDim.x;
-    const uint32_t tile0 = blockIdx.x;
-    if (tile0 >= n_tiles) return;
+    const uint32_t n_tiles = LIST ? *v.n_active : v.n_tiles, stride = gridDim.x;
+    const uint32_t tile0 = blockIdx.x;   // position in the walk; phys() is the tile it stands for
+    auto phys = [&](uint32_t i) -> uint32_t { return LIST ? v.tile_list[i] : i; };
+    // rows that are not tiled: every CTA takes its share of the list (8 lanes per row, straight from the CSR)
+    auto fallback_rows = [&]() {
+        if (v.n_fb)
+            kern::rowgroup_rows<HAS_AUX, HAS_WTS>(v.csr_row_ptr, v.csr_txp, v.csr_prob, v.csr_aux, v.csr_wts, v.fb_rows, prev, curr,
+                                                  (uint64_t)blockIdx.x * (kThreads >> 3) + (threadIdx.x >> 3),
+                                                  (uint64_t)gridDim.x * (kThreads >> 3), v.n_fb);
+    };
+    if (tile0 >= n_tiles) { fallback_rows(); return; }
     const uint32_t kStageBytes = g.stage_bytes;
     uint32_t sm0;   // shared-space address of the window, computed once (a plain cvta is rematerialised every iteration)
     asm volatile("{.reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t;}" : "=r"(sm0) : "l"(smem));
@@ -972,10 +968,11 @@ __global__ void __launch_bounds__(kThreads, (OAR_TILED_MIN_CTAS * 8) / kWarps) e
     const bool is_tma = tid == 32u * (kWarps - 2);
     auto issue = [&](uint32_t tile, uint32_t s, uint2 r) {   // the TMA thread only
         const uint32_t bar = bar0 + 8u * s, dst = stage0 + s * kStageBytes;
-        mbar_expect_tx(bar, 8u * kTile + r.y);
+        mbar_expect_tx(bar, 8u * kTile + r.y + (HAS_WTS ? 2u * kThreads : 0u));
         bulk_g2s(dst, v.prob + (size_t)tile * kTile, 4u * kTile, bar);
         bulk_g2s(dst + 4u * kTile, v.lpos + (size_t)tile * kTile, 4u * kTile, bar);
         bulk_g2s(dst + 8u * kTile, v.records + r.x, r.y, bar);
+        if (HAS_WTS) bulk_g2s(dst + g.w_off, v.wlane + (size_t)tile * kThreads, 2u * kThreads, bar);
     };
     // prev[] of a tile's transcripts into s_prev, by one warp (two gathers in flight per lane)
     auto gather_prev = [&](uint32_t rec_a) {
@@ -988,7 +985,6 @@ __global__ void __launch_bounds__(kThreads, (OAR_TILED_MIN_CTAS * 8) / kWarps) e
             sts_f64(sp_a + 8u * d, p0);
             if (d2 < Dn) sts_f64(sp_a + 8u * d2, p1);
         }
-        if (HAS_WTS) weights_touch(wperm + lds_u32(rec_a + kRecRow), lane);
     };
 
     uint2 r_pending = make_uint2(0, 0);   // record locator of the tile two ahead (TMA thread)
@@ -998,10 +994,12 @@ __global__ void __launch_bounds__(kThreads, (OAR_TILED_MIN_CTAS * 8) / kWarps) e
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    uint32_t t_pending = 0;               // and that tile itself
     if (is_tma) {
-        issue(tile0, 0, v.rec[tile0]);
-        if (tile0 + stride < n_tiles) issue(tile0 + stride, 1, v.rec[tile0 + stride]);
-        if (tile0 + 2 * stride < n_tiles) r_pending = v.rec[tile0 + 2 * stride];
+        const uint32_t p0 = phys(tile0);
+        issue(p0, 0, v.rec[p0]);
+        if (tile0 + stride < n_tiles) { const uint32_t p1 = phys(tile0 + stride); issue(p1, 1, v.rec[p1]); }
+        if (tile0 + 2 * stride < n_tiles) { t_pending = phys(tile0 + 2 * stride); r_pending = v.rec[t_pending]; }
     }
     // Only the last warp waits on the stage mbarriers and gathers prev[]; the CTA barrier that follows hands the
     // TMA-written stage on to the other warps (mbarrier completion observed by one thread + bar.sync is cumulative).
@@ -1018,7 +1016,7 @@ __global__ void __launch_bounds__(kThreads, (OAR_TILED_MIN_CTAS * 8) / kWarps) e
         __syncthreads();   // stage s and s_prev of this tile are in place; phase 2 of the previous tile has left xs
 
         uint32_t item; uint4 du;
-        tile_phase1<HAS_AUX, HAS_WTS>(v, tile, stg, rec, sp_a, xs_a, tid, lane, warp, curr, wperm, item, du);
+        tile_phase1<HAS_AUX, HAS_WTS>(v, HAS_AUX ? phys(tile) : 0u, stg, rec, stg + g.w_off, sp_a, xs_a, tid, lane, warp, curr, wperm, item, du);
         __syncthreads();   // xs complete; stage s and s_prev are free again
 
         // ---- refill stage s two tiles ahead; the last warp fetches prev[] of the next tile ----
@@ -1026,8 +1024,8 @@ __global__ void __launch_bounds__(kThreads, (OAR_TILED_MIN_CTAS * 8) / kWarps) e
         const bool has_next = next < n_tiles;
         if (warp >= kWarps - 2) {   // the two service warps
             if (is_tma && next + stride < n_tiles) {
-                issue(next + stride, s, r_pending);
-                if (next + 2 * stride < n_tiles) r_pending = v.rec[next + 2 * stride];
+                issue(LIST ? t_pending : next + stride, s, r_pending);
+                if (next + 2 * stride < n_tiles) { t_pending = phys(next + 2 * stride); r_pending = v.rec[t_pending]; }
             }
             if (warp == kWarps - 1 && has_next) {
                 mbar_wait(bar0 + 8u * (s ^ 1u), ((it + 1u) >> 1) & 1u);
@@ -1041,577 +1039,9 @@ __global__ void __launch_bounds__(kThreads, (OAR_TILED_MIN_CTAS * 8) / kWarps) e
         if (!has_next) break;
         tile = next;
     }
-    if (v.n_fb && blockIdx.x == gridDim.x - 1u)
-        kern::rowgroup_rows<HAS_AUX, HAS_WTS>(v.csr_row_ptr, v.csr_txp, v.csr_prob, v.csr_aux, v.csr_wts, v.fb_rows, prev, curr,
-                                              tid >> 3, kThreads >> 3, v.n_fb);
+    fallback_rows();
 }
 
-// ---------------------------------------------------------------------------
-// Single-barrier sweep (OAR_SWEEP=1b): phase 2 of tile i-1 runs next to phase 1 of tile i.
-//
-// The two-barrier kernel above idles most of its warps between the barriers of a tile (items keep about three
-// warps busy, one gathers prev[], one issues the copies).  Here the x array and s_prev are double-buffered and
-// the ring has three stages, and one CTA barrier per tile is all that is left:
-//
-//   iteration i, after the barrier:  TMA thread   tile i+2 -> stage[(i+2)%3]
-//                                    first warps  phase 2 of tile i-1 (reads xs[(i-1)&1], items kept in registers)
-//                                    all warps    phase 1 of tile i   (reads stage[i%3], s_prev[i&1]; writes xs[i&1])
-//                                    last warp    waits for stage[(i+1)%3] (requested one iteration ago), gathers
-//                                                 prev[] of tile i+1 into s_prev[(i+1)&1]
-//
-// Every buffer written in iteration i was last read in iteration i-1, i.e. before the barrier.  The price is
-// shared memory (54 KB per CTA on C3 against 31 KB) and registers (64): 4 CTAs per SM instead of 5.
-struct Geometry1 {
-    uint32_t xs_bytes;      // one x buffer (128 B multiple); the two buffers sit at the start of the window
-    uint32_t stage_off;     // three stages: prob (4 KB) | lpos (4 KB) | record
-    uint32_t stage_bytes;
-    uint32_t prev_off;      // two s_prev buffers
-    uint32_t prev_bytes;
-    uint32_t bar_off;       // three mbarriers
-    uint32_t total;
-};
-inline Geometry1 make_geometry1(uint32_t max_rec_bytes, uint32_t max_d, uint32_t max_x_doubles)
-{
-    Geometry1 g;
-    g.xs_bytes = (8u * ((max_x_doubles + 2u + 1u) & ~1u) + 127u) & ~127u;
-    g.stage_off = 2u * g.xs_bytes;
-    g.stage_bytes = 8u * kTile + ((max_rec_bytes + 15u) & ~15u);
-    g.prev_off = g.stage_off + 3u * g.stage_bytes;
-    g.prev_bytes = 8u * ((max_d + 1u) & ~1u);
-    g.bar_off = g.prev_off + 2u * g.prev_bytes;
-    g.total = g.bar_off + 3u * 8u;
-    return g;
-}
-
-template <bool HAS_AUX, bool HAS_WTS>
-__global__ void __launch_bounds__(kThreads, (4 * 8) / kWarps) em_sweep_tiled1(View v, Geometry1 g, const double *__restrict__ prev,
-                                                               double *__restrict__ curr,
-                                                               const uint32_t *__restrict__ wperm,
-                                                               const OarEmState *__restrict__ st, int check_done)
-{
-    extern __shared__ __align__(128) unsigned char smem[];
-    if (check_done && st->done) return;
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t n_tiles = v.n_tiles, stride = gridDim.x;
-    const uint32_t tile0 = blockIdx.x;
-    if (tile0 >= n_tiles) return;
-    uint32_t sm0;
-    asm volatile("{.reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t;}" : "=r"(sm0) : "l"(smem));
-    const uint32_t stage0 = sm0 + g.stage_off, sp0 = sm0 + g.prev_off, bar0 = sm0 + g.bar_off;
-    const uint32_t xs0 = smem_u32(smem);   // warp-uniform to the compiler (see em_sweep_tiled)
-    const bool is_tma = tid == 32u * (kWarps - 2);
-    const bool is_gather = warp == kWarps - 1;
-
-    auto issue = [&](uint32_t tile, uint32_t slot, uint2 r) {   // the TMA thread only
-        const uint32_t bar = bar0 + 8u * slot, dst = stage0 + slot * g.stage_bytes;
-        mbar_expect_tx(bar, 8u * kTile + r.y);
-        bulk_g2s(dst, v.prob + (size_t)tile * kTile, 4u * kTile, bar);
-        bulk_g2s(dst + 4u * kTile, v.lpos + (size_t)tile * kTile, 4u * kTile, bar);
-        bulk_g2s(dst + 8u * kTile, v.records + r.x, r.y, bar);
-    };
-    auto gather_prev = [&](uint32_t rec_a, uint32_t sp_a) {   // one warp, two gathers in flight per lane
-        const uint32_t Dn = lds_u32(rec_a + kRecDU);
-        for (uint32_t d = lane; d < Dn; d += 64u) {
-            const uint32_t d2 = d + 32u;
-            const double p0 = prev[lds_u32(rec_a + kRecTable + 4u * d)];
-            double p1 = 0.0;
-            if (d2 < Dn) p1 = prev[lds_u32(rec_a + kRecTable + 4u * d2)];
-            sts_f64(sp_a + 8u * d, p0);
-            if (d2 < Dn) sts_f64(sp_a + 8u * d2, p1);
-        }
-        if (HAS_WTS) weights_touch(wperm + lds_u32(rec_a + kRecRow), lane);
-    };
-
-    if (tid == 0) {
-#pragma unroll
-        for (uint32_t i = 0; i < 3; ++i) mbar_init(bar0 + 8u * i, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    uint2 r_pending = make_uint2(0, 0);   // record locator of the tile three ahead (TMA thread)
-    if (is_tma) {
-        issue(tile0, 0, v.rec[tile0]);
-        if (tile0 + stride < n_tiles) issue(tile0 + stride, 1, v.rec[tile0 + stride]);
-        if (tile0 + 2 * stride < n_tiles) r_pending = v.rec[tile0 + 2 * stride];
-    }
-    uint32_t spar = 0;                    // phase parity of the three stage mbarriers (gather warp)
-    if (is_gather) {
-        mbar_wait(bar0, 0); spar ^= 1u;
-        gather_prev(stage0 + 8u * kTile, sp0);
-    }
-
-    uint32_t tile = tile0;
-    uint32_t rs = 0;                      // stage of this tile = it % 3
-    uint32_t item_p = kNoTxp, U_p = 0, duz_p = 0;   // phase-2 inputs of the previous tile
-    uint32_t s_last = 0;
-    for (uint32_t it = 0;; ++it) {
-        const uint32_t s = it & 1u;
-        const uint32_t rs1 = rs == 2u ? 0u : rs + 1u, rs2 = rs1 == 2u ? 0u : rs1 + 1u;
-        const uint32_t next = tile + stride;
-        const bool has_next = next < n_tiles;
-        __syncthreads();   // tile `it` is in place (stage, s_prev); xs[s], stage[rs2], s_prev[s^1] are free
-
-        if (is_tma && next + stride < n_tiles) {
-            issue(next + stride, rs2, r_pending);
-            if (next + 2 * stride < n_tiles) r_pending = v.rec[next + 2 * stride];
-        }
-        if (it) tile_phase2(xs0 + (s ^ 1u) * g.xs_bytes, item_p, U_p, duz_p, tid, warp, curr);
-
-        uint32_t item; uint4 du;
-        const uint32_t stg = stage0 + rs * g.stage_bytes;
-        tile_phase1<HAS_AUX, HAS_WTS>(v, tile, stg, stg + 8u * kTile, sp0 + s * g.prev_bytes, xs0 + s * g.xs_bytes, tid, lane, warp,
-                                      curr, wperm, item, du);
-        item_p = item; U_p = du.y; duz_p = du.z;
-
-        if (!has_next) { s_last = s; break; }
-        if (is_gather) {
-            mbar_wait(bar0 + 8u * rs1, (spar >> rs1) & 1u); spar ^= 1u << rs1;
-            gather_prev(stage0 + rs1 * g.stage_bytes + 8u * kTile, sp0 + (s ^ 1u) * g.prev_bytes);
-        }
-        tile = next; rs = rs1;
-    }
-    __syncthreads();       // x values of the last tile
-    tile_phase2(xs0 + s_last * g.xs_bytes, item_p, U_p, duz_p, tid, warp, curr);
-    if (v.n_fb && blockIdx.x == gridDim.x - 1u)
-        kern::rowgroup_rows<HAS_AUX, HAS_WTS>(v.csr_row_ptr, v.csr_txp, v.csr_prob, v.csr_aux, v.csr_wts, v.fb_rows, prev, curr,
-                                              tid >> 3, kThreads >> 3, v.n_fb);
-}
-
-// ---------------------------------------------------------------------------
-// Single-barrier sweep with deeper rings (OAR_SWEEP=1c) -- PREPARED FOR ROUND 2, NOT YET RUN ON A GPU.
-//
-// ncu on em_sweep_tiled1 shows its gather warp polling ~75 times per tile for a stage requested one iteration
-// earlier: at 4 CTAs/SM an iteration (1.4 us) is about one HBM round trip, so the kernel is bound by prefetch depth.
-// A fourth unified stage does not fit next to the second x buffer, but a tile's record is small (1.3 KB on C3):
-// here the records travel in their own ring of four slots (requested three tiles ahead, needed two iterations
-// later by the gather warp) and the prob | lpos blocks in a ring of three (requested two tiles ahead).
-//
-//   iteration i, after the barrier:  TMA thread   bulk of tile i+2 -> bulk[(i+2)%3], record of tile i+3 -> rec[(i+3)%4]
-//                                    first warps  phase 2 of tile i-1
-//                                    all warps    phase 1 of tile i   (bulk[i%3], rec[i%4], s_prev[i&1] -> xs[i&1])
-//                                    last warp    waits for rec[(i+1)%4], gathers prev[] of tile i+1 into s_prev[(i+1)&1],
-//                                                 waits for bulk[(i+1)%3]
-struct Geometry2 {
-    uint32_t xs_bytes, bulk_off, rec_off, rec_bytes, prev_off, prev_bytes, bar_off, total;
-};
-inline Geometry2 make_geometry2(uint32_t max_rec_bytes, uint32_t max_d, uint32_t max_x_doubles)
-{
-    Geometry2 g;
-    g.xs_bytes = (8u * ((max_x_doubles + 2u + 1u) & ~1u) + 127u) & ~127u;
-    g.bulk_off = 2u * g.xs_bytes;
-    g.rec_off = g.bulk_off + 3u * 8u * kTile;
-    g.rec_bytes = (max_rec_bytes + 15u) & ~15u;
-    g.prev_off = g.rec_off + 4u * g.rec_bytes;
-    g.prev_bytes = 8u * ((max_d + 1u) & ~1u);
-    g.bar_off = g.prev_off + 2u * g.prev_bytes;
-    g.total = g.bar_off + 7u * 8u;   // mbarriers: bulk[3], rec[4]
-    return g;
-}
-
-template <bool HAS_AUX, bool HAS_WTS>
-__global__ void __launch_bounds__(kThreads, (4 * 8) / kWarps) em_sweep_tiled2(View v, Geometry2 g, const double *__restrict__ prev,
-                                                               double *__restrict__ curr,
-                                                               const uint32_t *__restrict__ wperm,
-                                                               const OarEmState *__restrict__ st, int check_done)
-{
-    extern __shared__ __align__(128) unsigned char smem[];
-    if (check_done && st->done) return;
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t n_tiles = v.n_tiles, stride = gridDim.x;
-    const uint32_t tile0 = blockIdx.x;
-    if (tile0 >= n_tiles) return;
-    uint32_t sm0;
-    asm volatile("{.reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t;}" : "=r"(sm0) : "l"(smem));
-    const uint32_t bulk0 = sm0 + g.bulk_off, rec0 = sm0 + g.rec_off, sp0 = sm0 + g.prev_off, bar0 = sm0 + g.bar_off;
-    const uint32_t xs0 = smem_u32(smem);   // warp-uniform to the compiler (see em_sweep_tiled)
-    const bool is_tma = tid == 32u * (kWarps - 2);
-    const bool is_gather = warp == kWarps - 1;
-
-    auto issue_bulk = [&](uint32_t tile, uint32_t b) {   // the TMA thread only
-        const uint32_t bar = bar0 + 8u * b, dst = bulk0 + b * (8u * kTile);
-        mbar_expect_tx(bar, 8u * kTile);
-        bulk_g2s(dst, v.prob + (size_t)tile * kTile, 4u * kTile, bar);
-        bulk_g2s(dst + 4u * kTile, v.lpos + (size_t)tile * kTile, 4u * kTile, bar);
-    };
-    auto issue_rec = [&](uint2 r, uint32_t slot) {
-        const uint32_t bar = bar0 + 24u + 8u * slot;
-        mbar_expect_tx(bar, r.y);
-        bulk_g2s(rec0 + slot * g.rec_bytes, v.records + r.x, r.y, bar);
-    };
-    auto gather_prev = [&](uint32_t rec_a, uint32_t sp_a) {   // one warp, two gathers in flight per lane
-        const uint32_t Dn = lds_u32(rec_a + kRecDU);
-        for (uint32_t d = lane; d < Dn; d += 64u) {
-            const uint32_t d2 = d + 32u;
-            const double p0 = prev[lds_u32(rec_a + kRecTable + 4u * d)];
-            double p1 = 0.0;
-            if (d2 < Dn) p1 = prev[lds_u32(rec_a + kRecTable + 4u * d2)];
-            sts_f64(sp_a + 8u * d, p0);
-            if (d2 < Dn) sts_f64(sp_a + 8u * d2, p1);
-        }
-        if (HAS_WTS) weights_touch(wperm + lds_u32(rec_a + kRecRow), lane);
-    };
-
-    if (tid == 0) {
-#pragma unroll
-        for (uint32_t i = 0; i < 7; ++i) mbar_init(bar0 + 8u * i, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    uint2 r_pending = make_uint2(0, 0);   // record locator of the tile three ahead of the current one (TMA thread)
-    if (is_tma) {
-        issue_rec(v.rec[tile0], 0);
-        issue_bulk(tile0, 0);
-        if (tile0 + stride < n_tiles) { issue_rec(v.rec[tile0 + stride], 1); issue_bulk(tile0 + stride, 1); }
-        if (tile0 + 2 * stride < n_tiles) issue_rec(v.rec[tile0 + 2 * stride], 2);
-        if (tile0 + 3 * stride < n_tiles) r_pending = v.rec[tile0 + 3 * stride];
-    }
-    uint32_t rpar = 0, bpar = 0;          // phase parities of the record / bulk mbarriers (gather warp)
-    if (is_gather) {
-        mbar_wait(bar0 + 24u, 0); rpar ^= 1u;
-        gather_prev(rec0, sp0);
-        mbar_wait(bar0, 0); bpar ^= 1u;
-    }
-
-    uint32_t tile = tile0;
-    uint32_t bs = 0, rs = 0;              // bulk stage = it % 3, record slot = it % 4 of this tile
-    uint32_t item_p = kNoTxp, U_p = 0, duz_p = 0;   // phase-2 inputs of the previous tile
-    uint32_t s_last = 0;
-    for (uint32_t it = 0;; ++it) {
-        const uint32_t s = it & 1u;
-        const uint32_t bs1 = bs == 2u ? 0u : bs + 1u, bs2 = bs1 == 2u ? 0u : bs1 + 1u;
-        const uint32_t rs1 = (rs + 1u) & 3u, rs3 = (rs + 3u) & 3u;
-        const uint32_t next = tile + stride;
-        const bool has_next = next < n_tiles;
-        __syncthreads();   // tile `it` is in place; xs[s], bulk[bs2], rec[rs3], s_prev[s^1] are free
-
-        if (is_tma) {
-            if (next + stride < n_tiles) issue_bulk(next + stride, bs2);
-            if (next + 2 * stride < n_tiles) {
-                issue_rec(r_pending, rs3);
-                if (next + 3 * stride < n_tiles) r_pending = v.rec[next + 3 * stride];
-            }
-        }
-        if (it) tile_phase2(xs0 + (s ^ 1u) * g.xs_bytes, item_p, U_p, duz_p, tid, warp, curr);
-
-        uint32_t item; uint4 du;
-        tile_phase1<HAS_AUX, HAS_WTS>(v, tile, bulk0 + bs * (8u * kTile), rec0 + rs * g.rec_bytes, sp0 + s * g.prev_bytes,
-                                      xs0 + s * g.xs_bytes, tid, lane, warp, curr, wperm, item, du);
-        item_p = item; U_p = du.y; duz_p = du.z;
-
-        if (!has_next) { s_last = s; break; }
-        if (is_gather) {
-            mbar_wait(bar0 + 24u + 8u * rs1, (rpar >> rs1) & 1u); rpar ^= 1u << rs1;
-            gather_prev(rec0 + rs1 * g.rec_bytes, sp0 + (s ^ 1u) * g.prev_bytes);
-            mbar_wait(bar0 + 8u * bs1, (bpar >> bs1) & 1u); bpar ^= 1u << bs1;
-        }
-        tile = next; bs = bs1; rs = rs1;
-    }
-    __syncthreads();       // x values of the last tile
-    tile_phase2(xs0 + s_last * g.xs_bytes, item_p, U_p, duz_p, tid, warp, curr);
-    if (v.n_fb && blockIdx.x == gridDim.x - 1u)
-        kern::rowgroup_rows<HAS_AUX, HAS_WTS>(v.csr_row_ptr, v.csr_txp, v.csr_prob, v.csr_aux, v.csr_wts, v.fb_rows, prev, curr,
-                                              tid >> 3, kThreads >> 3, v.n_fb);
-}
-
-// ---------------------------------------------------------------------------
-// Streaming single-barrier sweep (OAR_SWEEP=3).
-//
-// What the profile of em_sweep_tiled says (profiles/r1_tiled_sweep_ncu_full_summary.csv, source page): 43 % of a CTA's
-// time is the window between its two barriers in which three warps sum the items and one waits ~700 cycles for the
-// prev[] gather to come back from L2, and the shared-memory data pipe is 75 % busy -- 128 of its ~476 wavefronts per
-// tile are the 8 KB prob | lpos block going into shared memory by TMA and straight out again by LDS.128.  Here
-//   * the prob | lpos block never touches shared memory: every thread reads its own 2 x 16 B with coalesced
-//     LDG.128 (L1 no-allocate) at the END of the previous tile's phase 1, when the registers they land in are dead;
-//     the latency hides behind the barrier and phase 2.  One thread prefetches the blocks into L2 kL2Ahead tiles
-//     ahead (cp.async.bulk.prefetch.L2), so those loads are L2 hits;
-//   * only the small per-tile records travel by TMA, in a ring of kRing slots requested kRecAhead tiles ahead;
-//   * the prev[] gather of tile i+1 is issued by one warp as 8-byte cp.async (LDGSTS: global -> shared, no register,
-//     no wait) at the START of iteration i and completes under that warp's own phase 1;
-//   * x array and s_prev are double-buffered and phase 2 of tile i-1 runs inside iteration i: ONE CTA barrier per tile.
-// Shared memory per CTA on C3: 2 x 10.5 KB x arrays + 8 x 1.4 KB records + 2 x 1 KB prev -- less than the staged kernels,
-// so registers (48 at 5 CTAs/SM) are what bounds the occupancy.
-//
-//   iteration i, after the barrier:  TMA thread   record of tile i+kRecAhead -> rec[(i+kRecAhead)%kRing], L2 prefetch of the
-//                                                 prob | lpos blocks of tile i+kL2Ahead
-//                                    gather warp  waits for rec[(i+1)%kRing] (requested kRecAhead-1 iterations ago), issues the
-//                                                 cp.async gather of tile i+1's prev[] into s_prev[(i+1)&1]
-//                                    first warps  phase 2 of tile i-1 (x values in xs[(i-1)&1], items in rec[(i-1)%kRing])
-//                                    all warps    phase 1 of tile i (registers, rec[i%kRing], s_prev[i&1] -> xs[i&1]), then the
-//                                                 LDG.128 of tile i+1's slots
-// Every buffer written in iteration i was last read in iteration i-1, i.e. before the barrier.
-constexpr uint32_t kRing = 8;        // record slots (power of two)
-#ifndef OAR_REC_AHEAD
-#define OAR_REC_AHEAD 5
-#endif
-#ifndef OAR_L2_AHEAD
-#define OAR_L2_AHEAD 3
-#endif
-constexpr uint32_t kRecAhead = OAR_REC_AHEAD, kL2Ahead = OAR_L2_AHEAD;
-static_assert(kRecAhead + 2u <= kRing && kRecAhead >= 2u, "slots of tiles i-1 .. i+kRecAhead-1 are live while tile i+kRecAhead is requested");
-struct Geometry3 {
-    uint32_t xs_bytes;      // one x buffer (128 B multiple); the two buffers sit at the start of the window
-    uint32_t rec_off, rec_bytes;    // kRing record slots
-    uint32_t prev_off, prev_bytes;  // two s_prev buffers
-    uint32_t bar_off;       // kRing mbarriers
-    uint32_t total;
-};
-inline Geometry3 make_geometry3(uint32_t max_rec_bytes, uint32_t max_d, uint32_t max_x_doubles)
-{
-    Geometry3 g;
-    g.xs_bytes = (8u * ((max_x_doubles + 2u + 1u) & ~1u) + 127u) & ~127u;
-    g.rec_off = 2u * g.xs_bytes;
-    g.rec_bytes = (max_rec_bytes + 15u) & ~15u;
-    g.prev_off = g.rec_off + kRing * g.rec_bytes;
-    g.prev_bytes = 8u * ((max_d + 1u) & ~1u);
-    g.bar_off = g.prev_off + 2u * g.prev_bytes;
-    g.total = g.bar_off + kRing * 8u;
-    return g;
-}
-
-__device__ __forceinline__ float4 ldg_stream_v4f(const float *p)
-{ float4 r; asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p)); return r; }
-__device__ __forceinline__ uint4 ldg_stream_v4(const uint32_t *p)
-{ uint4 r; asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p)); return r; }
-__device__ __forceinline__ void l2_prefetch(const void *p, uint32_t bytes)
-{ asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory"); }
-__device__ __forceinline__ void cp_async_8(uint32_t dst, const void *src)
-{ asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-template <bool HAS_AUX, bool HAS_WTS>
-__global__ void __launch_bounds__(kThreads, (OAR_TILED_MIN_CTAS * 8) / kWarps) em_sweep_tiled3(View v, Geometry3 g, const double *__restrict__ prev,
-                                                               double *__restrict__ curr,
-                                                               const uint32_t *__restrict__ wperm,
-                                                               const OarEmState *__restrict__ st, int check_done)
-{
-    extern __shared__ __align__(128) unsigned char smem[];
-    if (check_done && st->done) return;
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t n_tiles = v.n_tiles, stride = gridDim.x;
-    const uint32_t tile0 = blockIdx.x;
-    if (tile0 >= n_tiles) return;
-    uint32_t sm0;
-    asm volatile("{.reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t;}" : "=r"(sm0) : "l"(smem));
-    const uint32_t rec0 = sm0 + g.rec_off, sp0 = sm0 + g.prev_off, bar0 = sm0 + g.bar_off;
-    const uint32_t xs0 = smem_u32(smem);   // warp-uniform to the compiler (see em_sweep_tiled)
-    const bool is_tma = tid == 32u * (kWarps - 2);
-    const bool is_gather = warp == kWarps - 1;
-
-    auto issue_rec = [&](uint2 r, uint32_t slot) {   // the TMA thread only
-        const uint32_t bar = bar0 + 8u * slot;
-        mbar_expect_tx(bar, r.y);
-        bulk_g2s(rec0 + slot * g.rec_bytes, v.records + r.x, r.y, bar);
-    };
-    // prev[] of a tile's transcripts, global -> shared without a register in between; completion: cp_async_wait_all()
-    auto gather_prev_async = [&](uint32_t rec_a, uint32_t sp_a) {
-        const uint32_t Dn = lds_u32(rec_a + kRecDU);
-        for (uint32_t d = lane; d < Dn; d += 32u) cp_async_8(sp_a + 8u * d, prev + lds_u32(rec_a + kRecTable + 4u * d));
-        if (HAS_WTS) weights_touch(wperm + lds_u32(rec_a + kRecRow), lane);
-    };
-
-    if (tid == 0) {
-#pragma unroll
-        for (uint32_t i = 0; i < kRing; ++i) mbar_init(bar0 + 8u * i, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    uint2 r_pending = make_uint2(0, 0);   // record locator of the tile to request next (TMA thread)
-    if (is_tma) {
-#pragma unroll
-        for (uint32_t k = 0; k < kRecAhead; ++k)
-            if (tile0 + k * stride < n_tiles) issue_rec(v.rec[tile0 + k * stride], k);
-        if (tile0 + kRecAhead * stride < n_tiles) r_pending = v.rec[tile0 + kRecAhead * stride];
-#pragma unroll
-        for (uint32_t k = 1; k < kL2Ahead; ++k)
-            if (tile0 + k * stride < n_tiles) {
-                l2_prefetch(v.prob + (size_t)(tile0 + k * stride) * kTile, 4u * kTile);
-                l2_prefetch(v.lpos + (size_t)(tile0 + k * stride) * kTile, 4u * kTile);
-            }
-    }
-    float4 p4 = ldg_stream_v4f(v.prob + (size_t)tile0 * kTile + 4u * tid);
-    uint4 lp4 = ldg_stream_v4(v.lpos + (size_t)tile0 * kTile + 4u * tid);
-    if (is_gather) {
-        mbar_wait(bar0, 0);
-        gather_prev_async(rec0, sp0);
-        cp_async_wait_all();
-    }
-
-    uint32_t tile = tile0;
-    uint32_t s_last = 0, rec_last = rec0;
-    for (uint32_t it = 0;; ++it) {
-        const uint32_t s = it & 1u;
-        const uint32_t rec = rec0 + (it & (kRing - 1u)) * g.rec_bytes;
-        const uint32_t next = tile + stride;
-        const bool has_next = next < n_tiles;
-        __syncthreads();   // tile `it` is in place (record, s_prev[s]); xs[s], s_prev[s^1] and rec[(it+kRecAhead)%kRing] are free
-
-        if (warp >= kWarps - 2) {   // the two service warps
-            if (is_tma) {
-                const uint32_t ta = tile + kRecAhead * stride;
-                if (ta < n_tiles) {
-                    issue_rec(r_pending, (it + kRecAhead) & (kRing - 1u));
-                    if (ta + stride < n_tiles) r_pending = v.rec[ta + stride];
-                }
-                const uint32_t tp = tile + kL2Ahead * stride;
-                if (tp < n_tiles) {
-                    l2_prefetch(v.prob + (size_t)tp * kTile, 4u * kTile);
-                    l2_prefetch(v.lpos + (size_t)tp * kTile, 4u * kTile);
-                }
-            }
-            if (is_gather && has_next) {
-                const uint32_t j = it + 1u;
-                mbar_wait(bar0 + 8u * (j & (kRing - 1u)), (j / kRing) & 1u);
-                gather_prev_async(rec0 + (j & (kRing - 1u)) * g.rec_bytes, sp0 + (s ^ 1u) * g.prev_bytes);
-            }
-            __syncwarp();
-        }
-        if (it) {   // phase 2 of the previous tile: its record is still in the ring
-            const uint32_t rec_p = rec0 + ((it - 1u) & (kRing - 1u)) * g.rec_bytes;
-            const uint4 du_p = lds_v4(rec_p + kRecDU);
-#if OAR_P2Q
-            tile_phase2q(xs0 + (s ^ 1u) * g.xs_bytes, rec_p, du_p.x, du_p.y, du_p.z, tid, curr);
-#else
-            uint32_t item_p = kNoTxp;
-            if (tid < du_p.y) item_p = lds_u32(rec_p + kRecTable + 4u * (((du_p.x + 3u) & ~3u) + tid));
-            tile_phase2(xs0 + (s ^ 1u) * g.xs_bytes, item_p, du_p.y, du_p.z, tid, warp, curr);
-#endif
-        }
-        const uint32_t trash = lds_u32(rec + kRecDU + 12u);
-        tile_phase1_core<HAS_AUX, HAS_WTS>(v, tile, p4, lp4, rec, sp0 + s * g.prev_bytes, xs0 + s * g.xs_bytes, trash, tid, lane, warp,
-                                           curr, wperm);
-        if (!has_next) { s_last = s; rec_last = rec; break; }
-        // the next tile's slots: issued now, needed after the barrier and phase 2
-        p4 = ldg_stream_v4f(v.prob + (size_t)next * kTile + 4u * tid);
-        lp4 = ldg_stream_v4(v.lpos + (size_t)next * kTile + 4u * tid);
-        if (is_gather) cp_async_wait_all();   // s_prev of the next tile has landed (issued before this warp's phase 1)
-        tile = next;
-    }
-    __syncthreads();       // x values of the last tile
-    {
-        const uint4 du_p = lds_v4(rec_last + kRecDU);
-#if OAR_P2Q
-        tile_phase2q(xs0 + s_last * g.xs_bytes, rec_last, du_p.x, du_p.y, du_p.z, tid, curr);
-#else
-        uint32_t item_p = kNoTxp;
-        if (tid < du_p.y) item_p = lds_u32(rec_last + kRecTable + 4u * (((du_p.x + 3u) & ~3u) + tid));
-        tile_phase2(xs0 + s_last * g.xs_bytes, item_p, du_p.y, du_p.z, tid, warp, curr);
-#endif
-    }
-    if (v.n_fb && blockIdx.x == gridDim.x - 1u)
-        kern::rowgroup_rows<HAS_AUX, HAS_WTS>(v.csr_row_ptr, v.csr_txp, v.csr_prob, v.csr_aux, v.csr_wts, v.fb_rows, prev, curr,
-                                              tid >> 3, kThreads >> 3, v.n_fb);
-}
-
-// ---------------------------------------------------------------------------
-// Two-barrier sweep with an EARLY prev[] gather (OAR_SWEEP=2e).
-//
-// em_sweep_tiled's window between the second barrier of a tile and the first barrier of the next one is as long as
-// its slower occupant: the item warps (phase 2) or the gather warp, which waits for the stage's TMA copy, loads the
-// table ids, gathers prev[] from L2 (~700 cycles) and stores it.  ncu puts the gather slightly ahead (the five idle
-// warps wait ~650 sample units per tile, phase 2 takes ~440).  Here the gather of tile i+1 is issued at the START of
-// tile i's phase 1 as 8-byte cp.async copies (LDGSTS: no register, no wait) into a second s_prev buffer and has landed
-// long before the second barrier; the ring has three stages, requested three tiles ahead, so the record of tile i+1
-// is in shared memory by then.  The window shrinks to phase 2 alone.
-struct GeometryE {
-    uint32_t stage_bytes, stage_off, prev_off, prev_bytes, bar_off, total;
-};
-inline GeometryE make_geometry_e(uint32_t max_rec_bytes, uint32_t max_d, uint32_t max_x_doubles)
-{
-    GeometryE g;
-    g.stage_bytes = 8u * kTile + ((max_rec_bytes + 15u) & ~15u);
-    g.stage_off = (8u * ((max_x_doubles + 2u + 1u) & ~1u) + 127u) & ~127u;
-    g.prev_off = g.stage_off + 3u * g.stage_bytes;
-    g.prev_bytes = 8u * ((max_d + 1u) & ~1u);
-    g.bar_off = g.prev_off + 2u * g.prev_bytes;
-    g.total = g.bar_off + 3u * 8u;
-    return g;
-}
-
-template <bool HAS_AUX, bool HAS_WTS>
-__global__ void __launch_bounds__(kThreads, (OAR_TILED_MIN_CTAS * 8) / kWarps) em_sweep_tiled_eg(View v, GeometryE g, const double *__restrict__ prev,
-                                                                 double *__restrict__ curr,
-                                                                 const uint32_t *__restrict__ wperm,
-                                                                 const OarEmState *__restrict__ st, int check_done)
-{
-    extern __shared__ __align__(128) unsigned char smem[];
-    // [xs][stage 0][stage 1][stage 2][s_prev 0][s_prev 1][mbarriers]; a stage = prob | lpos | record
-    if (check_done && st->done) return;
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t n_tiles = v.n_tiles, stride = gridDim.x;
-    const uint32_t tile0 = blockIdx.x;
-    if (tile0 >= n_tiles) return;
-    uint32_t sm0;
-    asm volatile("{.reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t;}" : "=r"(sm0) : "l"(smem));
-    const uint32_t stage0 = sm0 + g.stage_off, sp0 = sm0 + g.prev_off, bar0 = sm0 + g.bar_off;
-    const uint32_t xs_a = smem_u32(smem);
-    const bool is_tma = tid == 32u * (kWarps - 2);
-    const bool is_gather = warp == kWarps - 1;
-
-    auto issue = [&](uint32_t tile, uint32_t slot, uint2 r) {   // the TMA thread only
-        const uint32_t bar = bar0 + 8u * slot, dst = stage0 + slot * g.stage_bytes;
-        mbar_expect_tx(bar, 8u * kTile + r.y);
-        bulk_g2s(dst, v.prob + (size_t)tile * kTile, 4u * kTile, bar);
-        bulk_g2s(dst + 4u * kTile, v.lpos + (size_t)tile * kTile, 4u * kTile, bar);
-        bulk_g2s(dst + 8u * kTile, v.records + r.x, r.y, bar);
-    };
-    auto gather_prev_async = [&](uint32_t rec_a, uint32_t sp_a) {
-        const uint32_t Dn = lds_u32(rec_a + kRecDU);
-        for (uint32_t d = lane; d < Dn; d += 32u) cp_async_8(sp_a + 8u * d, prev + lds_u32(rec_a + kRecTable + 4u * d));
-        if (HAS_WTS) weights_touch(wperm + lds_u32(rec_a + kRecRow), lane);
-    };
-
-    if (tid == 0) {
-#pragma unroll
-        for (uint32_t i = 0; i < 3; ++i) mbar_init(bar0 + 8u * i, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    uint2 r_pending = make_uint2(0, 0);   // record locator of the tile three ahead (TMA thread)
-    if (is_tma) {
-        issue(tile0, 0, v.rec[tile0]);
-        if (tile0 + stride < n_tiles) issue(tile0 + stride, 1, v.rec[tile0 + stride]);
-        if (tile0 + 2 * stride < n_tiles) issue(tile0 + 2 * stride, 2, v.rec[tile0 + 2 * stride]);
-        if (tile0 + 3 * stride < n_tiles) r_pending = v.rec[tile0 + 3 * stride];
-    }
-    uint32_t spar = 0;                    // phase parities of the three stage mbarriers (gather warp)
-    if (is_gather) {
-        mbar_wait(bar0, 0); spar ^= 1u;
-        gather_prev_async(stage0 + 8u * kTile, sp0);
-        cp_async_wait_all();
-    }
-
-    uint32_t tile = tile0;
-    uint32_t rs = 0;                      // stage of this tile = it % 3
-    for (uint32_t it = 0;; ++it) {
-        const uint32_t s = it & 1u;
-        const uint32_t rs1 = rs == 2u ? 0u : rs + 1u;
-        const uint32_t stg = stage0 + rs * g.stage_bytes;
-        const uint32_t next = tile + stride;
-        const bool has_next = next < n_tiles;
-        __syncthreads();   // stage rs and s_prev[s] of this tile are in place; phase 2 of the previous tile has left xs
-
-        if (is_gather && has_next) {   // stage rs1 was requested a whole iteration ago: no polling to speak of
-            mbar_wait(bar0 + 8u * rs1, (spar >> rs1) & 1u); spar ^= 1u << rs1;
-            gather_prev_async(stage0 + rs1 * g.stage_bytes + 8u * kTile, sp0 + (s ^ 1u) * g.prev_bytes);
-        }
-        uint32_t item; uint4 du;
-        tile_phase1<HAS_AUX, HAS_WTS>(v, tile, stg, stg + 8u * kTile, sp0 + s * g.prev_bytes, xs_a, tid, lane, warp, curr, wperm, item, du);
-        if (is_gather) cp_async_wait_all();
-        __syncthreads();   // xs complete; stage rs is free again; s_prev[s^1] of the next tile is in place
-
-        if (is_tma && next + 2u * stride < n_tiles) {
-            issue(next + 2u * stride, rs, r_pending);
-            if (next + 3u * stride < n_tiles) r_pending = v.rec[next + 3u * stride];
-        }
-        tile_phase2(xs_a, item, du.y, du.z, tid, warp, curr);
-
-        if (!has_next) break;
-        tile = next; rs = rs1;
-    }
-    if (v.n_fb && blockIdx.x == gridDim.x - 1u)
-        kern::rowgroup_rows<HAS_AUX, HAS_WTS>(v.csr_row_ptr, v.csr_txp, v.csr_prob, v.csr_aux, v.csr_wts, v.fb_rows, prev, curr,
-                                              tid >> 3, kThreads >> 3, v.n_fb);
-}
 
 }  // namespace tiled
 }  // namespace oar

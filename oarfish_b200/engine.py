@@ -180,16 +180,22 @@ class DeviceStore:
         n = int(nnz.value)
         return cell_ptr, txp[:n].copy(), val[:n].copy(), niter[:n_cells]
 
-    def coverage_model(self, aln_start, aln_end, txp_len, bin_width: int = 100, growth_rate: float = 2.0):
+    def coverage_model(self, aln_start, aln_end, txp_len, bin_width: int = 100, growth_rate: float = 2.0, model: str = "logistic"):
         """--model-coverage (bulk.rs:103-108): computes coverage_probabilities on the device, installs them as the
-        store's aux factor and returns them (f64[nnz])."""
+        store's aux factor and returns them (f64[nnz]).  model="binomial" is the single-cell driver's bin model
+        (single_cell.rs:132-137, binomial_probability.rs)."""
         sp, n_s, _ = _addr(np.ascontiguousarray(aln_start, dtype=np.uint32), np.dtype(np.uint32), "aln_start")
         ep, n_e, _k = _addr(np.ascontiguousarray(aln_end, dtype=np.uint32), np.dtype(np.uint32), "aln_end")
         lp, n_l, _k2 = _addr(np.ascontiguousarray(txp_len, dtype=np.uint32), np.dtype(np.uint32), "txp_len")
         if n_s != self.nnz or n_e != self.nnz or n_l != self.n_txps:
             raise ValueError("aln_start/aln_end need nnz elements, txp_len n_txps")
         out = np.zeros(max(self.nnz, 1), dtype=np.float64)
-        check(self._lib.oar_store_coverage_model(self._h, sp, ep, lp, int(bin_width), float(growth_rate), out.ctypes.data))
+        if model == "binomial":
+            check(self._lib.oar_store_coverage_model_binomial(self._h, sp, ep, lp, int(bin_width), out.ctypes.data))
+        elif model == "logistic":
+            check(self._lib.oar_store_coverage_model(self._h, sp, ep, lp, int(bin_width), float(growth_rate), out.ctypes.data))
+        else:
+            raise ValueError(f"unknown coverage model {model!r}")
         return out[:self.nnz]
 
     def posteriors(self, counts, display_thresh: float = 0.0):
@@ -226,6 +232,108 @@ class DeviceStore:
         ms = C.c_float(0.0)
         check(self._lib.oar_sweep_timed(self._h, pp, cp, wp, int(reps), C.byref(ms)))
         return float(ms.value)
+
+
+class _BorrowedStore(DeviceStore):
+    """A DeviceStore view of a store owned by a MultiStore (never destroyed from here)."""
+
+    def __init__(self, lib, handle, n_reads, nnz, n_txps, device):
+        self._lib = lib
+        self._h = C.c_void_p(handle)
+        self.n_reads, self.nnz, self.n_txps, self.device = n_reads, nnz, n_txps, device
+
+    def close(self) -> None:
+        self._h = C.c_void_p()
+
+
+class MultiStore:
+    """One resident copy of a store on each of `devices`, driven from one host thread (oar_multi_*):
+    em::bootstrap's internal fan-out (em.rs:292-314) with devices in place of pool threads."""
+
+    def __init__(self, row_ptr, txp_id, prob, n_txps: int, aux=None, devices: Optional[Sequence[int]] = None):
+        lib = _lib.load_em_lib()
+        if devices is None:
+            devices = list(range(device_count()))
+        rp, n_rp, k0 = _addr(row_ptr, np.dtype(np.uint64), "row_ptr")
+        tp, n_t, k1 = _addr(txp_id, np.dtype(np.uint32), "txp_id")
+        pp, n_p, k2 = _addr(prob, np.dtype(np.float32), "prob")
+        ap, n_a, k3 = _addr(aux, np.dtype(np.float64), "aux")
+        self.n_reads, self.nnz, self.n_txps = n_rp - 1, n_t, int(n_txps)
+        self.devices = [int(d) for d in devices]
+        dv = (C.c_int * len(self.devices))(*self.devices)
+        self._lib = lib
+        self._h = C.c_void_p()
+        check(lib.oar_multi_create(rp, tp, pp, ap, self.n_reads, self.nnz, self.n_txps, dv, len(self.devices), C.byref(self._h)))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.oar_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def store(self, i: int = 0) -> DeviceStore:
+        h = self._lib.oar_multi_store(self._h, int(i))
+        if not h:
+            raise IndexError(i)
+        return _BorrowedStore(self._lib, h, self.n_reads, self.nnz, self.n_txps, self.devices[i])
+
+    def info(self):
+        n = C.c_int(0)
+        ms = (C.c_double * 2)()
+        per = np.zeros(len(self.devices), dtype=np.uint32)
+        check(self._lib.oar_multi_info(self._h, C.byref(n), ms, per.ctypes.data))
+        return {"n_devices": int(n.value), "upload_ms": ms[0], "replicate_ms": ms[1], "last_per_device": per.tolist()}
+
+    def bootstrap(self, num_boot: int, seed: int, max_iter: int = 1000, conv_thresh: float = 1e-3, out=None):
+        """em::bootstrap over all devices: (num_boot x M counts, niter per replicate); row g is replicate (seed, g)."""
+        if out is None:
+            out = np.empty((num_boot, self.n_txps), dtype=np.float64)
+        op, n_o, _ = _addr(out, np.dtype(np.float64), "out")
+        if n_o != num_boot * self.n_txps:
+            raise ValueError("out must have num_boot * n_txps elements")
+        niter = np.zeros(max(num_boot, 1), dtype=np.uint32)
+        check(self._lib.oar_multi_bootstrap(self._h, int(num_boot), int(seed), int(max_iter), float(conv_thresh), op,
+                                            niter.ctypes.data))
+        return out, niter[:num_boot]
+
+
+def em_batched_multi(row_ptr, txp_id, prob, n_txps: int, cell_row_ptr, devices: Optional[Sequence[int]] = None, aux=None,
+                     max_iter: int = 1000, conv_thresh: float = 1e-3, min_iter: int = 50):
+    """Per-cell EMs sharded over devices (oar_em_batched_multi).  Host arrays only.
+    Returns (cell_ptr u64[C+1], txp u32, val f64, niter u32[C], cells per device)."""
+    lib = _lib.load_em_lib()
+    if devices is None:
+        devices = list(range(device_count()))
+    rp, n_rp, k0 = _addr(row_ptr, np.dtype(np.uint64), "row_ptr")
+    tp, n_t, k1 = _addr(txp_id, np.dtype(np.uint32), "txp_id")
+    pp, n_p, k2 = _addr(prob, np.dtype(np.float32), "prob")
+    ap, n_a, k3 = _addr(aux, np.dtype(np.float64), "aux")
+    crp = np.ascontiguousarray(cell_row_ptr, dtype=np.uint64)
+    n_cells = len(crp) - 1
+    dv = (C.c_int * len(devices))(*[int(d) for d in devices])
+    cell_ptr = np.zeros(n_cells + 1, dtype=np.uint64)
+    cap = n_t
+    txp = np.empty(max(cap, 1), dtype=np.uint32)
+    val = np.empty(max(cap, 1), dtype=np.float64)
+    niter = np.zeros(max(n_cells, 1), dtype=np.uint32)
+    per = np.zeros(len(devices), dtype=np.uint32)
+    nnz = C.c_uint64(0)
+    check(lib.oar_em_batched_multi(rp, tp, pp, ap, n_rp - 1, n_t, int(n_txps), crp.ctypes.data, n_cells, dv, len(devices),
+                                   int(max_iter), float(conv_thresh), int(min_iter), cell_ptr.ctypes.data, txp.ctypes.data,
+                                   val.ctypes.data, cap, C.byref(nnz), niter.ctypes.data, per.ctypes.data))
+    n = int(nnz.value)
+    return cell_ptr, txp[:n].copy(), val[:n].copy(), niter[:n_cells], per.tolist()
 
 
 def device_count() -> int:

@@ -10,6 +10,8 @@
  *   logistic / logstic_function       src/util/logistic_probability.rs:7-38
  *   logistic_prob                     src/util/logistic_probability.rs:40-79 (min_cov = total_weight/100)
  *   normalize_read_probs              src/util/normalize_probability.rs:5-74
+ *   binomial_continuous_prob          src/util/binomial_probability.rs:180-224 (the single-cell driver's model)
+ *   binomial_probability              src/util/binomial_probability.rs:7-178 (ln_gamma: statrs 0.18, restated)
  *
  * Parity is unpinned by the reference (no tests touch these functions).  Quirks are kept as they are:
  * add_interval and normalize_read_probs iterate the half-open bin range start_bin..end_bin, so the bin
@@ -82,6 +84,75 @@ void oracle_cov_logistic(uint32_t n_txps, const uint64_t *bin_off, double *bins,
     }
 }
 
+/* statrs 0.18 (Cargo.toml:46, not vendored under /root/reference) statrs::function::gamma::ln_gamma: the Lanczos
+ * approximation with g = 10.900511 and the 11 coefficients below (Godfrey), branch x >= 0.5 -- the only one the
+ * coverage model reaches (arguments are counts + 1).  Restated from the crate's published source; pinned in
+ * tests/test_oracle_kat.py against libm's lgamma (agreement to ~1e-14 relative). */
+double oracle_statrs_ln_gamma(double x)
+{
+    static const double dk[11] = {
+        2.48574089138753565546e-5, 1.05142378581721974210, -3.45687097222016235469, 4.51227709466894823700,
+        -2.98285225323576655721, 1.05639711577126713077, -1.95428773191645869583e-1, 1.70970543404441224307e-2,
+        -5.71926117404305781283e-4, 4.63399473359905636708e-6, -2.71994908488607703910e-9 };
+    const double gamma_r = 10.900511, ln_2_sqrt_e_over_pi = 0.6207822376352452223455184457816472122518527279025978;
+    double sum = dk[0];
+    for (int k = 1; k < 11; ++k) sum += dk[k] / (x + (double)k - 1.0);
+    return log(sum) + ln_2_sqrt_e_over_pi + (x - 0.5) * log((x - 0.5 + gamma_r) / 2.718281828459045235360287471352662497757);
+}
+
+/* binomial_continuous_prob + binomial_probability (src/util/binomial_probability.rs:180-224, :7-178), the coverage
+ * model of the single-cell driver (single_cell.rs:132-137): bins += total_weight/100, f32 counts and f32 bin
+ * lengths (get_normalized_counts_and_lengths, oarfish_types.rs:471-493), counts rescaled so that the fullest bin is
+ * 709, binomial pmf of every bin against the rest in log space, normalised over the transcript's bins.  Sums that
+ * the reference takes in f32 (count_sum :14, sum_vec :74) are f32 here, in the same order.  The reference panics on
+ * NaN / infinite intermediates (:88-127); this restatement lets them through. */
+void oracle_cov_binomial(uint32_t n_txps, const uint32_t *txp_len, const uint64_t *bin_off, double *bins,
+                         const double *total_weight, double *cov_prob)
+{
+    const double zero_thresh = 1e-20, max_scale = 709.0;
+    for (uint32_t t = 0; t < n_txps; ++t) {
+        const uint64_t o = bin_off[t];
+        const uint32_t n = (uint32_t)(bin_off[t + 1] - o);
+        if (n == 0) continue;
+        const double min_cov = total_weight[t] / 100.0;                                   /* :191 */
+        const float bwf = (float)round((double)txp_len[t] / (double)n);                   /* oarfish_types.rs:475 */
+        float count_sum = 0.0f, max_count = NAN;
+        double rate = 0.0;
+        for (uint32_t i = 0; i < n; ++i) {
+            bins[o + i] += min_cov;                                                       /* :192 */
+            const float c = (float)bins[o + i];
+            const float bs = (float)i * bwf, be = fminf(((float)i + 1.0f) * bwf, (float)(double)txp_len[t]);
+            const float len = be - bs;                                                    /* oarfish_types.rs:480-483 */
+            rate += (double)c / (double)len;                                              /* :195-199 */
+            count_sum += c;                                                               /* :14 */
+            max_count = fmaxf(max_count, c);                                              /* :50 */
+        }
+        if (count_sum == 0.0f || rate == 0.0) { for (uint32_t i = 0; i < n; ++i) cov_prob[o + i] = 0.0; continue; }   /* :19-25 */
+        float sum_vec = 0.0f;
+        for (uint32_t i = 0; i < n; ++i) {
+            const float c = (float)bins[o + i];
+            const float m = c == max_count ? (float)max_scale : (float)(((double)c * max_scale) / (double)max_count);   /* :62-72 */
+            sum_vec += m;                                                                 /* :74 */
+        }
+        const double ln1 = oracle_statrs_ln_gamma((double)sum_vec + 1.0);                 /* :77 */
+        double total = 0.0;
+        for (uint32_t i = 0; i < n; ++i) {
+            const float c = (float)bins[o + i];
+            const float bs = (float)i * bwf, be = fminf(((float)i + 1.0f) * bwf, (float)(double)txp_len[t]);
+            const float len = be - bs;
+            const double prob = (c == 0.0f || len == 0.0f) ? 0.0 : (double)c / ((double)len * rate);   /* :27-43 */
+            const float m = c == max_count ? (float)max_scale : (float)(((double)c * max_scale) / (double)max_count);
+            const float rest = sum_vec - m;
+            const double den = oracle_statrs_ln_gamma((double)m + 1.0) + oracle_statrs_ln_gamma((double)rest + 1.0);   /* :78-81 */
+            const double num2 = (prob > zero_thresh ? log(prob) : log(zero_thresh)) * (double)m;                 /* :84 */
+            const double num3 = ((1.0 - prob) > zero_thresh ? log(1.0 - prob) : log(zero_thresh)) * (double)rest; /* :91 */
+            const double res = exp(ln1 - den + num2 + num3);                              /* :103 */
+            cov_prob[o + i] = res; total += res;
+        }
+        for (uint32_t i = 0; i < n; ++i) cov_prob[o + i] /= total;                        /* :120-134 */
+    }
+}
+
 /* normalize_read_probs (normalize_probability.rs:5-74) -> coverage_probabilities (nnz f64). */
 void oracle_cov_normalize(const uint64_t *row_ptr, const uint32_t *txp, const uint32_t *start, const uint32_t *end,
                           uint64_t n_reads, const uint32_t *txp_len, const uint64_t *bin_off, const double *cov_prob,
@@ -114,6 +185,22 @@ void oracle_cov_normalize(const uint64_t *row_ptr, const uint32_t *txp, const ui
         const double d = nsum > 0.0 ? nsum : 1.0;                                  /* :64 */
         for (uint64_t j = row_ptr[r]; j < row_ptr[r + 1]; ++j) out[j] /= d;
     }
+}
+
+/* The whole stage with the binomial model, as single_cell.rs:132-137 runs it per cell. */
+void oracle_coverage_model_binomial(const uint64_t *row_ptr, const uint32_t *txp, const uint32_t *start, const uint32_t *end,
+                                    uint64_t n_reads, uint64_t nnz, const uint32_t *txp_len, uint32_t n_txps, uint32_t bin_width,
+                                    double *out)
+{
+    uint64_t *bin_off = (uint64_t *)malloc(sizeof(uint64_t) * ((size_t)n_txps + 1));
+    const uint64_t nb = oracle_cov_bin_offsets(txp_len, n_txps, bin_width, bin_off);
+    double *bins = (double *)calloc(nb ? nb : 1, sizeof(double));
+    double *tw = (double *)calloc(n_txps ? n_txps : 1, sizeof(double));
+    double *cp = (double *)calloc(nb ? nb : 1, sizeof(double));
+    oracle_cov_add_intervals(txp, start, end, nnz, txp_len, bin_off, bins, tw);
+    oracle_cov_binomial(n_txps, txp_len, bin_off, bins, tw, cp);
+    oracle_cov_normalize(row_ptr, txp, start, end, n_reads, txp_len, bin_off, cp, bin_width, out);
+    free(bin_off); free(bins); free(tw); free(cp);
 }
 
 /* The whole stage, as bulk.rs:103-108 runs it. */

@@ -36,6 +36,10 @@ def lib() -> C.CDLL:
         L.oracle_posteriors.argtypes = [_vp, _vp, _vp, _vp, C.c_uint64, _vp, C.c_double, _vp, _vp]
         L.oracle_aux_counts.restype = None
         L.oracle_aux_counts.argtypes = [_vp, _vp, C.c_uint64, C.c_uint32, _vp, _vp]
+        L.oracle_coverage_model_binomial.restype = None
+        L.oracle_coverage_model_binomial.argtypes = [_vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64, _vp, C.c_uint32, C.c_uint32, _vp]
+        L.oracle_statrs_ln_gamma.restype = C.c_double
+        L.oracle_statrs_ln_gamma.argtypes = [C.c_double]
         L.oracle_coverage_model.restype = None
         L.oracle_coverage_model.argtypes = [_vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64, _vp, C.c_uint32, C.c_uint32, C.c_double, _vp]
         L.port_num_threads.restype = C.c_int
@@ -126,6 +130,20 @@ def coverage_model(row_ptr, txp, start, end, txp_len, bin_width=100, growth_rate
     lib().oracle_coverage_model(_p(row_ptr), _p(txp), _p(start), _p(end), len(row_ptr) - 1, len(txp), _p(txp_len), len(txp_len),
                                 bin_width, growth_rate, _p(out))
     return out
+
+
+def coverage_model_binomial(row_ptr, txp, start, end, txp_len, bin_width=100):
+    """The single-cell driver's coverage stage (single_cell.rs:132-137, binomial_probability.rs) -> f64[nnz]."""
+    row_ptr = _c(row_ptr, np.uint64); txp = _c(txp, np.uint32); start = _c(start, np.uint32); end = _c(end, np.uint32)
+    txp_len = _c(txp_len, np.uint32)
+    out = np.zeros(len(txp), dtype=np.float64)
+    lib().oracle_coverage_model_binomial(_p(row_ptr), _p(txp), _p(start), _p(end), len(row_ptr) - 1, len(txp), _p(txp_len),
+                                         len(txp_len), bin_width, _p(out))
+    return out
+
+
+def statrs_ln_gamma(x):
+    return float(lib().oracle_statrs_ln_gamma(float(x)))
 
 
 class PortStore:

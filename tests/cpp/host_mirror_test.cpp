@@ -1,12 +1,16 @@
 // Drives the C++ host mirror (include/oarfish_em.hpp) the way oarfish's bulk driver drives src/em.rs
 // (bulk.rs:131-193).  Usage: host_mirror_test <store.bin> <out.bin> [seed]
 //   store.bin: u64 n_reads, u64 nnz, u64 n_txps, u64 row_ptr[n_reads+1], u32 txp[nnz], f32 prob[nnz]
-//   out.bin  : f64 em[M], f64 em_par[M], f64 boot[2][M]
+//   out.bin  : f64 em[M], f64 em_par[M], f64 boot[2][M], f64 boot_multi[2][M]
+//              (boot_multi: the same two replicates through oar_multi_bootstrap on all visible devices, from two
+//               concurrent host threads with their own stores -- distinct handles are independent)
 // With "--selfcheck" only the host logic runs (no GPU needed).
 #include <cstdio>
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <cmath>
+#include <thread>
 
 #include "oarfish_em.hpp"
 
@@ -68,6 +72,29 @@ int main(int argc, char **argv)
         out.write(reinterpret_cast<const char *>(c1.data()), sizeof(double) * c1.size());
         out.write(reinterpret_cast<const char *>(c2.data()), sizeof(double) * c2.size());
         for (const auto &r : reps) out.write(reinterpret_cast<const char *>(r.data()), sizeof(double) * r.size());
+        // em::bootstrap over every visible device, called from two host threads at once (each with its own copy of
+        // the store, like the workers of single_cell.rs:91-193): both must reproduce the single-device replicates
+        const int ndev = oar_device_count();
+        std::vector<int> devs;
+        for (int d = 0; d < (ndev > 0 ? ndev : 1); ++d) devs.push_back(d);
+        std::vector<std::vector<double>> got[2];
+        std::string err[2];
+        auto worker = [&](int k) {
+            try {
+                InMemoryAlignmentStore mine = store;   // deep copy, own device handles
+                EMInfo e2 = emi; e2.eq_map = &mine; e2.devices = devs;
+                if (devs.size() == 1) { em(e2, 1); }
+                got[k] = bootstrap(e2, 2, 4, seed);
+            } catch (const std::exception &e) { err[k] = e.what(); }
+        };
+        std::thread t0(worker, 0), t1(worker, 1);
+        t0.join(); t1.join();
+        for (int k = 0; k < 2; ++k) if (!err[k].empty()) throw std::runtime_error("worker: " + err[k]);
+        for (size_t b = 0; b < 2; ++b)
+            for (size_t i = 0; i < got[0][b].size(); ++i)
+                if (got[0][b][i] != got[1][b][i] && std::abs(got[0][b][i] - got[1][b][i]) > 1e-9 * std::abs(got[0][b][i]))
+                    throw std::runtime_error("concurrent bootstraps disagree");
+        for (const auto &r : got[0]) out.write(reinterpret_cast<const char *>(r.data()), sizeof(double) * r.size());
     } catch (const std::exception &e) {
         std::fprintf(stderr, "error: %s\n", e.what());
         return 3;

@@ -11,6 +11,7 @@
                    of the same gene whose exons cover >= 95 % of the read, with
                    prob = expf((score - best)/5) as in oarfish_types.rs:1107-1118.
   tiny_store.npz   the synthetic "tiny" store (oarfish_b200.synth) for regression.
+  sirv_shaped.oarstore  the SIRV-shaped store as an .oarstore dump carrying the EM's answer (oarfish_b200/storefile.py)
 
 Each fixture holds the inputs AND the oracle's outputs (counts / niter for both
 stop rules, two index-list bootstrap replicates), so the tests need neither
@@ -154,6 +155,12 @@ def main():
     np.savez_compressed(os.path.join(HERE, "sirv_store.npz"), **sirv)
     print("sirv:", len(sirv["row_ptr"]) - 1, "reads", len(sirv["txp_id"]), "alignments", int(sirv["n_txps"]), "txps",
           "niter", int(sirv["niter_min50"]), int(sirv["niter_min1"]))
+    # the same store as an .oarstore dump WITH the EM's answer -- here the oracle's (flag bit 2 set); a file written by
+    # the Rust binary has the same layout with the bit clear and pins parity on the reference itself
+    from oarfish_b200 import storefile
+    storefile.write_store(os.path.join(HERE, "sirv_shaped.oarstore"), sirv["row_ptr"], sirv["txp_id"], sirv["prob"], int(sirv["n_txps"]),
+                          counts=sirv["counts_min50"], min_iter=50, max_iter=1000, conv_thresh=1e-3, niter=int(sirv["niter_min50"]),
+                          from_oracle=True)
     s = synth.make_config("tiny")
     tiny = add_oracle_outputs(dict(row_ptr=s.row_ptr, txp_id=s.txp_id, prob=s.prob, n_txps=np.int64(s.n_txps)))
     np.savez_compressed(os.path.join(HERE, "tiny_store.npz"), **tiny)

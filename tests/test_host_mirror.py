@@ -79,3 +79,42 @@ def test_oarstore_roundtrip(tmp_path):
     import pytest
     with pytest.raises(ValueError):
         storefile.read_store(str(tmp_path / "bad"))
+
+
+def test_oarstore_carries_the_em_answer(tmp_path):
+    """A dump of the reference's own run (the Rust side writes store + counts + EM parameters)."""
+    from oarfish_b200 import storefile, synth
+    s = synth.make_config("tiny")
+    counts = np.linspace(0.0, 5.0, s.n_txps)
+    p = str(tmp_path / "ref.oarstore")
+    storefile.write_store(p, s.row_ptr, s.txp_id, s.prob, s.n_txps, counts=counts, min_iter=50, max_iter=1000, conv_thresh=1e-3)
+    rp, tx, pr, m, ax, ref = storefile.read_store_full(p)
+    assert ax is None and m == s.n_txps
+    np.testing.assert_array_equal(rp, s.row_ptr)
+    np.testing.assert_array_equal(ref["counts"], counts)
+    assert (ref["min_iter"], ref["max_iter"], ref["conv_thresh"], ref["niter"], ref["from_oracle"]) == (50, 1000, 1e-3, None, False)
+    assert storefile.read_store(p)[3] == s.n_txps            # the five-tuple reader ignores the answer
+    assert storefile.read_store_full(p.replace("ref", "ref"))[5] is not None
+
+
+def test_golden_oarstore_fixture_matches_the_oracle(oracle_mod=None):
+    """tests/golden/sirv_shaped.oarstore: store + the ORACLE's answer (flag bit 2), written by tests/golden/make_golden.py.
+    It keeps the dump reader and the GPU test that consumes dumps exercised until a maintainer adds a file written
+    by the Rust binary (flag bit 2 clear)."""
+    import glob
+    import os
+    from oarfish_b200 import storefile
+    from oracle import oracle
+    files = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.oarstore")))
+    assert files, "tests/golden holds no .oarstore fixture"
+    for f in files:
+        rp, tx, pr, m, ax, ref = storefile.read_store_full(f)
+        assert ref is not None
+        want, niter, _, _ = oracle.do_em(np.asarray(rp), np.asarray(tx), np.asarray(pr), m, max_iter=ref["max_iter"],
+                                         conv_thresh=ref["conv_thresh"], min_iter=ref["min_iter"],
+                                         cov=None if ax is None else np.asarray(ax))
+        rtol = 1e-12 if ref["from_oracle"] else 1e-5
+        big = want > 1e-8
+        assert (np.abs(np.asarray(ref["counts"])[big] - want[big]) / want[big]).max() <= rtol
+        if ref["niter"] is not None:
+            assert ref["niter"] == niter

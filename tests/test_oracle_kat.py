@@ -244,3 +244,71 @@ def test_coverage_model_known_answers(oracle_mod):
     want = [e_t0_full / (e_t0_full + e_t1_full), e_t1_full / (e_t0_full + e_t1_full), 1.0, 1.0, 1.0, 1.0]
     np.testing.assert_allclose(out, want, rtol=1e-12)
     assert e_t0_short > 0   # (single-alignment reads normalise to 1 whatever their coverage probability)
+
+
+def test_statrs_ln_gamma_restated_matches_libm(oracle_mod):
+    """statrs 0.18 ln_gamma (Lanczos g = 10.900511, 11 coefficients) as restated for the binomial coverage model:
+    agrees with libm's lgamma on the argument range the model reaches (counts + 1, up to ~709 * bins)."""
+    import math
+    for x in [0.5, 1.0, 1.5, 2.0, 3.25, 10.0, 57.5, 710.0, 1234.567, 71000.0]:
+        got, want = oracle_mod.statrs_ln_gamma(x), math.lgamma(x)
+        assert abs(got - want) <= 5e-14 * max(1.0, abs(want)), (x, got, want)
+    assert oracle_mod.statrs_ln_gamma(1.0) == pytest.approx(0.0, abs=1e-14)
+    assert oracle_mod.statrs_ln_gamma(5.0) == pytest.approx(math.log(24.0), rel=1e-14)
+
+
+def _binomial_probability_py(counts32, lengths32, rate):
+    """binomial_probability (binomial_probability.rs:7-178) restated independently in numpy scalars."""
+    import math
+    f32 = np.float32
+    count_sum = f32(0)
+    for c in counts32:
+        count_sum = f32(count_sum + c)
+    if count_sum == 0 or rate == 0:
+        return [0.0] * len(counts32)
+    probs = [0.0 if (c == 0 or l == 0) else float(c) / (float(l) * rate) for c, l in zip(counts32, lengths32)]
+    mx = max(counts32)
+    mod = [f32(709.0) if c == mx else f32((float(c) * 709.0) / float(mx)) for c in counts32]
+    sum_vec = f32(0)
+    for m in mod:
+        sum_vec = f32(sum_vec + m)
+    ln1 = math.lgamma(float(sum_vec) + 1.0)
+    res = []
+    for p, m in zip(probs, mod):
+        rest = f32(sum_vec - m)
+        den = math.lgamma(float(m) + 1.0) + math.lgamma(float(rest) + 1.0)
+        n2 = (math.log(p) if p > 1e-20 else math.log(1e-20)) * float(m)
+        n3 = (math.log(1.0 - p) if (1.0 - p) > 1e-20 else math.log(1e-20)) * float(rest)
+        res.append(math.exp(ln1 - den + n2 + n3))
+    tot = sum(res)
+    return [r / tot for r in res]
+
+
+def test_binomial_coverage_model_known_answers(oracle_mod):
+    """single_cell.rs:132-137: add_interval -> binomial_continuous_prob -> normalize_read_probs."""
+    f32 = np.float32
+    # flat coverage: every bin has the same count -> the same probability, 1/3 each; a single-alignment read -> 1
+    rp = np.array([0, 1], dtype=np.uint64)
+    out = oracle_mod.coverage_model_binomial(rp, [0], [0], [300], [300], bin_width=100)
+    np.testing.assert_allclose(out, [1.0])
+    # the two-transcript pile-up of the logistic test, bins of transcript 0 = 5.05, 1.05, 1.05 (f32)
+    rows_t = [0, 1, 0, 0, 0, 0]
+    start = [0, 0, 0, 0, 0, 0]
+    end = [300, 300, 150, 150, 150, 150]
+    rp = np.array([0, 2, 3, 4, 5, 6], dtype=np.uint64)
+    out = oracle_mod.coverage_model_binomial(rp, rows_t, start, end, [300, 300], bin_width=100)
+    c0 = [f32(5.05), f32(1.05), f32(1.05)]
+    lens = [f32(100), f32(100), f32(100)]
+    rate0 = sum(float(c) / float(l) for c, l in zip(c0, lens))
+    p0 = _binomial_probability_py(c0, lens, rate0)
+    c1 = [f32(1.01)] * 3
+    p1 = _binomial_probability_py(c1, lens, sum(float(c) / 100.0 for c in c1))
+    np.testing.assert_allclose(p1, [1 / 3] * 3, rtol=1e-12)
+    assert abs(sum(p0) - 1.0) < 1e-12
+    e_t0_full = (p0[0] + p0[1]) / 2           # bins 0 and 1 visited (start_bin..end_bin excludes the end bin)
+    e_t1_full = (p1[0] + p1[1]) / 2
+    want = [e_t0_full / (e_t0_full + e_t1_full), e_t1_full / (e_t0_full + e_t1_full), 1.0, 1.0, 1.0, 1.0]
+    np.testing.assert_allclose(out, want, rtol=1e-10)
+    # a transcript nobody aligns to has no counts: probabilities 0, and nothing divides by zero elsewhere
+    out = oracle_mod.coverage_model_binomial(np.array([0, 1], dtype=np.uint64), [1], [0], [250], [300, 250], bin_width=100)
+    np.testing.assert_allclose(out, [1.0])

@@ -1,6 +1,6 @@
 """Dev helper (GPU box): A/B timing of sweep variants in ONE process (the synthetic store is generated once).
 
-usage: python tools/dev/ab.py <config> "<OAR_SWEEP>:<ctas/SM>[:<OAR_TILE_SPAN>]" ...
+usage: python tools/dev/ab.py <config> "<label>:<ctas/SM>[:<OAR_TILE_SPAN>]" ...
 The library is the product one unless OAR_EM_LIB points at a variant (tools/dev/build_variants.sh).
 Per variant: mean of 30 back-to-back sweeps (CUDA events on the store's stream), plain and bootstrap-weighted,
 max relative error of one sweep against the CSR row-group kernel, and a complete EM (em_par rule)."""
@@ -22,7 +22,6 @@ peak = 6551.0
 ref = None
 for spec in sys.argv[2:]:
     f = spec.split(":")
-    os.environ["OAR_SWEEP"] = f[0]
     os.environ["OAR_CTAS_PER_SM"] = f[1]
     if len(f) > 2 and f[2]:
         os.environ["OAR_TILE_SPAN"] = f[2]
@@ -49,6 +48,6 @@ for spec in sys.argv[2:]:
     li = ds.layout_info()
     sweeps = ds.counters()["sweeps"]
     t = time.perf_counter(); ds.close(); t_close = time.perf_counter() - t
-    print(f"{cfg} sweep={f[0]} ctas/SM={f[1]} span={li['span']} fb={li['fallback_rows']}: {ms*1e3:.1f} us/sweep (weighted {msw*1e3:.1f}) "
+    print(f"{cfg} {os.path.basename(os.environ.get('OAR_EM_LIB', 'product'))} {f[0]} ctas/SM={f[1]} span={li['span']} fb={li['fallback_rows']}: {ms*1e3:.1f} us/sweep (weighted {msw*1e3:.1f}) "
           f"frac {alg/ms/1e6/peak:.3f} relerr {err:.1e} | EM niter {r.niter}: {sweeps/wall:.0f} it/s | create {t_create*1e3:.0f} ms close {t_close*1e3:.1f} ms",
           flush=True)

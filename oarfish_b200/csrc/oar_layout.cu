@@ -6,6 +6,7 @@
 // warp-chunks, sorts the tile's alignments by transcript and emits the
 // per-alignment (table index, position) stream.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "oar_store.cuh"
@@ -56,7 +57,44 @@ static int build_chunk_layout(oar_store *s, uint32_t span)
     OAR_CUDA(cudaMemsetAsync(counters, 0, sizeof(uint32_t) * 12, st));
     const int threads = 256;
     const int gridN = (int)std::min<uint64_t>((N + threads - 1) / threads, (uint64_t)s->sm_count * 32);
-    row_keys<<<gridN, threads, 0, st>>>(s->d_row_ptr, s->d_txp, N, key, idx, counters);
+    // transcript ids that are not gene-local: key the rows by a co-occurrence numbering instead (see oar_tiled.cuh)
+    uint32_t *vid = nullptr;
+    {
+        const char *cl = getenv("OAR_CLUSTER_IDS");   // 0 = never, 1 = always, default: when > 2 % of the rows have widely spread ids
+        const int mode = cl ? atoi(cl) : -1;
+        bool cluster = mode == 1;
+        if (mode < 0) {
+            row_id_spread<<<gridN, threads, 0, st>>>(s->d_row_ptr, s->d_txp, N, counters + 11);
+            OAR_CUDA(cudaGetLastError());
+            uint32_t h_spread = 0;
+            OAR_CUDA(cudaMemcpyAsync(&h_spread, counters + 11, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            OAR_CUDA(cudaStreamSynchronize(st));
+            cluster = (uint64_t)h_spread * 50u > (uint64_t)N;
+        }
+        if (cluster) {
+            const uint32_t M = s->n_txps;
+            uint32_t *label = nullptr, *tidx = nullptr, *tsorted = nullptr;
+            uint64_t *lkey = nullptr, *lkey_s = nullptr;
+            OAR_CUDA(sc.alloc(&label, M)); OAR_CUDA(sc.alloc(&vid, M)); OAR_CUDA(sc.alloc(&tidx, M)); OAR_CUDA(sc.alloc(&tsorted, M));
+            OAR_CUDA(sc.alloc(&lkey, M)); OAR_CUDA(sc.alloc(&lkey_s, M));
+            const int gridM = (int)std::min<uint64_t>((M + threads - 1) / threads, (uint64_t)s->sm_count * 8);
+            label_init<<<gridM, threads, 0, st>>>(label, M);
+            for (int round = 0; round < 4; ++round) {
+                label_rows<<<gridN, threads, 0, st>>>(s->d_row_ptr, s->d_txp, N, label);
+                label_jump<<<gridM, threads, 0, st>>>(label, M);
+            }
+            label_keys<<<gridM, threads, 0, st>>>(label, M, lkey, tidx);
+            OAR_CUDA(cudaGetLastError());
+            size_t tmp_bytes = 0;
+            OAR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, lkey, lkey_s, tidx, tsorted, (int)M, 0, 64, st));
+            void *tmp = nullptr;
+            OAR_CUDA(sc.alloc((char **)&tmp, tmp_bytes));
+            OAR_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, lkey, lkey_s, tidx, tsorted, (int)M, 0, 64, st));
+            label_number<<<gridM, threads, 0, st>>>(tsorted, M, vid);
+            OAR_CUDA(cudaGetLastError());
+        }
+    }
+    row_keys<<<gridN, threads, 0, st>>>(s->d_row_ptr, s->d_txp, N, vid, key, idx, counters);
     OAR_CUDA(cudaGetLastError());
     {
         size_t tmp_bytes = 0;

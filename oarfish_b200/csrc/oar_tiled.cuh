@@ -82,6 +82,24 @@ constexpr int kMaxItems = kTile / 4;      // every item belongs to a transcript 
 // LDS.128 phase hit 8 different 16-byte banks.  One thread sums one item and issues one RED: no cross-lane scan, no
 // padding to clear.  (Measured on C3: 16-slot items 228 us, 32-slot items 232 us, 8-slot units + scan 244 us.)
 // padding and non-aggregated alignments write to a trash slot right after the last item of the tile
+// prev[] of a tile's transcripts sits in shared memory as SPLIT 32-bit words: blocks of 32 table entries, 128 bytes
+// of high words followed by 128 bytes of low words.  A warp-wide LDS.32 is one wavefront whenever its lanes hit 32
+// different banks or the same word, so the E-step's gather is conflict-free for tiles with up to 32 distinct
+// transcripts (C3: 24 on average); the former LDS.64 from an array of doubles conflicted from 17 entries on
+// (98 wavefronts per tile against 64).  An alignment stores the byte offset of its entry's high word:
+#ifndef OAR_PREV_SPLIT
+#define OAR_PREV_SPLIT 1        // 0: prev[] as an array of doubles read with LDS.64 (A/B timing only)
+#endif
+#if OAR_PREV_SPLIT
+__host__ __device__ constexpr uint32_t table_off(uint32_t d) { return ((d >> 5) << 8) | ((d & 31u) << 2); }
+__host__ __device__ constexpr uint32_t table_index(uint32_t off) { return ((off >> 8) << 5) | ((off & 127u) >> 2); }
+__host__ __device__ constexpr uint32_t table_bytes(uint32_t max_d) { return 256u * ((max_d + 31u) / 32u); }
+#else
+__host__ __device__ constexpr uint32_t table_off(uint32_t d) { return 8u * d; }
+__host__ __device__ constexpr uint32_t table_index(uint32_t off) { return off >> 3; }
+__host__ __device__ constexpr uint32_t table_bytes(uint32_t max_d) { return 8u * ((max_d + 1u) & ~1u); }
+#endif
+constexpr uint32_t kPrevLo = 128u;        // low word = high word + 128 bytes
 constexpr uint32_t kInfoStray = 8u;       // chunk_info bit 3: chunk holds alignments that RED straight to global
 constexpr uint32_t kInfoMulti = 16u;      // chunk_info bit 4: some lane holds >= 2 row heads (general path)
 constexpr uint32_t kNoTxp = 0xFFFFFFFFu;
@@ -129,7 +147,7 @@ inline Geometry make_geometry(uint32_t max_rec_bytes, uint32_t max_d, uint32_t m
     g.xs_doubles = (max_x_doubles + 2u + 1u) & ~1u;
     g.stage_off = (8u * g.xs_doubles + 127u) & ~127u;
     g.prev_off = g.stage_off + kStages * g.stage_bytes;
-    g.bar_off = g.prev_off + 8u * ((max_d + 1u) & ~1u);
+    g.bar_off = g.prev_off + table_bytes(max_d);   // split high / low words, see table_off()
     g.total = g.bar_off + 16u;
     return g;
 }
@@ -137,7 +155,7 @@ inline Geometry make_geometry(uint32_t max_rec_bytes, uint32_t max_d, uint32_t m
 struct View {
     uint32_t n_tiles;
     const float *prob;         // n_tiles * kTile
-    const uint32_t *lpos;      // n_tiles * kTile : (table index * 8) | (pos * 8) << 16  (smem byte offsets)
+    const uint32_t *lpos;      // n_tiles * kTile : table_off(table index) | (pos * 8) << 16  (smem byte offsets)
     const double *aux;         // n_tiles * kTile or null
     const uint2 *rec;          // n_tiles : {record offset in 16-byte granules, record bytes}
     const uint4 *records;      // all records
@@ -155,8 +173,11 @@ struct View {
 
 // key = smallest transcript id of the row (locality key); rows that cannot be
 // tiled (empty, or longer than a warp-chunk) get kNoTxp and sort to the end.
+// `vid` (optional): a locality numbering of the transcripts (cluster_ids below) used INSTEAD of the ids for the key,
+// for stores whose transcript ids are not gene-local.
 static __global__ void row_keys(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ txp, uint64_t n_rows,
-                                uint32_t *__restrict__ key, uint32_t *__restrict__ idx, uint32_t *__restrict__ counters)
+                                const uint32_t *__restrict__ vid, uint32_t *__restrict__ key, uint32_t *__restrict__ idx,
+                                uint32_t *__restrict__ counters)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     uint32_t n_long = 0, n_skip = 0;
@@ -164,7 +185,8 @@ static __global__ void row_keys(const uint32_t *__restrict__ row_ptr, const uint
         const uint32_t s = row_ptr[r], e = row_ptr[r + 1];
         uint32_t k = kNoTxp;
         if (e > s && e - s <= (uint32_t)kChunkCap) {
-            for (uint32_t j = s; j < e; ++j) k = min(k, txp[j]);
+            if (vid) { for (uint32_t j = s; j < e; ++j) k = min(k, vid[txp[j]]); }
+            else     { for (uint32_t j = s; j < e; ++j) k = min(k, txp[j]); }
         } else {
             ++n_skip;
             if (e > s) ++n_long;
@@ -174,6 +196,75 @@ static __global__ void row_keys(const uint32_t *__restrict__ row_ptr, const uint
     }
     if (n_skip) atomicAdd(counters + 0, n_skip);   // rows not tiled
     if (n_long) atomicAdd(counters + 1, n_long);   // of which: too long (go to fallback)
+}
+
+// ---- transcript ids that are not gene-local --------------------------------------------------------------
+// The row order above clusters the reads of a gene only if its isoforms have neighbouring ids.  When they do not (a
+// reference not grouped by gene; tools/bench_robust.py "permuted"), the layout first clusters the transcripts by
+// co-occurrence: min-label propagation over the reads (every read pulls its transcripts to the smallest label among
+// them) with pointer jumping, a few rounds -- genes are small, dense components -- then transcripts are numbered by
+// (label, id) and the rows are keyed by that number.  For gene-local ids the numbering is the identity, and the
+// whole step is skipped when few rows have widely spread ids (row_id_spread).
+
+// counters[0] += rows whose ids span more than 16 * (alignments) + 64: not what reads of one gene look like
+static __global__ void row_id_spread(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ txp, uint64_t n_rows,
+                                     uint32_t *__restrict__ counters)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint32_t n = 0;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
+        const uint32_t s = row_ptr[r], e = row_ptr[r + 1];
+        if (e - s < 2u) continue;
+        uint32_t lo = kNoTxp, hi = 0;
+        for (uint32_t j = s; j < e; ++j) { const uint32_t t = txp[j]; lo = min(lo, t); hi = max(hi, t); }
+        if (hi - lo > 16u * (e - s) + 64u) ++n;
+    }
+    if (n) atomicAdd(counters, n);
+}
+
+static __global__ void label_init(uint32_t *__restrict__ label, uint32_t M)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < M; t += stride) label[t] = t;
+}
+
+// one round: every row pulls the labels of its transcripts (and of their current labels: hooking) down to the row's minimum
+static __global__ void label_rows(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ txp, uint64_t n_rows,
+                                  uint32_t *__restrict__ label)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
+        const uint32_t s = row_ptr[r], e = row_ptr[r + 1];
+        if (e - s < 2u) continue;
+        uint32_t m = kNoTxp;
+        for (uint32_t j = s; j < e; ++j) m = min(m, label[txp[j]]);
+        for (uint32_t j = s; j < e; ++j) {
+            const uint32_t t = txp[j], l = label[t];
+            if (l > m) { atomicMin(label + t, m); atomicMin(label + l, m); }
+        }
+    }
+}
+
+static __global__ void label_jump(uint32_t *__restrict__ label, uint32_t M)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < M; t += stride) {
+        uint32_t l = label[t], ll = label[l];
+        while (ll != l) { l = ll; ll = label[l]; }   // labels only decrease and label[x] <= x: the chain ends at a root
+        label[t] = l;
+    }
+}
+
+static __global__ void label_keys(const uint32_t *__restrict__ label, uint32_t M, uint64_t *__restrict__ key, uint32_t *__restrict__ idx)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < M; t += stride) { key[t] = ((uint64_t)label[t] << 32) | t; idx[t] = t; }
+}
+
+static __global__ void label_number(const uint32_t *__restrict__ sorted_t, uint32_t M, uint32_t *__restrict__ vid)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += stride) vid[sorted_t[i]] = i;
 }
 
 // lengths of the tiled rows in sorted order
@@ -554,7 +645,9 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
                 // one winner per (transcript, residue) and per (half-warp, residue): the lane whose transcript has the
                 // fewest residues left on offer (model, tools/layout_model.py: 89 -> 80 scatter wavefronts per tile);
                 // the lane with the smallest key of the warp wins both of its groups, so every round places someone
-                const bool go = prop && __reduce_min_sync(m1, key) == key && __reduce_min_sync(m2, key) == key;
+                // (both reductions are executed by every lane: a lane named in a mask must take part)
+                const uint32_t win1 = __reduce_min_sync(m1, key), win2 = __reduce_min_sync(m2, key);
+                const bool go = prop && win1 == key && win2 == key;
                 uint32_t took = 0;
                 if (go) {
                     uint32_t m = q ? s_fulluse[ci][rho] : 0u;
@@ -593,7 +686,7 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
                 const uint32_t j = dj >> 16, n32 = (pb >> 12) & 0x3FFu;
                 pos = j < kI * n32 ? kS0 * ((pa >> 11) + j / kI) + j % kI : (pb & 0xFFFu) + (j - kI * n32);
             } else atomicOr(&s_info[slot / kChunk], kInfoStray);
-            s_lpos[slot] = (d * 8u) | ((pos * 8u) << 16);
+            s_lpos[slot] = table_off(d) | ((pos * 8u) << 16);
         } else {
             s_lpos[slot] = 0u | ((XD * 8u) << 16);
         }
@@ -611,7 +704,7 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
                 const uint32_t rr = r - (pa & 0x7FFu), n32 = (pb >> 12) & 0x3FFu;
                 pos = rr < kI * n32 ? kS0 * ((pa >> 11) + rr / kI) + rr % kI : (pb & 0xFFFu) + (rr - kI * n32);
             } else atomicOr(&s_info[vals[i] / kChunk], kInfoStray);
-            s_lpos[vals[i]] = (d * 8u) | ((pos * 8u) << 16);
+            s_lpos[vals[i]] = table_off(d) | ((pos * 8u) << 16);
         } else {
             s_lpos[vals[i]] = 0u | ((XD * 8u) << 16);
         }
@@ -708,6 +801,27 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t a)
 { uint4 r; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a)); return r; }
 __device__ __forceinline__ float4 lds_v4f(uint32_t a)
 { float4 r; asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a)); return r; }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// prev[] entry from its split words (see table_off): two LDS.32, the second at a constant offset
+__device__ __forceinline__ double lds_prev(uint32_t a)
+{
+#if OAR_PREV_SPLIT
+    uint32_t hi, lo;
+    asm volatile("ld.shared.u32 %0, [%2];\n\tld.shared.u32 %1, [%2+128];" : "=r"(hi), "=r"(lo) : "r"(a));
+    return __hiloint2double((int)hi, (int)lo);
+#else
+    double r; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(a)); return r;
+#endif
+}
+__device__ __forceinline__ void sts_prev(uint32_t a, double v)
+{
+#if OAR_PREV_SPLIT
+    sts_u32(a, (uint32_t)__double2hiint(v));
+    sts_u32(a + kPrevLo, (uint32_t)__double2loint(v));
+#else
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+#endif
+}
 __device__ __forceinline__ double lds_f64(uint32_t a) { double r; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(a)); return r; }
 __device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 __device__ __forceinline__ void sts_f64_if(uint32_t a, double v, bool on)
@@ -751,10 +865,10 @@ __device__ __forceinline__ void tile_phase1_core(const View &v, uint32_t tile, c
     const uint32_t info = lds_u32(rec + kRecInfo + 4u * warp);
     const uint32_t table_a = rec + kRecTable;
 
-    double w0 = lds_f64(sp_a + (lp4.x & 0xFFFFu)) * (double)p4.x;
-    double w1 = lds_f64(sp_a + (lp4.y & 0xFFFFu)) * (double)p4.y;
-    double w2 = lds_f64(sp_a + (lp4.z & 0xFFFFu)) * (double)p4.z;
-    double w3 = lds_f64(sp_a + (lp4.w & 0xFFFFu)) * (double)p4.w;
+    double w0 = lds_prev(sp_a + (lp4.x & 0xFFFFu)) * (double)p4.x;
+    double w1 = lds_prev(sp_a + (lp4.y & 0xFFFFu)) * (double)p4.y;
+    double w2 = lds_prev(sp_a + (lp4.z & 0xFFFFu)) * (double)p4.z;
+    double w3 = lds_prev(sp_a + (lp4.w & 0xFFFFu)) * (double)p4.w;
     if (HAS_AUX) {
         const double *ax = v.aux + (size_t)tile * kTile + 4u * tid;
         const double2 q0 = *reinterpret_cast<const double2 *>(ax);
@@ -867,10 +981,10 @@ __device__ __forceinline__ void tile_phase1_core(const View &v, uint32_t tile, c
 #endif
     if (strays) {
         // transcripts with fewer than kAggMin alignments in this tile: straight to global
-        if (q0 == trash && x0 != 0.0) atomicAdd(curr + lds_u32(table_a + ((lp4.x & 0xFFFFu) >> 1)), x0);
-        if (q1 == trash && x1 != 0.0) atomicAdd(curr + lds_u32(table_a + ((lp4.y & 0xFFFFu) >> 1)), x1);
-        if (q2 == trash && x2 != 0.0) atomicAdd(curr + lds_u32(table_a + ((lp4.z & 0xFFFFu) >> 1)), x2);
-        if (q3 == trash && x3 != 0.0) atomicAdd(curr + lds_u32(table_a + ((lp4.w & 0xFFFFu) >> 1)), x3);
+        if (q0 == trash && x0 != 0.0) atomicAdd(curr + lds_u32(table_a + 4u * table_index(lp4.x & 0xFFFFu)), x0);
+        if (q1 == trash && x1 != 0.0) atomicAdd(curr + lds_u32(table_a + 4u * table_index(lp4.y & 0xFFFFu)), x1);
+        if (q2 == trash && x2 != 0.0) atomicAdd(curr + lds_u32(table_a + 4u * table_index(lp4.z & 0xFFFFu)), x2);
+        if (q3 == trash && x3 != 0.0) atomicAdd(curr + lds_u32(table_a + 4u * table_index(lp4.w & 0xFFFFu)), x3);
     }
 }
 
@@ -982,8 +1096,8 @@ __global__ void __launch_bounds__(kThreads, (OAR_TILED_MIN_CTAS * 8) / kWarps) e
             const double p0 = prev[lds_u32(rec_a + kRecTable + 4u * d)];
             double p1 = 0.0;
             if (d2 < Dn) p1 = prev[lds_u32(rec_a + kRecTable + 4u * d2)];
-            sts_f64(sp_a + 8u * d, p0);
-            if (d2 < Dn) sts_f64(sp_a + 8u * d2, p1);
+            sts_prev(sp_a + table_off(d), p0);
+            if (d2 < Dn) sts_prev(sp_a + table_off(d2), p1);
         }
     };
 

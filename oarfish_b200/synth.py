@@ -70,6 +70,48 @@ def make_config(name: str, **kw) -> SynthStore:
     return make_store(**CONFIGS[name], **kw)
 
 
+def permute_ids(store: SynthStore, seed: int) -> SynthStore:
+    """The same store with transcript ids shuffled: isoforms of a gene are no longer neighbours in id space (a
+    reference whose sequences are not grouped by gene).  Robustness workload; the EM result is the permuted one."""
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(store.n_txps).astype(np.uint32)
+    return SynthStore(store.row_ptr, perm[store.txp_id], store.prob, store.n_txps, None, None)
+
+
+def with_long_rows(store: SynthStore, frac: float, lo: int, hi: int, seed: int) -> SynthStore:
+    """Replace a fraction of the reads by reads with lo..hi alignments (beyond --best-n's default of 100): a window of
+    neighbouring transcripts starting at the read's first target.  Robustness workload for the layout's row-length cliff."""
+    rng = np.random.default_rng(seed)
+    n = store.n_reads
+    lens = np.diff(store.row_ptr).astype(np.int64)
+    pick = rng.random(n) < frac
+    new_lens = lens.copy()
+    new_lens[pick] = rng.integers(lo, hi + 1, size=int(pick.sum()))
+    new_lens = np.minimum(new_lens, store.n_txps)
+    rp = np.zeros(n + 1, dtype=np.uint64)
+    np.cumsum(new_lens, out=rp[1:])
+    nnz = int(rp[-1])
+    txp = np.empty(nnz, dtype=np.uint32)
+    prob = np.empty(nnz, dtype=np.float32)
+    keep = ~pick
+    # unchanged rows: copy their alignments
+    src_idx = np.repeat(store.row_ptr[:-1][keep].astype(np.int64), lens[keep]) + (np.arange(int(lens[keep].sum())) - np.repeat(np.cumsum(lens[keep]) - lens[keep], lens[keep]))
+    dst_idx = np.repeat(rp[:-1][keep].astype(np.int64), lens[keep]) + (np.arange(int(lens[keep].sum())) - np.repeat(np.cumsum(lens[keep]) - lens[keep], lens[keep]))
+    txp[dst_idx] = store.txp_id[src_idx]
+    prob[dst_idx] = store.prob[src_idx]
+    # long rows: first target of the old read, then the following transcripts (wrapping), probabilities from the generator's table
+    L = new_lens[pick]
+    first = store.txp_id[store.row_ptr[:-1][pick].astype(np.int64)].astype(np.int64)
+    off = np.arange(int(L.sum())) - np.repeat(np.cumsum(L) - L, L)
+    d_idx = np.repeat(rp[:-1][pick].astype(np.int64), L) + off
+    txp[d_idx] = ((np.repeat(first, L) + off) % store.n_txps).astype(np.uint32)
+    ptab = np.exp(-np.arange(61, dtype=np.float32) / np.float32(5.0)).astype(np.float32)
+    pr = ptab[rng.integers(0, 61, size=len(d_idx))]
+    pr[off == 0] = 1.0
+    prob[d_idx] = pr
+    return SynthStore(rp, txp, prob, store.n_txps, None, None)
+
+
 def make_cells(cell_reads, n_txps: int, avg_aln: float, seed: int):
     """Concatenated store of several cells (single-cell mode): cell c has cell_reads[c] reads drawn
     from its own abundance vector.  Returns (SynthStore, cell_row_ptr u64[C+1])."""

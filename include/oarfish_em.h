@@ -105,6 +105,16 @@ int oar_em(oar_store *store, const double *init_or_null, uint32_t max_iter, doub
            uint32_t min_iter, double *out_counts, uint32_t *out_niter, double *out_rel_diff);
 
 /*
+ * Progress of a running EM, the counterpart of the reference's log lines ("iteration {niter}; rel diff {rel_diff}",
+ * em.rs:219-233: every 10 iterations up to 100, then every 100).  The convergence test runs on the device and the
+ * host looks at it once per batch of 16 iterations, so `fn` is called from the calling thread of oar_em /
+ * oar_bootstrap with the state after every such batch: niter (the loop counter) and the last rel_diff evaluated.
+ * NULL removes the callback.
+ */
+typedef void (*oar_progress_fn)(uint32_t niter, double rel_diff, void *user);
+int oar_store_set_progress(oar_store *store, oar_progress_fn fn, void *user);
+
+/*
  * Bootstrap replicates (em::bootstrap, em.rs:292-314).  Replicate b of this
  * call is global replicate  g = first_replicate + b * replicate_stride ; its
  * resampling weights are a pure function of (seed, g), so sharding replicates

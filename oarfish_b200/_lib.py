@@ -55,6 +55,7 @@ ABI = {
     "oar_sweep": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int]),
     "oar_sweep_timed": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.POINTER(C.c_float)]),
     "oar_store_stream": (_vp, [_vp]),
+    "oar_store_set_progress": (C.c_int, [_vp, _vp, _vp]),
     "oar_multi_create": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64, C.c_uint32, _vp, C.c_int, C.POINTER(_vp)]),
     "oar_multi_destroy": (None, [_vp]),
     "oar_multi_store": (_vp, [_vp, C.c_int]),
@@ -63,6 +64,8 @@ ABI = {
     "oar_em_batched_multi": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64, C.c_uint32, _vp, C.c_uint32, _vp, C.c_int,
                                         C.c_uint32, C.c_double, C.c_uint32, _vp, _vp, _vp, C.c_uint64, _u64p, _vp, _vp]),
 }
+
+PROGRESS_FN = C.CFUNCTYPE(None, C.c_uint32, C.c_double, C.c_void_p)
 
 _em_lib = None
 _synth_lib = None

@@ -17,7 +17,9 @@
 #include <algorithm>
 #include <vector>
 
+#include <cstdio>
 #include <cstdlib>
+#include <ctime>
 
 #include "oar_store.cuh"
 
@@ -407,8 +409,12 @@ extern "C" int oar_em_batched(oar_store *s, const uint64_t *cell_row_ptr, uint32
             oar_store *sub = nullptr;
             // d_lid belongs to the sub-store from here on (substore_create frees it when it fails)
             sc.p.erase(std::remove(sc.p.begin(), sc.p.end(), (void *)d_lid), sc.p.end());
+            const bool trace = getenv("OAR_TRACE") != nullptr;   // development: wall-clock split on stderr
+            auto wall = [&]() { cudaStreamSynchronize(st); timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+            const double t_a = trace ? wall() : 0.0;
             int rc = substore_create(s, d_lid, (uint32_t)total, &sub);
             if (rc != OAR_OK) return rc;
+            const double t_b = trace ? wall() : 0.0;
             struct SubGuard { oar_store *p; ~SubGuard() { oar_store_destroy(p); } } sg{sub};
             // chunks of at most 4096 ids, never crossing a cell
             std::vector<cells::Chunk> h_chunks;
@@ -472,6 +478,7 @@ extern "C" int oar_em_batched(oar_store *s, const uint64_t *cell_row_ptr, uint32
             cudaGraphDestroy(graph);
             if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate");
             struct ExecGuard { cudaGraphExec_t x; ~ExecGuard() { cudaGraphExecDestroy(x); } } eg{exec};
+            const double t_c = trace ? wall() : 0.0;
             // two graph launches in flight; the state copied after each is polled (launches after the end are no-ops)
             uint64_t launched = 0;
             int inflight = 0, head = 0;
@@ -489,6 +496,11 @@ extern "C" int oar_em_batched(oar_store *s, const uint64_t *cell_row_ptr, uint32
                 head ^= 1; --inflight;
             }
             OAR_CUDA(cudaStreamSynchronize(st));
+            if (trace) {
+                const double t_d = wall();
+                fprintf(stderr, "[oar] cells: sub-store layout %.1f ms (%u tiles), setup + graph %.1f ms, EM loop %.1f ms (%llu graph launches of 16 iterations, %u cells, %llu pairs)\n",
+                        t_b - t_a, sub->tl.n_tiles, t_c - t_b, t_d - t_c, (unsigned long long)(launched / 65), n_cells, (unsigned long long)total);
+            }
             s->counters[0] += launched + 4;
             // per-cell iteration counts
             std::vector<cells::CellState> h_cs(n_cells);

@@ -305,6 +305,13 @@ extern "C" int oar_store_set_kernel(oar_store *s, int kernel)
     return OAR_OK;
 }
 
+extern "C" int oar_store_set_progress(oar_store *s, oar_progress_fn fn, void *user)
+{
+    if (!s) return fail(OAR_ERR_INVALID, "oar_store_set_progress: store is null");
+    s->progress = fn; s->progress_user = user;
+    return OAR_OK;
+}
+
 extern "C" int oar_store_layout_info(const oar_store *s, uint64_t out[8])
 {
     if (!s || !out) return fail(OAR_ERR_INVALID, "oar_store_layout_info: null argument");
@@ -552,6 +559,7 @@ static int run_em(oar_store *s, const double *init_dev, uint32_t max_iter, doubl
             }
             OAR_CUDA(cudaEventSynchronize(s->slot_ev[head]));
             const OarEmState &hs = s->h_state[head];
+            if (s->progress) s->progress(hs.niter, hs.last_rel, s->progress_user);
             if (hs.done) { done = true; sweeps = hs.sweeps; niter = hs.niter; rel = hs.last_rel; }
             head ^= 1; --inflight;
         }

@@ -6,6 +6,7 @@
 // warp-chunks, sorts the tile's alignments by transcript and emits the
 // per-alignment (table index, position) stream.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -155,8 +156,18 @@ static int build_chunk_layout(oar_store *s, uint32_t span)
         a.srow = srow; a.tile_row = tile_row;
         a.o_prob = t.prob; a.o_lpos = t.lpos; a.o_aux = t.aux; a.o_rec = t.rec; a.o_records = records_tmp;
         a.o_trow = t.trow; a.fallback = t.fallback; a.cursors = counters + 4;
+        const bool trace = getenv("OAR_TRACE") != nullptr;   // development: time of the tile builder on stderr
+        if (trace) OAR_CUDA(cudaEventRecord(s->ev[2], st));
         build_tiles<<<n_tiles, kThreads, 0, st>>>(a);
         OAR_CUDA(cudaGetLastError());
+        if (trace) {
+            OAR_CUDA(cudaEventRecord(s->ev[3], st));
+            OAR_CUDA(cudaEventSynchronize(s->ev[3]));
+            float ms_pre = 0.f, ms_tiles = 0.f;
+            cudaEventElapsedTime(&ms_pre, s->ev[0], s->ev[2]);
+            cudaEventElapsedTime(&ms_tiles, s->ev[2], s->ev[3]);
+            fprintf(stderr, "[oar] layout: upload + keys + sort %.2f ms, build_tiles %.2f ms (%u tiles)\n", ms_pre, ms_tiles, n_tiles);
+        }
     }
     if (n_long > 0) {
         const int g = (int)std::min<uint64_t>((N - n_tiled + threads - 1) / threads, (uint64_t)s->sm_count * 8);

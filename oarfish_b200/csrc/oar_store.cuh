@@ -63,6 +63,9 @@ struct oar_store {
 
     oar::GraphSlot graphs[2];  // [0] unweighted, [1] weighted
 
+    oar_progress_fn progress = nullptr;   // called after every polled batch of iterations (em.rs:219-233's log lines)
+    void *progress_user = nullptr;
+
     double timings[4] = {0, 0, 0, 0};
     uint64_t counters[2] = {0, 0};
 };

@@ -627,13 +627,23 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
                 br = (cw >> 15) ? (2u * (i32 + q)) & 15u : pb & 15u;
             }
             uint32_t G = 0;   // residues taken in this lane's half-warp
-            while (__any_sync(full, todo)) {
-                uint32_t rho = 0, st = 0, key = 0xFFFF0000u | lane;
-                bool prop = todo;                          // does this lane propose in this round?
-                if (prop) {
+            // Scarce first (model, tools/layout_model.py: 89 -> 80 scatter wavefronts per tile): lanes whose transcript
+            // offers at most kScarce residues (remainder items of 4 or 8 slots) choose in a first phase, the others
+            // after them.  (Ranking the lanes with __reduce_min_sync over the match groups did the same in one phase,
+            // but a reduction whose mask differs between the lanes is serialised group by group: build_tiles 17 -> 45 ms.)
+            constexpr uint32_t kScarce = 8;
+#pragma unroll 1
+            for (uint32_t phase = OAR_GREEDY_SCARCE ? 0u : 1u; phase < 2u; ++phase)
+            for (;;) {
+                uint32_t rho = 0, st = 0;
+                bool prop = false;                         // does this lane propose in this round?
+                if (todo) {
                     st = s_state[d];
+                    prop = phase == 1u || (uint32_t)__popc(st & 0xFFFFu) <= kScarce;
+                }
+                if (!__any_sync(full, prop)) break;
+                if (prop) {
                     const uint32_t av = st & 0xFFFFu;      // never 0 here: the transcript still owes this lane a position
-                    key = ((OAR_GREEDY_SCARCE ? (uint32_t)__popc(av) : 0u) << 5) | lane;   // scarce first: the fewer residues on offer, the higher the priority
                     uint32_t cand = av & ~G;
                     if (cand == 0u) cand = av;             // no unused residue on offer: accept a bank conflict
                     const uint32_t rot = ((cand >> l16) | (cand << (16u - l16))) & 0xFFFFu;
@@ -642,12 +652,9 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
                 const uint32_t idle = 0x80000000u | lane;
                 const unsigned m1 = __match_any_sync(full, prop ? ((d << 4) | rho) : idle);
                 const unsigned m2 = __match_any_sync(full, prop ? ((half << 4) | rho) : idle);
-                // one winner per (transcript, residue) and per (half-warp, residue): the lane whose transcript has the
-                // fewest residues left on offer (model, tools/layout_model.py: 89 -> 80 scatter wavefronts per tile);
-                // the lane with the smallest key of the warp wins both of its groups, so every round places someone
-                // (both reductions are executed by every lane: a lane named in a mask must take part)
-                const uint32_t win1 = __reduce_min_sync(m1, key), win2 = __reduce_min_sync(m2, key);
-                const bool go = prop && win1 == key && win2 == key;
+                // one winner per (transcript, residue) and per (half-warp, residue): the lowest lane of each group; the
+                // lowest proposing lane of the warp wins both of its groups, so every round places someone
+                const bool go = prop && (uint32_t)(__ffs((int)m1) - 1) == lane && (uint32_t)(__ffs((int)m2) - 1) == lane;
                 uint32_t took = 0;
                 if (go) {
                     uint32_t m = q ? s_fulluse[ci][rho] : 0u;

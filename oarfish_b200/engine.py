@@ -91,6 +91,15 @@ class DeviceStore:
     def set_kernel(self, kernel: int) -> None:
         check(self._lib.oar_store_set_kernel(self._h, int(kernel)))
 
+    def set_progress(self, fn=None) -> None:
+        """fn(niter, rel_diff) after every polled batch of EM iterations (the reference's em.rs:219-233 log lines)."""
+        if fn is None:
+            self._progress = None
+            check(self._lib.oar_store_set_progress(self._h, None, None))
+            return
+        self._progress = _lib.PROGRESS_FN(lambda niter, rel, _user: fn(int(niter), float(rel)))
+        check(self._lib.oar_store_set_progress(self._h, C.cast(self._progress, C.c_void_p), None))
+
     @property
     def stream(self) -> int:
         return int(self._lib.oar_store_stream(self._h) or 0)

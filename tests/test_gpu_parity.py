@@ -151,6 +151,21 @@ def test_reference_dumps(DS, path):
             assert r.niter == ref["niter"]
 
 
+def test_progress_callback_reports_the_running_em(DS, small_store):
+    """em.rs:219-233 logs niter / rel_diff while the EM runs; the ABI reports them after every polled batch."""
+    s = small_store
+    seen = []
+    with DS(s.row_ptr, s.txp_id, s.prob, s.n_txps) as ds:
+        ds.set_progress(lambda niter, rel: seen.append((niter, rel)))
+        r = ds.em(min_iter=50)
+        assert seen and seen[-1][0] == r.niter and seen[-1][1] == r.rel_diff
+        assert [n for n, _ in seen] == sorted(n for n, _ in seen) and all(rel >= 0.0 for _, rel in seen)
+        n_calls = len(seen)
+        ds.set_progress(None)
+        ds.em(min_iter=50)
+        assert len(seen) == n_calls
+
+
 def test_empty_store(DS):
     rp = np.zeros(1, dtype=np.uint64)
     with DS(rp, np.zeros(0, np.uint32), np.zeros(0, np.float32), 5) as ds:

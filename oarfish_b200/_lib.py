@@ -88,6 +88,8 @@ def load_em_lib() -> C.CDLL:
             "oarfish_b200 has no CPU fallback.")
     lib = C.CDLL(EM_LIB_PATH, mode=C.RTLD_GLOBAL)
     for name, (res, args) in ABI.items():
+        if os.environ.get("OAR_EM_LIB") and not hasattr(lib, name):
+            continue  # an older build selected for A/B timing (tools/dev): entry points added since are simply absent
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args

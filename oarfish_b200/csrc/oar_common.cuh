@@ -26,6 +26,8 @@ struct OarEmState {
     uint32_t ticket;
     uint32_t max_iter;
     uint32_t min_iter;
+    uint32_t primed;              // fused update: the first sweep of an EM has no predecessor to judge
+    uint32_t pad_;
 };
 
 namespace oar {

@@ -79,9 +79,19 @@ void ctx_give_host_state(DeviceCtx *c, OarEmState *p)
     c->host_states.push_back(p);
 }
 
-cudaError_t ctx_ensure_smem(DeviceCtx *c, const void *fn, int bytes)
+cudaError_t ctx_ensure_smem(DeviceCtx *c, const void *fn, int bytes, int *static_bytes_or_null)
 {
     std::lock_guard<std::mutex> lk(c->mu);
+    if (static_bytes_or_null) {
+        auto st = c->smem_static.find(fn);
+        if (st == c->smem_static.end()) {
+            cudaFuncAttributes a;
+            cudaError_t e = cudaFuncGetAttributes(&a, fn);
+            if (e != cudaSuccess) return e;
+            st = c->smem_static.emplace(fn, (int)a.sharedSizeBytes).first;
+        }
+        *static_bytes_or_null = st->second;
+    }
     auto it = c->smem_attr.find(fn);
     if (it != c->smem_attr.end() && it->second >= bytes) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);

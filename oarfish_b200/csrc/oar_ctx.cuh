@@ -28,6 +28,7 @@ struct DeviceCtx {
     std::vector<cudaEvent_t> timing_events, plain_events;
     std::vector<OarEmState *> host_states;
     std::unordered_map<const void *, int> smem_attr;   // kernel -> cudaFuncAttributeMaxDynamicSharedMemorySize granted
+    std::unordered_map<const void *, int> smem_static; // kernel -> its static shared memory (cudaFuncGetAttributes)
 };
 
 // The context of `device` (current device is switched to it); null + *err on failure.
@@ -40,6 +41,7 @@ void ctx_give_event(DeviceCtx *c, bool timing, cudaEvent_t e);
 cudaError_t ctx_take_host_state(DeviceCtx *c, OarEmState **out);
 void ctx_give_host_state(DeviceCtx *c, OarEmState *p);
 // Raise the dynamic shared-memory limit of kernel `fn` to at least `bytes` (once per device and size).
-cudaError_t ctx_ensure_smem(DeviceCtx *c, const void *fn, int bytes);
+// *static_bytes_or_null receives the kernel's static shared-memory size.
+cudaError_t ctx_ensure_smem(DeviceCtx *c, const void *fn, int bytes, int *static_bytes_or_null = nullptr);
 
 }  // namespace oar

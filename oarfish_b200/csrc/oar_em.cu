@@ -37,7 +37,7 @@ using namespace oar;
 // store
 // ---------------------------------------------------------------------------
 
-static const int kGraphIters = 16;  // EM iterations per graph launch (even)
+static const int kGraphIters = 18;  // EM iterations per graph launch (a multiple of 3: three count buffers rotate)
 
 static void destroy_graphs(oar_store *s)
 {
@@ -68,7 +68,7 @@ extern "C" void oar_store_destroy(oar_store *s)
     free_tiled_layout(s);
     if (!s->borrowed) { dfree(s->d_row_ptr, s->stream); dfree(s->d_prob, s->stream); dfree(s->d_aux, s->stream); }
     dfree(s->d_txp, s->stream);
-    dfree(s->d_counts[0], s->stream); dfree(s->d_counts[1], s->stream); dfree(s->d_state, s->stream); dfree(s->d_weights, s->stream);
+    dfree(s->d_counts[0], s->stream); dfree(s->d_counts[1], s->stream); dfree(s->d_counts[2], s->stream); dfree(s->d_state, s->stream); dfree(s->d_weights, s->stream);
     if (s->stream) cudaStreamSynchronize(s->stream);
     // stream, events and the pinned state block go back to the device context's pools (cudaFreeHost / cudaStreamDestroy
     // synchronise the whole context: 0.8-400 ms per store on the GPU box)
@@ -96,7 +96,7 @@ int substore_create(oar_store *parent, uint32_t *d_txp, uint32_t n_txps, oar_sto
     s->d_row_ptr = parent->d_row_ptr; s->d_prob = parent->d_prob; s->d_aux = parent->d_aux; s->d_txp = d_txp;
     for (int i = 0; i < 4; ++i) s->ev[i] = parent->ev[i];
     for (int i = 0; i < 2; ++i) s->slot_ev[i] = parent->slot_ev[i];
-    s->ctas_per_sm = parent->ctas_per_sm;
+    s->ctas_per_sm = parent->ctas_per_sm; s->allow_fused = parent->allow_fused;
     int rc = [&]() -> int {
         OAR_CUDA(dmalloc(&s->d_state, sizeof(OarEmState) * 3, s->stream));
         OAR_CUDA(cudaMemsetAsync(s->d_state, 0, sizeof(OarEmState) * 3, s->stream));
@@ -127,6 +127,8 @@ static int finish_store(oar_store *s)
         if (rc2 == OAR_OK) s->kernel = OAR_KERNEL_TILED;
         else if (rc2 != OAR_ERR_UNSUPPORTED) return rc2;   // unsupported shape: keep the CSR kernel
     }
+    const char *fu = getenv("OAR_FUSED_UPDATE");   // 0: em_update as its own launch between the sweeps (A/B timing)
+    s->allow_fused = !(fu && fu[0] == '0');
     const char *cps = getenv("OAR_CTAS_PER_SM");
     if (cps && atoi(cps) > 0) s->ctas_per_sm = atoi(cps);
     return OAR_OK;
@@ -156,6 +158,7 @@ static int new_store(int device, uint64_t n_reads, uint64_t nnz, uint32_t n_txps
         OAR_CUDA(ctx_take_host_state(ctx, &s->h_state));
         OAR_CUDA(dmalloc(&s->d_counts[0], sizeof(double) * n_txps, s->stream));
         OAR_CUDA(dmalloc(&s->d_counts[1], sizeof(double) * n_txps, s->stream));
+        OAR_CUDA(dmalloc(&s->d_counts[2], sizeof(double) * n_txps, s->stream));
         OAR_CUDA(dmalloc(&s->d_state, sizeof(OarEmState) * 2, s->stream));
         return OAR_OK;
     }();
@@ -351,6 +354,7 @@ static tiled::View tiled_view(const oar_store *s)
     tiled::View v;
     v.n_tiles = t.n_tiles; v.prob = t.prob; v.lpos = t.lpos; v.aux = t.aux; v.rec = t.rec; v.records = t.records; v.wlane = t.wlane;
     v.tile_list = nullptr; v.n_active = nullptr;
+    v.upd_old = nullptr; v.upd_state = nullptr; v.upd_m = 0;
     // a handful of fallback rows rides along in the tiled kernel; a long list gets its own launch
     const bool fold = t.n_fallback <= kFoldFallbackMax;
     v.fb_rows = t.fallback; v.n_fb = fold ? t.n_fallback : 0u;
@@ -364,13 +368,18 @@ static cudaError_t launch_tiled(oar_store *s, const tiled::View &v, const double
 {
     auto kfn = tiled::em_sweep_tiled<AUX, WTS, LIST>;
     const tiled::Geometry g = tiled::make_geometry(s->tl.max_rec, s->tl.max_d, s->tl.max_u, WTS);
-    cudaError_t ae = ctx_ensure_smem(s->ctx, reinterpret_cast<const void *>(kfn), (int)g.total);
+    int static_bytes = 0;
+    cudaError_t ae = ctx_ensure_smem(s->ctx, reinterpret_cast<const void *>(kfn), (int)g.total, &static_bytes);
     if (ae != cudaSuccess) return ae;
+    // shared-space address of the dynamic window: 1 KB reserved by the system, then the kernel's static shared memory,
+    // rounded up to the 128-byte alignment of the extern array (the kernel checks it against its own cvta)
+    tiled::Geometry gg = g;
+    gg.xs_base = (1024u + (uint32_t)static_bytes + 127u) & ~127u;
     // persistent CTAs: as many per SM as shared memory allows, capped by the register budget (5)
     int per_sm = (int)((227u * 1024u) / (g.total + 1024u));
     per_sm = std::max(1, std::min(per_sm, s->ctas_per_sm));
     const uint32_t grid = std::min<uint32_t>(v.n_tiles, (uint32_t)s->sm_count * (uint32_t)per_sm);
-    kfn<<<grid, tiled::kThreads, g.total, s->stream>>>(v, g, prev, curr, wperm, state, check_done);
+    kfn<<<grid, tiled::kThreads, g.total, s->stream>>>(v, gg, prev, curr, wperm, state, check_done);
     return cudaGetLastError();
 }
 
@@ -396,8 +405,12 @@ static cudaError_t enqueue_rowgroup(oar_store *s, const uint32_t *list, uint64_t
 // Enqueue one fused E+M sweep prev -> curr (curr must already be zero).
 // `wts` are per-read weights in read order; the tiled kernel reads the copy
 // permuted into tile order (s->tl.wperm, refreshed by refresh_wperm()).
+// the sweep can carry the convergence bookkeeping of the PREVIOUS iteration (tiled kernel only, see fused_update())
+static bool fused_update(const oar_store *s)
+{ return s->allow_fused && s->kernel == OAR_KERNEL_TILED && s->tl.ready && s->tl.n_tiles > 0; }
+
 static cudaError_t enqueue_sweep(oar_store *s, const double *prev, double *curr, const uint32_t *wts,
-                                 const OarEmState *state, int check_done)
+                                 const OarEmState *state, int check_done, double *upd_old = nullptr)
 {
     if (s->n_reads == 0) return cudaSuccess;
     if (s->kernel != OAR_KERNEL_TILED || !s->tl.ready)   // no layout (OAR_TILED=0, unsupported shape, failed rebuild): the CSR kernel
@@ -406,6 +419,7 @@ static cudaError_t enqueue_sweep(oar_store *s, const double *prev, double *curr,
     if (t.n_tiles > 0) {
         tiled::View v = tiled_view(s);
         v.csr_wts = wts;
+        if (upd_old) { v.upd_old = upd_old; v.upd_state = s->d_state; v.upd_m = s->n_txps; }
         const uint32_t *wp = wts ? t.wperm : nullptr;
         cudaError_t le;
         if (s->d_aux) le = wts ? launch_tiled<true, true>(s, v, prev, curr, wp, state, check_done)
@@ -492,17 +506,20 @@ static cudaError_t enqueue_update(oar_store *s, double *prev, const double *curr
 static int ensure_graph(oar_store *s, bool weighted)
 {
     GraphSlot &g = s->graphs[weighted ? 1 : 0];
-    if (g.exec && g.kernel == s->kernel) return OAR_OK;
+    if (g.exec && g.kernel == s->kernel && g.fused == fused_update(s)) return OAR_OK;
     if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
     const uint32_t *wts = weighted ? s->d_weights : nullptr;
     uint64_t saved = s->counters[0];
     cudaGraph_t graph = nullptr;
     OAR_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
     cudaError_t e = cudaSuccess;
+    const bool fused = fused_update(s);
     for (int it = 0; it < kGraphIters && e == cudaSuccess; ++it) {
-        double *prev = s->d_counts[it & 1], *curr = s->d_counts[(it + 1) & 1];
-        e = enqueue_sweep(s, prev, curr, wts, s->d_state, 1);
-        if (e == cudaSuccess) e = enqueue_update(s, prev, curr);
+        // sweep k: X[k % 3] -> X[(k + 1) % 3].  Fused: its head judges sweep k-1 (X[(k + 2) % 3] against X[k % 3]) and zeroes
+        // X[(k + 2) % 3], the target of sweep k+1.  Otherwise em_update judges sweep k right after it and zeroes X[k % 3].
+        double *prev = s->d_counts[it % 3], *curr = s->d_counts[(it + 1) % 3], *old = s->d_counts[(it + 2) % 3];
+        e = enqueue_sweep(s, prev, curr, wts, s->d_state, 1, fused ? old : nullptr);
+        if (e == cudaSuccess && !fused) e = enqueue_update(s, prev, curr);
     }
     cudaError_t e2 = cudaStreamEndCapture(s->stream, &graph);
     s->counters[0] = saved;
@@ -511,7 +528,7 @@ static int ensure_graph(oar_store *s, bool weighted)
     e = cudaGraphInstantiate(&g.exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) { g.exec = nullptr; return cuda_fail(e, "cudaGraphInstantiate"); }
-    g.kernel = s->kernel;
+    g.kernel = s->kernel; g.fused = fused;
     return OAR_OK;
 }
 
@@ -534,7 +551,7 @@ static int run_em(oar_store *s, const double *init_dev, uint32_t max_iter, doubl
         const int threads = 256;
         const int blocks = (int)std::max<uint32_t>(1, std::min<uint32_t>((M + threads - 1) / threads, (uint32_t)s->sm_count * 8));
         const double avg = (double)s->n_reads / (double)M;
-        kern::em_init<<<blocks, threads, 0, s->stream>>>(s->d_counts[0], s->d_counts[1], init_dev, avg, M);
+        kern::em_init<<<blocks, threads, 0, s->stream>>>(s->d_counts[0], s->d_counts[1], s->d_counts[2], init_dev, avg, M);
         s->counters[0] += 1;
         OAR_CUDA(cudaGetLastError());
     }
@@ -565,10 +582,12 @@ static int run_em(oar_store *s, const double *init_dev, uint32_t max_iter, doubl
         }
         // the launches still in flight are no-ops (done is set); they finish before the final sweep (same stream)
         // every kernel node of every graph launch is a launch of ours (those after convergence exit at once)
-        const uint64_t per_iter = 2 + ((s->kernel != OAR_KERNEL_ROWGROUP && s->tl.n_tiles > 0 && s->tl.n_fallback > kFoldFallbackMax) ? 1 : 0);
+        const uint64_t per_iter = (fused_update(s) ? 1 : 2) + ((s->kernel != OAR_KERNEL_ROWGROUP && s->tl.n_tiles > 0 && s->tl.n_fallback > kFoldFallbackMax) ? 1 : 0);
         s->counters[0] += launched_iters * per_iter;
     }
-    double *prev = s->d_counts[sweeps & 1], *curr = s->d_counts[(sweeps + 1) & 1];
+    // `sweeps` loop sweeps were judged: the last result is X[sweeps % 3]; X[(sweeps + 2) % 3] is zero (zeroed by the head of
+    // the sweep after it, or by em_update / em_init), whatever a speculative sweep wrote into X[(sweeps + 1) % 3]
+    double *prev = s->d_counts[sweeps % 3], *curr = s->d_counts[(sweeps + 2) % 3];
     {
         const int threads = 256;
         const int blocks = (int)std::max<uint32_t>(1, std::min<uint32_t>((M + threads - 1) / threads, (uint32_t)s->sm_count * 8));

@@ -43,13 +43,14 @@ static __global__ void validate_txp(const uint32_t *__restrict__ txp, uint64_t n
 // ---------------------------------------------------------------------------
 
 // prev = init or avg (em.rs:160-167); curr = 0 (em.rs:158)
-static __global__ void em_init(double *__restrict__ prev, double *__restrict__ curr, const double *__restrict__ init,
-                        double avg, uint32_t M)
+static __global__ void em_init(double *__restrict__ prev, double *__restrict__ curr, double *__restrict__ third,
+                        const double *__restrict__ init, double avg, uint32_t M)
 {
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += stride) {
         prev[i] = init ? init[i] : avg;
         curr[i] = 0.0;
+        third[i] = 0.0;
     }
 }
 
@@ -59,6 +60,25 @@ static __global__ void em_threshold(double *__restrict__ prev, uint32_t M)
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += stride)
         if (prev[i] < OAR_MIN_READ_THRESH) prev[i] = 0.0;
+}
+
+// The stop rule of do_em / em_par (em.rs:212-218, :399, :181), applied by whoever holds the last ticket of an
+// iteration's rel-diff reduction: consumes rel_bits, advances niter / sweeps, sets done.
+__device__ __forceinline__ void em_decide(OarEmState *st)
+{
+    const unsigned long long bits = atomicAdd(&st->rel_bits, 0ull);
+    const double rel = __longlong_as_double((long long)bits);
+    st->last_rel = rel;
+    st->sweeps += 1;
+    if (rel < st->conv_thresh && st->niter > st->min_iter) {
+        st->done = 1;                       // break (em.rs:212-214)
+    } else {
+        st->niter += 1;                     // em.rs:218
+        if (st->niter >= st->max_iter) st->done = 1;  // while niter < max_iter (em.rs:181)
+    }
+    st->rel_bits = 0ull;                    // em.rs:234
+    st->ticket = 0;
+    __threadfence();
 }
 
 // After a sweep prev -> curr:  rel_diff = max_i{(curr_i - prev_i)/prev_i : prev_i > 1e-5}
@@ -101,20 +121,52 @@ static __global__ void __launch_bounds__(256) em_update(double *__restrict__ pre
     __syncthreads();
     if (is_last && threadIdx.x == 0) {
         __threadfence();
-        const unsigned long long bits = atomicAdd(&st->rel_bits, 0ull);
-        const double rel = __longlong_as_double((long long)bits);
-        st->last_rel = rel;
-        st->sweeps += 1;
-        if (rel < st->conv_thresh && st->niter > st->min_iter) {
-            st->done = 1;                       // break (em.rs:212-214)
-        } else {
-            st->niter += 1;                     // em.rs:218
-            if (st->niter >= st->max_iter) st->done = 1;  // while niter < max_iter (em.rs:181)
-        }
-        st->rel_bits = 0ull;                    // em.rs:234
-        st->ticket = 0;
-        __threadfence();
+        em_decide(st);
     }
+}
+
+// The same bookkeeping FUSED into the head of the next sweep (em_sweep_tiled): every CTA of sweep k+1 judges its slice
+// of iteration k -- old = prev of sweep k, now = its result (the prev of sweep k+1) -- zeroes old (the target of sweep
+// k+2; three buffers rotate) and takes a ticket; the last one applies the stop rule.  Sweep k+1 itself runs on: if
+// the rule says stop, its output is simply not used (the result is `now`, thresholded, swept once more into the
+// buffer zeroed here).  Saves the em_update launch between every two sweeps (6.6 us of 195 on C3).
+__device__ __forceinline__ void em_update_slice(double *__restrict__ old, const double *__restrict__ now, uint32_t M, OarEmState *st)
+{
+    __shared__ double s_wmax[32];
+    __shared__ bool s_last;
+    const uint32_t per = (M + gridDim.x - 1) / gridDim.x;
+    const uint32_t b = blockIdx.x * per, e = min(M, b + per);
+    double m = 0.0;
+    for (uint32_t i = b + threadIdx.x; i < e; i += blockDim.x) {
+        const double pc = old[i];
+        const double cc = now[i];
+        if (pc > OAR_MIN_READ_THRESH) {
+            const double rd = (cc - pc) / pc;
+            m = rd > m ? rd : m;
+        }
+        old[i] = 0.0;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double other = __shfl_xor_sync(0xffffffffu, m, o);
+        m = other > m ? other : m;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_wmax[warp] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double bm = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) bm = s_wmax[w] > bm ? s_wmax[w] : bm;
+        if (bm > 0.0) atomicMax(&st->rel_bits, (unsigned long long)__double_as_longlong(bm));
+        __threadfence();
+        const uint32_t t = atomicAdd(&st->ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+        if (s_last) {
+            __threadfence();
+            if (st->primed) em_decide(st);
+            else { st->primed = 1; st->rel_bits = 0ull; st->ticket = 0; __threadfence(); }   // first sweep of the EM: nothing to judge
+        }
+    }
+    __syncthreads();
 }
 
 // ---------------------------------------------------------------------------

@@ -30,6 +30,7 @@ struct TiledLayout {
 struct GraphSlot {
     cudaGraphExec_t exec = nullptr;
     int kernel = 0;
+    bool fused = false;   // built with the convergence bookkeeping inside the sweep
 };
 
 }  // namespace oar
@@ -42,6 +43,7 @@ struct oar_store {
     uint64_t n_reads = 0, nnz = 0;
     uint32_t n_txps = 0;
     int kernel = OAR_KERNEL_ROWGROUP;
+    bool allow_fused = true;   // convergence bookkeeping inside the sweep's head (OAR_FUSED_UPDATE=0 turns it off)
     bool borrowed = false;  // sub-store of another store: row_ptr / prob / aux / stream / events are not owned
     int ctas_per_sm = 40 / OAR_TILE_WARPS_DEFAULT;  // persistent CTAs of the tiled sweep per SM (upper bound; shared memory may allow fewer)
 
@@ -54,7 +56,7 @@ struct oar_store {
     oar::TiledLayout tl;
 
     // EM work buffers
-    double *d_counts[2] = {nullptr, nullptr};
+    double *d_counts[3] = {nullptr, nullptr, nullptr};   // three rotate: prev, curr, and the one being zeroed for the sweep after
     OarEmState *d_state = nullptr;
     OarEmState *h_state = nullptr;  // pinned, oar::kHostStateSlots slots (from the context's pool)
     uint32_t *d_weights = nullptr;  // N, bootstrap weights of the current replicate (read order)

@@ -128,8 +128,13 @@ constexpr int kStages = 2;
 struct Geometry {
     uint32_t stage_bytes;   // prob (4 KB) | lpos (4 KB) | record (max over tiles, 16 B multiple) [| lane weights u16[256]]
     uint32_t w_off;         // offset of the lane weights inside a stage (bootstrap only)
-    uint32_t xs_off;        // 0: transcript-sorted x values in items (+ trash) sit at the start of the window, so the
-                            // scatter addresses are the stored offsets themselves
+    uint32_t xs_base;       // shared-space address of the dynamic window = of the x array (transcript-sorted x values in
+                            // items + trash), which sits at its start.  Filled in by the launcher (1 KB reserved by the
+                            // system + the kernel's static shared memory) and handed over as a kernel PARAMETER so that it
+                            // is warp-uniform by construction: the scatter and the item reads are `[offset + UR]`.  Left to
+                            // the compiler (a cvta on the extern array) the base was rematerialised per tile either with
+                            // S2UR + ULEA or -- after unrelated changes to the parameter list -- with S2R + LEA and four
+                            // vector adds per thread: 185 vs 191 us.  The kernel traps if the address is not the real one.
     uint32_t stage_off;     // the two stages
     uint32_t prev_off;      // prev[] of the tile's transcripts
     uint32_t bar_off;       // two mbarriers
@@ -142,7 +147,7 @@ inline Geometry make_geometry(uint32_t max_rec_bytes, uint32_t max_d, uint32_t m
     const uint32_t rec = (max_rec_bytes + 15u) & ~15u;
     g.w_off = 8u * kTile + rec;
     g.stage_bytes = g.w_off + (weighted ? 2u * kThreads : 0u);
-    g.xs_off = 0;
+    g.xs_base = 0;   // set by the launcher
     // the items of the fullest tile, then the trash slot; even count
     g.xs_doubles = (max_x_doubles + 2u + 1u) & ~1u;
     g.stage_off = (8u * g.xs_doubles + 127u) & ~127u;
@@ -165,6 +170,10 @@ struct View {
     const uint32_t *fb_rows; uint32_t n_fb;
     const uint32_t *csr_row_ptr; const uint32_t *csr_txp; const float *csr_prob; const double *csr_aux;
     const uint32_t *csr_wts;   // bootstrap weights in read order (fallback rows are not in tile order)
+    // fused convergence bookkeeping (kern::em_update_slice): the previous sweep's prev buffer, or null.  (Kept at the END
+    // of the struct: with these fields in the middle ptxas stopped treating the shared window base as warp-uniform in
+    // phase 1 -- S2R + LEA per use instead of S2UR + ULEA -- and the sweep went from 185 to 191 us.)
+    double *upd_old; OarEmState *upd_state; uint32_t upd_m;
 };
 
 // ---------------------------------------------------------------------------
@@ -1080,9 +1089,9 @@ __global__ void __launch_bounds__(kThreads, (OAR_TILED_MIN_CTAS * 8) / kWarps) e
     uint32_t sm0;   // shared-space address of the window, computed once (a plain cvta is rematerialised every iteration)
     asm volatile("{.reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t;}" : "=r"(sm0) : "l"(smem));
     const uint32_t stage0 = sm0 + g.stage_off, sp_a = sm0 + g.prev_off, bar0 = sm0 + g.bar_off;
-    // xs sits at the start of the window; the plain cvta is warp-uniform to the compiler, so the scatter and the
-    // item reads address it as [offset + uniform base]
-    const uint32_t xs_a = smem_u32(smem);
+    // xs sits at the start of the window; its address comes as a parameter (see Geometry::xs_base)
+    const uint32_t xs_a = g.xs_base;
+    if (sm0 != xs_a) __trap();
 
     // Work between the two CTA barriers of a tile is spread over the warps: the first warps sum the items
     // (phase 2), lane 0 of the last-but-one warp issues the TMA copies, the last warp gathers prev[].
@@ -1122,6 +1131,11 @@ __global__ void __launch_bounds__(kThreads, (OAR_TILED_MIN_CTAS * 8) / kWarps) e
         if (tile0 + stride < n_tiles) { const uint32_t p1 = phys(tile0 + stride); issue(p1, 1, v.rec[p1]); }
         if (tile0 + 2 * stride < n_tiles) { t_pending = phys(tile0 + 2 * stride); r_pending = v.rec[t_pending]; }
     }
+    // the first copies are in flight: judge the previous iteration on this CTA's slice of the count vectors
+#ifndef OAR_FUSED_PROLOGUE
+#define OAR_FUSED_PROLOGUE 1    // 0 compiles the fused bookkeeping out (A/B timing of the sweep itself)
+#endif
+    if (OAR_FUSED_PROLOGUE && !LIST && v.upd_old) kern::em_update_slice(v.upd_old, prev, v.upd_m, v.upd_state);
     // Only the last warp waits on the stage mbarriers and gathers prev[]; the CTA barrier that follows hands the
     // TMA-written stage on to the other warps (mbarrier completion observed by one thread + bar.sync is cumulative).
     if (warp == kWarps - 1) {

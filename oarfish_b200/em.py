@@ -132,10 +132,24 @@ class InMemoryAlignmentStore:
         aux = np.ascontiguousarray(self.coverage_probabilities) if self.filter_opts.model_coverage else None
         return np.ascontiguousarray(self._boundaries), txp, np.ascontiguousarray(self.as_probabilities), aux
 
+    def invalidate_device(self) -> None:
+        """Drop the HBM copy: the next em / em_par / bootstrap uploads the store again."""
+        if self._device_store is not None:
+            self._device_store.close()
+        self._device_store = None
+        self._device_key = None
+
     def device_store(self, n_txps: int, device: int = 0) -> DeviceStore:
+        """The HBM copy of the store (created on first use, reused by em then bootstrap like bulk.rs:155-179).  It is
+        a snapshot keyed on the store's shape AND on the identity of its arrays: replacing `alignments`,
+        `as_probabilities` or `coverage_probabilities` (normalize_read_probs does that once the store is built) or
+        changing `filter_opts.model_coverage` uploads again; after mutating an array IN PLACE call invalidate_device()."""
         self._flush()
-        key = (int(n_txps), int(device), len(self.alignments), self.filter_opts.model_coverage)
+        key = (int(n_txps), int(device), len(self.alignments), self.filter_opts.model_coverage, id(self.alignments),
+               id(self.as_probabilities), id(self.coverage_probabilities))
         if self._device_store is None or self._device_key != key:
+            if self._device_store is not None:
+                self._device_store.close()
             rp, txp, prob, aux = self.csr()
             self._device_store = DeviceStore(rp, txp, prob, n_txps, aux=aux, device=device)
             self._device_key = key

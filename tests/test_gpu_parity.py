@@ -280,6 +280,26 @@ def test_reference_interface_mirror(DS, oracle_mod, tiny_store):
     assert all(abs(r.sum() - s.n_reads) < 1e-6 * s.n_reads for r in reps)
 
 
+def test_mirror_store_reuploads_when_its_arrays_are_replaced(DS, oracle_mod, tiny_store):
+    """The mirror's HBM copy is a snapshot: replacing coverage_probabilities after the first EM (what
+    normalize_read_probs does in the reference) must not reuse the stale copy."""
+    from oarfish_b200 import EMInfo, InMemoryAlignmentStore, TranscriptInfo, em
+    s = tiny_store
+    cov0 = np.full(s.nnz, 1.0)
+    store = InMemoryAlignmentStore.from_csr(s.row_ptr, s.txp_id, s.prob, coverage=cov0, model_coverage=True)
+    emi = EMInfo(eq_map=store, txp_info=[TranscriptInfo() for _ in range(s.n_txps)])
+    first = em(emi, 1)
+    cov1 = 0.25 + 0.75 * ((np.arange(s.nnz) * 2654435761 % 1000) / 999.0)
+    store.coverage_probabilities = cov1
+    want, *_ = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps, min_iter=50, cov=cov1)
+    second = em(emi, 1)
+    assert_counts_close(second, want)
+    assert not np.allclose(first, second)
+    store.coverage_probabilities[:] = 1.0        # in place: the caller says so
+    store.invalidate_device()
+    assert_counts_close(em(emi, 1), first)
+
+
 def test_cpp_host_mirror_matches_oracle(DS, oracle_mod, tiny_store, tmp_path):
     """The C++ host layer (include/oarfish_em.hpp) driven like bulk.rs drives src/em.rs."""
     import subprocess

@@ -27,7 +27,8 @@ struct OarEmState {
     uint32_t max_iter;
     uint32_t min_iter;
     uint32_t primed;              // fused update: the first sweep of an EM has no predecessor to judge
-    uint32_t pad_;
+    uint32_t n_txps;              // fused update: length of the count vectors
+    double *bufs[3];              // fused update: the three rotating count vectors
 };
 
 namespace oar {

@@ -354,7 +354,6 @@ static tiled::View tiled_view(const oar_store *s)
     tiled::View v;
     v.n_tiles = t.n_tiles; v.prob = t.prob; v.lpos = t.lpos; v.aux = t.aux; v.rec = t.rec; v.records = t.records; v.wlane = t.wlane;
     v.tile_list = nullptr; v.n_active = nullptr;
-    v.upd_old = nullptr; v.upd_state = nullptr; v.upd_m = 0;
     // a handful of fallback rows rides along in the tiled kernel; a long list gets its own launch
     const bool fold = t.n_fallback <= kFoldFallbackMax;
     v.fb_rows = t.fallback; v.n_fb = fold ? t.n_fallback : 0u;
@@ -362,11 +361,11 @@ static tiled::View tiled_view(const oar_store *s)
     return v;
 }
 
-template <bool AUX, bool WTS, bool LIST = false>
+template <bool AUX, bool WTS, bool LIST = false, bool FUSED = false>
 static cudaError_t launch_tiled(oar_store *s, const tiled::View &v, const double *prev, double *curr,
                                 const uint32_t *wperm, const OarEmState *state, int check_done)
 {
-    auto kfn = tiled::em_sweep_tiled<AUX, WTS, LIST>;
+    auto kfn = tiled::em_sweep_tiled<AUX, WTS, LIST, FUSED>;
     const tiled::Geometry g = tiled::make_geometry(s->tl.max_rec, s->tl.max_d, s->tl.max_u, WTS);
     int static_bytes = 0;
     cudaError_t ae = ctx_ensure_smem(s->ctx, reinterpret_cast<const void *>(kfn), (int)g.total, &static_bytes);
@@ -410,7 +409,7 @@ static bool fused_update(const oar_store *s)
 { return s->allow_fused && s->kernel == OAR_KERNEL_TILED && s->tl.ready && s->tl.n_tiles > 0; }
 
 static cudaError_t enqueue_sweep(oar_store *s, const double *prev, double *curr, const uint32_t *wts,
-                                 const OarEmState *state, int check_done, double *upd_old = nullptr)
+                                 const OarEmState *state, int check_done, bool fused = false)
 {
     if (s->n_reads == 0) return cudaSuccess;
     if (s->kernel != OAR_KERNEL_TILED || !s->tl.ready)   // no layout (OAR_TILED=0, unsupported shape, failed rebuild): the CSR kernel
@@ -419,13 +418,19 @@ static cudaError_t enqueue_sweep(oar_store *s, const double *prev, double *curr,
     if (t.n_tiles > 0) {
         tiled::View v = tiled_view(s);
         v.csr_wts = wts;
-        if (upd_old) { v.upd_old = upd_old; v.upd_state = s->d_state; v.upd_m = s->n_txps; }
         const uint32_t *wp = wts ? t.wperm : nullptr;
         cudaError_t le;
-        if (s->d_aux) le = wts ? launch_tiled<true, true>(s, v, prev, curr, wp, state, check_done)
-                               : launch_tiled<true, false>(s, v, prev, curr, wp, state, check_done);
-        else          le = wts ? launch_tiled<false, true>(s, v, prev, curr, wp, state, check_done)
-                               : launch_tiled<false, false>(s, v, prev, curr, wp, state, check_done);
+        if (fused) {
+            if (s->d_aux) le = wts ? launch_tiled<true, true, false, true>(s, v, prev, curr, wp, state, check_done)
+                                   : launch_tiled<true, false, false, true>(s, v, prev, curr, wp, state, check_done);
+            else          le = wts ? launch_tiled<false, true, false, true>(s, v, prev, curr, wp, state, check_done)
+                                   : launch_tiled<false, false, false, true>(s, v, prev, curr, wp, state, check_done);
+        } else {
+            if (s->d_aux) le = wts ? launch_tiled<true, true>(s, v, prev, curr, wp, state, check_done)
+                                   : launch_tiled<true, false>(s, v, prev, curr, wp, state, check_done);
+            else          le = wts ? launch_tiled<false, true>(s, v, prev, curr, wp, state, check_done)
+                                   : launch_tiled<false, false>(s, v, prev, curr, wp, state, check_done);
+        }
         if (le != cudaSuccess) return le;
         s->counters[0] += 1;
         cudaError_t e = cudaGetLastError();
@@ -517,8 +522,8 @@ static int ensure_graph(oar_store *s, bool weighted)
     for (int it = 0; it < kGraphIters && e == cudaSuccess; ++it) {
         // sweep k: X[k % 3] -> X[(k + 1) % 3].  Fused: its head judges sweep k-1 (X[(k + 2) % 3] against X[k % 3]) and zeroes
         // X[(k + 2) % 3], the target of sweep k+1.  Otherwise em_update judges sweep k right after it and zeroes X[k % 3].
-        double *prev = s->d_counts[it % 3], *curr = s->d_counts[(it + 1) % 3], *old = s->d_counts[(it + 2) % 3];
-        e = enqueue_sweep(s, prev, curr, wts, s->d_state, 1, fused ? old : nullptr);
+        double *prev = s->d_counts[it % 3], *curr = s->d_counts[(it + 1) % 3];
+        e = enqueue_sweep(s, prev, curr, wts, s->d_state, 1, fused);
         if (e == cudaSuccess && !fused) e = enqueue_update(s, prev, curr);
     }
     cudaError_t e2 = cudaStreamEndCapture(s->stream, &graph);
@@ -544,6 +549,8 @@ static int run_em(oar_store *s, const double *init_dev, uint32_t max_iter, doubl
     memset(&init_state, 0, sizeof(init_state));
     init_state.conv_thresh = thr; init_state.max_iter = max_iter; init_state.min_iter = min_iter;
     init_state.done = (max_iter == 0) ? 1u : 0u;
+    init_state.n_txps = M;
+    for (int i = 0; i < 3; ++i) init_state.bufs[i] = s->d_counts[i];
     s->h_state[3] = init_state;
     OAR_CUDA(cudaMemcpyAsync(s->d_state, &s->h_state[3], sizeof(OarEmState), cudaMemcpyHostToDevice, s->stream));
     // prev = init or N/M (em.rs:160-167); curr = 0 (em.rs:158)

@@ -130,10 +130,9 @@ static __global__ void __launch_bounds__(256) em_update(double *__restrict__ pre
 // k+2; three buffers rotate) and takes a ticket; the last one applies the stop rule.  Sweep k+1 itself runs on: if
 // the rule says stop, its output is simply not used (the result is `now`, thresholded, swept once more into the
 // buffer zeroed here).  Saves the em_update launch between every two sweeps (6.6 us of 195 on C3).
-__device__ __forceinline__ void em_update_slice(double *__restrict__ old, const double *__restrict__ now, uint32_t M, OarEmState *st)
+// `s_wmax`: 33 doubles of shared memory the caller is not using yet (the sweep's x array).
+__device__ __forceinline__ void em_update_slice(double *__restrict__ old, const double *__restrict__ now, uint32_t M, OarEmState *st, double *s_wmax)
 {
-    __shared__ double s_wmax[32];
-    __shared__ bool s_last;
     const uint32_t per = (M + gridDim.x - 1) / gridDim.x;
     const uint32_t b = blockIdx.x * per, e = min(M, b + per);
     double m = 0.0;
@@ -159,8 +158,7 @@ __device__ __forceinline__ void em_update_slice(double *__restrict__ old, const 
         if (bm > 0.0) atomicMax(&st->rel_bits, (unsigned long long)__double_as_longlong(bm));
         __threadfence();
         const uint32_t t = atomicAdd(&st->ticket, 1u);
-        s_last = (t == gridDim.x - 1);
-        if (s_last) {
+        if (t == gridDim.x - 1) {
             __threadfence();
             if (st->primed) em_decide(st);
             else { st->primed = 1; st->rel_bits = 0ull; st->ticket = 0; __threadfence(); }   // first sweep of the EM: nothing to judge

@@ -170,10 +170,6 @@ struct View {
     const uint32_t *fb_rows; uint32_t n_fb;
     const uint32_t *csr_row_ptr; const uint32_t *csr_txp; const float *csr_prob; const double *csr_aux;
     const uint32_t *csr_wts;   // bootstrap weights in read order (fallback rows are not in tile order)
-    // fused convergence bookkeeping (kern::em_update_slice): the previous sweep's prev buffer, or null.  (Kept at the END
-    // of the struct: with these fields in the middle ptxas stopped treating the shared window base as warp-uniform in
-    // phase 1 -- S2R + LEA per use instead of S2UR + ULEA -- and the sweep went from 185 to 191 us.)
-    double *upd_old; OarEmState *upd_state; uint32_t upd_m;
 };
 
 // ---------------------------------------------------------------------------
@@ -871,7 +867,12 @@ __device__ __forceinline__ bool any_bits(uint32_t v, uint32_t mask)
 //   bulk, rec: shared-space addresses of the tile's prob | lpos block and of its record; sp_a: prev[] of the tile's
 //   transcripts; xs_a: the x array.  Returns the thread's item and the record's DU word for phase 2.
 //   The thread's four slots (prob, lpos) come in registers: p4 / lp4 = slots warp * kChunk + lane * 4 ...
-template <bool HAS_AUX, bool HAS_WTS>
+#ifndef OAR_COMMON_PATH
+#define OAR_COMMON_PATH 1       // sweep: one vote sends chunks without a rare feature down a copy of phase 1 that has none of them
+#endif
+// COMMON: the chunk has no lane with two row heads, no row spanning more than 8 lanes and no stray alignments (90 % of
+// the chunks on C3): those three tests are compile-time false and cost neither votes nor branches.
+template <bool HAS_AUX, bool HAS_WTS, bool COMMON = false>
 __device__ __forceinline__ void tile_phase1_core(const View &v, uint32_t tile, const float4 p4, const uint4 lp4, uint32_t rec, uint32_t sp_a,
                                                  uint32_t xs_a, uint32_t trash, uint32_t w_in, uint32_t tid, uint32_t lane, uint32_t warp,
                                                  double *__restrict__ curr, const uint32_t *__restrict__ wperm)
@@ -896,9 +897,9 @@ __device__ __forceinline__ void tile_phase1_core(const View &v, uint32_t tile, c
     // bootstrap: w_in = the resampling weight of the row that ends in this lane (fast path; staged with the tile,
     // see lane_weights)
     // chunk_info is the same word for the whole warp; votes make that visible to the compiler
-    const bool multi = any_bits(info, kInfoMulti);
-    const bool strays = any_bits(info, kInfoStray);
-    const bool long_rows = any_bits(info, 4u);   // scan steps > 3: rows spanning more than 8 lanes
+    const bool multi = !COMMON && any_bits(info, kInfoMulti);
+    const bool strays = !COMMON && any_bits(info, kInfoStray);
+    const bool long_rows = !COMMON && any_bits(info, 4u);   // scan steps > 3: rows spanning more than 8 lanes
     const bool mid_rows = !OAR_SCAN_COND || __any_sync(full, (info & 7u) >= 3u);   // scan steps > 2
     double x0, x1, x2, x3;
     if (!multi) {
@@ -1018,7 +1019,16 @@ __device__ __forceinline__ void tile_phase1(const View &v, uint32_t tile, uint32
     if (tid < du.y) item = lds_u32(rec + kRecTable + 4u * (((du.x + 3u) & ~3u) + tid));
     uint32_t w_in = 0;
     if (HAS_WTS) w_in = lds_u16(wl_a + 2u * tid);
-    tile_phase1_core<HAS_AUX, HAS_WTS>(v, tile, p4, lp4, rec, sp_a, xs_a, du.w, w_in, tid, lane, warp, curr, wperm);
+#ifndef OAR_COMMON_PATH_WTS
+#define OAR_COMMON_PATH_WTS 0   // the bootstrap-weighted sweep keeps the single general copy of phase 1 (measured: 185.3 vs 186.6 us)
+#endif
+#if OAR_COMMON_PATH
+    // chunk_info is the same word in every lane of the warp: one vote decides between the two copies of phase 1
+    if ((OAR_COMMON_PATH_WTS || !HAS_WTS) && !any_bits(lds_u32(rec + kRecInfo + 4u * warp), kInfoMulti | kInfoStray | 4u))
+        tile_phase1_core<HAS_AUX, HAS_WTS, true>(v, tile, p4, lp4, rec, sp_a, xs_a, du.w, w_in, tid, lane, warp, curr, wperm);
+    else
+#endif
+    tile_phase1_core<HAS_AUX, HAS_WTS, false>(v, tile, p4, lp4, rec, sp_a, xs_a, du.w, w_in, tid, lane, warp, curr, wperm);
 }
 
 // ---- phase 2 of a tile: one thread sums one item (<= 16 consecutive x slots of one transcript), one RED -------
@@ -1063,7 +1073,10 @@ __device__ __forceinline__ void tile_phase2(uint32_t xs_a, uint32_t item, uint32
 // m_step (em.rs:87-133), persistent and TMA-fed.
 // LIST: the sweep walks v.tile_list[0 .. *v.n_active) instead of all tiles (batched per-cell EM: tiles whose cells
 // have all converged are dropped from the list between graph launches, oar_cells.cu).
-template <bool HAS_AUX, bool HAS_WTS, bool LIST = false>
+// FUSED: the head of the sweep carries the convergence bookkeeping of the previous iteration (kern::em_update_slice).  A
+// separate instantiation, because the mere presence of that code changes the register allocation of the tile loop
+// (+3.5 us per sweep on C3): stores whose sweep is long enough not to care about one launch keep the lean kernel.
+template <bool HAS_AUX, bool HAS_WTS, bool LIST = false, bool FUSED = false>
 __global__ void __launch_bounds__(kThreads, (OAR_TILED_MIN_CTAS * 8) / kWarps) em_sweep_tiled(View v, Geometry g, const double *__restrict__ prev,
                                                               double *__restrict__ curr,
                                                               const uint32_t *__restrict__ wperm,
@@ -1090,8 +1103,15 @@ __global__ void __launch_bounds__(kThreads, (OAR_TILED_MIN_CTAS * 8) / kWarps) e
     asm volatile("{.reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t;}" : "=r"(sm0) : "l"(smem));
     const uint32_t stage0 = sm0 + g.stage_off, sp_a = sm0 + g.prev_off, bar0 = sm0 + g.bar_off;
     // xs sits at the start of the window; its address comes as a parameter (see Geometry::xs_base)
-    const uint32_t xs_a = g.xs_base;
-    if (sm0 != xs_a) __trap();
+#ifndef OAR_XS_PARAM
+#define OAR_XS_PARAM 1          // 0: the x-array base as a cvta on the extern array (A/B timing)
+#endif
+#ifndef OAR_XS_PARAM_WTS
+#define OAR_XS_PARAM_WTS 0      // the bootstrap-weighted instantiation is faster with the cvta (185.3 vs 186.6 us): ptxas again
+#endif
+    uint32_t xs_a;
+    if (OAR_XS_PARAM && (OAR_XS_PARAM_WTS || !HAS_WTS)) { xs_a = g.xs_base; if (sm0 != xs_a) __trap(); }
+    else xs_a = smem_u32(smem);
 
     // Work between the two CTA barriers of a tile is spread over the warps: the first warps sum the items
     // (phase 2), lane 0 of the last-but-one warp issues the TMA copies, the last warp gathers prev[].
@@ -1132,10 +1152,14 @@ __global__ void __launch_bounds__(kThreads, (OAR_TILED_MIN_CTAS * 8) / kWarps) e
         if (tile0 + 2 * stride < n_tiles) { t_pending = phys(tile0 + 2 * stride); r_pending = v.rec[t_pending]; }
     }
     // the first copies are in flight: judge the previous iteration on this CTA's slice of the count vectors
-#ifndef OAR_FUSED_PROLOGUE
-#define OAR_FUSED_PROLOGUE 1    // 0 compiles the fused bookkeeping out (A/B timing of the sweep itself)
-#endif
-    if (OAR_FUSED_PROLOGUE && !LIST && v.upd_old) kern::em_update_slice(v.upd_old, prev, v.upd_m, v.upd_state);
+    if (FUSED && !LIST) {
+        // the three count buffers rotate: the one that is neither this sweep's prev nor its curr was the previous sweep's prev.
+        // (Everything the bookkeeping needs comes from the EM state in device memory: growing the kernel's parameter list
+        // for it changed how ptxas treats the shared window base in the tile loop, 185 -> 191 us.)
+        OarEmState *stw = const_cast<OarEmState *>(st);
+        double *old = stw->bufs[0] != prev && stw->bufs[0] != curr ? stw->bufs[0] : (stw->bufs[1] != prev && stw->bufs[1] != curr ? stw->bufs[1] : stw->bufs[2]);
+        kern::em_update_slice(old, prev, stw->n_txps, stw, reinterpret_cast<double *>(smem));   // scratch: the x array, not in use yet
+    }
     // Only the last warp waits on the stage mbarriers and gathers prev[]; the CTA barrier that follows hands the
     // TMA-written stage on to the other warps (mbarrier completion observed by one thread + bar.sync is cumulative).
     if (warp == kWarps - 1) {

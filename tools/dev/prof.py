@@ -9,4 +9,5 @@ curr = torch.zeros(M, dtype=torch.float64, device="cuda")
 r = ds.em(min_iter=1, max_iter=30)
 prev.copy_(torch.from_numpy(r.counts))
 for _ in range(6): ds.sweep(prev, curr, sync=True)
+torch.cuda.synchronize(); torch.cuda.profiler.start()   # ncu --profile-from-start off: only the steady-state sweeps below
 print(ds.sweep_timed(prev, curr, 20) / 20 * 1e3, "us")

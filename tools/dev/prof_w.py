@@ -11,4 +11,5 @@ r = ds.em(min_iter=1, max_iter=30)
 prev.copy_(torch.from_numpy(r.counts))
 wts = torch.from_numpy(ds.sample_weights(7, 0).astype(np.int32)).cuda()
 ds.sweep_timed(prev, curr, 6, wts)
+torch.cuda.synchronize(); torch.cuda.profiler.start()   # ncu --profile-from-start off: only the steady-state sweeps below
 print(ds.sweep_timed(prev, curr, 20, wts) / 20 * 1e3, "us (weighted)")

@@ -16,9 +16,9 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 4
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-c2 --no-c5 > gpurun_out/bench_under_ncu.log 2>&1
 tail -c 200 gpurun_out/bench_under_ncu.log
 echo "== ncu --set full, one steady-state sweep, plain and weighted"
-timeout 200 ncu --set full --clock-control none --import-source on -k regex:em_sweep_tiled -s 50 -c 1 -f \
+timeout 200 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:em_sweep_tiled -s 5 -c 1 -f \
     -o gpurun_out/sweep_plain python tools/dev/prof.py C3 > gpurun_out/ncu_plain.log 2>&1; tail -1 gpurun_out/ncu_plain.log
-timeout 200 ncu --set full --clock-control none --import-source on -k regex:em_sweep_tiled -s 50 -c 1 -f \
+timeout 200 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:em_sweep_tiled -s 5 -c 1 -f \
     -o gpurun_out/sweep_weighted python tools/dev/prof_w.py C3 > gpurun_out/ncu_weighted.log 2>&1; tail -1 gpurun_out/ncu_weighted.log
 echo "== f-rows, robustness"
 timeout 300 python tools/bench_frows.py C3 2>/dev/null | tail -1 > gpurun_out/frows.json; head -c 300 gpurun_out/frows.json; echo

@@ -479,6 +479,7 @@ extern "C" int oar_em_batched(oar_store *s, const uint64_t *cell_row_ptr, uint32
             if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate");
             struct ExecGuard { cudaGraphExec_t x; ~ExecGuard() { cudaGraphExecDestroy(x); } } eg{exec};
             const double t_c = trace ? wall() : 0.0;
+            std::vector<uint32_t> trace_active;
             // two graph launches in flight; the state copied after each is polled (launches after the end are no-ops)
             uint64_t launched = 0;
             int inflight = 0, head = 0;
@@ -492,6 +493,7 @@ extern "C" int oar_em_batched(oar_store *s, const uint64_t *cell_row_ptr, uint32
                     ++inflight;
                 }
                 OAR_CUDA(cudaEventSynchronize(sub->slot_ev[head]));
+                if (trace && listed) { uint32_t na = 0; cudaMemcpy(&na, d_nact, sizeof(na), cudaMemcpyDeviceToHost); trace_active.push_back(na); }
                 done = sub->h_state[head].done != 0;
                 head ^= 1; --inflight;
             }
@@ -500,6 +502,9 @@ extern "C" int oar_em_batched(oar_store *s, const uint64_t *cell_row_ptr, uint32
                 const double t_d = wall();
                 fprintf(stderr, "[oar] cells: sub-store layout %.1f ms (%u tiles), setup + graph %.1f ms, EM loop %.1f ms (%llu graph launches of 16 iterations, %u cells, %llu pairs)\n",
                         t_b - t_a, sub->tl.n_tiles, t_c - t_b, t_d - t_c, (unsigned long long)(launched / 65), n_cells, (unsigned long long)total);
+                fprintf(stderr, "[oar] cells: tiles in the sweep after each graph launch:");
+                for (size_t i = 0; i < trace_active.size(); i += std::max<size_t>(1, trace_active.size() / 16)) fprintf(stderr, " %u", trace_active[i]);
+                fprintf(stderr, "\n");
             }
             s->counters[0] += launched + 4;
             // per-cell iteration counts

@@ -112,9 +112,11 @@ def with_long_rows(store: SynthStore, frac: float, lo: int, hi: int, seed: int) 
     return SynthStore(rp, txp, prob, store.n_txps, None, None)
 
 
-def make_cells(cell_reads, n_txps: int, avg_aln: float, seed: int):
+def make_cells(cell_reads, n_txps: int, avg_aln: float, seed: int, expressed: Optional[int] = None):
     """Concatenated store of several cells (single-cell mode): cell c has cell_reads[c] reads drawn
-    from its own abundance vector.  Returns (SynthStore, cell_row_ptr u64[C+1])."""
+    from its own abundance vector.  With `expressed` (about 5 k expressed
+    transcripts per cell) a cell's reads come from its own sorted random subset of that many transcripts, picked as
+    runs of neighbouring ids (genes).  Returns (SynthStore, cell_row_ptr u64[C+1])."""
     rps, txs, prs = [np.zeros(1, dtype=np.uint64)], [], []
     cell_row_ptr = np.zeros(len(cell_reads) + 1, dtype=np.uint64)
     off = 0
@@ -122,7 +124,15 @@ def make_cells(cell_reads, n_txps: int, avg_aln: float, seed: int):
         cell_row_ptr[c + 1] = cell_row_ptr[c] + n
         if n == 0:
             continue
-        st = make_store(int(n), n_txps, avg_aln, seed * 1000003 + c)
+        if expressed is not None and expressed < n_txps:
+            rng = np.random.default_rng(seed * 7919 + c)
+            starts = rng.choice(n_txps // 8, size=max(1, expressed // 8), replace=False).astype(np.int64) * 8
+            subset = np.unique((starts[:, None] + np.arange(8)[None, :]).ravel())
+            subset = subset[subset < n_txps].astype(np.uint32)
+            st = make_store(int(n), len(subset), avg_aln, seed * 1000003 + c)
+            st = SynthStore(st.row_ptr, subset[st.txp_id], st.prob, n_txps, None, None)
+        else:
+            st = make_store(int(n), n_txps, avg_aln, seed * 1000003 + c)
         rps.append(st.row_ptr[1:] + np.uint64(off))
         txs.append(st.txp_id)
         prs.append(st.prob)

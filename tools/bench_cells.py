@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Config 5 (scaled): batched per-cell EM, cells/s on one GPU, with a per-cell oracle spot check.
-   python tools/bench_cells.py [n_cells] [reads_per_cell] [n_txps]"""
+   python tools/bench_cells.py [n_cells] [reads_per_cell] [n_txps] [expressed_per_cell]"""
 import json, os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -10,7 +10,8 @@ n_cells = int(sys.argv[1]) if len(sys.argv) > 1 else 296
 reads = int(sys.argv[2]) if len(sys.argv) > 2 else 50_000
 M = int(sys.argv[3]) if len(sys.argv) > 3 else 200_000
 t0 = time.time()
-s, crp = synth.make_cells([reads] * n_cells, M, 6.0, seed=5)
+expressed = int(sys.argv[4]) if len(sys.argv) > 4 else 5000      # about 5 k expressed transcripts per cell (0: all)
+s, crp = synth.make_cells([reads] * n_cells, M, 6.0, seed=5, expressed=expressed or None)
 gen_s = time.time() - t0
 ds = DeviceStore(s.row_ptr, s.txp_id, s.prob, M)
 ds.em_batched(crp[:3].copy() if False else crp)  # warm-up (allocations, module load)

@@ -48,6 +48,27 @@ SEED = 4
 THR = 1e-3
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the JSON record: everything libraries print (NCCL's version banner on the first
+    communicator, torchrun notices) is sent to stderr by pointing fd 1 at fd 2 for the life of the process."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def algorithmic_bytes(n_reads, nnz, n_txps, weighted=False):
     """B_iter = 8*nnz + 4*(N+1) + 24*M (+ 4*N for u32 bootstrap weights)."""
     return 8 * nnz + 4 * (n_reads + 1) + 24 * n_txps + (4 * n_reads if weighted else 0)
@@ -179,7 +200,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -483,7 +504,7 @@ def run_gpu(args):
             "gpu_launches": int(total_launches), "c2": c2, "c5": c5, "clocks": clocks,
             "store_build_ms": build_ms, "bcast_ms": bcast_ms if multi else None,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if multi:
         dist.barrier()
         dist.destroy_process_group()
@@ -507,6 +528,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
+    claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_gpu(args)

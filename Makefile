@@ -42,7 +42,7 @@ $(LIBDIR)/host_mirror_test: tests/cpp/host_mirror_test.cpp include/oarfish_em.hp
 
 oracle: oracle/liboarfish_oracle.so
 
-oracle/liboarfish_oracle.so: oracle/em_oracle.c oracle/em_par_port.c oracle/coverage_oracle.c
+oracle/liboarfish_oracle.so: oracle/em_oracle.c oracle/em_par_port.c oracle/coverage_oracle.c oracle/filter_oracle.c
 	$(HOSTCC) $(CFLAGS) -shared -o $@ $^ -lm
 
 clean:

@@ -17,6 +17,9 @@
  *                            made explicit (test hook: exact per-weight-vector parity)
  *   oar_em_batched        <- the per-cell em::em(&emi, 1) calls of
  *                            single_cell.rs:150 batched into one call
+ *   oar_multi_*           <- the internal fan-out of em::bootstrap / the single-cell driver over workers
+ *   oar_store_create_filtered <- AlignmentFilters::filter (src/util/oarfish_types.rs:955-1130)
+ *   oar_store_coverage_model[_binomial] <- logistic_prob / binomial_continuous_prob + normalize_read_probs
  *
  * Conventions
  *   - every function returns 0 on success or a negative oar_status; nothing
@@ -159,6 +162,45 @@ int oar_em_batched(oar_store *store, const uint64_t *cell_row_ptr, uint32_t n_ce
                    uint32_t max_iter, double conv_thresh, uint32_t min_iter,
                    uint64_t *out_cell_ptr, uint32_t *out_txp, double *out_val, uint64_t capacity,
                    uint64_t *out_nnz, uint32_t *out_niter);
+
+/*
+ * ---- store construction from alignment records: the filters and the score -> probability formula ----------------
+ * AlignmentFilters::filter (src/util/oarfish_types.rs:955-1130) applied to every read's group of records on the
+ * device; BAM decoding and grouping by read name (alignment_parser.rs:301-437) stay with the caller, who passes the
+ * fields filter() reads through AlnRecordLike (oarfish_types.rs:186-202) as columns, one entry per record:
+ *   group_ptr  G+1 u64   records of read g are [group_ptr[g], group_ptr[g+1])
+ *   ref_id, aln_start, aln_end, aln_span   u32 (aln_span: reference span from the CIGAR)
+ *   score      i32       the AS tag (a missing tag is i32::MIN, :993)
+ *   flags      u8        OAR_REC_* bits
+ *   seq_len    u32       length of the record's sequence, 0 if the record carries none (:981-984 takes the first non-zero)
+ *   txp_len    M u32     TranscriptInfo.len
+ * Groups without a retained alignment are dropped (add_filtered_group, :718-738).  The result is a store exactly as
+ * oar_store_create would build it from the reference's own InMemoryAlignmentStore.
+ *   out_discard        10 u64 or NULL: DiscardTable in declaration order (:812-826): discard_5p, discard_3p, discard_score,
+ *                      discard_aln_frac, discard_aln_len, discard_ori, discard_supp, no_mapping, no_valid_aln, valid_best_aln
+ *   out_src_or_null    per retained alignment the index of its record (capacity n_records u32, host or device)
+ *   out_group_or_null  per retained read the index of its group (capacity n_groups u32)
+ * All inputs may be host or device pointers.
+ */
+enum { OAR_REC_UNMAPPED = 1, OAR_REC_REVERSE = 2, OAR_REC_SUPPLEMENTARY = 4 };
+enum { OAR_STRAND_UNKNOWN = 0, OAR_STRAND_FORWARD = 1, OAR_STRAND_REVERSE = 2 };
+typedef struct {
+    int32_t which_strand;          /* OAR_STRAND_*: keep both / forward-only / reverse-only alignments (:1003-1022) */
+    uint32_t min_aligned_len;      /* :1033 */
+    int64_t three_prime_clip;      /* :1040 */
+    uint32_t five_prime_clip;      /* :1047 */
+    float min_aligned_fraction;    /* :1077 */
+    float score_threshold;         /* :1100 */
+    float score_prob_denom;        /* :1102, --score-prob-denom, default 5.0 */
+} oar_filter_opts;
+int oar_store_create_filtered(const uint64_t *group_ptr, const uint32_t *ref_id, const uint32_t *aln_start,
+                              const uint32_t *aln_end, const uint32_t *aln_span, const int32_t *score,
+                              const uint8_t *flags, const uint32_t *seq_len, uint64_t n_groups, uint64_t n_records,
+                              const uint32_t *txp_len, uint32_t n_txps, const oar_filter_opts *opts, int device,
+                              oar_store **out, uint64_t out_discard[10], uint32_t *out_src_or_null,
+                              uint32_t *out_group_or_null);
+/* The CSR a store holds (row_ptr as u64 like `boundaries`, txp_id, prob); each output may be NULL. */
+int oar_store_export(oar_store *store, uint64_t *out_row_ptr, uint32_t *out_txp_id, float *out_prob);
 
 /*
  * ---- all GPUs of the box behind one call from one host thread ---------------------------------

@@ -55,6 +55,9 @@ ABI = {
     "oar_sweep": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int]),
     "oar_sweep_timed": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.POINTER(C.c_float)]),
     "oar_store_stream": (_vp, [_vp]),
+    "oar_store_create_filtered": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64, _vp, C.c_uint32, _vp, C.c_int,
+                                             C.POINTER(_vp), _vp, _vp, _vp]),
+    "oar_store_export": (C.c_int, [_vp, _vp, _vp, _vp]),
     "oar_store_set_progress": (C.c_int, [_vp, _vp, _vp]),
     "oar_multi_create": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64, C.c_uint32, _vp, C.c_int, C.POINTER(_vp)]),
     "oar_multi_destroy": (None, [_vp]),
@@ -64,6 +67,13 @@ ABI = {
     "oar_em_batched_multi": (C.c_int, [_vp, _vp, _vp, _vp, C.c_uint64, C.c_uint64, C.c_uint32, _vp, C.c_uint32, _vp, C.c_int,
                                         C.c_uint32, C.c_double, C.c_uint32, _vp, _vp, _vp, C.c_uint64, _u64p, _vp, _vp]),
 }
+
+class FilterOpts(C.Structure):
+    """oar_filter_opts (include/oarfish_em.h) == the fields of AlignmentFilters that filter() reads."""
+    _fields_ = [("which_strand", C.c_int32), ("min_aligned_len", C.c_uint32), ("three_prime_clip", C.c_int64),
+                ("five_prime_clip", C.c_uint32), ("min_aligned_fraction", C.c_float), ("score_threshold", C.c_float),
+                ("score_prob_denom", C.c_float)]
+
 
 PROGRESS_FN = C.CFUNCTYPE(None, C.c_uint32, C.c_double, C.c_void_p)
 

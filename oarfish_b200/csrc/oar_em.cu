@@ -117,7 +117,7 @@ int substore_create(oar_store *parent, uint32_t *d_txp, uint32_t n_txps, oar_sto
 namespace oar {
 // Shared tail of store creation: the CSR arrays are resident (d_row_ptr u32, d_txp, d_prob, d_aux); build the tiled
 // layout and read the tuning environment.
-static int finish_store(oar_store *s)
+int finish_store(oar_store *s)
 {
     // OAR_TILED=0 keeps only the CSR (row-group kernel); OAR_TILE_SPAN tunes the tile fill
     const char *env = getenv("OAR_TILED");
@@ -135,7 +135,7 @@ static int finish_store(oar_store *s)
 }
 
 // Handle + stream + events + pinned state from the device context; EM work buffers.
-static int new_store(int device, uint64_t n_reads, uint64_t nnz, uint32_t n_txps, const char *who, oar_store **out)
+int new_store(int device, uint64_t n_reads, uint64_t nnz, uint32_t n_txps, const char *who, oar_store **out)
 {
     *out = nullptr;
     if (n_txps == 0) return fail(OAR_ERR_INVALID, std::string(who) + ": n_txps must be > 0");

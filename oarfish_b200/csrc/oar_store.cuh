@@ -89,6 +89,11 @@ cudaError_t sweep_enqueue_list(oar_store *s, const double *prev, double *curr, c
 // d_group_rows[0 .. n_groups] (cells of the batched per-cell EM)
 cudaError_t tile_group_ranges_enqueue(oar_store *s, const uint64_t *d_group_rows, uint32_t n_groups, uint2 *d_out);
 void free_tiled_layout(oar_store *s);
+// Handle + stream + events + pinned state + EM work buffers for a store whose CSR arrays the caller fills in on
+// s->stream (d_row_ptr u32 N+1, d_txp, d_prob[, d_aux]; n_reads / nnz may be set afterwards); finish_store() then
+// builds the tiled layout and reads the tuning environment.
+int new_store(int device, uint64_t n_reads, uint64_t nnz, uint32_t n_txps, const char *who, oar_store **out);
+int finish_store(oar_store *s);
 // oar_store_create for a slice of a larger store (row_ptr[0] == row_base; txp_id / prob / aux start at the slice's first alignment)
 int store_create_slice(const uint64_t *row_ptr, uint64_t row_base, const uint32_t *txp_id, const float *prob,
                        const double *aux_or_null, uint64_t n_reads, uint64_t nnz, uint32_t n_txps, int device, oar_store **out);

@@ -69,6 +69,51 @@ class DeviceStore:
         self._h = C.c_void_p()
         check(lib.oar_store_create(rp, tp, pp, ap, self.n_reads, self.nnz, self.n_txps, self.device, C.byref(self._h)))
 
+    @classmethod
+    def from_records(cls, group_ptr, ref_id, aln_start, aln_end, aln_span, score, flags, seq_len, txp_len, *,
+                     which_strand: int = 0, min_aligned_len: int = 50, three_prime_clip: int = 2**31 - 1,
+                     five_prime_clip: int = 2**32 - 1, min_aligned_fraction: float = 0.5, score_threshold: float = 0.95,
+                     score_prob_denom: float = 5.0, device: int = 0, want_index: bool = False):
+        """AlignmentFilters::filter (oarfish_types.rs:955-1130) over all read groups on the device: returns
+        (store, discard table dict[, (src record of every retained alignment, group of every retained read)])."""
+        lib = _lib.load_em_lib()
+        gp = np.ascontiguousarray(group_ptr, dtype=np.uint64)
+        cols = [np.ascontiguousarray(a, dtype=np.uint32) for a in (ref_id, aln_start, aln_end, aln_span)]
+        sc = np.ascontiguousarray(score, dtype=np.int32)
+        fl = np.ascontiguousarray(flags, dtype=np.uint8)
+        sl = np.ascontiguousarray(seq_len, dtype=np.uint32)
+        tl = np.ascontiguousarray(txp_len, dtype=np.uint32)
+        n_groups, n_rec = len(gp) - 1, len(sc)
+        opts = _lib.FilterOpts(int(which_strand), int(min_aligned_len), int(three_prime_clip), int(five_prime_clip),
+                               float(min_aligned_fraction), float(score_threshold), float(score_prob_denom))
+        disc = (C.c_uint64 * 10)()
+        src = np.zeros(max(n_rec, 1), dtype=np.uint32) if want_index else None
+        grp = np.zeros(max(n_groups, 1), dtype=np.uint32) if want_index else None
+        self = cls.__new__(cls)
+        self._lib = lib
+        self._h = C.c_void_p()
+        check(lib.oar_store_create_filtered(gp.ctypes.data, cols[0].ctypes.data, cols[1].ctypes.data, cols[2].ctypes.data,
+                                            cols[3].ctypes.data, sc.ctypes.data, fl.ctypes.data, sl.ctypes.data, n_groups, n_rec,
+                                            tl.ctypes.data, len(tl), C.byref(opts), int(device), C.byref(self._h), disc,
+                                            src.ctypes.data if want_index else None, grp.ctypes.data if want_index else None))
+        nr, nz, nt, dv = C.c_uint64(0), C.c_uint64(0), C.c_uint32(0), C.c_int(0)
+        check(lib.oar_store_info(self._h, C.byref(nr), C.byref(nz), C.byref(nt), C.byref(dv)))
+        self.n_reads, self.nnz, self.n_txps, self.device = int(nr.value), int(nz.value), int(nt.value), int(dv.value)
+        names = ("discard_5p", "discard_3p", "discard_score", "discard_aln_frac", "discard_aln_len", "discard_ori", "discard_supp",
+                 "no_mapping", "no_valid_aln", "valid_best_aln")
+        table = {k: int(v) for k, v in zip(names, disc)}
+        if want_index:
+            return self, table, (src[:self.nnz].copy(), grp[:self.n_reads].copy())
+        return self, table
+
+    def export_csr(self):
+        """(row_ptr u64, txp_id u32, prob f32) of the store as it sits in HBM."""
+        rp = np.zeros(self.n_reads + 1, dtype=np.uint64)
+        tx = np.zeros(max(self.nnz, 1), dtype=np.uint32)
+        pr = np.zeros(max(self.nnz, 1), dtype=np.float32)
+        check(self._lib.oar_store_export(self._h, rp.ctypes.data, tx.ctypes.data, pr.ctypes.data))
+        return rp, tx[:self.nnz], pr[:self.nnz]
+
     # -- lifetime ------------------------------------------------------------
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h:

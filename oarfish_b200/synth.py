@@ -153,3 +153,38 @@ def make_coordinates(store: SynthStore, seed: int):
     start = (rng.uniform(0.0, 1.0, size=store.nnz) * (L - span + 1)).astype(np.int64)
     end = np.minimum(start + span, L)
     return start.astype(np.uint32), end.astype(np.uint32), txp_len.astype(np.uint32)
+
+
+def make_records(n_groups: int, n_txps: int, seed: int, mean_records: float = 6.0):
+    """Raw alignment records for the filter stage (AlignmentFilters::filter, oarfish_types.rs:955-1130): columns as
+    oar_store_create_filtered takes them, with every reason for a discard represented (unmapped, supplementary and
+    wrong-strand records, short spans, 3' / 5' clipping, low scores, groups with nothing valid, non-positive best
+    scores, groups whose sequence length sits on a later record or on none).
+    Returns dict(group_ptr, ref_id, aln_start, aln_end, aln_span, score, flags, seq_len, txp_len)."""
+    rng = np.random.default_rng(seed)
+    k = 1 + rng.poisson(mean_records - 1.0, size=n_groups)
+    k[rng.random(n_groups) < 0.02] = 0                                  # reads without any record
+    gp = np.zeros(n_groups + 1, dtype=np.uint64); np.cumsum(k, out=gp[1:])
+    R = int(gp[-1])
+    grp = np.repeat(np.arange(n_groups), k)
+    txp_len = rng.integers(300, 6000, size=n_txps).astype(np.uint32)
+    base_t = rng.integers(0, n_txps, size=n_groups)
+    ref = ((base_t[grp] + rng.integers(0, 12, size=R)) % n_txps).astype(np.uint32)
+    L = txp_len[ref].astype(np.int64)
+    span = np.maximum((rng.uniform(0.02, 1.0, size=R) * L).astype(np.int64), 1)
+    start = (rng.uniform(0, 1, size=R) * (L - span + 1)).astype(np.int64) + 1
+    end = start + span - 1
+    best = rng.integers(-20, 400, size=n_groups)
+    score = (best[grp] - rng.integers(0, 40, size=R) * (rng.random(R) < 0.7)).astype(np.int32)
+    flags = np.zeros(R, dtype=np.uint8)
+    flags[rng.random(R) < 0.05] |= 1
+    flags[rng.random(R) < 0.30] |= 2
+    flags[rng.random(R) < 0.05] |= 4
+    read_len = rng.integers(200, 4000, size=n_groups)
+    seq = np.zeros(R, dtype=np.uint32)
+    first = gp[:-1][k > 0].astype(np.int64)
+    carrier = first + (rng.integers(0, 3, size=len(first)) % k[k > 0])   # the record that carries the sequence
+    seq[carrier] = read_len[k > 0]
+    seq[carrier[rng.random(len(carrier)) < 0.03]] = 0                    # some reads carry no sequence at all
+    return dict(group_ptr=gp, ref_id=ref, aln_start=start.astype(np.uint32), aln_end=end.astype(np.uint32),
+                aln_span=span.astype(np.uint32), score=score, flags=flags, seq_len=seq, txp_len=txp_len)

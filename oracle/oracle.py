@@ -146,6 +146,38 @@ def statrs_ln_gamma(x):
     return float(lib().oracle_statrs_ln_gamma(float(x)))
 
 
+class _FilterOpts(C.Structure):
+    _fields_ = [("which_strand", C.c_int32), ("min_aligned_len", C.c_uint32), ("three_prime_clip", C.c_int64),
+                ("five_prime_clip", C.c_uint32), ("min_aligned_fraction", C.c_float), ("score_threshold", C.c_float),
+                ("score_prob_denom", C.c_float)]
+
+
+DISCARD_NAMES = ("discard_5p", "discard_3p", "discard_score", "discard_aln_frac", "discard_aln_len", "discard_ori", "discard_supp",
+                 "no_mapping", "no_valid_aln", "valid_best_aln")
+
+
+def filter_records(group_ptr, ref_id, aln_start, aln_end, aln_span, score, flags, seq_len, txp_len, *, which_strand=0,
+                   min_aligned_len=50, three_prime_clip=2**31 - 1, five_prime_clip=2**32 - 1, min_aligned_fraction=0.5,
+                   score_threshold=0.95, score_prob_denom=5.0):
+    """AlignmentFilters::filter + add_filtered_group (oarfish_types.rs:955-1130, :718-738):
+    -> (row_ptr u64, txp u32, prob f32, src u32, group u32, discard dict)."""
+    gp = _c(group_ptr, np.uint64)
+    cols = [_c(a, np.uint32) for a in (ref_id, aln_start, aln_end, aln_span)]
+    sc = _c(score, np.int32); fl = _c(flags, np.uint8); sl = _c(seq_len, np.uint32); tl = _c(txp_len, np.uint32)
+    G, R = len(gp) - 1, len(sc)
+    rp = np.zeros(G + 1, dtype=np.uint64); tx = np.zeros(max(R, 1), dtype=np.uint32); pr = np.zeros(max(R, 1), dtype=np.float32)
+    src = np.zeros(max(R, 1), dtype=np.uint32); grp = np.zeros(max(G, 1), dtype=np.uint32)
+    rows = C.c_uint64(0); disc = (C.c_uint64 * 10)()
+    o = _FilterOpts(which_strand, min_aligned_len, three_prime_clip, five_prime_clip, min_aligned_fraction, score_threshold, score_prob_denom)
+    L = lib()
+    L.oracle_filter.restype = C.c_uint64
+    L.oracle_filter.argtypes = [_vp] * 8 + [C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+    nnz = L.oracle_filter(_p(gp), _p(cols[0]), _p(cols[1]), _p(cols[2]), _p(cols[3]), _p(sc), _p(fl), _p(sl), G, _p(tl), C.byref(o),
+                          _p(rp), _p(tx), _p(pr), _p(src), _p(grp), C.byref(rows), disc)
+    n = int(rows.value)
+    return rp[:n + 1].copy(), tx[:nnz].copy(), pr[:nnz].copy(), src[:nnz].copy(), grp[:n].copy(), {k: int(v) for k, v in zip(DISCARD_NAMES, disc)}
+
+
 class PortStore:
     """AoS copy of a store laid out like the Rust InMemoryAlignmentStore (CPU baseline timing)."""
 

@@ -505,6 +505,33 @@ def test_binomial_coverage_model_matches_oracle(DS, oracle_mod, small_store):
             assert_counts_close(r.counts, want)
 
 
+@pytest.mark.parametrize("opts", [dict(), dict(which_strand=1, min_aligned_len=120, three_prime_clip=400, five_prime_clip=900,
+                                               min_aligned_fraction=0.3, score_threshold=0.9, score_prob_denom=3.0),
+                                  dict(which_strand=2, score_threshold=0.5)])
+def test_filtered_store_matches_oracle(DS, oracle_mod, opts):
+    """AlignmentFilters::filter on the device (oar_store_create_filtered): the store, the discard table and the index
+    of every retained record against the restated filter; then the EM on that store."""
+    from oarfish_b200 import synth
+    rec = synth.make_records(30_000, 3_000, seed=41)
+    rp, tx, pr, src, grp, disc = oracle_mod.filter_records(**rec, **opts)
+    ds, table, (gsrc, ggrp) = DS.from_records(**rec, **opts, want_index=True)
+    with ds:
+        assert table == disc
+        grp_rp, gtx, gpr = ds.export_csr()
+        np.testing.assert_array_equal(grp_rp, rp)
+        np.testing.assert_array_equal(gtx, tx)
+        np.testing.assert_array_equal(gsrc, src)
+        np.testing.assert_array_equal(ggrp, grp)
+        # prob = exp((score - best) / D) in f32: the device rounds an f64 exp once, glibc's expf is correctly rounded for
+        # all but a handful of arguments: allow one ulp
+        assert np.max(np.abs(gpr.view(np.int32).astype(np.int64) - pr.view(np.int32).astype(np.int64))) <= 1
+        assert len(rp) - 1 > 1000 and disc["valid_best_aln"] == len(rp) - 1
+        want, niter, _, _ = oracle_mod.do_em(rp, tx, gpr, len(rec["txp_len"]), min_iter=50)
+        r = ds.em(min_iter=50)
+        assert r.niter == niter
+        assert_counts_close(r.counts, want)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # BASELINE configs C2 and C3 at full size against the CPU oracle (em.rs:144-255, :320-447)
 # ---------------------------------------------------------------------------------------------------------

@@ -312,3 +312,32 @@ def test_binomial_coverage_model_known_answers(oracle_mod):
     # a transcript nobody aligns to has no counts: probabilities 0, and nothing divides by zero elsewhere
     out = oracle_mod.coverage_model_binomial(np.array([0, 1], dtype=np.uint64), [1], [0], [250], [300, 250], bin_width=100)
     np.testing.assert_allclose(out, [1.0])
+
+
+def test_filter_known_answers(oracle_mod):
+    """AlignmentFilters::filter (oarfish_types.rs:955-1130) on hand-made groups."""
+    import math
+    f32 = np.float32
+    txp_len = [1000, 1000, 1000]
+    # group 0: best score 100 on txp 0; 96 kept (>= 0.95 * 100), 90 dropped by the score threshold; one supplementary,
+    #          one unmapped, one too short.  group 1: only an unmapped record.  group 2: best score 0 -> no valid alignment.
+    # group 3: aligned fraction 100/1000 < 0.5 -> dropped.  group 4: reverse strand only, forward-only filter.
+    gp = [0, 6, 7, 8, 9, 10]
+    ref = [0, 1, 2, 1, 0, 2, 0, 1, 2, 0]
+    start = [1, 1, 1, 1, 1, 1, 1, 1, 1, 1]
+    span = [500, 500, 500, 500, 500, 10, 500, 500, 100, 500]
+    end = [s0 + sp - 1 for s0, sp in zip(start, span)]
+    score = [100, 96, 90, 99, 99, 99, 50, 0, 80, 70]
+    flags = [0, 0, 0, 4, 1, 0, 1, 0, 0, 2]
+    seq = [600, 0, 0, 0, 0, 0, 600, 600, 1000, 600]
+    rp, tx, pr, src, grp, disc = oracle_mod.filter_records(gp, ref, start, end, span, score, flags, seq, txp_len, which_strand=1,
+                                                           min_aligned_len=50, min_aligned_fraction=0.5, score_threshold=0.95)
+    assert list(rp) == [0, 2] and list(tx) == [0, 1] and list(src) == [0, 1] and list(grp) == [0]
+    want = [f32(1.0), f32(math.exp(float(f32(f32(96 - 100) / f32(5.0)))))]
+    np.testing.assert_allclose(pr, want, rtol=1e-6)
+    assert disc == {"discard_5p": 0, "discard_3p": 0, "discard_score": 1, "discard_aln_frac": 1, "discard_aln_len": 1,
+                    "discard_ori": 1, "discard_supp": 1, "no_mapping": 1, "no_valid_aln": 2, "valid_best_aln": 1}
+    # clipping: with three_prime_clip = 100 an alignment must end beyond len - 100; with five_prime_clip = 50 it must start before 50
+    rp, tx, pr, src, grp, disc = oracle_mod.filter_records([0, 3], [0, 0, 0], [1, 60, 1], [950, 990, 800], [950, 931, 800], [10, 10, 10],
+                                                           [0, 0, 0], [1000, 0, 0], [1000], three_prime_clip=100, five_prime_clip=50)
+    assert list(src) == [0] and disc["discard_5p"] == 1 and disc["discard_3p"] == 1

@@ -118,3 +118,26 @@ def test_golden_oarstore_fixture_matches_the_oracle(oracle_mod=None):
         assert (np.abs(np.asarray(ref["counts"])[big] - want[big]) / want[big]).max() <= rtol
         if ref["niter"] is not None:
             assert ref["niter"] == niter
+
+
+def test_synthetic_workload_generators():
+    """The generators behind bench.py / tools (no GPU): shuffled ids, long rows, sparse cells, raw alignment records."""
+    from oarfish_b200 import synth
+    s = synth.make_config("tiny")
+    p = synth.permute_ids(s, 3)
+    assert p.nnz == s.nnz and np.array_equal(np.sort(np.unique(p.txp_id)), np.sort(np.unique(p.txp_id)))
+    assert np.array_equal(p.row_ptr, s.row_ptr) and not np.array_equal(p.txp_id, s.txp_id)
+    l = synth.with_long_rows(s, 0.1, 128, 200, 4)
+    lens, lens0 = np.diff(l.row_ptr.astype(np.int64)), np.diff(s.row_ptr.astype(np.int64))
+    assert lens.max() >= 128 and (lens != lens0).mean() > 0.05 and int(l.row_ptr[-1]) == l.nnz == len(l.txp_id) == len(l.prob)
+    rp = l.row_ptr.astype(np.int64)
+    i = int(np.argmax(lens))
+    assert len(np.unique(l.txp_id[rp[i]:rp[i + 1]])) == lens[i] and l.txp_id.max() < l.n_txps   # distinct transcripts within a read
+    st, crp = synth.make_cells([300, 0, 500], 4000, 5.0, 9, expressed=400)
+    assert list(crp) == [0, 300, 300, 800] and st.n_reads == 800
+    a0, a1 = int(st.row_ptr[0]), int(st.row_ptr[300])
+    assert len(np.unique(st.txp_id[a0:a1])) <= 400 and st.txp_id.max() < 4000
+    rec = synth.make_records(2000, 300, 1)
+    assert int(rec["group_ptr"][-1]) == len(rec["score"]) == len(rec["flags"]) == len(rec["ref_id"])
+    assert rec["ref_id"].max() < 300 and np.all(rec["aln_end"] >= rec["aln_start"])
+    assert np.all(rec["aln_end"].astype(np.int64) <= rec["txp_len"][rec["ref_id"]].astype(np.int64) + 0)

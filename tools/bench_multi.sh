@@ -1,6 +1,7 @@
 #!/bin/bash
-# N-GPU call: multi-GPU ABI tests, torchrun bench at N = $1 (driver settings: --steps 20 --warmup 3)
-cd "$(dirname "$0")/../.."
+# N-GPU measurement: multi-GPU ABI tests, then the bench under torchrun at N = $1 (driver settings: --steps 20 --warmup 3).
+#   gpurun --gpus N -- bash tools/bench_multi.sh N      -> gpurun_out/bench_nN.json
+cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 N=${1:-2}
 {
@@ -17,4 +18,4 @@ d=json.load(open('gpurun_out/bench_n$N.json'))
 print({k:d[k] for k in ['value','replicates_per_sec','n_gpus','ms_per_step']}, d['job']['replicates_by_rank'], 'bcast', d['bcast_ms'], 'c5', d['c5']['cells_per_sec'] if d.get('c5') else None, d['clocks'])
 PY
   tail -2 gpurun_out/bench_n$N.err
-} 2>&1 | tee gpurun_out/call19_n$N.log
+} 2>&1 | tee gpurun_out/bench_multi_n$N.log

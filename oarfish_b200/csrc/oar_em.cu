@@ -405,8 +405,15 @@ static cudaError_t enqueue_rowgroup(oar_store *s, const uint32_t *list, uint64_t
 // `wts` are per-read weights in read order; the tiled kernel reads the copy
 // permuted into tile order (s->tl.wperm, refreshed by refresh_wperm()).
 // the sweep can carry the convergence bookkeeping of the PREVIOUS iteration (tiled kernel only, see fused_update())
-static bool fused_update(const oar_store *s)
-{ return s->allow_fused && s->kernel == OAR_KERNEL_TILED && s->tl.ready && s->tl.n_tiles > 0; }
+// Measured on B200: fused wins wherever one launch matters (C2: 40 -> 48 k it/s, plain and weighted) and on the plain C3
+// sweep (+0.3 %); the weighted instantiation with the bookkeeping head is ~8 us slower than the lean one on C3, more
+// than the launch it saves (4 965 vs 5 035 it/s over four replicates), so long weighted sweeps keep em_update.
+static const uint32_t kFusedWeightedMaxTiles = 32768;
+static bool fused_update(const oar_store *s, bool weighted)
+{
+    if (!(s->allow_fused && s->kernel == OAR_KERNEL_TILED && s->tl.ready && s->tl.n_tiles > 0)) return false;
+    return !weighted || s->tl.n_tiles <= kFusedWeightedMaxTiles;
+}
 
 static cudaError_t enqueue_sweep(oar_store *s, const double *prev, double *curr, const uint32_t *wts,
                                  const OarEmState *state, int check_done, bool fused = false)
@@ -511,14 +518,14 @@ static cudaError_t enqueue_update(oar_store *s, double *prev, const double *curr
 static int ensure_graph(oar_store *s, bool weighted)
 {
     GraphSlot &g = s->graphs[weighted ? 1 : 0];
-    if (g.exec && g.kernel == s->kernel && g.fused == fused_update(s)) return OAR_OK;
+    if (g.exec && g.kernel == s->kernel && g.fused == fused_update(s, weighted)) return OAR_OK;
     if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
     const uint32_t *wts = weighted ? s->d_weights : nullptr;
     uint64_t saved = s->counters[0];
     cudaGraph_t graph = nullptr;
     OAR_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
     cudaError_t e = cudaSuccess;
-    const bool fused = fused_update(s);
+    const bool fused = fused_update(s, weighted);
     for (int it = 0; it < kGraphIters && e == cudaSuccess; ++it) {
         // sweep k: X[k % 3] -> X[(k + 1) % 3].  Fused: its head judges sweep k-1 (X[(k + 2) % 3] against X[k % 3]) and zeroes
         // X[(k + 2) % 3], the target of sweep k+1.  Otherwise em_update judges sweep k right after it and zeroes X[k % 3].
@@ -589,7 +596,7 @@ static int run_em(oar_store *s, const double *init_dev, uint32_t max_iter, doubl
         }
         // the launches still in flight are no-ops (done is set); they finish before the final sweep (same stream)
         // every kernel node of every graph launch is a launch of ours (those after convergence exit at once)
-        const uint64_t per_iter = (fused_update(s) ? 1 : 2) + ((s->kernel != OAR_KERNEL_ROWGROUP && s->tl.n_tiles > 0 && s->tl.n_fallback > kFoldFallbackMax) ? 1 : 0);
+        const uint64_t per_iter = (fused_update(s, weighted) ? 1 : 2) + ((s->kernel != OAR_KERNEL_ROWGROUP && s->tl.n_tiles > 0 && s->tl.n_fallback > kFoldFallbackMax) ? 1 : 0);
         s->counters[0] += launched_iters * per_iter;
     }
     // `sweeps` loop sweeps were judged: the last result is X[sweeps % 3]; X[(sweeps + 2) % 3] is zero (zeroed by the head of

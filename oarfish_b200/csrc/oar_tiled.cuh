@@ -1007,7 +1007,7 @@ __device__ __forceinline__ void tile_phase1_core(const View &v, uint32_t tile, c
 
 // phase 1 with the tile's prob | lpos block staged in shared memory (`bulk`); also returns the thread's item and the
 // record's DU word for phase 2 (read now: the record's stage is refilled before phase 2).
-template <bool HAS_AUX, bool HAS_WTS>
+template <bool HAS_AUX, bool HAS_WTS, bool COMMON_OK>
 __device__ __forceinline__ void tile_phase1(const View &v, uint32_t tile, uint32_t bulk, uint32_t rec, uint32_t wl_a, uint32_t sp_a, uint32_t xs_a,
                                             uint32_t tid, uint32_t lane, uint32_t warp, double *__restrict__ curr,
                                             const uint32_t *__restrict__ wperm, uint32_t &item, uint4 &du)
@@ -1019,12 +1019,9 @@ __device__ __forceinline__ void tile_phase1(const View &v, uint32_t tile, uint32
     if (tid < du.y) item = lds_u32(rec + kRecTable + 4u * (((du.x + 3u) & ~3u) + tid));
     uint32_t w_in = 0;
     if (HAS_WTS) w_in = lds_u16(wl_a + 2u * tid);
-#ifndef OAR_COMMON_PATH_WTS
-#define OAR_COMMON_PATH_WTS 0   // the bootstrap-weighted sweep keeps the single general copy of phase 1 (measured: 185.3 vs 186.6 us)
-#endif
 #if OAR_COMMON_PATH
     // chunk_info is the same word in every lane of the warp: one vote decides between the two copies of phase 1
-    if ((OAR_COMMON_PATH_WTS || !HAS_WTS) && !any_bits(lds_u32(rec + kRecInfo + 4u * warp), kInfoMulti | kInfoStray | 4u))
+    if (COMMON_OK && !any_bits(lds_u32(rec + kRecInfo + 4u * warp), kInfoMulti | kInfoStray | 4u))
         tile_phase1_core<HAS_AUX, HAS_WTS, true>(v, tile, p4, lp4, rec, sp_a, xs_a, du.w, w_in, tid, lane, warp, curr, wperm);
     else
 #endif
@@ -1106,11 +1103,24 @@ __global__ void __launch_bounds__(kThreads, (OAR_TILED_MIN_CTAS * 8) / kWarps) e
 #ifndef OAR_XS_PARAM
 #define OAR_XS_PARAM 1          // 0: the x-array base as a cvta on the extern array (A/B timing)
 #endif
+    // Which instantiation gets the parameter base and the common-path copy of phase 1 was settled by A/B timing on C3
+    // (profiles/experiments/r2_kernel_experiments.md): ptxas moves 1-3 % either way with each of them.
 #ifndef OAR_XS_PARAM_WTS
-#define OAR_XS_PARAM_WTS 0      // the bootstrap-weighted instantiation is faster with the cvta (185.3 vs 186.6 us): ptxas again
+#define OAR_XS_PARAM_WTS 0      // lean weighted: cvta (185.3 vs 186.6 us)
 #endif
+#ifndef OAR_COMMON_PATH_WTS
+#define OAR_COMMON_PATH_WTS 0   // lean weighted: single general copy of phase 1
+#endif
+#ifndef OAR_XS_PARAM_FUSED_WTS
+#define OAR_XS_PARAM_FUSED_WTS 0
+#endif
+#ifndef OAR_COMMON_PATH_FUSED_WTS
+#define OAR_COMMON_PATH_FUSED_WTS 0
+#endif
+    constexpr bool kXsParam = OAR_XS_PARAM && (!HAS_WTS || (FUSED ? OAR_XS_PARAM_FUSED_WTS : OAR_XS_PARAM_WTS));
+    constexpr bool kCommonOk = !HAS_WTS || (FUSED ? OAR_COMMON_PATH_FUSED_WTS : OAR_COMMON_PATH_WTS);
     uint32_t xs_a;
-    if (OAR_XS_PARAM && (OAR_XS_PARAM_WTS || !HAS_WTS)) { xs_a = g.xs_base; if (sm0 != xs_a) __trap(); }
+    if (kXsParam) { xs_a = g.xs_base; if (sm0 != xs_a) __trap(); }
     else xs_a = smem_u32(smem);
 
     // Work between the two CTA barriers of a tile is spread over the warps: the first warps sum the items
@@ -1175,7 +1185,7 @@ __global__ void __launch_bounds__(kThreads, (OAR_TILED_MIN_CTAS * 8) / kWarps) e
         __syncthreads();   // stage s and s_prev of this tile are in place; phase 2 of the previous tile has left xs
 
         uint32_t item; uint4 du;
-        tile_phase1<HAS_AUX, HAS_WTS>(v, HAS_AUX ? phys(tile) : 0u, stg, rec, stg + g.w_off, sp_a, xs_a, tid, lane, warp, curr, wperm, item, du);
+        tile_phase1<HAS_AUX, HAS_WTS, kCommonOk>(v, HAS_AUX ? phys(tile) : 0u, stg, rec, stg + g.w_off, sp_a, xs_a, tid, lane, warp, curr, wperm, item, du);
         __syncthreads();   // xs complete; stage s and s_prev are free again
 
         // ---- refill stage s two tiles ahead; the last warp fetches prev[] of the next tile ----

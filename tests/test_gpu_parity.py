@@ -166,6 +166,26 @@ def test_progress_callback_reports_the_running_em(DS, small_store):
         assert len(seen) == n_calls
 
 
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_fused_and_separate_bookkeeping_match_the_oracle(DS, oracle_mod, small_store, monkeypatch, fused):
+    """The convergence bookkeeping runs in the head of the next sweep (default where it pays) or as its own launch
+    (OAR_FUSED_UPDATE=0, and long bootstrap-weighted sweeps): both against the oracle, plain and weighted, with every
+    max_iter around the 18-iteration graph and the three rotating buffers."""
+    monkeypatch.setenv("OAR_FUSED_UPDATE", fused)
+    s = small_store
+    with DS(s.row_ptr, s.txp_id, s.prob, s.n_txps) as ds:
+        for max_iter in (0, 1, 2, 3, 17, 18, 19, 36, 37, 1000):
+            want, niter, _, _ = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps, max_iter=max_iter, min_iter=1)
+            r = ds.em(max_iter=max_iter, min_iter=1)
+            assert r.niter == niter, max_iter
+            assert_counts_close(r.counts, want)
+        w = ds.sample_weights(9, 0)
+        want, niter, _, _ = oracle_mod.do_em(s.row_ptr, s.txp_id, s.prob, s.n_txps, min_iter=50, wts=w)
+        out, nit = ds.bootstrap(1, 9)
+        assert nit[0] == niter
+        assert_counts_close(out[0], want)
+
+
 def test_empty_store(DS):
     rp = np.zeros(1, dtype=np.uint64)
     with DS(rp, np.zeros(0, np.uint32), np.zeros(0, np.float32), 5) as ds:

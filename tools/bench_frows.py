@@ -91,10 +91,4 @@ for _ in range(3):
 out["filtered_store"] = {"groups": n_groups, "records": n_rec, "reads_kept": kept[0], "alignments_kept": kept[1], "call_ms": best,
                          "records_per_sec": n_rec / best * 1e3, "ref": "oarfish_types.rs:955-1130",
                          "includes": "upload of the record columns (25 B per record, pageable host), filter + count, scans, filter + write, layout build"}
-try:
-    from oracle import oracle
-    t0 = time.perf_counter(); oracle.filter_records(**rec); cpu_ms = (time.perf_counter() - t0) * 1e3
-    out["filtered_store"]["cpu_restatement_ms_1_core"] = cpu_ms
-except Exception as e:  # oracle not built
-    out["filtered_store"]["cpu_restatement"] = str(e)
 print(json.dumps(out))

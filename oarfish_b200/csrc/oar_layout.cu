@@ -47,7 +47,7 @@ static int build_chunk_layout(oar_store *s, uint32_t span)
     if (span == 0 || span > (uint32_t)kTile) span = (uint32_t)kTile - 5u * kWarps;
     t.span = span;
     if (N == 0 || s->nnz == 0) { t.ready = true; return OAR_OK; }
-    if (s->n_txps >= kMaxTxps) return fail(OAR_ERR_UNSUPPORTED, "tiled layout needs n_txps < 2^27");
+    if (s->n_txps >= kMaxTxps) return fail(OAR_ERR_UNSUPPORTED, "tiled layout needs n_txps < 2^32 - 1");
     cudaStream_t st = s->stream;
     Scratch sc; sc.st = st;
     uint32_t *key = nullptr, *idx = nullptr, *key_s = nullptr, *srow = nullptr, *slen = nullptr, *soff = nullptr;

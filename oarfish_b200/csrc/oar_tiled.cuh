@@ -81,7 +81,7 @@ constexpr int kMaxItems = kTile / 4;      // every item belongs to a transcript 
 // ordered by class (largest first); a class-c item sits c + 2 doubles behind its predecessor, so the 8 lanes of an
 // LDS.128 phase hit 8 different 16-byte banks.  One thread sums one item and issues one RED: no cross-lane scan, no
 // padding to clear.  (Measured on C3: 16-slot items 228 us, 32-slot items 232 us, 8-slot units + scan 244 us.)
-// padding and non-aggregated alignments write to a trash slot right after the last item of the tile
+// padding and non-aggregated alignments write to the trash slots right after the last item of the tile (kTrashSlots)
 // prev[] of a tile's transcripts sits in shared memory as SPLIT 32-bit words: blocks of 32 table entries, 128 bytes
 // of high words followed by 128 bytes of low words.  A warp-wide LDS.32 is one wavefront whenever its lanes hit 32
 // different banks or the same word, so the E-step's gather is conflict-free for tiles with up to 32 distinct
@@ -103,21 +103,30 @@ constexpr uint32_t kPrevLo = 128u;        // low word = high word + 128 bytes
 constexpr uint32_t kInfoStray = 8u;       // chunk_info bit 3: chunk holds alignments that RED straight to global
 constexpr uint32_t kInfoMulti = 16u;      // chunk_info bit 4: some lane holds >= 2 row heads (general path)
 constexpr uint32_t kNoTxp = 0xFFFFFFFFu;
-constexpr uint32_t kMaxTxps = 1u << 27;   // item descriptors pack (slots - 1) above bit 27
+constexpr uint32_t kMaxTxps = 0xFFFFFFFFu; // kNoTxp is reserved
+constexpr uint32_t kDescRare = 1u << 9, kDescMid = 1u << 10;
+constexpr uint32_t kTrashSlots = 16;      // x slots behind the tile's items that take the stores of padding and stray alignments: lane l writes slot l & 15
 static_assert(kMaxItems == kThreads, "one item per thread in phase 2");
 static_assert(!OAR_SCATTER_GREEDY || kItemMax == 16, "the bank-aware x positions assume 16-slot items at a stride of 18 doubles: one slot per 8-byte bank residue");
 
 // Per-tile record (variable length, 16-byte granules), one TMA bulk copy:
-//   [0,512)    lane descriptors u16[8][32]: hb(4) | dist(5) | E(5)
+//   [0,512)    lane descriptors u16[8][32]: hb(4) | dist(5) << 4 | rare << 9 | mid << 10 | E(5) << 11
 //                hb    row-head bits of the lane's 4 slots
 //                dist  lanes back to the nearest lane (<= this one) holding a head
+//                rare  (same in all lanes of a chunk) the chunk needs the general copy of phase 1: a lane with two
+//                      heads, stray alignments or a row spanning more than 8 lanes
+//                mid   (same in all lanes of a chunk) some row spans more than 4 lanes: third scan step needed
 //                E     first later lane holding a head (where the row leaving this lane ends);
-//                      the lane itself if there is none (then only padding follows)
+//                      the lane itself if there is none (then only padding follows).  Top bits: `desc >> 11` is
+//                      the shuffle's source lane without a mask
+//              The sweep tests the fields in place (`desc & 0xE`, `desc & 0x1E0`, ...: one LOP3 with predicate
+//              output each) instead of extracting them first.
 //   [512,544)  chunk_info u32[8]: scan steps (bits 0-2) | kInfoStray | kInfoMulti
 //   [544,576)  chunk_row  u32[8]: tile-order index of the chunk's first row (bootstrap weights)
-//   [576,592)  D, items, n0 | n1 << 16 (items of the largest and the middle size class), trash x offset in bytes
-//   [592, ..)  table u32[roundup4(D)]      : distinct transcript ids
-//              items u32[roundup4(items)]  : transcript id | (slots - 1) << 27
+//   [576,592)  D, byte offset of the table in the record, items, trash x offset in bytes
+//   [592, ..)  items u32[roundup4(items)]  : 4 * table index | (x offset in doubles) << 12 | slots << 24   (0 = no item)
+//              table u32[roundup4(D)]      : distinct transcript ids
+//              (items first: thread t's item sits at a fixed offset, 592 + 4 t)
 constexpr int kRecDesc = 0, kRecInfo = 64 * kWarps, kRecRow = kRecInfo + 4 * kWarps, kRecDU = kRecRow + 4 * kWarps,
               kRecTable = kRecDU + 16;
 constexpr int kRecMax = kRecTable + 4 * kTile + 4 * kMaxItems;   // 5712
@@ -148,8 +157,8 @@ inline Geometry make_geometry(uint32_t max_rec_bytes, uint32_t max_d, uint32_t m
     g.w_off = 8u * kTile + rec;
     g.stage_bytes = g.w_off + (weighted ? 2u * kThreads : 0u);
     g.xs_base = 0;   // set by the launcher
-    // the items of the fullest tile, then the trash slot; even count
-    g.xs_doubles = (max_x_doubles + 2u + 1u) & ~1u;
+    // the items of the fullest tile, then the trash slots; even count
+    g.xs_doubles = (max_x_doubles + kTrashSlots + 1u) & ~1u;
     g.stage_off = (8u * g.xs_doubles + 127u) & ~127u;
     g.prev_off = g.stage_off + kStages * g.stage_bytes;
     g.bar_off = g.prev_off + table_bytes(max_d);   // split high / low words, see table_off()
@@ -464,7 +473,7 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
         const int P = 31 - __clz(lanes_h & (full >> (31u - lane)));
         const unsigned later = lanes_h & ~(full >> (31u - lane));
         const uint32_t E = later ? (uint32_t)(__ffs(later) - 1) : lane;
-        const uint32_t desc = hb | ((lane - (uint32_t)P) << 4) | (E << 9);
+        const uint32_t desc = hb | ((lane - (uint32_t)P) << 4) | (E << 11);   // the chunk's rare / mid bits are added at the end
         reinterpret_cast<uint16_t *>(s_rec)[kRecDesc / 2 + tid] = (uint16_t)desc;
     }
     for (uint32_t i = tid; i < (uint32_t)kTile; i += kThreads) {
@@ -546,8 +555,8 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
         atomicMax(a.cursors + 5, D);
         atomicMax(a.cursors + 6, XD);
         s_rec[kRecDU / 4 + 0] = D;
-        s_rec[kRecDU / 4 + 1] = U;
-        s_rec[kRecDU / 4 + 2] = N32 | (N16 << 16);
+        s_rec[kRecDU / 4 + 1] = kRecTable + 4u * U4;
+        s_rec[kRecDU / 4 + 2] = U;
         s_rec[kRecDU / 4 + 3] = XD * 8u;
     }
     // table and item descriptors; per segment: where its alignments go
@@ -557,22 +566,22 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
         const uint32_t d = tid * 4 + i;
         sega[i] = segb[i] = 0;
         if (d < D) {
-            const uint32_t key = s_txp[startd[i]];
-            s_rec[kRecTable / 4 + d] = key;
-            uint32_t *items = s_rec + kRecTable / 4 + D4;
+            s_rec[kRecTable / 4 + U4 + d] = s_txp[startd[i]];
+            uint32_t *items = s_rec + kRecTable / 4;
             const uint32_t i32 = pbase[i] & 0x3FFu, i16 = (pbase[i] >> 10) & 0x3FFu, i8 = pbase[i] >> 20;
             const uint32_t n32 = pk[i] & 0x3FFu, rem = cntd[i] % kI;
             if (pk[i] == 0u) { segb[i] = 1u << 31; sega[i] = startd[i]; continue; }
-            for (uint32_t v = 0; v < n32; ++v) items[i32 + v] = key | ((min(kI, cntd[i] - kI * v) - 1u) << 27);
+            // item = 4 * table index | x offset (doubles) << 12 | valid slots << 24
+            for (uint32_t v = 0; v < n32; ++v) items[i32 + v] = (d << 2) | ((kS0 * (i32 + v)) << 12) | (min(kI, cntd[i] - kI * v) << 24);
             uint32_t rem_x = 0;
-            if (rem > kI / 4u && rem <= kI / 2u) { items[N32 + i16] = key | ((rem - 1u) << 27); rem_x = kS0 * N32 + kS1 * i16; }
-            else if (rem >= 1u && rem <= kI / 4u) { items[N32 + N16 + i8] = key | ((rem - 1u) << 27); rem_x = kS0 * N32 + kS1 * N16 + kS2 * i8; }
+            if (rem > kI / 4u && rem <= kI / 2u) { rem_x = kS0 * N32 + kS1 * i16; items[N32 + i16] = (d << 2) | (rem_x << 12) | (rem << 24); }
+            else if (rem >= 1u && rem <= kI / 4u) { rem_x = kS0 * N32 + kS1 * N16 + kS2 * i8; items[N32 + N16 + i8] = (d << 2) | (rem_x << 12) | (rem << 24); }
             sega[i] = startd[i] | (i32 << 11);
             segb[i] = rem_x | (n32 << 12);
         }
     }
     __syncthreads();  // everyone has read s_seg[d+1]; s_misc[2] visible
-    for (uint32_t u = U + tid; u < U4; u += kThreads) s_rec[kRecTable / 4 + D4 + u] = kNoTxp;
+    for (uint32_t u = U + tid; u < U4; u += kThreads) s_rec[kRecTable / 4 + u] = 0u;   // no item
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const uint32_t d = tid * 4 + i;
@@ -631,7 +640,10 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
                 i32 = pa >> 11; q = ((pb >> 12) & 0x3FFu) - (cw >> 15); ci = cw & 0x7FFFu;
                 br = (cw >> 15) ? (2u * (i32 + q)) & 15u : pb & 15u;
             }
-            uint32_t G = 0;   // residues taken in this lane's half-warp
+            // residues taken in this lane's half-warp.  Lanes without an x position (padding, stray alignments) store to
+            // trash slot XD + (lane & 15) unconditionally: their banks are taken from the start
+            const uint32_t nopos = (__ballot_sync(full, !todo) >> (16u * half)) & 0xFFFFu, rotx = XD & 15u;
+            uint32_t G = ((nopos << rotx) | (nopos >> (16u - rotx))) & 0xFFFFu;
             // Scarce first (model, tools/layout_model.py: 89 -> 80 scatter wavefronts per tile): lanes whose transcript
             // offers at most kScarce residues (remainder items of 4 or 8 slots) choose in a first phase, the others
             // after them.  (Ranking the lanes with __reduce_min_sync over the match groups did the same in one phase,
@@ -693,14 +705,14 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
         if (dj != kNoTxp) {
             const uint32_t d = dj & 0xFFFFu;
             const uint32_t pa = s_seg[d], pb = s_seg2[d];
-            uint32_t pos = XD;   // trash slot of this tile
+            uint32_t pos = XD + ((slot >> 2) & 15u);   // trash slot of this lane
             if ((pb >> 31) == 0u) {
                 const uint32_t j = dj >> 16, n32 = (pb >> 12) & 0x3FFu;
                 pos = j < kI * n32 ? kS0 * ((pa >> 11) + j / kI) + j % kI : (pb & 0xFFFu) + (j - kI * n32);
             } else atomicOr(&s_info[slot / kChunk], kInfoStray);
             s_lpos[slot] = table_off(d) | ((pos * 8u) << 16);
         } else {
-            s_lpos[slot] = 0u | ((XD * 8u) << 16);
+            s_lpos[slot] = 0u | (((XD + ((slot >> 2) & 15u)) * 8u) << 16);
         }
     }
 #else
@@ -711,20 +723,25 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
         if (keys[i] != kNoTxp) {
             const uint32_t d = seg[i] - 1;
             const uint32_t pa = s_seg[d], pb = s_seg2[d];
-            uint32_t pos = XD;   // trash slot of this tile
+            uint32_t pos = XD + ((vals[i] >> 2) & 15u);   // trash slot of this lane
             if ((pb >> 31) == 0u) {
                 const uint32_t rr = r - (pa & 0x7FFu), n32 = (pb >> 12) & 0x3FFu;
                 pos = rr < kI * n32 ? kS0 * ((pa >> 11) + rr / kI) + rr % kI : (pb & 0xFFFu) + (rr - kI * n32);
             } else atomicOr(&s_info[vals[i] / kChunk], kInfoStray);
             s_lpos[vals[i]] = table_off(d) | ((pos * 8u) << 16);
         } else {
-            s_lpos[vals[i]] = 0u | ((XD * 8u) << 16);
+            s_lpos[vals[i]] = 0u | (((XD + ((vals[i] >> 2) & 15u)) * 8u) << 16);
         }
     }
 #endif
     __syncthreads();
     for (uint32_t i = tid; i < (uint32_t)kTile; i += kThreads) a.o_lpos[(size_t)tile * kTile + i] = s_lpos[i];
     if (tid < kWarps) s_rec[kRecInfo / 4 + tid] = s_info[tid];
+    {
+        const uint32_t info = s_info[tid >> 5];
+        uint16_t *dp = reinterpret_cast<uint16_t *>(s_rec) + kRecDesc / 2 + tid;
+        *dp = (uint16_t)(*dp | ((info & (kInfoMulti | kInfoStray | 4u)) ? kDescRare : 0u) | ((info & 7u) >= 3u ? kDescMid : 0u));
+    }
     __syncthreads();
     const uint32_t rec_off = s_misc[2];
     uint4 *dst = a.o_records + rec_off;
@@ -811,6 +828,8 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t r; asm volati
 __device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t r; asm volatile("{.reg .u16 h; ld.shared.u16 h, [%1]; cvt.u32.u16 %0, h;}" : "=r"(r) : "r"(a)); return r; }
 __device__ __forceinline__ uint4 lds_v4(uint32_t a)
 { uint4 r; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a)); return r; }
+__device__ __forceinline__ uint2 lds_v2(uint32_t a)
+{ uint2 r; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a)); return r; }
 __device__ __forceinline__ float4 lds_v4f(uint32_t a)
 { float4 r; asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a)); return r; }
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
@@ -836,8 +855,6 @@ __device__ __forceinline__ void sts_prev(uint32_t a, double v)
 }
 __device__ __forceinline__ double lds_f64(uint32_t a) { double r; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(a)); return r; }
 __device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
-__device__ __forceinline__ void sts_f64_if(uint32_t a, double v, bool on)
-{ asm volatile("{.reg .pred p; setp.ne.u32 p, %2, 0; @p st.shared.f64 [%0], %1;}" ::"r"(a), "d"(v), "r"((uint32_t)on) : "memory"); }
 // 0.0 unless `on`
 __device__ __forceinline__ double lds_f64_if(uint32_t a, bool on)
 {
@@ -873,14 +890,12 @@ __device__ __forceinline__ bool any_bits(uint32_t v, uint32_t mask)
 // COMMON: the chunk has no lane with two row heads, no row spanning more than 8 lanes and no stray alignments (90 % of
 // the chunks on C3): those three tests are compile-time false and cost neither votes nor branches.
 template <bool HAS_AUX, bool HAS_WTS, bool COMMON = false>
-__device__ __forceinline__ void tile_phase1_core(const View &v, uint32_t tile, const float4 p4, const uint4 lp4, uint32_t rec, uint32_t sp_a,
-                                                 uint32_t xs_a, uint32_t trash, uint32_t w_in, uint32_t tid, uint32_t lane, uint32_t warp,
+__device__ __forceinline__ void tile_phase1_core(const View &v, uint32_t tile, const float4 p4, const uint4 lp4, uint32_t desc, uint32_t rec, uint32_t sp_a,
+                                                 uint32_t xs_a, uint32_t w_in, uint32_t tid, uint32_t lane, uint32_t warp,
                                                  double *__restrict__ curr, const uint32_t *__restrict__ wperm)
 {
     const unsigned full = 0xffffffffu;
-    const uint32_t desc = lds_u16(rec + kRecDesc + 2u * tid);
-    const uint32_t info = lds_u32(rec + kRecInfo + 4u * warp);
-    const uint32_t table_a = rec + kRecTable;
+    const uint32_t info = COMMON ? 0u : lds_u32(rec + kRecInfo + 4u * warp);
 
     double w0 = lds_prev(sp_a + (lp4.x & 0xFFFFu)) * (double)p4.x;
     double w1 = lds_prev(sp_a + (lp4.y & 0xFFFFu)) * (double)p4.y;
@@ -893,20 +908,23 @@ __device__ __forceinline__ void tile_phase1_core(const View &v, uint32_t tile, c
         w0 *= q0.x; w1 *= q0.y; w2 *= q1.x; w3 *= q1.y;
     }
 
-    const uint32_t hb = desc & 15u, dist = (desc >> 4) & 31u, E = (desc >> 9) & 31u;
+    // the descriptor's fields are tested in place: hb = desc & 15, dist >= 2^i <=> desc & (0x1F0 & ~((2^i - 1) << 4)), and the
+    // shuffle takes its source lane modulo 32, so E = desc >> 11 needs no mask
+    const uint32_t hb = desc & 15u, E = desc >> 11;
+    auto dist_ge = [&](uint32_t d) -> bool { return (desc & (0x1F0u & ~((d - 1u) << 4))) != 0u; };   // d a power of two
     // bootstrap: w_in = the resampling weight of the row that ends in this lane (fast path; staged with the tile,
     // see lane_weights)
     // chunk_info is the same word for the whole warp; votes make that visible to the compiler
     const bool multi = !COMMON && any_bits(info, kInfoMulti);
     const bool strays = !COMMON && any_bits(info, kInfoStray);
     const bool long_rows = !COMMON && any_bits(info, 4u);   // scan steps > 3: rows spanning more than 8 lanes
-    const bool mid_rows = !OAR_SCAN_COND || __any_sync(full, (info & 7u) >= 3u);   // scan steps > 2
+    const bool mid_rows = !OAR_SCAN_COND || any_bits(desc, kDescMid);   // scan steps > 2
     double x0, x1, x2, x3;
     if (!multi) {
         // fast path: no lane holds more than one row head.  Slot i lies before that head (it
         // closes the row entering the lane) iff hb >> (i+1) != 0; slot 3 never does.
         //   a = slots before the head, z = slots from the head on (all four if there is none)
-        const bool c0 = (hb >> 1) != 0u, c1 = (hb >> 2) != 0u, c2 = (hb >> 3) != 0u;
+        const bool c0 = (desc & 0xEu) != 0u, c1 = (desc & 0xCu) != 0u, c2 = (desc & 0x8u) != 0u;
         double a = w0 * mask01(c0);
         a = fma(w1, mask01(c1), a);
         a = fma(w2, mask01(c2), a);
@@ -915,12 +933,12 @@ __device__ __forceinline__ void tile_phase1_core(const View &v, uint32_t tile, c
         z = fma(w2, mask01(!c2), z);
         // segmented inclusive scan over lanes: what each lane adds to the row open at its end
         double incl = z;
-        incl = fma(__shfl_up_sync(full, incl, 1), mask01(dist >= 1u), incl);
-        incl = fma(__shfl_up_sync(full, incl, 2), mask01(dist >= 2u), incl);
-        if (mid_rows) incl = fma(__shfl_up_sync(full, incl, 4), mask01(dist >= 4u), incl);   // rows spanning more than 4 lanes (a third of the chunks on C3)
+        incl = fma(__shfl_up_sync(full, incl, 1), mask01(dist_ge(1u)), incl);
+        incl = fma(__shfl_up_sync(full, incl, 2), mask01(dist_ge(2u)), incl);
+        if (mid_rows) incl = fma(__shfl_up_sync(full, incl, 4), mask01(dist_ge(4u)), incl);   // rows spanning more than 4 lanes (a third of the chunks on C3)
         if (long_rows) {   // rows spanning more than 8 lanes (rare)
-            incl = fma(__shfl_up_sync(full, incl, 8), mask01(dist >= 8u), incl);
-            incl = fma(__shfl_up_sync(full, incl, 16), mask01(dist >= 16u), incl);
+            incl = fma(__shfl_up_sync(full, incl, 8), mask01(dist_ge(8u)), incl);
+            incl = fma(__shfl_up_sync(full, incl, 16), mask01(dist_ge(16u)), incl);
         }
         const double carry = __shfl_up_sync(full, incl, 1);       // sum of the row entering this lane
         const double t_in = carry + a;                            // its total, if it ends here
@@ -945,7 +963,7 @@ __device__ __forceinline__ void tile_phase1_core(const View &v, uint32_t tile, c
         for (uint32_t i = 0; i < 5; ++i) {
             if (i >= nsteps) break;
             const uint32_t d = 1u << i;
-            incl = fma(__shfl_up_sync(full, incl, d), mask01(dist >= d), incl);
+            incl = fma(__shfl_up_sync(full, incl, d), mask01(dist_ge(d)), incl);
         }
         double carry = __shfl_up_sync(full, incl, 1);
         if (lane == 0) carry = 0.0;
@@ -983,25 +1001,21 @@ __device__ __forceinline__ void tile_phase1_core(const View &v, uint32_t tile, c
     }
 
     // ---- M-step scatter into the transcript-sorted smem order -----------------------------
-    // (padding and non-aggregated alignments carry the tile's trash offset and are not stored)
+    // (padding and non-aggregated alignments carry the address of their lane's trash slot: every store is unconditional and the
+    // layout's bank-aware positions count the trash slots in)
     const uint32_t q0 = lp4.x >> 16, q1 = lp4.y >> 16, q2 = lp4.z >> 16, q3 = lp4.w >> 16;
-#ifdef OAR_FAKE_SCATTER   // timing experiment only (wrong results): conflict-free scatter addresses
-    sts_f64_if(xs_a + 8u * lane + 256u * warp, x0, q0 != trash);
-    sts_f64_if(xs_a + 8u * lane + 256u * warp + 2048u, x1, q1 != trash);
-    sts_f64_if(xs_a + 8u * lane + 256u * warp + 4096u, x2, q2 != trash);
-    sts_f64_if(xs_a + 8u * lane + 256u * warp + 6144u, x3, q3 != trash);
-#else
-    sts_f64_if(xs_a + q0, x0, q0 != trash);
-    sts_f64_if(xs_a + q1, x1, q1 != trash);
-    sts_f64_if(xs_a + q2, x2, q2 != trash);
-    sts_f64_if(xs_a + q3, x3, q3 != trash);
-#endif
+    sts_f64(xs_a + q0, x0);
+    sts_f64(xs_a + q1, x1);
+    sts_f64(xs_a + q2, x2);
+    sts_f64(xs_a + q3, x3);
     if (strays) {
         // transcripts with fewer than kAggMin alignments in this tile: straight to global
-        if (q0 == trash && x0 != 0.0) atomicAdd(curr + lds_u32(table_a + 4u * table_index(lp4.x & 0xFFFFu)), x0);
-        if (q1 == trash && x1 != 0.0) atomicAdd(curr + lds_u32(table_a + 4u * table_index(lp4.y & 0xFFFFu)), x1);
-        if (q2 == trash && x2 != 0.0) atomicAdd(curr + lds_u32(table_a + 4u * table_index(lp4.z & 0xFFFFu)), x2);
-        if (q3 == trash && x3 != 0.0) atomicAdd(curr + lds_u32(table_a + 4u * table_index(lp4.w & 0xFFFFu)), x3);
+        const uint4 du = lds_v4(rec + kRecDU);   // D, table offset, items, trash offset
+        const uint32_t trash = du.w, table_a = rec + du.y;
+        if (q0 >= trash && x0 != 0.0) atomicAdd(curr + lds_u32(table_a + 4u * table_index(lp4.x & 0xFFFFu)), x0);
+        if (q1 >= trash && x1 != 0.0) atomicAdd(curr + lds_u32(table_a + 4u * table_index(lp4.y & 0xFFFFu)), x1);
+        if (q2 >= trash && x2 != 0.0) atomicAdd(curr + lds_u32(table_a + 4u * table_index(lp4.z & 0xFFFFu)), x2);
+        if (q3 >= trash && x3 != 0.0) atomicAdd(curr + lds_u32(table_a + 4u * table_index(lp4.w & 0xFFFFu)), x3);
     }
 }
 
@@ -1010,37 +1024,38 @@ __device__ __forceinline__ void tile_phase1_core(const View &v, uint32_t tile, c
 template <bool HAS_AUX, bool HAS_WTS, bool COMMON_OK>
 __device__ __forceinline__ void tile_phase1(const View &v, uint32_t tile, uint32_t bulk, uint32_t rec, uint32_t wl_a, uint32_t sp_a, uint32_t xs_a,
                                             uint32_t tid, uint32_t lane, uint32_t warp, double *__restrict__ curr,
-                                            const uint32_t *__restrict__ wperm, uint32_t &item, uint4 &du)
+                                            const uint32_t *__restrict__ wperm, uint32_t &item, uint32_t &item_txp, uint32_t &U)
 {
     const float4 p4 = lds_v4f(bulk + 16u * tid);
     const uint4 lp4 = lds_v4(bulk + 4u * kTile + 16u * tid);
-    du = lds_v4(rec + kRecDU);   // D, items, n32 | n16 << 16, trash offset
-    item = kNoTxp;
-    if (tid < du.y) item = lds_u32(rec + kRecTable + 4u * (((du.x + 3u) & ~3u) + tid));
+    const uint32_t desc = lds_u16(rec + kRecDesc + 2u * tid);
+    const uint4 du = lds_v4(rec + kRecDU);   // D, table offset, items, trash offset
+    U = du.z;
+    item = 0; item_txp = 0;
+    if (tid < U) {
+        item = lds_u32(rec + kRecTable + 4u * tid);
+        item_txp = lds_u32(rec + du.y + (item & 0xFFCu));
+    }
     uint32_t w_in = 0;
     if (HAS_WTS) w_in = lds_u16(wl_a + 2u * tid);
 #if OAR_COMMON_PATH
-    // chunk_info is the same word in every lane of the warp: one vote decides between the two copies of phase 1
-    if (COMMON_OK && !any_bits(lds_u32(rec + kRecInfo + 4u * warp), kInfoMulti | kInfoStray | 4u))
-        tile_phase1_core<HAS_AUX, HAS_WTS, true>(v, tile, p4, lp4, rec, sp_a, xs_a, du.w, w_in, tid, lane, warp, curr, wperm);
+    // the rare bit is the same in every lane of the warp: one vote decides between the two copies of phase 1
+    if (COMMON_OK && !any_bits(desc, kDescRare))
+        tile_phase1_core<HAS_AUX, HAS_WTS, true>(v, tile, p4, lp4, desc, rec, sp_a, xs_a, w_in, tid, lane, warp, curr, wperm);
     else
 #endif
-    tile_phase1_core<HAS_AUX, HAS_WTS, false>(v, tile, p4, lp4, rec, sp_a, xs_a, du.w, w_in, tid, lane, warp, curr, wperm);
+    tile_phase1_core<HAS_AUX, HAS_WTS, false>(v, tile, p4, lp4, desc, rec, sp_a, xs_a, w_in, tid, lane, warp, curr, wperm);
 }
 
 // ---- phase 2 of a tile: one thread sums one item (<= 16 consecutive x slots of one transcript), one RED -------
-__device__ __forceinline__ void tile_phase2(uint32_t xs_a, uint32_t item, uint32_t U, uint32_t duz, uint32_t tid, uint32_t warp,
+__device__ __forceinline__ void tile_phase2(uint32_t xs_a, uint32_t item, uint32_t item_txp, uint32_t U, uint32_t warp,
                                             double *__restrict__ curr)
 {
     const unsigned full = 0xffffffffu;
     if (__any_sync(full, warp * 32u < U)) {
-        const uint32_t N32 = duz & 0xFFFFu, N16 = duz >> 16;
-        const uint32_t slots = item == kNoTxp ? 0u : (item >> 27) + 1u, npair = slots >> 1;
-        constexpr uint32_t kS0 = kItemMax + 2, kS1 = kItemMax / 2 + 2, kS2 = kItemMax / 4 + 2, kP = kItemMax / 2;
-        uint32_t bd = kS0 * tid;   // x offset in doubles: the three size classes at strides c + 2
-        if (tid >= N32) bd = kS1 * tid + (kS0 - kS1) * N32;
-        if (tid >= N32 + N16) bd = kS2 * tid + (kS0 - kS2) * N32 + (kS1 - kS2) * N16;
-        const uint32_t b = xs_a + 8u * bd;
+        const uint32_t slots = item >> 24, npair = slots >> 1;   // 0 slots: no item
+        constexpr uint32_t kP = kItemMax / 2;
+        const uint32_t b = xs_a + ((item >> 9) & 0x7FF8u);       // x offset in doubles at bit 12 -> bytes
         double a0 = lds_f64_if(b + 8u * (slots - 1u), (slots & 1u) != 0u), a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
         for (uint32_t k = 0; k < kP / 4u; k += 2) {
@@ -1062,7 +1077,7 @@ __device__ __forceinline__ void tile_phase2(uint32_t xs_a, uint32_t item, uint32
             }
         }
         const double acc = (a0 + a2) + (a1 + a3);
-        if (item != kNoTxp && acc != 0.0) atomicAdd(curr + (item & (kMaxTxps - 1u)), acc);
+        if (acc != 0.0) atomicAdd(curr + item_txp, acc);   // (no item: nothing was loaded, acc == 0)
     }
 
 }
@@ -1106,10 +1121,10 @@ __global__ void __launch_bounds__(kThreads, (OAR_TILED_MIN_CTAS * 8) / kWarps) e
     // Which instantiation gets the parameter base and the common-path copy of phase 1 was settled by A/B timing on C3
     // (profiles/experiments/r2_kernel_experiments.md): ptxas moves 1-3 % either way with each of them.
 #ifndef OAR_XS_PARAM_WTS
-#define OAR_XS_PARAM_WTS 0      // lean weighted: cvta (185.3 vs 186.6 us)
-#endif
+#define OAR_XS_PARAM_WTS 1      // lean weighted: parameter base + common path since the descriptor carries the chunk's rare / mid bits
+#endif                          // (179.6 us; common path alone 181.4, parameter base alone 186.7, neither 187.7-188.4)
 #ifndef OAR_COMMON_PATH_WTS
-#define OAR_COMMON_PATH_WTS 0   // lean weighted: single general copy of phase 1
+#define OAR_COMMON_PATH_WTS 1
 #endif
 #ifndef OAR_XS_PARAM_FUSED_WTS
 #define OAR_XS_PARAM_FUSED_WTS 0
@@ -1136,12 +1151,13 @@ __global__ void __launch_bounds__(kThreads, (OAR_TILED_MIN_CTAS * 8) / kWarps) e
     };
     // prev[] of a tile's transcripts into s_prev, by one warp (two gathers in flight per lane)
     auto gather_prev = [&](uint32_t rec_a) {
-        const uint32_t Dn = lds_u32(rec_a + kRecDU);
+        const uint2 du = lds_v2(rec_a + kRecDU);   // D, table offset
+        const uint32_t Dn = du.x, table_a = rec_a + du.y;
         for (uint32_t d = lane; d < Dn; d += 64u) {
             const uint32_t d2 = d + 32u;
-            const double p0 = prev[lds_u32(rec_a + kRecTable + 4u * d)];
+            const double p0 = prev[lds_u32(table_a + 4u * d)];
             double p1 = 0.0;
-            if (d2 < Dn) p1 = prev[lds_u32(rec_a + kRecTable + 4u * d2)];
+            if (d2 < Dn) p1 = prev[lds_u32(table_a + 4u * d2)];
             sts_prev(sp_a + table_off(d), p0);
             if (d2 < Dn) sts_prev(sp_a + table_off(d2), p1);
         }
@@ -1184,8 +1200,8 @@ __global__ void __launch_bounds__(kThreads, (OAR_TILED_MIN_CTAS * 8) / kWarps) e
         const uint32_t rec = stg + 8u * kTile;
         __syncthreads();   // stage s and s_prev of this tile are in place; phase 2 of the previous tile has left xs
 
-        uint32_t item; uint4 du;
-        tile_phase1<HAS_AUX, HAS_WTS, kCommonOk>(v, HAS_AUX ? phys(tile) : 0u, stg, rec, stg + g.w_off, sp_a, xs_a, tid, lane, warp, curr, wperm, item, du);
+        uint32_t item, item_txp, U;
+        tile_phase1<HAS_AUX, HAS_WTS, kCommonOk>(v, HAS_AUX ? phys(tile) : 0u, stg, rec, stg + g.w_off, sp_a, xs_a, tid, lane, warp, curr, wperm, item, item_txp, U);
         __syncthreads();   // xs complete; stage s and s_prev are free again
 
         // ---- refill stage s two tiles ahead; the last warp fetches prev[] of the next tile ----
@@ -1203,7 +1219,7 @@ __global__ void __launch_bounds__(kThreads, (OAR_TILED_MIN_CTAS * 8) / kWarps) e
         }
         __syncwarp();
 
-        tile_phase2(xs_a, item, du.y, du.z, tid, warp, curr);
+        tile_phase2(xs_a, item, item_txp, U, warp, curr);
 
         if (!has_next) break;
         tile = next;

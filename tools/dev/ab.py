@@ -48,9 +48,9 @@ for spec in sys.argv[2:]:
     li = ds.layout_info()
     sweeps = ds.counters()["sweeps"]
     ds.bootstrap(1, 5)
-    t = time.perf_counter(); ds.bootstrap(4, 5); wallb = time.perf_counter() - t
+    t = time.perf_counter(); ds.bootstrap(2, 5); wallb = time.perf_counter() - t
     sweepsb = ds.counters()["sweeps"]
     t = time.perf_counter(); ds.close(); t_close = time.perf_counter() - t
     print(f"{cfg} {os.path.basename(os.environ.get('OAR_EM_LIB', 'product'))} {f[0]} ctas/SM={f[1]} span={li['span']} fb={li['fallback_rows']}: {ms*1e3:.1f} us/sweep (weighted {msw*1e3:.1f}) "
-          f"frac {alg/ms/1e6/peak:.3f} relerr {err:.1e} | EM niter {r.niter}: {sweeps/wall:.0f} it/s, 4 replicates {sweepsb/wallb:.0f} it/s | create {t_create*1e3:.0f} ms close {t_close*1e3:.1f} ms",
+          f"frac {alg/ms/1e6/peak:.3f} relerr {err:.1e} | EM niter {r.niter}: {sweeps/wall:.0f} it/s, 2 replicates {sweepsb/wallb:.0f} it/s | create {t_create*1e3:.0f} ms close {t_close*1e3:.1f} ms",
           flush=True)

@@ -326,6 +326,17 @@ extern "C" int oar_store_layout_info(const oar_store *s, uint64_t out[8])
     return OAR_OK;
 }
 
+extern "C" int oar_store_layout_lpos(oar_store *s, uint32_t first_tile, uint32_t n_tiles, uint32_t *out)
+{
+    if (!s || !out) return fail(OAR_ERR_INVALID, "oar_store_layout_lpos: null argument");
+    const TiledLayout &t = s->tl;
+    if (!t.ready || (uint64_t)first_tile + n_tiles > t.n_tiles) return fail(OAR_ERR_INVALID, "oar_store_layout_lpos: tile range outside the layout");
+    cudaSetDevice(s->device);
+    OAR_CUDA(cudaStreamSynchronize(s->stream));
+    OAR_CUDA(cudaMemcpy(out, t.lpos + (size_t)first_tile * tiled::kTile, sizeof(uint32_t) * (size_t)n_tiles * tiled::kTile, cudaMemcpyDeviceToHost));
+    return OAR_OK;
+}
+
 extern "C" int oar_store_timings(const oar_store *s, double out_ms[4])
 {
     if (!s || !out_ms) return fail(OAR_ERR_INVALID, "oar_store_timings: null argument");

@@ -68,6 +68,9 @@ constexpr int kAggMin = 4;                // transcripts with >= kAggMin alignme
 #ifndef OAR_GREEDY_SCARCE
 #define OAR_GREEDY_SCARCE 1     // layout: in the x position greedy the lane whose transcript offers the fewest residues wins a contested bank
 #endif
+#ifndef OAR_GREEDY_SUPPLY
+#define OAR_GREEDY_SUPPLY 1     // layout: a lane takes the candidate residue its transcript has most slots of left
+#endif
 #ifndef OAR_SCAN_COND
 #define OAR_SCAN_COND 1         // sweep: the 4-lane step of the segmented scan only in chunks that hold a row spanning more than 4 lanes
 #endif
@@ -105,7 +108,7 @@ constexpr uint32_t kInfoMulti = 16u;      // chunk_info bit 4: some lane holds >
 constexpr uint32_t kNoTxp = 0xFFFFFFFFu;
 constexpr uint32_t kMaxTxps = 0xFFFFFFFFu; // kNoTxp is reserved
 constexpr uint32_t kDescRare = 1u << 9, kDescMid = 1u << 10;
-constexpr uint32_t kTrashSlots = 16;      // x slots behind the tile's items that take the stores of padding and stray alignments: lane l writes slot l & 15
+constexpr uint32_t kTrashSlots = 16;      // x slots behind the tile's items that take the stores of padding and stray alignments: per half-warp store the one in a bank the other lanes leave free
 static_assert(kMaxItems == kThreads, "one item per thread in phase 2");
 static_assert(!OAR_SCATTER_GREEDY || kItemMax == 16, "the bank-aware x positions assume 16-slot items at a stride of 18 doubles: one slot per 8-byte bank residue");
 
@@ -598,6 +601,8 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
     // half-warp store took 3.1 wavefronts on C3 -- the same as positions drawn at random.)
     uint32_t *s_state = s_txp;          // per transcript: residues on offer (bits 0-15) | free remainder slots (16-31); s_txp is dead
     uint16_t *s_ci = s_rnew;            // per transcript: compact index of its full-item counters | partial << 15; dead since the rows were placed
+    uint32_t *s_best = reinterpret_cast<uint32_t *>(&tmp);   // per transcript: the residues it has the MOST slots of left (the sort / scan scratch is dead)
+    static_assert(sizeof(tmp) >= 4 * kTile, "s_best is carved out of the sort scratch");
     __shared__ __align__(16) uint8_t s_fulluse[kTile / kItemMax][16];                 // [compact transcript][residue] -> full items used
     if (tid == 0) s_misc[3] = 0;
     for (uint32_t i = tid; i < (uint32_t)(kTile / kItemMax) * 16u; i += kThreads) (&s_fulluse[0][0])[i] = 0;
@@ -608,7 +613,7 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
     for (int i = 0; i < 4; ++i) {
         const uint32_t d = tid * 4 + i;
         if (d < D) {
-            uint32_t avail = 0, remfree = 0, ci = 0;
+            uint32_t avail = 0, remfree = 0, ci = 0, best = 0;
             if ((segb[i] >> 31) == 0u) {
                 // q full 16-slot items, then `rem` valid slots in the remainder item -- a smaller-class item at
                 // x offset rem_x, or (rem > 8) one more 16-slot item right behind the full ones
@@ -616,10 +621,12 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
                 const uint32_t br = partial ? (2u * ((pbase[i] & 0x3FFu) + q)) & 15u : segb[i] & 15u;
                 remfree = (1u << rem) - 1u;
                 avail = ((remfree << br) | (remfree << br >> 16)) & 0xFFFFu;   // bank residues of the remainder's slots
+                best = avail;   // residues the transcript has the most slots of: those of the remainder item, if it has one
                 if (q) { avail = 0xFFFFu; ci = atomicAdd(&s_misc[3], 1u); }
+                if (best == 0u) best = avail;
                 ci |= partial << 15;
             }
-            s_state[d] = avail | (remfree << 16); s_ci[d] = (uint16_t)ci;
+            s_state[d] = avail | (remfree << 16); s_ci[d] = (uint16_t)ci; s_best[d] = best;
         }
     }
     __syncthreads();
@@ -640,10 +647,8 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
                 i32 = pa >> 11; q = ((pb >> 12) & 0x3FFu) - (cw >> 15); ci = cw & 0x7FFFu;
                 br = (cw >> 15) ? (2u * (i32 + q)) & 15u : pb & 15u;
             }
-            // residues taken in this lane's half-warp.  Lanes without an x position (padding, stray alignments) store to
-            // trash slot XD + (lane & 15) unconditionally: their banks are taken from the start
-            const uint32_t nopos = (__ballot_sync(full, !todo) >> (16u * half)) & 0xFFFFu, rotx = XD & 15u;
-            uint32_t G = ((nopos << rotx) | (nopos >> (16u - rotx))) & 0xFFFFu;
+            const bool nopos = !todo;   // padding or stray alignment: stores to a trash slot, chosen below
+            uint32_t G = 0;   // residues taken in this lane's half-warp
             // Scarce first (model, tools/layout_model.py: 89 -> 80 scatter wavefronts per tile): lanes whose transcript
             // offers at most kScarce residues (remainder items of 4 or 8 slots) choose in a first phase, the others
             // after them.  (Ranking the lanes with __reduce_min_sync over the match groups did the same in one phase,
@@ -663,6 +668,30 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
                     const uint32_t av = st & 0xFFFFu;      // never 0 here: the transcript still owes this lane a position
                     uint32_t cand = av & ~G;
                     if (cand == 0u) cand = av;             // no unused residue on offer: accept a bank conflict
+#if OAR_GREEDY_SUPPLY
+                    // Of the candidates prefer the residues the transcript has MOST slots of left (unused full items plus
+                    // the remainder item's slot): that keeps a transcript's supply level across the residues, so the later
+                    // instructions of the tile still find every bank on offer.  s_best[d] holds that set; a lane that finds
+                    // it exhausted recomputes it (all lanes of the transcript write the same word).  Real C3 tiles: 99 -> 75
+                    // scatter wavefronts per tile, 64 is the floor; the exact "largest supply first" rule gives the same.
+                    uint32_t best = s_best[d] & av;
+                    if (best == 0u) {
+                        uint4 used = make_uint4(0, 0, 0, 0);
+                        if (q) used = *reinterpret_cast<const uint4 *>(&s_fulluse[ci][0]);
+                        const uint32_t remfree = st >> 16, remrot = ((remfree << br) | (remfree << br >> 16)) & 0xFFFFu;
+                        const uint32_t uw[4] = {used.x, used.y, used.z, used.w};
+                        uint32_t top = 0;
+#pragma unroll
+                        for (uint32_t r = 0; r < 16u; ++r) {
+                            const uint32_t sup = q - ((uw[r >> 2] >> (8u * (r & 3u))) & 0xFFu) + ((remrot >> r) & 1u);
+                            if (sup > top) { top = sup; best = 0u; }
+                            if (sup == top) best |= 1u << r;
+                        }
+                        best &= av;   // (top >= 1: av is not empty)
+                        s_best[d] = best;
+                    }
+                    if (cand & best) cand &= best;
+#endif
                     const uint32_t rot = ((cand >> l16) | (cand << (16u - l16))) & 0xFFFFu;
                     rho = (l16 + (uint32_t)__ffs((int)rot) - 1u) & 15u;
                 }
@@ -688,11 +717,20 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
                     }
                     if (m >= q && !((st >> (16u + orem)) & 1u)) clear |= 1u << rho;   // residue no longer on offer
                     if (clear) atomicAnd(&s_state[d], ~clear);   // lanes of other residues may update the same word
+#if OAR_GREEDY_SUPPLY
+                    atomicAnd(&s_best[d], ~(1u << rho));
+#endif
                     todo = false;
                     took = 1u << (rho + 16u * half);
                 }
                 __syncwarp();
                 G |= (__reduce_or_sync(full, took) >> (16u * half)) & 0xFFFFu;
+            }
+            // the lanes without a position all store to ONE trash slot per half-warp, in a bank the others left free
+            // (a store to the same address from several lanes is a single wavefront)
+            if (nopos) {
+                const uint32_t freeb = ~G & 0xFFFFu, r = freeb ? (uint32_t)__ffs((int)freeb) - 1u : 0u;
+                s_lpos[slot] = (r - XD) & 15u;   // trash slot index: (XD + index) & 15 == r
             }
         }
     }
@@ -705,14 +743,14 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
         if (dj != kNoTxp) {
             const uint32_t d = dj & 0xFFFFu;
             const uint32_t pa = s_seg[d], pb = s_seg2[d];
-            uint32_t pos = XD + ((slot >> 2) & 15u);   // trash slot of this lane
+            uint32_t pos = XD + s_lpos[slot];   // the trash slot picked for this lane's half-warp
             if ((pb >> 31) == 0u) {
                 const uint32_t j = dj >> 16, n32 = (pb >> 12) & 0x3FFu;
                 pos = j < kI * n32 ? kS0 * ((pa >> 11) + j / kI) + j % kI : (pb & 0xFFFu) + (j - kI * n32);
             } else atomicOr(&s_info[slot / kChunk], kInfoStray);
             s_lpos[slot] = table_off(d) | ((pos * 8u) << 16);
         } else {
-            s_lpos[slot] = 0u | (((XD + ((slot >> 2) & 15u)) * 8u) << 16);
+            s_lpos[slot] = 0u | (((XD + s_lpos[slot]) * 8u) << 16);
         }
     }
 #else
@@ -1001,8 +1039,8 @@ __device__ __forceinline__ void tile_phase1_core(const View &v, uint32_t tile, c
     }
 
     // ---- M-step scatter into the transcript-sorted smem order -----------------------------
-    // (padding and non-aggregated alignments carry the address of their lane's trash slot: every store is unconditional and the
-    // layout's bank-aware positions count the trash slots in)
+    // (padding and non-aggregated alignments carry the address of a trash slot in a bank their half-warp leaves free: every
+    // store is unconditional)
     const uint32_t q0 = lp4.x >> 16, q1 = lp4.y >> 16, q2 = lp4.z >> 16, q3 = lp4.w >> 16;
     sts_f64(xs_a + q0, x0);
     sts_f64(xs_a + q1, x1);
@@ -1127,10 +1165,10 @@ __global__ void __launch_bounds__(kThreads, (OAR_TILED_MIN_CTAS * 8) / kWarps) e
 #define OAR_COMMON_PATH_WTS 1
 #endif
 #ifndef OAR_XS_PARAM_FUSED_WTS
-#define OAR_XS_PARAM_FUSED_WTS 0
+#define OAR_XS_PARAM_FUSED_WTS 1
 #endif
 #ifndef OAR_COMMON_PATH_FUSED_WTS
-#define OAR_COMMON_PATH_FUSED_WTS 0
+#define OAR_COMMON_PATH_FUSED_WTS 1
 #endif
     constexpr bool kXsParam = OAR_XS_PARAM && (!HAS_WTS || (FUSED ? OAR_XS_PARAM_FUSED_WTS : OAR_XS_PARAM_WTS));
     constexpr bool kCommonOk = !HAS_WTS || (FUSED ? OAR_COMMON_PATH_FUSED_WTS : OAR_COMMON_PATH_WTS);

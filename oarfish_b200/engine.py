@@ -160,6 +160,12 @@ class DeviceStore:
         keys = ("tiled", "n_tiles", "slots", "fallback_rows", "sum_distinct", "sum_units", "span", "kernel")
         return {k: int(v) for k, v in zip(keys, out)}
 
+    def layout_lpos(self, first_tile: int, n_tiles: int) -> np.ndarray:
+        """Per-slot layout words of a range of tiles (inspection; see oar_store_layout_lpos)."""
+        out = np.empty((n_tiles, 1024), dtype=np.uint32)
+        check(self._lib.oar_store_layout_lpos(self._h, first_tile, n_tiles, out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def counters(self):
         out = (C.c_uint64 * 2)()
         check(self._lib.oar_store_counters(self._h, out))

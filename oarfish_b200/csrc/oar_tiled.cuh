@@ -156,7 +156,10 @@ struct Geometry {
 inline Geometry make_geometry(uint32_t max_rec_bytes, uint32_t max_d, uint32_t max_x_doubles, bool weighted)
 {
     Geometry g;
-    const uint32_t rec = (max_rec_bytes + 15u) & ~15u;
+#ifndef OAR_STAGE_ALIGN
+#define OAR_STAGE_ALIGN 128u    // every TMA destination of a stage starts on a 128-byte line
+#endif
+    const uint32_t rec = (max_rec_bytes + OAR_STAGE_ALIGN - 1u) & ~(OAR_STAGE_ALIGN - 1u);
     g.w_off = 8u * kTile + rec;
     g.stage_bytes = g.w_off + (weighted ? 2u * kThreads : 0u);
     g.xs_base = 0;   // set by the launcher
@@ -330,7 +333,7 @@ struct BuildArgs {
 };
 
 // One CTA lays out one tile.
-static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
+static __global__ void __launch_bounds__(kThreads, 4) build_tiles(BuildArgs a)   // 64 registers: four CTAs per SM (42 KB of shared memory each)
 {
     using Sort = cub::BlockRadixSort<uint32_t, kThreads, 4, uint32_t>;
     using Scan = cub::BlockScan<uint32_t, kThreads>;
@@ -495,9 +498,25 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
         const uint32_t slot = (j & ~127u) | ((j & 31u) << 2) | ((j >> 5) & 3u);
         keys[i] = s_txp[slot]; vals[i] = slot;
     }
+    // the ids of a tile span a narrow range (rows are ordered by their smallest id): sort the keys relative to the
+    // tile's smallest id, on as many bits as the range needs (2-3 radix passes instead of 8); padding sorts last
+    {
+        uint32_t lo = kNoTxp, hi = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (keys[i] != kNoTxp) { lo = min(lo, keys[i]); hi = max(hi, keys[i]); }
+        lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
+        if (tid == 0) { s_misc[1] = kNoTxp; s_misc[3] = 0; }
+        __syncthreads();
+        if ((tid & 31u) == 0u && lo != kNoTxp) { atomicMin(&s_misc[1], lo); atomicMax(&s_misc[3], hi); }
+        __syncthreads();
+    }
+    const uint32_t key_lo = s_misc[1], key_pad = s_misc[1] == kNoTxp ? 0u : s_misc[3] - s_misc[1] + 1u;   // relative key of the padding
+#pragma unroll
+    for (int i = 0; i < 4; ++i) keys[i] = keys[i] != kNoTxp ? keys[i] - key_lo : key_pad;
+    Sort(tmp.sort).Sort(keys, vals, 0, 32 - __clz((int)key_pad | 1));
     __syncthreads();
-    Sort(tmp.sort).Sort(keys, vals);
-    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) keys[i] = keys[i] != key_pad ? keys[i] + key_lo : kNoTxp;
 #pragma unroll
     for (int i = 0; i < 4; ++i) s_txp[tid * 4 + i] = keys[i];
     __syncthreads();
@@ -676,14 +695,11 @@ static __global__ void __launch_bounds__(kThreads) build_tiles(BuildArgs a)
                     // scatter wavefronts per tile, 64 is the floor; the exact "largest supply first" rule gives the same.
                     uint32_t best = s_best[d] & av;
                     if (best == 0u) {
-                        uint4 used = make_uint4(0, 0, 0, 0);
-                        if (q) used = *reinterpret_cast<const uint4 *>(&s_fulluse[ci][0]);
                         const uint32_t remfree = st >> 16, remrot = ((remfree << br) | (remfree << br >> 16)) & 0xFFFFu;
-                        const uint32_t uw[4] = {used.x, used.y, used.z, used.w};
                         uint32_t top = 0;
-#pragma unroll
-                        for (uint32_t r = 0; r < 16u; ++r) {
-                            const uint32_t sup = q - ((uw[r >> 2] >> (8u * (r & 3u))) & 0xFFu) + ((remrot >> r) & 1u);
+#pragma unroll 1
+                        for (uint32_t r = 0; r < 16u; ++r) {   // rare (once per ~16 positions of a transcript): kept small
+                            const uint32_t sup = q - (q ? (uint32_t)s_fulluse[ci][r] : 0u) + ((remrot >> r) & 1u);
                             if (sup > top) { top = sup; best = 0u; }
                             if (sup == top) best |= 1u << r;
                         }

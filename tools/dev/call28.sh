@@ -1,0 +1,12 @@
+#!/bin/bash
+cd "$(dirname "$0")/../.."
+mkdir -p gpurun_out
+{
+  timeout 150 python __graft_entry__.py smoke 2>&1 | tail -1
+  if [ ${PIPESTATUS[0]} -ne 0 ]; then echo "SMOKE FAILED -- stopping"; exit 1; fi
+  OAR_TRACE=1 timeout 150 python tools/dev/ab.py C3 new:5 new:5 2>&1 | grep -v "^\[oar\] cells" | tail -4
+  echo "== parity (small)"
+  timeout 600 python -m pytest tests -m gpu -x -q -k "not c3 and not c2" 2>&1 | tail -3
+  echo "== robustness"
+  timeout 400 python tools/bench_robust.py C3 2>/dev/null | tail -3 | cut -c1-400
+} 2>&1 | tee gpurun_out/call28.log

@@ -387,7 +387,7 @@ static cudaError_t launch_tiled(oar_store *s, const tiled::View &v, const double
     gg.xs_base = (1024u + (uint32_t)static_bytes + 127u) & ~127u;
     // persistent CTAs: as many per SM as shared memory allows, capped by the register budget (5)
     int per_sm = (int)((227u * 1024u) / (g.total + 1024u));
-    per_sm = std::max(1, std::min(per_sm, s->ctas_per_sm));
+    per_sm = std::max(1, std::min(per_sm, s->ctas_per_sm > 0 ? std::min(s->ctas_per_sm, tiled::sweep_ctas(AUX, WTS, LIST)) : tiled::sweep_ctas(AUX, WTS, LIST)));
     const uint32_t grid = std::min<uint32_t>(v.n_tiles, (uint32_t)s->sm_count * (uint32_t)per_sm);
     kfn<<<grid, tiled::kThreads, g.total, s->stream>>>(v, gg, prev, curr, wperm, state, check_done);
     return cudaGetLastError();

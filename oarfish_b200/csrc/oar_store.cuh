@@ -45,7 +45,7 @@ struct oar_store {
     int kernel = OAR_KERNEL_ROWGROUP;
     bool allow_fused = true;   // convergence bookkeeping inside the sweep's head (OAR_FUSED_UPDATE=0 turns it off)
     bool borrowed = false;  // sub-store of another store: row_ptr / prob / aux / stream / events are not owned
-    int ctas_per_sm = 40 / OAR_TILE_WARPS_DEFAULT;  // persistent CTAs of the tiled sweep per SM (upper bound; shared memory may allow fewer)
+    int ctas_per_sm = 0;  // persistent CTAs of the tiled sweep per SM: 0 = the instantiation's own register budget (tiled::sweep_ctas), else a cap (OAR_CTAS_PER_SM); shared memory may allow fewer
 
     // CSR in HBM (original read order)
     uint32_t *d_row_ptr = nullptr;  // N+1

@@ -60,8 +60,11 @@ constexpr int kAggMin = 4;                // transcripts with >= kAggMin alignme
 #define OAR_ITEM_MAX 16
 #endif
 #ifndef OAR_TILED_MIN_CTAS
-#define OAR_TILED_MIN_CTAS 5    // register budget of the two-barrier sweep: 48 registers per thread
+#define OAR_TILED_MIN_CTAS 5    // register budget of the sweep: 48 registers per thread, 5 CTAs per SM ...
 #endif
+#ifndef OAR_TILED_MIN_CTAS_PLAIN
+#define OAR_TILED_MIN_CTAS_PLAIN 6   // ... and 40 registers, 6 CTAs per SM for the plain sweep (no aux factor, no weights, no tile list), which
+#endif                               // fits them with 0-12 bytes of spills: 169.8 vs 173.2 us on C3 (the weighted one spills 40 bytes: 178.6 vs 175.5 us)
 #ifndef OAR_SCATTER_GREEDY
 #define OAR_SCATTER_GREEDY 1    // layout: x positions chosen so that the M-step scatter spreads over the banks
 #endif
@@ -77,6 +80,7 @@ constexpr int kAggMin = 4;                // transcripts with >= kAggMin alignme
 #ifndef OAR_SHORT_ROW_DEFER
 #define OAR_SHORT_ROW_DEFER 1   // layout: keep rows shorter than a lane from starting and ending inside one lane
 #endif
+__host__ __device__ constexpr int sweep_ctas(bool aux, bool wts, bool list) { return (!aux && !wts && !list) ? OAR_TILED_MIN_CTAS_PLAIN : OAR_TILED_MIN_CTAS; }
 constexpr int kItemMax = OAR_ITEM_MAX;    // x slots of the largest item size class; the classes are kItemMax, /2, /4
 constexpr int kMaxItems = kTile / 4;      // every item belongs to a transcript with >= 4 alignments and holds >= 4 of them
 // An aggregated transcript with cnt alignments in the tile owns cnt / kItemMax items of kItemMax consecutive x slots
@@ -362,65 +366,65 @@ static __global__ void __launch_bounds__(kThreads, 4) build_tiles(BuildArgs a)  
     }
     __syncthreads();
 
-    // first-fit packing of rows into warp-chunks (rows never straddle a chunk)
-    if (tid == 0) {
-        uint32_t used[kWarps], cnt[kWarps], span[kWarps];
-#pragma unroll
-        for (int c = 0; c < kWarps; ++c) { used[c] = 0; cnt[c] = 0; span[c] = 0; }
+    // first-fit packing of rows into warp-chunks (rows never straddle a chunk): rows in order, one warp, lane c keeps
+    // the fill state of chunk c and a ballot finds the first chunk that fits
+    __shared__ uint16_t s_pend[12];
+    if (tid < 32u) {
+        const unsigned full = 0xffffffffu;
+        uint32_t used = 0, cnt = 0, span = 0;   // of chunk `tid` (lanes 0 .. kWarps-1)
         // Rows shorter than a lane (4 slots) must not start and end inside one lane: two row heads in a lane
         // send the whole chunk down the general segmented-sum path of the sweep.  The order of the rows inside a
         // tile is free, so a short row waits until a chunk's fill position lets it cross a lane boundary
         // ((used & 3) + len >= 4); what is still waiting at the end is placed wherever it fits.
         auto place = [&](uint32_t i, int pick) {
-            const uint32_t len = s_rlen[i];
-#pragma unroll
-            for (int c = 0; c < kWarps; ++c) if (c == pick) {
-                s_rslot[i] = (uint16_t)(c * kChunk + used[c]);
-                s_rnew[i] = (uint16_t)cnt[c];  // order inside the chunk
-                const uint32_t lanes = ((used[c] + len - 1) >> 2) - (used[c] >> 2);  // lanes the row's tail must travel
-                span[c] = max(span[c], lanes);
-                used[c] += len; cnt[c] += 1;
+            if ((int)tid == pick) {
+                const uint32_t len = s_rlen[i];
+                s_rslot[i] = (uint16_t)(tid * kChunk + used);
+                s_rnew[i] = (uint16_t)cnt;  // order inside the chunk
+                const uint32_t lanes = ((used + len - 1) >> 2) - (used >> 2);  // lanes the row's tail must travel
+                span = max(span, lanes);
+                used += len; cnt += 1;
             }
         };
-        auto first_fit = [&](uint32_t len, bool clean) {
-            int pick = -1;
-#pragma unroll
-            for (int c = 0; c < kWarps; ++c)
-                if (pick < 0 && used[c] + len <= (uint32_t)kChunkCap && (!clean || (used[c] & 3u) + len >= 4u)) pick = c;
-            return pick;
+        auto first_fit = [&](uint32_t len, bool clean) -> int {
+            const bool fits = tid < (uint32_t)kWarps && used + len <= (uint32_t)kChunkCap && (!clean || (used & 3u) + len >= 4u);
+            const unsigned m = __ballot_sync(full, fits);
+            return m ? __ffs((int)m) - 1 : -1;
         };
         constexpr uint32_t kPend = 12;
-        uint32_t pend[kPend], np = 0;
+        uint32_t np = 0;
         for (uint32_t i = 0; i < nrows; ++i) {
             const uint32_t len = s_rlen[i];
             if (OAR_SHORT_ROW_DEFER && len < 4u && np < kPend) {
                 const int pc = first_fit(len, true);
-                if (pc >= 0) place(i, pc); else pend[np++] = i;
+                if (pc >= 0) place(i, pc); else { if (tid == 0) s_pend[np] = (uint16_t)i; ++np; __syncwarp(); }
                 continue;
             }
             const int pick = first_fit(len, false);
-            if (pick < 0) { s_rslot[i] = 0xFFFF; continue; }
+            if (pick < 0) { if (tid == 0) s_rslot[i] = 0xFFFF; continue; }
             place(i, pick);
             for (uint32_t k = 0; k < np;) {       // waiting short rows: does one fit cleanly now?
-                const int pc = first_fit(s_rlen[pend[k]], true);
+                const uint32_t pi = s_pend[k];
+                const int pc = first_fit(s_rlen[pi], true);
                 if (pc < 0) { ++k; continue; }
-                place(pend[k], pc);
-                for (uint32_t m = k + 1; m < np; ++m) pend[m - 1] = pend[m];
+                place(pi, pc);
+                __syncwarp();
+                if (tid == 0) for (uint32_t m = k + 1; m < np; ++m) s_pend[m - 1] = s_pend[m];
                 --np;
+                __syncwarp();
             }
         }
         for (uint32_t k = 0; k < np; ++k) {
-            const uint32_t i = pend[k];
+            const uint32_t i = s_pend[k];
             int pick = first_fit(s_rlen[i], true);
             if (pick < 0) pick = first_fit(s_rlen[i], false);
-            if (pick < 0) s_rslot[i] = 0xFFFF; else place(i, pick);
+            if (pick < 0) { if (tid == 0) s_rslot[i] = 0xFFFF; } else place(i, pick);
         }
-#pragma unroll
-        for (int c = 0; c < kWarps; ++c) {
-            s_used[c] = used[c]; s_nrow[c] = cnt[c];
+        if (tid < (uint32_t)kWarps) {
+            s_used[tid] = used; s_nrow[tid] = cnt;
             uint32_t steps = 0;
-            while ((1u << steps) <= span[c]) ++steps;  // Hillis-Steele steps 1,2,..,2^(steps-1) cover `span` lanes
-            s_info[c] = steps;
+            while ((1u << steps) <= span) ++steps;  // Hillis-Steele steps 1,2,..,2^(steps-1) cover `span` lanes
+            s_info[tid] = steps;
         }
     }
     __syncthreads();
@@ -1143,7 +1147,7 @@ __device__ __forceinline__ void tile_phase2(uint32_t xs_a, uint32_t item, uint32
 // separate instantiation, because the mere presence of that code changes the register allocation of the tile loop
 // (+3.5 us per sweep on C3): stores whose sweep is long enough not to care about one launch keep the lean kernel.
 template <bool HAS_AUX, bool HAS_WTS, bool LIST = false, bool FUSED = false>
-__global__ void __launch_bounds__(kThreads, (OAR_TILED_MIN_CTAS * 8) / kWarps) em_sweep_tiled(View v, Geometry g, const double *__restrict__ prev,
+__global__ void __launch_bounds__(kThreads, (sweep_ctas(HAS_AUX, HAS_WTS, LIST) * 8) / kWarps) em_sweep_tiled(View v, Geometry g, const double *__restrict__ prev,
                                                               double *__restrict__ curr,
                                                               const uint32_t *__restrict__ wperm,
                                                               const OarEmState *__restrict__ st, int check_done)

@@ -423,7 +423,8 @@ static const uint32_t kFusedWeightedMaxTiles = 32768;
 static bool fused_update(const oar_store *s, bool weighted)
 {
     if (!(s->allow_fused && s->kernel == OAR_KERNEL_TILED && s->tl.ready && s->tl.n_tiles > 0)) return false;
-    return !weighted || s->tl.n_tiles <= kFusedWeightedMaxTiles;
+    static const char *env = getenv("OAR_FUSED_WTS_MAX_TILES");   // development: A/B of the policy
+    return !weighted || s->tl.n_tiles <= (env ? (uint32_t)strtoul(env, nullptr, 10) : kFusedWeightedMaxTiles);
 }
 
 static cudaError_t enqueue_sweep(oar_store *s, const double *prev, double *curr, const uint32_t *wts,

@@ -60,11 +60,11 @@ constexpr int kAggMin = 4;                // transcripts with >= kAggMin alignme
 #define OAR_ITEM_MAX 16
 #endif
 #ifndef OAR_TILED_MIN_CTAS
-#define OAR_TILED_MIN_CTAS 5    // register budget of the sweep: 48 registers per thread, 5 CTAs per SM ...
+#define OAR_TILED_MIN_CTAS 5    // register budget of the sweep with an aux factor or a tile list: 48 registers per thread, 5 CTAs per SM ...
 #endif
 #ifndef OAR_TILED_MIN_CTAS_PLAIN
-#define OAR_TILED_MIN_CTAS_PLAIN 6   // ... and 40 registers, 6 CTAs per SM for the plain sweep (no aux factor, no weights, no tile list), which
-#endif                               // fits them with 0-12 bytes of spills: 169.8 vs 173.2 us on C3 (the weighted one spills 40 bytes: 178.6 vs 175.5 us)
+#define OAR_TILED_MIN_CTAS_PLAIN 6   // ... and 40 registers, 6 CTAs per SM without them: the plain sweep fits with 0-12 bytes of spills (C3: 170-172.7
+#endif                               // vs 173.2 us), the bootstrap-weighted one with 4-32 bytes since its lane weights sit in front of the record (173.5 vs 175.5 us)
 #ifndef OAR_SCATTER_GREEDY
 #define OAR_SCATTER_GREEDY 1    // layout: x positions chosen so that the M-step scatter spreads over the banks
 #endif
@@ -80,7 +80,7 @@ constexpr int kAggMin = 4;                // transcripts with >= kAggMin alignme
 #ifndef OAR_SHORT_ROW_DEFER
 #define OAR_SHORT_ROW_DEFER 1   // layout: keep rows shorter than a lane from starting and ending inside one lane
 #endif
-__host__ __device__ constexpr int sweep_ctas(bool aux, bool wts, bool list) { return (!aux && !wts && !list) ? OAR_TILED_MIN_CTAS_PLAIN : OAR_TILED_MIN_CTAS; }
+__host__ __device__ constexpr int sweep_ctas(bool aux, bool /*wts*/, bool list) { return (!aux && !list) ? OAR_TILED_MIN_CTAS_PLAIN : OAR_TILED_MIN_CTAS; }
 constexpr int kItemMax = OAR_ITEM_MAX;    // x slots of the largest item size class; the classes are kItemMax, /2, /4
 constexpr int kMaxItems = kTile / 4;      // every item belongs to a transcript with >= 4 alignments and holds >= 4 of them
 // An aggregated transcript with cnt alignments in the tile owns cnt / kItemMax items of kItemMax consecutive x slots
@@ -142,8 +142,7 @@ constexpr int kStages = 2;
 // Shared-memory geometry of the sweep, sized for the store at hand (largest record, table and
 // unit count over all tiles) so that as many CTAs as possible fit on an SM.
 struct Geometry {
-    uint32_t stage_bytes;   // prob (4 KB) | lpos (4 KB) | record (max over tiles, 16 B multiple) [| lane weights u16[256]]
-    uint32_t w_off;         // offset of the lane weights inside a stage (bootstrap only)
+    uint32_t stage_bytes;   // prob (4 KB) | lpos (4 KB) | [lane weights u16[256] (bootstrap) |] record (max over tiles, rounded up to 128 B)
     uint32_t xs_base;       // shared-space address of the dynamic window = of the x array (transcript-sorted x values in
                             // items + trash), which sits at its start.  Filled in by the launcher (1 KB reserved by the
                             // system + the kernel's static shared memory) and handed over as a kernel PARAMETER so that it
@@ -164,8 +163,7 @@ inline Geometry make_geometry(uint32_t max_rec_bytes, uint32_t max_d, uint32_t m
 #define OAR_STAGE_ALIGN 128u    // every TMA destination of a stage starts on a 128-byte line
 #endif
     const uint32_t rec = (max_rec_bytes + OAR_STAGE_ALIGN - 1u) & ~(OAR_STAGE_ALIGN - 1u);
-    g.w_off = 8u * kTile + rec;
-    g.stage_bytes = g.w_off + (weighted ? 2u * kThreads : 0u);
+    g.stage_bytes = 8u * kTile + (weighted ? 2u * kThreads : 0u) + rec;   // the weights sit right in front of the record: one base register serves both
     g.xs_base = 0;   // set by the launcher
     // the items of the fullest tile, then the trash slots; even count
     g.xs_doubles = (max_x_doubles + kTrashSlots + 1u) & ~1u;
@@ -1080,7 +1078,7 @@ __device__ __forceinline__ void tile_phase1_core(const View &v, uint32_t tile, c
 // phase 1 with the tile's prob | lpos block staged in shared memory (`bulk`); also returns the thread's item and the
 // record's DU word for phase 2 (read now: the record's stage is refilled before phase 2).
 template <bool HAS_AUX, bool HAS_WTS, bool COMMON_OK>
-__device__ __forceinline__ void tile_phase1(const View &v, uint32_t tile, uint32_t bulk, uint32_t rec, uint32_t wl_a, uint32_t sp_a, uint32_t xs_a,
+__device__ __forceinline__ void tile_phase1(const View &v, uint32_t tile, uint32_t bulk, uint32_t rec, uint32_t sp_a, uint32_t xs_a,
                                             uint32_t tid, uint32_t lane, uint32_t warp, double *__restrict__ curr,
                                             const uint32_t *__restrict__ wperm, uint32_t &item, uint32_t &item_txp, uint32_t &U)
 {
@@ -1095,7 +1093,7 @@ __device__ __forceinline__ void tile_phase1(const View &v, uint32_t tile, uint32
         item_txp = lds_u32(rec + du.y + (item & 0xFFCu));
     }
     uint32_t w_in = 0;
-    if (HAS_WTS) w_in = lds_u16(wl_a + 2u * tid);
+    if (HAS_WTS) w_in = lds_u16(rec - 2u * kThreads + 2u * tid);   // the lane weights sit right in front of the record
 #if OAR_COMMON_PATH
     // the rare bit is the same in every lane of the warp: one vote decides between the two copies of phase 1
     if (COMMON_OK && !any_bits(desc, kDescRare))
@@ -1169,6 +1167,7 @@ __global__ void __launch_bounds__(kThreads, (sweep_ctas(HAS_AUX, HAS_WTS, LIST) 
     };
     if (tile0 >= n_tiles) { fallback_rows(); return; }
     const uint32_t kStageBytes = g.stage_bytes;
+    constexpr uint32_t kRecOff = 8u * kTile + (HAS_WTS ? 2u * kThreads : 0u);   // record's offset in a stage
     uint32_t sm0;   // shared-space address of the window, computed once (a plain cvta is rematerialised every iteration)
     asm volatile("{.reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t;}" : "=r"(sm0) : "l"(smem));
     const uint32_t stage0 = sm0 + g.stage_off, sp_a = sm0 + g.prev_off, bar0 = sm0 + g.bar_off;
@@ -1204,8 +1203,8 @@ __global__ void __launch_bounds__(kThreads, (sweep_ctas(HAS_AUX, HAS_WTS, LIST) 
         mbar_expect_tx(bar, 8u * kTile + r.y + (HAS_WTS ? 2u * kThreads : 0u));
         bulk_g2s(dst, v.prob + (size_t)tile * kTile, 4u * kTile, bar);
         bulk_g2s(dst + 4u * kTile, v.lpos + (size_t)tile * kTile, 4u * kTile, bar);
-        bulk_g2s(dst + 8u * kTile, v.records + r.x, r.y, bar);
-        if (HAS_WTS) bulk_g2s(dst + g.w_off, v.wlane + (size_t)tile * kThreads, 2u * kThreads, bar);
+        bulk_g2s(dst + kRecOff, v.records + r.x, r.y, bar);
+        if (HAS_WTS) bulk_g2s(dst + 8u * kTile, v.wlane + (size_t)tile * kThreads, 2u * kThreads, bar);
     };
     // prev[] of a tile's transcripts into s_prev, by one warp (two gathers in flight per lane)
     auto gather_prev = [&](uint32_t rec_a) {
@@ -1248,18 +1247,18 @@ __global__ void __launch_bounds__(kThreads, (sweep_ctas(HAS_AUX, HAS_WTS, LIST) 
     // TMA-written stage on to the other warps (mbarrier completion observed by one thread + bar.sync is cumulative).
     if (warp == kWarps - 1) {
         mbar_wait(bar0, 0);
-        gather_prev(stage0 + 8u * kTile);
+        gather_prev(stage0 + kRecOff);
     }
 
     uint32_t tile = tile0;
     for (uint32_t it = 0;; ++it) {
         const uint32_t s = it & 1u;
         const uint32_t stg = stage0 + s * kStageBytes;
-        const uint32_t rec = stg + 8u * kTile;
+        const uint32_t rec = stg + kRecOff;
         __syncthreads();   // stage s and s_prev of this tile are in place; phase 2 of the previous tile has left xs
 
         uint32_t item, item_txp, U;
-        tile_phase1<HAS_AUX, HAS_WTS, kCommonOk>(v, HAS_AUX ? phys(tile) : 0u, stg, rec, stg + g.w_off, sp_a, xs_a, tid, lane, warp, curr, wperm, item, item_txp, U);
+        tile_phase1<HAS_AUX, HAS_WTS, kCommonOk>(v, HAS_AUX ? phys(tile) : 0u, stg, rec, sp_a, xs_a, tid, lane, warp, curr, wperm, item, item_txp, U);
         __syncthreads();   // xs complete; stage s and s_prev are free again
 
         // ---- refill stage s two tiles ahead; the last warp fetches prev[] of the next tile ----
@@ -1272,7 +1271,7 @@ __global__ void __launch_bounds__(kThreads, (sweep_ctas(HAS_AUX, HAS_WTS, LIST) 
             }
             if (warp == kWarps - 1 && has_next) {
                 mbar_wait(bar0 + 8u * (s ^ 1u), ((it + 1u) >> 1) & 1u);
-                gather_prev(stage0 + (s ^ 1u) * kStageBytes + 8u * kTile);
+                gather_prev(stage0 + (s ^ 1u) * kStageBytes + kRecOff);
             }
         }
         __syncwarp();

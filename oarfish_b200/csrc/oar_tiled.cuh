@@ -706,7 +706,7 @@ static __global__ void __launch_bounds__(kThreads, 4) build_tiles(BuildArgs a)  
                             if (sup == top) best |= 1u << r;
                         }
                         best &= av;   // (top >= 1: av is not empty)
-                        s_best[d] = best;
+                        atomicExch(&s_best[d], best);   // (every lane of the transcript writes the same word)
                     }
                     if (cand & best) cand &= best;
 #endif
@@ -1058,21 +1058,21 @@ __device__ __forceinline__ void tile_phase1_core(const View &v, uint32_t tile, c
 
     // ---- M-step scatter into the transcript-sorted smem order -----------------------------
     // (padding and non-aggregated alignments carry the address of a trash slot in a bank their half-warp leaves free: every
-    // store is unconditional)
+    // store is unconditional; what lands in a trash slot is always +0.0 -- padding has w = 0, strays are zeroed below)
     const uint32_t q0 = lp4.x >> 16, q1 = lp4.y >> 16, q2 = lp4.z >> 16, q3 = lp4.w >> 16;
-    sts_f64(xs_a + q0, x0);
-    sts_f64(xs_a + q1, x1);
-    sts_f64(xs_a + q2, x2);
-    sts_f64(xs_a + q3, x3);
     if (strays) {
         // transcripts with fewer than kAggMin alignments in this tile: straight to global
         const uint4 du = lds_v4(rec + kRecDU);   // D, table offset, items, trash offset
         const uint32_t trash = du.w, table_a = rec + du.y;
-        if (q0 >= trash && x0 != 0.0) atomicAdd(curr + lds_u32(table_a + 4u * table_index(lp4.x & 0xFFFFu)), x0);
-        if (q1 >= trash && x1 != 0.0) atomicAdd(curr + lds_u32(table_a + 4u * table_index(lp4.y & 0xFFFFu)), x1);
-        if (q2 >= trash && x2 != 0.0) atomicAdd(curr + lds_u32(table_a + 4u * table_index(lp4.z & 0xFFFFu)), x2);
-        if (q3 >= trash && x3 != 0.0) atomicAdd(curr + lds_u32(table_a + 4u * table_index(lp4.w & 0xFFFFu)), x3);
+        if (q0 >= trash) { if (x0 != 0.0) atomicAdd(curr + lds_u32(table_a + 4u * table_index(lp4.x & 0xFFFFu)), x0); x0 = 0.0; }
+        if (q1 >= trash) { if (x1 != 0.0) atomicAdd(curr + lds_u32(table_a + 4u * table_index(lp4.y & 0xFFFFu)), x1); x1 = 0.0; }
+        if (q2 >= trash) { if (x2 != 0.0) atomicAdd(curr + lds_u32(table_a + 4u * table_index(lp4.z & 0xFFFFu)), x2); x2 = 0.0; }
+        if (q3 >= trash) { if (x3 != 0.0) atomicAdd(curr + lds_u32(table_a + 4u * table_index(lp4.w & 0xFFFFu)), x3); x3 = 0.0; }
     }
+    sts_f64(xs_a + q0, x0);
+    sts_f64(xs_a + q1, x1);
+    sts_f64(xs_a + q2, x2);
+    sts_f64(xs_a + q3, x3);
 }
 
 // phase 1 with the tile's prob | lpos block staged in shared memory (`bulk`); also returns the thread's item and the

@@ -203,7 +203,7 @@ def main():
         print(f"  {k:24s} {v / nt:8.1f}")
 
 
-if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] in ("matching", "heuristics", "table")):
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] in ("matching", "heuristics", "table", "dump")):
     main()
 
 
@@ -374,3 +374,119 @@ def main4():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "table":
     main4()
+
+
+# ---- real tiles: layout words dumped from the device (oar_store_layout_lpos, tools/dev/dump_lpos.py) -----------------
+# usage: python tools/layout_model.py dump gpurun_out/lpos_C3.npy [every]
+# Recovers each tile's slot -> transcript map and its trash offset XD from the words, counts the scatter wavefronts of
+# the layout as built (the half-warp rule was checked against ncu with tools/dev/sts_bank_probe.cu: exact), and
+# re-runs the device's round-based greedy (build_tiles) in emulation with its switches, so that a change to the rule
+# can be judged on real tiles before any GPU time is spent.
+
+def _xd_of(slots):
+    items, _ = items_of(slots)
+    n32 = n16 = n8 = 0
+    for its in items.values():
+        c = sum(n for _, n in its); q, rem = divmod(c, IMAX)
+        n32 += q + (1 if rem > IMAX // 2 else 0); n16 += 1 if IMAX // 4 < rem <= IMAX // 2 else 0; n8 += 1 if 1 <= rem <= IMAX // 4 else 0
+    return 18 * n32 + 10 * n16 + 6 * n8
+
+
+def dump_tile(words):
+    """(slot -> transcript index or -1, slot -> x position, XD) of one tile's 1024 layout words."""
+    pos = (words >> 16).astype(np.int64) // 8
+    off = (words & 0xFFFF).astype(np.int64)
+    tr = ((off >> 8) << 5) | ((off & 127) >> 2)
+    mx = int(pos.max())
+    for xd in range(max(0, mx - 15), mx + 2):   # padding and stray alignments sit in the 16 trash slots behind the items
+        slots = np.where(pos >= xd, -1, tr)
+        if _xd_of(slots) == xd:
+            return slots, pos, xd
+    raise ValueError("tile does not parse")
+
+
+def emulate_build_greedy(slots, xd, supply=True, premark=False, kscarce=8):
+    """build_tiles' position greedy: per scatter instruction (chunk, k) rounds of proposals over the 32 lanes, two phases
+    (lanes whose transcript offers <= kscarce residues first), one winner per (transcript, residue) and per (half-warp,
+    residue): the lowest lane.  supply: prefer the residues the transcript has most slots of; premark: lanes without a
+    position occupy bank (xd + lane) & 15 from the start (the per-lane trash slots of an earlier revision)."""
+    items, _ = items_of(slots)
+    posl = {}
+    for t, its in items.items():
+        d = {}
+        for x, n in its:
+            for o in range(n): d.setdefault((x + o) & 15, []).append(x + o)
+        posl[t] = d
+    out = {}
+    for c in range(NW):
+        for k in range(4):
+            lanes = [c * CHUNK + 4 * l + k for l in range(32)]
+            todo = [slots[s] >= 0 and slots[s] in posl for s in lanes]
+            G = [0, 0]
+            if premark:
+                for l in range(32):
+                    if not todo[l]: G[l >> 4] |= 1 << ((xd + (l & 15)) & 15)
+            for phase in (0, 1):
+                while True:
+                    props = {}
+                    for l in range(32):
+                        if not todo[l]: continue
+                        t = slots[lanes[l]]
+                        av = sum(1 << r for r in posl[t])
+                        if phase == 0 and bin(av).count("1") > kscarce: continue
+                        cand = av & ~G[l >> 4] or av
+                        if supply:
+                            top = max(len(v) for v in posl[t].values())
+                            best = sum(1 << r for r, v in posl[t].items() if len(v) == top)
+                            if cand & best: cand &= best
+                        props[l] = (t, min((r for r in range(16) if cand >> r & 1), key=lambda r: (r - (l & 15)) & 15))
+                    if not props: break
+                    took = [0, 0]
+                    for l, (t, rho) in sorted(props.items()):
+                        if min(l2 for l2, p in props.items() if p == (t, rho)) != l: continue
+                        if min(l2 for l2, p in props.items() if (l2 >> 4) == (l >> 4) and p[1] == rho) != l: continue
+                        out[lanes[l]] = posl[t][rho].pop(0)
+                        if not posl[t][rho]: del posl[t][rho]
+                        todo[l] = False; took[l >> 4] |= 1 << rho
+                    G[0] |= took[0]; G[1] |= took[1]
+    return out
+
+
+def wavefronts_with_trash(posd, xd, trash):
+    """scatter wavefronts of a tile; trash = 'lane' (slot xd + lane & 15 per lane), 'free' (one slot per half-warp in a bank
+    the others leave free) or 'none' (stores of lanes without a position predicated off)"""
+    w = 0
+    for g in groups():
+        banks = {}
+        for s in g:
+            if s in posd: banks.setdefault(posd[s] & 15, set()).add(posd[s])
+        missing = [li for li, s in enumerate(g) if s not in posd]
+        if trash == "lane":
+            for li in missing: banks.setdefault((xd + li) & 15, set()).add(xd + li)
+        elif trash == "free" and missing:
+            free = [r for r in range(16) if r not in banks]
+            banks.setdefault(free[0] if free else 0, set()).add(-1)
+        w += max(len(v) for v in banks.values()) if banks else 0
+    return w
+
+
+def main5():
+    words = np.load(sys.argv[2]); every = int(sys.argv[3]) if len(sys.argv) > 3 else 60
+    acc = {}; nt = 0
+    for t in range(0, words.shape[0], every):
+        slots, pos, xd = dump_tile(words[t]); nt += 1
+        def add(k, v): acc[k] = acc.get(k, 0) + v
+        add("layout as dumped (every store, distinct words per bank)",
+            sum(max(len({int(pos[s]) for s in g if int(pos[s]) & 15 == r}) for r in range(16)) for g in groups()))
+        for name, kw, tm in (("greedy of round 1/2a: nearest residue, per-lane trash", dict(supply=False, premark=True), "lane"),
+                             ("nearest residue, free-bank trash", dict(supply=False), "free"),
+                             ("by supply, per-lane trash", dict(premark=True), "lane"),
+                             ("by supply, free-bank trash (shipped)", dict(), "free"),
+                             ("by supply, trash stores predicated off", dict(), "none")):
+            add(name, wavefronts_with_trash(emulate_build_greedy(slots, xd, **kw), xd, tm))
+    print(f"{nt} tiles, scatter wavefronts per tile (64 half-warp stores, floor 64):")
+    for k, v in acc.items(): print(f"  {k:58s} {v / nt:7.1f}")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "dump":
+    main5()

@@ -149,7 +149,7 @@ static int build_chunk_layout(oar_store *s, uint32_t span)
         if (s->d_aux) OAR_CUDA(dmalloc(&t.aux, sizeof(double) * slots, st));
         OAR_CUDA(dmalloc(&t.rec, sizeof(uint2) * n_tiles, st));
         // a record holds at most (slots of the tile) table entries: bound the total by the real slot count
-        const size_t worst = (size_t)n_tiles * (kRecTable + 16) + 4 * (size_t)total + 4 * ((size_t)total / kAggMin) + 64;
+        const size_t worst = (size_t)n_tiles * (kRecTable + 16 + kRecAlign) + 4 * (size_t)total + 4 * ((size_t)total / kAggMin) + 64;
         OAR_CUDA(sc.alloc((char **)&records_tmp, worst));
         BuildArgs a;
         a.row_ptr = s->d_row_ptr; a.txp = s->d_txp; a.prob = s->d_prob; a.aux = s->d_aux;

@@ -137,6 +137,10 @@ static_assert(!OAR_SCATTER_GREEDY || kItemMax == 16, "the bank-aware x positions
 constexpr int kRecDesc = 0, kRecInfo = 64 * kWarps, kRecRow = kRecInfo + 4 * kWarps, kRecDU = kRecRow + 4 * kWarps,
               kRecTable = kRecDU + 16;
 constexpr int kRecMax = kRecTable + 4 * kTile + 4 * kMaxItems;   // 5712
+#ifndef OAR_REC_ALIGN
+#define OAR_REC_ALIGN 128
+#endif
+constexpr uint32_t kRecAlign = OAR_REC_ALIGN;   // alignment of a record in global memory (the TMA copy's source)
 constexpr int kStages = 2;
 
 // Shared-memory geometry of the sweep, sized for the store at hand (largest record, table and
@@ -574,7 +578,7 @@ static __global__ void __launch_bounds__(kThreads, 4) build_tiles(BuildArgs a)  
     if (tid == 0) {
         atomicAdd(a.cursors + 1, D);
         atomicAdd(a.cursors + 2, U);
-        s_misc[2] = atomicAdd(a.cursors + 3, rec_bytes / 16u);
+        s_misc[2] = atomicAdd(a.cursors + 3, ((rec_bytes + kRecAlign - 1u) / kRecAlign) * (kRecAlign / 16u));   // records start on kRecAlign-byte boundaries
         atomicMax(a.cursors + 4, rec_bytes);
         atomicMax(a.cursors + 5, D);
         atomicMax(a.cursors + 6, XD);

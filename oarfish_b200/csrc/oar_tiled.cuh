@@ -913,6 +913,8 @@ __device__ __forceinline__ void sts_prev(uint32_t a, double v)
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
 #endif
 }
+__device__ __forceinline__ void sts_f64_if(uint32_t a, double v, bool on)
+{ asm volatile("{.reg .pred p; setp.ne.u32 p, %2, 0; @p st.shared.f64 [%0], %1;}" ::"r"(a), "d"(v), "r"((uint32_t)on) : "memory"); }
 __device__ __forceinline__ double lds_f64(uint32_t a) { double r; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(a)); return r; }
 __device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 // 0.0 unless `on`
@@ -1061,22 +1063,28 @@ __device__ __forceinline__ void tile_phase1_core(const View &v, uint32_t tile, c
     }
 
     // ---- M-step scatter into the transcript-sorted smem order -----------------------------
-    // (padding and non-aggregated alignments carry the address of a trash slot in a bank their half-warp leaves free: every
-    // store is unconditional; what lands in a trash slot is always +0.0 -- padding has w = 0, strays are zeroed below)
+    // (padding and non-aggregated alignments carry the address of a trash slot in a bank their half-warp leaves free, so the
+    // stores are unconditional.  What lands in a trash slot is always +0.0: padding has w = 0, and a chunk with stray
+    // alignments takes the predicated stores below)
     const uint32_t q0 = lp4.x >> 16, q1 = lp4.y >> 16, q2 = lp4.z >> 16, q3 = lp4.w >> 16;
-    if (strays) {
+    if (!strays) {
+        sts_f64(xs_a + q0, x0);
+        sts_f64(xs_a + q1, x1);
+        sts_f64(xs_a + q2, x2);
+        sts_f64(xs_a + q3, x3);
+    } else {
         // transcripts with fewer than kAggMin alignments in this tile: straight to global
         const uint4 du = lds_v4(rec + kRecDU);   // D, table offset, items, trash offset
         const uint32_t trash = du.w, table_a = rec + du.y;
-        if (q0 >= trash) { if (x0 != 0.0) atomicAdd(curr + lds_u32(table_a + 4u * table_index(lp4.x & 0xFFFFu)), x0); x0 = 0.0; }
-        if (q1 >= trash) { if (x1 != 0.0) atomicAdd(curr + lds_u32(table_a + 4u * table_index(lp4.y & 0xFFFFu)), x1); x1 = 0.0; }
-        if (q2 >= trash) { if (x2 != 0.0) atomicAdd(curr + lds_u32(table_a + 4u * table_index(lp4.z & 0xFFFFu)), x2); x2 = 0.0; }
-        if (q3 >= trash) { if (x3 != 0.0) atomicAdd(curr + lds_u32(table_a + 4u * table_index(lp4.w & 0xFFFFu)), x3); x3 = 0.0; }
+        sts_f64_if(xs_a + q0, x0, q0 < trash);
+        sts_f64_if(xs_a + q1, x1, q1 < trash);
+        sts_f64_if(xs_a + q2, x2, q2 < trash);
+        sts_f64_if(xs_a + q3, x3, q3 < trash);
+        if (q0 >= trash && x0 != 0.0) atomicAdd(curr + lds_u32(table_a + 4u * table_index(lp4.x & 0xFFFFu)), x0);
+        if (q1 >= trash && x1 != 0.0) atomicAdd(curr + lds_u32(table_a + 4u * table_index(lp4.y & 0xFFFFu)), x1);
+        if (q2 >= trash && x2 != 0.0) atomicAdd(curr + lds_u32(table_a + 4u * table_index(lp4.z & 0xFFFFu)), x2);
+        if (q3 >= trash && x3 != 0.0) atomicAdd(curr + lds_u32(table_a + 4u * table_index(lp4.w & 0xFFFFu)), x3);
     }
-    sts_f64(xs_a + q0, x0);
-    sts_f64(xs_a + q1, x1);
-    sts_f64(xs_a + q2, x2);
-    sts_f64(xs_a + q3, x3);
 }
 
 // phase 1 with the tile's prob | lpos block staged in shared memory (`bulk`); also returns the thread's item and the

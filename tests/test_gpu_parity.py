@@ -645,3 +645,37 @@ def test_full_size_properties_c3(DS):
         r3 = ds.em(min_iter=1, init=r1.counts, max_iter=1)
         m = r1.counts > 1.0
         assert (np.abs(r3.counts[m] - r1.counts[m]) / r1.counts[m]).max() < 5e-3
+
+
+# ---- the tiled layout itself (oar_store_layout_lpos): what the M-step scatter relies on -----------------------
+def test_layout_positions_are_a_perfect_assignment(DS, small_store):
+    """Every x slot of a tile's items is handed to exactly one alignment (the M-step sums items without clearing them),
+    alignments without a position -- padding, transcripts below the aggregation threshold -- store into the 16 trash
+    slots behind the items, all such lanes of a half-warp into ONE slot, in a bank no positioned lane of that store uses."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("layout_model", os.path.join(os.path.dirname(GOLD), "..", "tools", "layout_model.py"))
+    lm = importlib.util.module_from_spec(spec); spec.loader.exec_module(lm)
+    s = small_store
+    ds = DS(s.row_ptr, s.txp_id, s.prob, s.n_txps)
+    li = ds.layout_info()
+    assert li["tiled"] == 1 and li["n_tiles"] > 0
+    words = ds.layout_lpos(0, li["n_tiles"])
+    ds.close()
+    assert words.shape == (li["n_tiles"], 1024)
+    real_slots = 0
+    for t in range(li["n_tiles"]):
+        slots, pos, xd = lm.dump_tile(words[t])          # parses only if the trash offset is consistent with the items
+        real = pos[slots >= 0]
+        assert len(np.unique(real)) == len(real)          # no x slot handed out twice
+        items, _ = lm.items_of(slots)
+        want = sorted(x + o for its in items.values() for x, n in its for o in range(n))
+        assert sorted(real.tolist()) == want               # ... and every valid slot of every item is used
+        assert pos[slots < 0].min(initial=xd) >= xd and pos.max() < xd + 16
+        real_slots += len(real)
+        for g in lm.groups():                              # the 64 half-warp stores of the tile
+            tr = {int(pos[i]) for i in g if slots[i] < 0}
+            assert len(tr) <= 1
+            if tr and len([i for i in g if slots[i] >= 0]) < 16:
+                used = {int(pos[i]) & 15 for i in g if slots[i] >= 0}
+                assert len(used) == 16 or (next(iter(tr)) & 15) not in used
+    assert 0 < real_slots <= int(s.nnz)

@@ -398,9 +398,13 @@ def dump_tile(words):
     off = (words & 0xFFFF).astype(np.int64)
     tr = ((off >> 8) << 5) | ((off & 127) >> 2)
     mx = int(pos.max())
-    for xd in range(max(0, mx - 15), mx + 2):   # padding and stray alignments sit in the 16 trash slots behind the items
+    # padding and stray alignments sit in the 16 trash slots behind the items, so XD is one of mx-15 .. mx+1.  Largest first: a
+    # smaller value can be consistent too (dropping the whole last item of a transcript that has nothing else gives a shorter,
+    # valid-looking tile), a larger one would make shared trash slots look like x slots handed out twice
+    for xd in range(mx + 1, max(0, mx - 15) - 1, -1):
         slots = np.where(pos >= xd, -1, tr)
-        if _xd_of(slots) == xd:
+        real = pos[slots >= 0]
+        if _xd_of(slots) == xd and len(np.unique(real)) == len(real):
             return slots, pos, xd
     raise ValueError("tile does not parse")
 

@@ -292,8 +292,10 @@ int oar_store_layout_info(const oar_store *store, uint64_t out[8]);
 
 /* Inspection (tools/layout_model.py): the per-slot words of tiles [first_tile, first_tile + n_tiles) of the
  * tiled layout, 1024 u32 per tile to host memory: byte offset of the slot's transcript in the tile's prev[] table
- * (low 16 bits) | byte offset of its x position (high 16 bits).  No counterpart in the reference. */
-int oar_store_layout_lpos(oar_store *store, uint32_t first_tile, uint32_t n_tiles, uint32_t *out);
+ * (low 16 bits) | byte offset of its x position (high 16 bits); optionally (n_tiles u32) the byte offset of each
+ * tile's trash slots, i.e. the end of its items: positions at or above it belong to padding and to alignments whose
+ * transcript is not aggregated in the tile.  No counterpart in the reference. */
+int oar_store_layout_lpos(oar_store *store, uint32_t first_tile, uint32_t n_tiles, uint32_t *out, uint32_t *out_trash_or_null);
 
 /* Timings of the last compute call on this store, milliseconds (CUDA events):
  * [0] upload+layout, [1] EM loop (device), [2] result download, [3] weight generation. */

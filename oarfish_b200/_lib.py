@@ -50,7 +50,7 @@ ABI = {
     "oar_posteriors": (C.c_int, [_vp, _vp, C.c_double, _vp, _vp]),
     "oar_aux_counts": (C.c_int, [_vp, _vp, _vp]),
     "oar_store_layout_info": (C.c_int, [_vp, _u64p]),
-    "oar_store_layout_lpos": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp]),
+    "oar_store_layout_lpos": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp, _vp]),
     "oar_store_timings": (C.c_int, [_vp, _f64p]),
     "oar_store_counters": (C.c_int, [_vp, _u64p]),
     "oar_sweep": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int]),

@@ -328,7 +328,15 @@ extern "C" int oar_store_layout_info(const oar_store *s, uint64_t out[8])
     return OAR_OK;
 }
 
-extern "C" int oar_store_layout_lpos(oar_store *s, uint32_t first_tile, uint32_t n_tiles, uint32_t *out)
+namespace {
+__global__ void layout_trash_offsets(const uint2 *__restrict__ rec, const uint4 *__restrict__ records, uint32_t first, uint32_t n, uint32_t *__restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = reinterpret_cast<const uint32_t *>(reinterpret_cast<const unsigned char *>(records + rec[first + i].x) + tiled::kRecDU)[3];
+}
+}  // namespace
+
+extern "C" int oar_store_layout_lpos(oar_store *s, uint32_t first_tile, uint32_t n_tiles, uint32_t *out, uint32_t *out_trash_or_null)
 {
     if (!s || !out) return fail(OAR_ERR_INVALID, "oar_store_layout_lpos: null argument");
     const TiledLayout &t = s->tl;
@@ -336,6 +344,16 @@ extern "C" int oar_store_layout_lpos(oar_store *s, uint32_t first_tile, uint32_t
     cudaSetDevice(s->device);
     OAR_CUDA(cudaStreamSynchronize(s->stream));
     OAR_CUDA(cudaMemcpy(out, t.lpos + (size_t)first_tile * tiled::kTile, sizeof(uint32_t) * (size_t)n_tiles * tiled::kTile, cudaMemcpyDeviceToHost));
+    if (out_trash_or_null && n_tiles > 0) {
+        uint32_t *d = nullptr;
+        OAR_CUDA(dmalloc(&d, sizeof(uint32_t) * n_tiles, s->stream));
+        layout_trash_offsets<<<(n_tiles + 255) / 256, 256, 0, s->stream>>>(t.rec, t.records, first_tile, n_tiles, d);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out_trash_or_null, d, sizeof(uint32_t) * n_tiles, cudaMemcpyDeviceToHost, s->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        dfree(d, s->stream);
+        OAR_CUDA(e);
+    }
     return OAR_OK;
 }
 

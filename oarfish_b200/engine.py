@@ -160,11 +160,13 @@ class DeviceStore:
         keys = ("tiled", "n_tiles", "slots", "fallback_rows", "sum_distinct", "sum_units", "span", "kernel")
         return {k: int(v) for k, v in zip(keys, out)}
 
-    def layout_lpos(self, first_tile: int, n_tiles: int) -> np.ndarray:
-        """Per-slot layout words of a range of tiles (inspection; see oar_store_layout_lpos)."""
+    def layout_lpos(self, first_tile: int, n_tiles: int, with_trash: bool = False):
+        """Per-slot layout words of a range of tiles [and each tile's trash offset in doubles] (inspection; see oar_store_layout_lpos)."""
         out = np.empty((n_tiles, 1024), dtype=np.uint32)
-        check(self._lib.oar_store_layout_lpos(self._h, first_tile, n_tiles, out.ctypes.data_as(C.c_void_p)))
-        return out
+        trash = np.empty(n_tiles, dtype=np.uint32)
+        check(self._lib.oar_store_layout_lpos(self._h, first_tile, n_tiles, out.ctypes.data_as(C.c_void_p),
+                                              trash.ctypes.data_as(C.c_void_p) if with_trash else None))
+        return (out, trash // 8) if with_trash else out
 
     def counters(self):
         out = (C.c_uint64 * 2)()

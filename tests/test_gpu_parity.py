@@ -659,12 +659,13 @@ def test_layout_positions_are_a_perfect_assignment(DS, small_store):
     ds = DS(s.row_ptr, s.txp_id, s.prob, s.n_txps)
     li = ds.layout_info()
     assert li["tiled"] == 1 and li["n_tiles"] > 0
-    words = ds.layout_lpos(0, li["n_tiles"])
+    words, trash = ds.layout_lpos(0, li["n_tiles"], with_trash=True)
     ds.close()
     assert words.shape == (li["n_tiles"], 1024)
     real_slots = 0
     for t in range(li["n_tiles"]):
-        slots, pos, xd = lm.dump_tile(words[t])          # parses only if the trash offset is consistent with the items
+        slots, pos, xd = lm.dump_tile(words[t], trash[t])
+        assert lm._xd_of(slots) == xd                      # the trash slots start right behind the items
         real = pos[slots >= 0]
         assert len(np.unique(real)) == len(real)          # no x slot handed out twice
         items, _ = lm.items_of(slots)

@@ -392,11 +392,15 @@ def _xd_of(slots):
     return 18 * n32 + 10 * n16 + 6 * n8
 
 
-def dump_tile(words):
-    """(slot -> transcript index or -1, slot -> x position, XD) of one tile's 1024 layout words."""
+def dump_tile(words, xd=None):
+    """(slot -> transcript index or -1, slot -> x position, XD) of one tile's 1024 layout words.  XD (the trash offset, in
+    doubles) comes with the dump when oar_store_layout_lpos was asked for it; otherwise it is inferred, which can be
+    ambiguous for a tile whose trash slots happen to be used once each."""
     pos = (words >> 16).astype(np.int64) // 8
     off = (words & 0xFFFF).astype(np.int64)
     tr = ((off >> 8) << 5) | ((off & 127) >> 2)
+    if xd is not None:
+        return np.where(pos >= int(xd), -1, tr), pos, int(xd)
     mx = int(pos.max())
     # padding and stray alignments sit in the 16 trash slots behind the items, so XD is one of mx-15 .. mx+1.  Largest first: a
     # smaller value can be consistent too (dropping the whole last item of a transcript that has nothing else gives a shorter,

@@ -79,8 +79,6 @@ extern "C" void oar_store_destroy(oar_store *s)
             for (auto &e : s->slot_ev) ctx_give_event(s->ctx, false, e);
             ctx_give_stream(s->ctx, s->stream);
         }
-        if (s->side) ctx_give_stream(s->ctx, s->side);
-        for (auto &e : s->cap_ev) if (e) ctx_give_event(s->ctx, false, e);
     }
     delete s;
     (void)cudaGetLastError();
@@ -446,28 +444,6 @@ static bool fused_update(const oar_store *s, bool weighted)
     static const char *env = getenv("OAR_FUSED_WTS_MAX_TILES");   // development: A/B of the policy
     return !weighted || s->tl.n_tiles <= (env ? (uint32_t)strtoul(env, nullptr, 10) : kFusedWeightedMaxTiles);
 }
-// Where the convergence bookkeeping of iteration k runs:
-//   serial  em_update right behind sweep k, sweep k+1 behind it (CSR kernel; OAR_UPDATE_MODE=serial)
-//   fused   in the head of sweep k+1 (one launch per iteration: small stores, where a launch is a sixth of a sweep)
-//   side    em_update on a side branch of the graph, next to sweep k+1, which does not need its verdict: it is speculative exactly
-//           as in the fused scheme, and sweep k+2 waits for it because it zeroes that sweep's target.  The sweep is the lean kernel
-//           and nothing but sweeps sits on the critical path (long sweeps)
-enum { kUpdateSerial = 0, kUpdateFused = 1, kUpdateSide = 2 };
-static const uint32_t kSideMinTiles = 16384;
-static int update_mode(const oar_store *s, bool weighted)
-{
-    static const char *env = getenv("OAR_UPDATE_MODE");   // development: serial | fused | side
-    const bool tiled = s->kernel == OAR_KERNEL_TILED && s->tl.ready && s->tl.n_tiles > 0;
-    if (env && tiled) {
-        if (!strcmp(env, "serial")) return kUpdateSerial;
-        if (!strcmp(env, "side")) return kUpdateSide;
-        if (!strcmp(env, "fused") && s->allow_fused) return kUpdateFused;
-    }
-    if (!tiled) return kUpdateSerial;
-    if (s->tl.n_tiles >= kSideMinTiles) return kUpdateSide;
-    return fused_update(s, weighted) ? kUpdateFused : kUpdateSerial;
-}
-
 static cudaError_t enqueue_sweep(oar_store *s, const double *prev, double *curr, const uint32_t *wts,
                                  const OarEmState *state, int check_done, bool fused = false)
 {
@@ -557,13 +533,11 @@ static cudaError_t refresh_wperm(oar_store *s, const uint32_t *wts)
     return cudaGetLastError();
 }
 
-static cudaError_t enqueue_update(oar_store *s, double *prev, const double *curr, cudaStream_t stream)
+static cudaError_t enqueue_update(oar_store *s, double *prev, const double *curr)
 {
-    // 128 threads at <= 32 registers: a CTA fits next to the six resident CTAs of the sweep (4 K registers are left per SM),
-    // so on the side branch the bookkeeping runs WHILE the next sweep does
-    const int threads = 128;
+    const int threads = 256;
     const int blocks = (int)std::max<uint32_t>(1, std::min<uint32_t>((s->n_txps + threads * 4 - 1) / (threads * 4), (uint32_t)s->sm_count * 4));
-    kern::em_update<<<blocks, threads, 0, stream>>>(prev, curr, s->n_txps, s->d_state);
+    kern::em_update<<<blocks, threads, 0, s->stream>>>(prev, curr, s->n_txps, s->d_state);
     s->counters[0] += 1;
     return cudaGetLastError();
 }
@@ -573,36 +547,22 @@ static cudaError_t enqueue_update(oar_store *s, double *prev, const double *curr
 static int ensure_graph(oar_store *s, bool weighted)
 {
     GraphSlot &g = s->graphs[weighted ? 1 : 0];
-    const int mode = update_mode(s, weighted);
-    if (g.exec && g.kernel == s->kernel && g.mode == mode) return OAR_OK;
+    if (g.exec && g.kernel == s->kernel && g.fused == fused_update(s, weighted)) return OAR_OK;
     if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
-    if (mode == kUpdateSide && !s->side) {
-        OAR_CUDA(ctx_take_stream(s->ctx, &s->side));
-        for (auto &e : s->cap_ev) OAR_CUDA(ctx_take_event(s->ctx, false, &e));
-    }
     const uint32_t *wts = weighted ? s->d_weights : nullptr;
     uint64_t saved = s->counters[0];
     cudaGraph_t graph = nullptr;
     OAR_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
     cudaError_t e = cudaSuccess;
+    const bool fused = fused_update(s, weighted);
     for (int it = 0; it < kGraphIters && e == cudaSuccess; ++it) {
         // sweep k: X[k % 3] -> X[(k + 1) % 3].  Fused: its head judges sweep k-1 (X[(k + 2) % 3] against X[k % 3]) and zeroes
-        // X[(k + 2) % 3], the target of sweep k+1.  Otherwise em_update judges sweep k and zeroes X[k % 3], the target of sweep
-        // k+2 -- right behind sweep k (serial), or on the side branch: S(k) -> U(k), U(k-1) -> U(k), U(k) -> S(k+2).
+        // X[(k + 2) % 3], the target of sweep k+1.  Otherwise em_update judges sweep k right after it and zeroes X[k % 3].
+        // (Tried in round 2: em_update on a side branch of the graph, next to sweep k+1 -- no faster than behind sweep k,
+        // 5 350 it/s either way on C3: the update is not what the iteration waits for.)
         double *prev = s->d_counts[it % 3], *curr = s->d_counts[(it + 1) % 3];
-        if (mode == kUpdateSide && it >= 2) e = cudaStreamWaitEvent(s->stream, s->cap_ev[it & 1], 0);   // U(it - 2) has zeroed curr
-        if (e == cudaSuccess) e = enqueue_sweep(s, prev, curr, wts, s->d_state, 1, mode == kUpdateFused);
-        if (e != cudaSuccess) break;
-        if (mode == kUpdateSerial) e = enqueue_update(s, prev, curr, s->stream);
-        else if (mode == kUpdateSide) {
-            e = cudaEventRecord(s->cap_ev[2], s->stream);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(s->side, s->cap_ev[2], 0);
-            if (e == cudaSuccess) e = enqueue_update(s, prev, curr, s->side);
-            if (e == cudaSuccess) e = cudaEventRecord(s->cap_ev[it & 1], s->side);
-        }
-    }
-    if (mode == kUpdateSide && e == cudaSuccess) {   // join: the graph ends when the last two updates have
-        e = cudaStreamWaitEvent(s->stream, s->cap_ev[(kGraphIters - 1) & 1], 0);
+        e = enqueue_sweep(s, prev, curr, wts, s->d_state, 1, fused);
+        if (e == cudaSuccess && !fused) e = enqueue_update(s, prev, curr);
     }
     cudaError_t e2 = cudaStreamEndCapture(s->stream, &graph);
     s->counters[0] = saved;
@@ -611,7 +571,7 @@ static int ensure_graph(oar_store *s, bool weighted)
     e = cudaGraphInstantiate(&g.exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) { g.exec = nullptr; return cuda_fail(e, "cudaGraphInstantiate"); }
-    g.kernel = s->kernel; g.mode = mode;
+    g.kernel = s->kernel; g.fused = fused;
     return OAR_OK;
 }
 
@@ -667,7 +627,7 @@ static int run_em(oar_store *s, const double *init_dev, uint32_t max_iter, doubl
         }
         // the launches still in flight are no-ops (done is set); they finish before the final sweep (same stream)
         // every kernel node of every graph launch is a launch of ours (those after convergence exit at once)
-        const uint64_t per_iter = (update_mode(s, weighted) == kUpdateFused ? 1 : 2) + ((s->kernel != OAR_KERNEL_ROWGROUP && s->tl.n_tiles > 0 && s->tl.n_fallback > kFoldFallbackMax) ? 1 : 0);
+        const uint64_t per_iter = (fused_update(s, weighted) ? 1 : 2) + ((s->kernel != OAR_KERNEL_ROWGROUP && s->tl.n_tiles > 0 && s->tl.n_fallback > kFoldFallbackMax) ? 1 : 0);
         s->counters[0] += launched_iters * per_iter;
     }
     // `sweeps` loop sweeps were judged: the last result is X[sweeps % 3]; X[(sweeps + 2) % 3] is zero (zeroed by the head of
@@ -780,13 +740,25 @@ static int bootstrap_impl(oar_store *s, const uint32_t *weights_or_null, uint32_
             rc = enqueue_sample_weights(s, seed, first + b * stride, s->d_weights);
             if (rc != OAR_OK) return rc;
         }
+        static const bool trace = getenv("OAR_TRACE") != nullptr;   // development: where a replicate's time goes (adds syncs)
+        if (trace) OAR_CUDA(cudaEventRecord(s->ev[2], s->stream));
         OAR_CUDA(refresh_wperm(s, s->d_weights));
+        if (trace) OAR_CUDA(cudaEventRecord(s->ev[3], s->stream));
         double *res = nullptr;
         uint32_t niter = 0;
         rc = run_em(s, nullptr, max_iter, thr, min_iter, true, &res, &niter, nullptr, nullptr);
         if (rc != OAR_OK) { cudaStreamSynchronize(s->stream); return rc; }
         if (out_niter) out_niter[b] = niter;
         OAR_CUDA(cudaMemcpyAsync(out + (uint64_t)b * s->n_txps, res, sizeof(double) * s->n_txps, cudaMemcpyDefault, s->stream));
+        if (trace) {
+            OAR_CUDA(cudaEventRecord(s->ev[1], s->stream));
+            OAR_CUDA(cudaStreamSynchronize(s->stream));
+            float w1 = 0.f, w2 = 0.f, em = 0.f;
+            cudaEventElapsedTime(&w1, s->ev[0], s->ev[2]); cudaEventElapsedTime(&w2, s->ev[2], s->ev[3]); cudaEventElapsedTime(&em, s->ev[3], s->ev[1]);
+            fprintf(stderr, "[oar] replicate %u: draw weights %.3f ms, tile order + lane weights %.3f ms, EM + download %.3f ms (%u iterations: %.1f us each)\n",
+                    first + b * stride, w1, w2, em, niter, em * 1e3f / (float)(niter + 1));
+            OAR_CUDA(cudaEventRecord(s->ev[0], s->stream));
+        }
     }
     OAR_CUDA(cudaEventRecord(s->ev[1], s->stream));
     OAR_CUDA(cudaStreamSynchronize(s->stream));

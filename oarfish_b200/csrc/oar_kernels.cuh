@@ -85,7 +85,7 @@ __device__ __forceinline__ void em_decide(OarEmState *st)
 // (signed, starts from 0; em.rs:194-201), then "swap + fill(0)" (em.rs:204-207)
 // == zero the old prev, which is the next sweep's target.  The last CTA applies
 // the stop rule (em.rs:212 / :399) and advances niter (em.rs:218).
-static __global__ void __launch_bounds__(128, 16) em_update(double *__restrict__ prev, const double *__restrict__ curr,
+static __global__ void __launch_bounds__(256) em_update(double *__restrict__ prev, const double *__restrict__ curr,
                                                  uint32_t M, OarEmState *st)
 {
     if (st->done) return;

@@ -30,7 +30,7 @@ struct TiledLayout {
 struct GraphSlot {
     cudaGraphExec_t exec = nullptr;
     int kernel = 0;
-    int mode = 0;         // where the convergence bookkeeping runs (oar_em.cu: kUpdateSerial / kUpdateFused / kUpdateSide)
+    bool fused = false;   // built with the convergence bookkeeping inside the sweep
 };
 
 }  // namespace oar
@@ -62,9 +62,6 @@ struct oar_store {
     uint32_t *d_weights = nullptr;  // N, bootstrap weights of the current replicate (read order)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t slot_ev[2] = {nullptr, nullptr};
-    // side branch of the EM graph (convergence bookkeeping next to the following sweep): taken from the context on first use
-    cudaStream_t side = nullptr;
-    cudaEvent_t cap_ev[3] = {nullptr, nullptr, nullptr};
 
     oar::GraphSlot graphs[2];  // [0] unweighted, [1] weighted
 

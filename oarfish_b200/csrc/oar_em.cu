@@ -816,8 +816,30 @@ extern "C" int oar_sweep_timed(oar_store *s, const double *prev_dev, double *cur
         OAR_CUDA(refresh_wperm(s, weights_or_null));
     }
     OAR_CUDA(cudaMemsetAsync(curr_dev, 0, sizeof(double) * s->n_txps, s->stream));
+    // development (OAR_TIMED_MODE): the same sweeps with the EM's early-exit test ("done"), as nodes of a CUDA graph ("graph"), or both
+    static const char *tmode = getenv("OAR_TIMED_MODE");
+    const int check_done = tmode && strstr(tmode, "done") ? 1 : 0;
+    if (check_done) OAR_CUDA(cudaMemsetAsync(s->d_state, 0, sizeof(OarEmState), s->stream));
+    if (tmode && strstr(tmode, "graph")) {
+        cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+        OAR_CUDA(cudaStreamSynchronize(s->stream));
+        OAR_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        for (int i = 0; i < kGraphIters; ++i) OAR_CUDA(enqueue_sweep(s, prev_dev, curr_dev, weights_or_null, s->d_state, check_done));
+        OAR_CUDA(cudaStreamEndCapture(s->stream, &graph));
+        OAR_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+        OAR_CUDA(cudaGraphLaunch(exec, s->stream));
+        OAR_CUDA(cudaEventRecord(s->ev[0], s->stream));
+        const int launches = (reps + kGraphIters - 1) / kGraphIters;
+        for (int i = 0; i < launches; ++i) OAR_CUDA(cudaGraphLaunch(exec, s->stream));
+        OAR_CUDA(cudaEventRecord(s->ev[1], s->stream));
+        OAR_CUDA(cudaStreamSynchronize(s->stream));
+        OAR_CUDA(cudaEventElapsedTime(out_ms_total, s->ev[0], s->ev[1]));
+        *out_ms_total *= (float)reps / (float)(launches * kGraphIters);
+        cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+        return OAR_OK;
+    }
     OAR_CUDA(cudaEventRecord(s->ev[0], s->stream));
-    for (int i = 0; i < reps; ++i) OAR_CUDA(enqueue_sweep(s, prev_dev, curr_dev, weights_or_null, s->d_state, 0));
+    for (int i = 0; i < reps; ++i) OAR_CUDA(enqueue_sweep(s, prev_dev, curr_dev, weights_or_null, s->d_state, check_done));
     OAR_CUDA(cudaEventRecord(s->ev[1], s->stream));
     OAR_CUDA(cudaStreamSynchronize(s->stream));
     OAR_CUDA(cudaEventElapsedTime(out_ms_total, s->ev[0], s->ev[1]));

@@ -91,6 +91,9 @@ static __global__ void __launch_bounds__(256) em_update(double *__restrict__ pre
     if (st->done) return;
     double m = 0.0;
     const uint32_t stride = gridDim.x * blockDim.x;
+#ifdef OAR_UPDATE_FAKE   // timing experiment only (wrong results): the launch and the ticket without the pass over the counts
+    M = 0;
+#endif
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += stride) {
         const double pc = prev[i];
         const double cc = curr[i];

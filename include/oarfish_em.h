@@ -286,7 +286,7 @@ int oar_aux_counts(oar_store *store, uint32_t *out_unique, uint32_t *out_total);
 
 /* Layout of the store in HBM: [0] tiled layout built, [1] tiles, [2] alignment
  * slots in tiles, [3] rows swept from the CSR instead (too long / did not fit),
- * [4] sum of per-tile distinct transcripts, [5] sum of per-tile 8-slot units,
+ * [4] sum of per-tile distinct transcripts, [5] sum of per-tile M-step items,
  * [6] tile span, [7] active kernel (oar_kernel). */
 int oar_store_layout_info(const oar_store *store, uint64_t out[8]);
 

@@ -434,9 +434,9 @@ static cudaError_t enqueue_rowgroup(oar_store *s, const uint32_t *list, uint64_t
 // `wts` are per-read weights in read order; the tiled kernel reads the copy
 // permuted into tile order (s->tl.wperm, refreshed by refresh_wperm()).
 // the sweep can carry the convergence bookkeeping of the PREVIOUS iteration (tiled kernel only, see fused_update())
-// Measured on B200: fused wins wherever one launch matters (C2: 40 -> 48 k it/s, plain and weighted) and on the plain C3
-// sweep (+0.3 %); the weighted instantiation with the bookkeeping head is ~8 us slower than the lean one on C3, more
-// than the launch it saves (4 965 vs 5 035 it/s over four replicates), so long weighted sweeps keep em_update.
+// Measured on B200: fused wins wherever one launch matters (C2: 41.7 -> 50.2 k it/s, plain and weighted) and, barely, on the
+// plain C3 sweep; for the weighted sweep on C3 the head costs what the launch it saves does (5 408 vs 5 417 it/s at five CTAs
+// per SM, 5 466 vs 5 480 at six; earlier builds: 4 965 vs 5 035), so long weighted sweeps keep em_update.
 static const uint32_t kFusedWeightedMaxTiles = 32768;
 static bool fused_update(const oar_store *s, bool weighted)
 {

@@ -9,7 +9,7 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "r2"
 for src, dst in (("bench_n1.json", f"{tag}_bench_n1.json"), ("bench_ref.json", f"{tag}_bench_reference_arm.json"),
                  ("launches.csv", f"{tag}_bench_launches.csv"), ("frows.json", f"{tag}_frows.json"),
                  ("robust.jsonl", f"{tag}_robustness.jsonl"), ("sanitizer.log", f"{tag}_sanitizer.txt"),
-                 ("bench_n2.json", f"{tag}_bench_n2.json"), ("bench_n8.json", f"{tag}_bench_n8.json")):
+                 ("bench_n2.json", f"{tag}_bench_n2.json"), ("bench_n4.json", f"{tag}_bench_n4.json"), ("bench_n8.json", f"{tag}_bench_n8.json")):
     if os.path.exists(os.path.join(G, src)) and os.path.getsize(os.path.join(G, src)) > 0:
         shutil.copy(os.path.join(G, src), os.path.join(P, dst))
 if os.path.exists(os.path.join(G, "launches.csv")):
